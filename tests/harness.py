@@ -1,0 +1,466 @@
+"""Shared test/bench harness: ctypes bindings and synthetic PCM generators.
+
+Three libraries can be driven through the *same* LINNE C API shape:
+  * the product      linne_b200/liblinne_b200.so         (CUDA, sm_100a)      -> linne_b200.api
+  * the reference    oracle/_ref/liblinne_ref.so         (unmodified C, built by oracle/Makefile)
+  * the oracle port  oracle/liblinne_oracle.so           (our plain-C restatement)
+
+The reference and the oracle are CHECKERS: only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs import this module's `Ref` / `Oracle` classes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "liblinne_ref.so")
+ORACLE_SO = os.path.join(ROOT, "oracle", "liblinne_oracle.so")
+
+OK, INVALID_ARGUMENT, INVALID_FORMAT, INSUFFICIENT_BUFFER, INSUFFICIENT_DATA, \
+    PARAMETER_NOT_SET, DATA_CORRUPTION, NG = range(8)
+
+PRESET_LAYERS = {0: (2, 32), 1: (2, 32), 2: (4, 64, 8), 3: (4, 64, 8), 4: (4, 64, 8),
+                 5: (4, 128, 16), 6: (4, 128, 16), 7: (4, 128, 16)}
+
+
+# ----------------------------------------------------------------------------------------------
+# ctypes mirrors of the public structs (include/linne.h, linne_encoder.h, linne_decoder.h)
+# ----------------------------------------------------------------------------------------------
+class LINNEHeader(C.Structure):
+    _fields_ = [("format_version", C.c_uint32), ("codec_version", C.c_uint32),
+                ("num_channels", C.c_uint16), ("num_samples", C.c_uint32),
+                ("sampling_rate", C.c_uint32), ("bits_per_sample", C.c_uint16),
+                ("num_samples_per_block", C.c_uint32), ("preset", C.c_uint8),
+                ("ch_process_method", C.c_int)]
+
+
+class LINNEEncodeParameter(C.Structure):
+    _fields_ = [("num_channels", C.c_uint16), ("bits_per_sample", C.c_uint16),
+                ("sampling_rate", C.c_uint32), ("num_samples_per_block", C.c_uint16),
+                ("preset", C.c_uint8), ("ch_process_method", C.c_int),
+                ("enable_learning", C.c_uint8), ("num_afmethod_iterations", C.c_uint8)]
+
+
+class LINNEEncoderConfig(C.Structure):
+    _fields_ = [("max_num_channels", C.c_uint32), ("max_num_samples_per_block", C.c_uint32),
+                ("max_num_layers", C.c_uint32), ("max_num_parameters_per_layer", C.c_uint32)]
+
+
+class LINNEDecoderConfig(C.Structure):
+    _fields_ = [("max_num_channels", C.c_uint32), ("max_num_layers", C.c_uint32),
+                ("max_num_parameters_per_layer", C.c_uint32), ("check_crc", C.c_uint8)]
+
+
+def bind_linne_api(lib):
+    """Declare argtypes/restype of the 14 public entry points on a loaded library."""
+    u8p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+    i32pp = C.POINTER(C.POINTER(C.c_int32))
+    lib.LINNEEncoder_EncodeHeader.argtypes = [C.POINTER(LINNEHeader), u8p, C.c_uint32]
+    lib.LINNEEncoder_EncodeHeader.restype = C.c_int
+    lib.LINNEEncoder_CalculateWorkSize.argtypes = [C.POINTER(LINNEEncoderConfig)]
+    lib.LINNEEncoder_CalculateWorkSize.restype = C.c_int32
+    lib.LINNEEncoder_Create.argtypes = [C.POINTER(LINNEEncoderConfig), C.c_void_p, C.c_int32]
+    lib.LINNEEncoder_Create.restype = C.c_void_p
+    lib.LINNEEncoder_Destroy.argtypes = [C.c_void_p]
+    lib.LINNEEncoder_Destroy.restype = None
+    lib.LINNEEncoder_SetEncodeParameter.argtypes = [C.c_void_p, C.POINTER(LINNEEncodeParameter)]
+    lib.LINNEEncoder_SetEncodeParameter.restype = C.c_int
+    for name in ("LINNEEncoder_EncodeBlock", "LINNEEncoder_EncodeWhole"):
+        f = getattr(lib, name)
+        f.argtypes = [C.c_void_p, i32pp, C.c_uint32, u8p, C.c_uint32, u32p]
+        f.restype = C.c_int
+    lib.LINNEDecoder_DecodeHeader.argtypes = [u8p, C.c_uint32, C.POINTER(LINNEHeader)]
+    lib.LINNEDecoder_DecodeHeader.restype = C.c_int
+    lib.LINNEDecoder_CalculateWorkSize.argtypes = [C.POINTER(LINNEDecoderConfig)]
+    lib.LINNEDecoder_CalculateWorkSize.restype = C.c_int32
+    lib.LINNEDecoder_Create.argtypes = [C.POINTER(LINNEDecoderConfig), C.c_void_p, C.c_int32]
+    lib.LINNEDecoder_Create.restype = C.c_void_p
+    lib.LINNEDecoder_Destroy.argtypes = [C.c_void_p]
+    lib.LINNEDecoder_Destroy.restype = None
+    lib.LINNEDecoder_SetHeader.argtypes = [C.c_void_p, C.POINTER(LINNEHeader)]
+    lib.LINNEDecoder_SetHeader.restype = C.c_int
+    lib.LINNEDecoder_DecodeBlock.argtypes = [C.c_void_p, u8p, C.c_uint32, i32pp, C.c_uint32,
+                                             C.c_uint32, u32p, u32p]
+    lib.LINNEDecoder_DecodeBlock.restype = C.c_int
+    lib.LINNEDecoder_DecodeWhole.argtypes = [C.c_void_p, u8p, C.c_uint32, i32pp, C.c_uint32, C.c_uint32]
+    lib.LINNEDecoder_DecodeWhole.restype = C.c_int
+    return lib
+
+
+def _chan_ptrs(pcm: np.ndarray):
+    """pcm: int32 [C][n] C-contiguous -> (int32**) array of row pointers (keeps pcm alive by ref)."""
+    assert pcm.dtype == np.int32 and pcm.ndim == 2 and pcm.flags["C_CONTIGUOUS"]
+    arr = (C.POINTER(C.c_int32) * pcm.shape[0])()
+    for c in range(pcm.shape[0]):
+        arr[c] = pcm[c].ctypes.data_as(C.POINTER(C.c_int32))
+    return arr
+
+
+class LinneApi:
+    """Drives any library exporting the LINNE public C API (reference or product)."""
+
+    def __init__(self, lib):
+        self.lib = bind_linne_api(lib)
+
+    # -- encode ---------------------------------------------------------------------------------
+    def make_encoder(self, channels, block, layers=3, params=128):
+        cfg = LINNEEncoderConfig(channels, block, layers, params)
+        h = self.lib.LINNEEncoder_Create(C.byref(cfg), None, 0)
+        if not h:
+            raise RuntimeError("LINNEEncoder_Create failed")
+        return h
+
+    def encode(self, pcm, bits=16, rate=44100, block=10240, preset=0, ms=None, learning=0, af=0,
+               max_block=None, cap=None, whole=True, return_code=False):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        nch, n = pcm.shape
+        if ms is None:
+            ms = 1 if nch >= 2 else 0
+        enc = self.make_encoder(nch, max_block or block)
+        try:
+            prm = LINNEEncodeParameter(nch, bits, rate, block, preset, ms, learning, af)
+            rc = self.lib.LINNEEncoder_SetEncodeParameter(enc, C.byref(prm))
+            if rc != OK:
+                if return_code:
+                    return rc, b""
+                raise RuntimeError(f"SetEncodeParameter rc={rc}")
+            if cap is None:
+                cap = 30 + 2 * nch * n * 4 + 1024 * (n // block + 2)
+            out = np.zeros(cap + 64, dtype=np.uint8)
+            size = C.c_uint32(0)
+            ptrs = _chan_ptrs(pcm)
+            if whole:
+                rc = self.lib.LINNEEncoder_EncodeWhole(enc, ptrs, n, out.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                       cap, C.byref(size))
+            else:  # the CLI's loop: header + EncodeBlock per block (tools/linne_codec/linne_codec.c:123-161)
+                hdr = LINNEHeader(1, 2, nch, n, rate, bits, block, preset, ms)
+                rc = self.lib.LINNEEncoder_EncodeHeader(C.byref(hdr), out.ctypes.data_as(C.POINTER(C.c_uint8)), cap)
+                off, done = 30, 0
+                while rc == OK and done < n:
+                    m = min(block, n - done)
+                    sub = (C.POINTER(C.c_int32) * nch)()
+                    for c in range(nch):
+                        sub[c] = C.cast(pcm[c].ctypes.data + 4 * done, C.POINTER(C.c_int32))
+                    rc = self.lib.LINNEEncoder_EncodeBlock(
+                        enc, sub, m, C.cast(out.ctypes.data + off, C.POINTER(C.c_uint8)), cap - off, C.byref(size))
+                    off += size.value
+                    done += m
+                size = C.c_uint32(off)
+            if return_code:
+                return rc, out[:size.value].tobytes() if rc == OK else b""
+            if rc != OK:
+                raise RuntimeError(f"encode rc={rc}")
+            return out[:size.value].tobytes()
+        finally:
+            self.lib.LINNEEncoder_Destroy(enc)
+
+    # -- decode ---------------------------------------------------------------------------------
+    def decode_header(self, data: bytes):
+        buf = np.frombuffer(data, dtype=np.uint8)
+        hdr = LINNEHeader()
+        rc = self.lib.LINNEDecoder_DecodeHeader(buf.ctypes.data_as(C.POINTER(C.c_uint8)), len(data), C.byref(hdr))
+        return rc, hdr
+
+    def decode(self, data: bytes, check_crc=1, return_code=False, out_channels=None, out_samples=None,
+               fill=0):
+        rc, hdr = self.decode_header(data)
+        if rc != OK:
+            if return_code:
+                return rc, None
+            raise RuntimeError(f"DecodeHeader rc={rc}")
+        nch = out_channels if out_channels is not None else hdr.num_channels
+        n = out_samples if out_samples is not None else hdr.num_samples
+        cfg = LINNEDecoderConfig(max(nch, hdr.num_channels, 1), 3, 128, check_crc)
+        dec = self.lib.LINNEDecoder_Create(C.byref(cfg), None, 0)
+        if not dec:
+            raise RuntimeError("LINNEDecoder_Create failed")
+        try:
+            # pad the stream: the reference's reader may touch up to 3 bytes past the end
+            buf = np.zeros(len(data) + 16, dtype=np.uint8)
+            buf[:len(data)] = np.frombuffer(data, dtype=np.uint8)
+            out = np.full((max(nch, 1), max(n, 1)), fill, dtype=np.int32)
+            rc = self.lib.LINNEDecoder_DecodeWhole(dec, buf.ctypes.data_as(C.POINTER(C.c_uint8)), len(data),
+                                                   _chan_ptrs(out), nch, n)
+            if return_code:
+                return rc, out
+            if rc != OK:
+                raise RuntimeError(f"decode rc={rc}")
+            return out
+        finally:
+            self.lib.LINNEDecoder_Destroy(dec)
+
+
+# ----------------------------------------------------------------------------------------------
+# The unmodified reference (oracle/_ref) with the probe entry points of oracle/ref_probe.c
+# ----------------------------------------------------------------------------------------------
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+class Ref(LinneApi):
+    def __init__(self):
+        super().__init__(C.CDLL(REF_SO, mode=getattr(os, "RTLD_LOCAL", 0)))
+        L = self.lib
+        L.RefProbe_EncoderLastParams.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32),
+                                                 C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.c_uint32]
+        L.RefProbe_EncoderLastPreemphasis.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.RefProbe_EncoderLastResidual.argtypes = [C.c_void_p, C.c_uint32]
+        L.RefProbe_EncoderLastResidual.restype = C.POINTER(C.c_int32)
+        L.RefProbe_CRC16.argtypes = [C.POINTER(C.c_uint8), C.c_uint64]
+        L.RefProbe_CRC16.restype = C.c_uint16
+        L.RefProbe_HuffmanCodes.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
+        L.RefProbe_QuantizeCoefficients.argtypes = [C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
+
+    def crc16(self, data: bytes) -> int:
+        buf = np.frombuffer(data, dtype=np.uint8)
+        return int(self.lib.RefProbe_CRC16(buf.ctypes.data_as(C.POINTER(C.c_uint8)), len(data)))
+
+    def huffman_codes(self, counts):
+        cnt = np.asarray(counts, dtype=np.uint32)
+        codes = np.zeros(len(cnt), dtype=np.uint32)
+        lens = np.zeros(len(cnt), dtype=np.uint8)
+        self.lib.RefProbe_HuffmanCodes(cnt.ctypes.data_as(C.POINTER(C.c_uint32)), len(cnt),
+                                       codes.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       lens.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return codes, lens
+
+    def encode_blocks_traced(self, pcm, bits=16, rate=44100, block=10240, preset=0, ms=None, learning=0, af=0):
+        """Encode block by block; returns (stream bytes, [per-block dict with type, bytes, per-channel
+        params: units/rshift/coef/preem]) -- the reference's analysis results for the
+        'identical coefficients -> identical bytes' leg."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        nch, n = pcm.shape
+        if ms is None:
+            ms = 1 if nch >= 2 else 0
+        layers = PRESET_LAYERS[preset]
+        enc = self.make_encoder(nch, block)
+        try:
+            prm = LINNEEncodeParameter(nch, bits, rate, block, preset, ms, learning, af)
+            assert self.lib.LINNEEncoder_SetEncodeParameter(enc, C.byref(prm)) == OK
+            cap = 11 + 2 * nch * block * 4 + 4096
+            out = np.zeros(cap, dtype=np.uint8)
+            hdr = LINNEHeader(1, 2, nch, n, rate, bits, block, preset, ms)
+            hbuf = np.zeros(30, dtype=np.uint8)
+            assert self.lib.LINNEEncoder_EncodeHeader(C.byref(hdr), hbuf.ctypes.data_as(C.POINTER(C.c_uint8)), 30) == OK
+            stream = [hbuf.tobytes()]
+            blocks = []
+            done = 0
+            while done < n:
+                m = min(block, n - done)
+                sub = (C.POINTER(C.c_int32) * nch)()
+                for c in range(nch):
+                    sub[c] = C.cast(pcm[c].ctypes.data + 4 * done, C.POINTER(C.c_int32))
+                size = C.c_uint32(0)
+                rc = self.lib.LINNEEncoder_EncodeBlock(enc, sub, m, out.ctypes.data_as(C.POINTER(C.c_uint8)), cap, C.byref(size))
+                assert rc == OK, rc
+                blk = out[:size.value].tobytes()
+                info = {"type": blk[8], "nsamples": m, "bytes": blk, "channels": []}
+                if blk[8] == 0:
+                    for c in range(nch):
+                        chd = {"units": [], "rshift": [], "coef": []}
+                        for l, P in enumerate(layers):
+                            u, r = C.c_uint32(0), C.c_uint32(0)
+                            q = np.zeros(P, dtype=np.int32)
+                            self.lib.RefProbe_EncoderLastParams(enc, c, l, C.byref(u), C.byref(r),
+                                                                q.ctypes.data_as(C.POINTER(C.c_int32)), P)
+                            chd["units"].append(u.value); chd["rshift"].append(r.value); chd["coef"].append(q)
+                        prev = (C.c_int32 * 2)(); pc = (C.c_int32 * 2)()
+                        self.lib.RefProbe_EncoderLastPreemphasis(enc, c, prev, pc)
+                        chd["preem_prev"] = [prev[0], prev[1]]; chd["preem_coef"] = [pc[0], pc[1]]
+                        rp = self.lib.RefProbe_EncoderLastResidual(enc, c)
+                        chd["residual"] = np.ctypeslib.as_array(rp, shape=(m,)).copy()
+                        info["channels"].append(chd)
+                blocks.append(info)
+                stream.append(blk)
+                done += m
+            return b"".join(stream), blocks
+        finally:
+            self.lib.LINNEEncoder_Destroy(enc)
+
+
+# ----------------------------------------------------------------------------------------------
+# Our plain-C restatement (oracle/liblinne_oracle.so)
+# ----------------------------------------------------------------------------------------------
+class LoChannelTrace(C.Structure):
+    _fields_ = [("preem_prev", C.c_int32 * 2), ("preem_coef", C.c_int32 * 2),
+                ("num_units", C.c_uint32 * 3), ("rshift", C.c_uint32 * 3),
+                ("coef", (C.c_int32 * 128) * 3), ("coef_f64", (C.c_double * 128) * 3),
+                ("porder", C.c_uint32), ("residual_bits", C.c_uint32)]
+
+
+class Oracle:
+    def __init__(self):
+        L = self.lib = C.CDLL(ORACLE_SO, mode=getattr(os, "RTLD_LOCAL", 0))
+        u8p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+        i32pp = C.POINTER(C.POINTER(C.c_int32))
+        L.lo_crc16.argtypes = [u8p, C.c_size_t]; L.lo_crc16.restype = C.c_uint16
+        L.lo_huffman_build.argtypes = [u32p, C.c_uint32, u32p, u8p]
+        L.lo_coef_huffman_table.argtypes = [u32p, u8p]
+        L.lo_rice_parameter.argtypes = [C.c_double, u32p, u32p]
+        L.lo_encoder_create.argtypes = [C.c_uint32, C.c_uint32]; L.lo_encoder_create.restype = C.c_void_p
+        L.lo_encoder_destroy.argtypes = [C.c_void_p]
+        L.lo_encoder_configure.argtypes = [C.c_void_p] + [C.c_uint32] * 8
+        L.lo_encode_whole.argtypes = [C.c_void_p, i32pp, C.c_uint32, u8p, C.c_uint32, u32p]
+        L.lo_encode_block.argtypes = [C.c_void_p, i32pp, C.c_uint32, u8p, C.c_uint32, u32p]
+        L.lo_encode_block_forced.argtypes = [C.c_void_p, i32pp, C.c_uint32, C.POINTER(LoChannelTrace), u8p, C.c_uint32, u32p]
+        L.lo_encoder_trace.argtypes = [C.c_void_p, C.c_uint32]; L.lo_encoder_trace.restype = C.POINTER(LoChannelTrace)
+        L.lo_encoder_last_residual.argtypes = [C.c_void_p, C.c_uint32]
+        L.lo_encoder_last_residual.restype = C.POINTER(C.c_int32)
+        L.lo_encoder_last_block_type.argtypes = [C.c_void_p]
+        L.lo_decode_whole.argtypes = [u8p, C.c_uint32, C.c_int, i32pp, C.c_uint32, C.c_uint32]
+        L.lo_quantize.argtypes = [C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_int32), u32p]
+        L.lo_coder_plan.argtypes = [C.POINTER(C.c_int32), C.c_uint32, u32p, u32p]
+        L.lo_coder_plan.restype = C.c_uint32
+
+    def crc16(self, data: bytes) -> int:
+        buf = np.frombuffer(data, dtype=np.uint8)
+        return int(self.lib.lo_crc16(buf.ctypes.data_as(C.POINTER(C.c_uint8)), len(data)))
+
+    def huffman_codes(self, counts):
+        cnt = np.asarray(counts, dtype=np.uint32)
+        codes = np.zeros(len(cnt), dtype=np.uint32)
+        lens = np.zeros(len(cnt), dtype=np.uint8)
+        self.lib.lo_huffman_build(cnt.ctypes.data_as(C.POINTER(C.c_uint32)), len(cnt),
+                                  codes.ctypes.data_as(C.POINTER(C.c_uint32)), lens.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return codes, lens
+
+    def coef_table(self):
+        codes = np.zeros(256, dtype=np.uint32); lens = np.zeros(256, dtype=np.uint8)
+        self.lib.lo_coef_huffman_table(codes.ctypes.data_as(C.POINTER(C.c_uint32)), lens.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return codes, lens
+
+    def rice_k2(self, mean: float) -> int:
+        k1, k2 = C.c_uint32(0), C.c_uint32(0)
+        self.lib.lo_rice_parameter(mean, C.byref(k1), C.byref(k2))
+        return k2.value
+
+    def encode(self, pcm, bits=16, rate=44100, block=10240, preset=0, ms=None, learning=0, af=0,
+               max_block=None, cap=None, return_code=False):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        nch, n = pcm.shape
+        if ms is None:
+            ms = 1 if nch >= 2 else 0
+        enc = self.lib.lo_encoder_create(nch, max_block or block)
+        try:
+            rc = self.lib.lo_encoder_configure(enc, nch, bits, rate, block, preset, ms, learning, af)
+            if rc != OK:
+                if return_code:
+                    return rc, b""
+                raise RuntimeError(f"configure rc={rc}")
+            if cap is None:
+                cap = 30 + 2 * nch * n * 4 + 1024 * (n // block + 2)
+            out = np.zeros(cap, dtype=np.uint8)
+            size = C.c_uint32(0)
+            rc = self.lib.lo_encode_whole(enc, _chan_ptrs(pcm), n, out.ctypes.data_as(C.POINTER(C.c_uint8)), cap, C.byref(size))
+            if return_code:
+                return rc, out[:size.value].tobytes() if rc == OK else b""
+            if rc != OK:
+                raise RuntimeError(f"encode rc={rc}")
+            return out[:size.value].tobytes()
+        finally:
+            self.lib.lo_encoder_destroy(enc)
+
+    def decode(self, data: bytes, check_crc=1, return_code=False):
+        buf = np.frombuffer(data, dtype=np.uint8)
+        nch = int.from_bytes(data[12:14], "big"); n = int.from_bytes(data[14:18], "big")
+        out = np.zeros((max(nch, 1), max(n, 1)), dtype=np.int32)
+        rc = self.lib.lo_decode_whole(buf.ctypes.data_as(C.POINTER(C.c_uint8)), len(data), check_crc,
+                                      _chan_ptrs(out), nch, n)
+        if return_code:
+            return rc, out
+        if rc != OK:
+            raise RuntimeError(f"decode rc={rc}")
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Synthetic PCM (SURVEY Appendix B.1 recipe family: sinusoid mixture + coloured noise + transients)
+# ----------------------------------------------------------------------------------------------
+def synth_channel(n, sr, seed):
+    r = np.random.default_rng(seed)
+    t = np.arange(n) / sr
+    x = np.zeros(n)
+    for f, a in [(220, 0.25), (440, 0.15), (1000 * r.uniform(0.9, 1.1), 0.1), (3300, 0.05)]:
+        x += a * np.sin(2 * np.pi * f * t + r.uniform(0, 6.28))
+    w = r.standard_normal(n)
+    # one-pole-ish colouring: 200-tap exponential FIR, applied by FFT for long signals
+    k = 0.95 ** np.arange(200)
+    if n > 1 << 16:
+        L = 1 << int(np.ceil(np.log2(n + 200)))
+        x += np.fft.irfft(np.fft.rfft(w, L) * np.fft.rfft(k, L), L)[:n] * 0.01
+    else:
+        x += np.convolve(w, k)[:n] * 0.01
+    num_tr = max(1, int(round(20 * n / (sr * 10))))
+    if n > 2000:
+        for p in r.integers(0, n - 2000, size=num_tr):
+            x[p:p + 2000] += 0.3 * np.exp(-np.arange(2000) / 200.0) * r.standard_normal(2000)
+    return x
+
+
+def synth_pcm(seconds=10.0, sr=44100, channels=2, bits=16, seed=1, n=None):
+    """int32 [C][n] right-justified PCM.  channels=2, bits=16, seconds=10, seed=1 reproduces the
+    SURVEY B.1 clip exactly (R = 0.7 L + 0.3 other)."""
+    if n is None:
+        n = int(round(seconds * sr))
+    base = synth_channel(n, sr, seed)
+    chans = [base]
+    for c in range(1, channels):
+        chans.append(0.7 * base + 0.3 * synth_channel(n, sr, seed + c))
+    scale = 20000.0 * (1 << (bits - 16)) if bits >= 16 else 20000.0 / (1 << (16 - bits))
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    return np.clip(np.round(np.stack(chans, 0) * scale), lo, hi).astype(np.int32)
+
+
+def reference_test_generators():
+    """The nine waveform generators of the reference's round-trip test
+    (test/linne_encode_decode/main.cpp:47-188), as float arrays in [-1, 1]."""
+    def silence(c, n): return np.zeros((c, n))
+    def sine(c, n): return np.tile(np.sin(440.0 * 2 * np.pi * np.arange(n) / 44100.0), (c, 1))
+    def sine_flip(c, n): return np.stack([(-1.0) ** ch * np.sin(440.0 * 2 * np.pi * np.arange(n) / 44100.0) for ch in range(c)])
+    def white(c, n): return np.random.default_rng(0).uniform(-1.0, 1.0, size=(c, n))
+    def chirp(c, n):
+        s = np.arange(n); return np.tile(np.sin((2.0 * np.pi * s) / (n - s)), (c, 1))
+    def pos(c, n): return np.ones((c, n))
+    def neg(c, n): return -np.ones((c, n))
+    def nyquist(c, n): return np.tile(np.where(np.arange(n) % 2 == 0, 1.0, -1.0), (c, 1))
+    def gauss(c, n): return np.clip(0.25 * np.random.default_rng(1).standard_normal((c, n)), -1.0, 1.0)
+    return {"silence": silence, "sine": sine, "sine_flip": sine_flip, "white": white, "chirp": chirp,
+            "pos_const": pos, "neg_const": neg, "nyquist": nyquist, "gauss": gauss}
+
+
+def to_fixed(x, bits):
+    """test/linne_encode_decode/main.cpp:191-214: round half away from zero, clip the top."""
+    v = np.where(x >= 0, np.floor(x * (1 << (bits - 1)) + 0.5), -np.floor(-x * (1 << (bits - 1)) + 0.5))
+    return np.minimum(v, (1 << (bits - 1)) - 1).astype(np.int32)
+
+
+def mixed_types_pcm(sr=44100, bits=16):
+    """3 s stereo: full-scale white noise / digital silence / 440 Hz sine -> RAW, SILENT and
+    compressed blocks in one stream."""
+    r = np.random.default_rng(7)
+    full = (1 << (bits - 1)) - 1
+    a = r.integers(-full - 1, full + 1, size=(2, sr))
+    b = np.zeros((2, sr), dtype=np.int64)
+    c = np.tile(np.round(0.5 * full * np.sin(2 * np.pi * 440 * np.arange(sr) / sr)), (2, 1))
+    return np.concatenate([a, b, c], axis=1).astype(np.int32)
+
+
+def tile_stream(stream: bytes, times: int, block: int) -> bytes:
+    """Repeat the full-size blocks of a stream `times` times behind one patched header (legal because
+    blocks are self-contained, SURVEY Appendix B 'Block tiling verified')."""
+    nch = int.from_bytes(stream[12:14], "big")
+    off = 30
+    spans = []
+    while off < len(stream):
+        size = int.from_bytes(stream[off + 2:off + 6], "big") + 6
+        ns = int.from_bytes(stream[off + 9:off + 11], "big")
+        if ns == block:
+            spans.append((off, off + size))
+        off += size
+    body = b"".join(stream[a:b] for a, b in spans)
+    total = len(spans) * block * times
+    hdr = bytearray(stream[:30])
+    hdr[14:18] = total.to_bytes(4, "big")
+    return bytes(hdr) + body * times
