@@ -1,0 +1,23 @@
+/* linne_b200_ext.c -- extension entry points declared in include/linne_b200.h. */
+#include "linne_b200.h"
+#include "lnb_shim.h"
+
+/* both handle structs start with their LINNEHeader; the device context is reached through accessors
+ * defined next to the struct definitions */
+LnbDevice *lnb_encoder_device(const struct LINNEEncoder *enc);
+LnbDevice *lnb_decoder_device(const struct LINNEDecoder *dec);
+
+const char *LINNEB200_Backend(void) { return lnb_shim_backend(); }
+
+int LINNEB200_DeviceAvailable(void)
+{
+    LnbDevice *dev = NULL;
+    if (lnb_shim_open(&dev, -1) != 0) return 0;
+    lnb_shim_close(dev);
+    return 1;
+}
+
+uint64_t LINNEB200_EncoderLaunchCount(const struct LINNEEncoder *e) { return e ? lnb_shim_launch_count(lnb_encoder_device(e)) : 0; }
+uint64_t LINNEB200_DecoderLaunchCount(const struct LINNEDecoder *d) { return d ? lnb_shim_launch_count(lnb_decoder_device(d)) : 0; }
+void LINNEB200_EncoderUseStream(struct LINNEEncoder *e, void *s) { if (e) lnb_shim_use_stream(lnb_encoder_device(e), s); }
+void LINNEB200_DecoderUseStream(struct LINNEDecoder *d, void *s) { if (d) lnb_shim_use_stream(lnb_decoder_device(d), s); }

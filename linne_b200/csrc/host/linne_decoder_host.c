@@ -1,0 +1,317 @@
+/* linne_decoder_host.c -- LINNEDecoder_* entry points (include/linne_decoder.h) on top of the CUDA shim.
+ *
+ * Replaces reference libs/linne_decoder/src/linne_decoder.c.  The host side does what is serial and
+ * tiny (argument checks, the 30-byte header, hopping over the block size fields to build the block
+ * table); everything that touches samples or payload bits runs on the GPU, batched over every block
+ * of the call.  Error results and their precedence follow the reference (cited per check).
+ */
+#include "linne_decoder.h"
+#include "lnb_host_util.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define DEC_FLAG_OWN_WORK   (1u << 0)
+#define DEC_FLAG_HEADER_SET (1u << 1)
+#define DEC_FLAG_CHECK_CRC  (1u << 2)
+
+struct LINNEDecoder {
+    struct LINNEHeader header;
+    uint32_t max_num_channels, max_num_layers, max_num_parameters_per_layer;
+    uint32_t flags;
+    void *work;
+    LnbDevice *dev;
+    LnbBuf d_stream, d_blocks, d_params, d_pcm;
+    LnbBuf h_blocks;                       /* pinned LnbBlockDesc[] */
+};
+
+/* reference linne_decoder.c:60-131 */
+LINNEApiResult LINNEDecoder_DecodeHeader(const uint8_t *data, uint32_t data_size, struct LINNEHeader *header)
+{
+    if (data == NULL || header == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (data_size < LINNE_HEADER_SIZE) return LINNE_APIRESULT_INSUFFICIENT_DATA;
+    if (data[0] != 'I' || data[1] != 'B' || data[2] != 'R' || data[3] != 'A') return LINNE_APIRESULT_INVALID_FORMAT;
+    lnb_header_read(data, header);
+    return LINNE_APIRESULT_OK;
+}
+
+static int config_ok(const struct LINNEDecoderConfig *c)
+{
+    return c && c->max_num_channels && c->max_num_layers && c->max_num_parameters_per_layer;
+}
+
+/* reference linne_decoder.c:187-216: the work area only has to hold the host handle here */
+int32_t LINNEDecoder_CalculateWorkSize(const struct LINNEDecoderConfig *config)
+{
+    if (!config_ok(config)) return -1;
+    return (int32_t)(sizeof(struct LINNEDecoder) + LNB_ALIGNMENT);
+}
+
+/* reference linne_decoder.c:219-296 */
+struct LINNEDecoder *LINNEDecoder_Create(const struct LINNEDecoderConfig *config, void *work, int32_t work_size)
+{
+    struct LINNEDecoder *dec;
+    int own = 0;
+    if (work == NULL && work_size == 0) {
+        if ((work_size = LINNEDecoder_CalculateWorkSize(config)) < 0) return NULL;
+        work = malloc((size_t)work_size);
+        own = 1;
+    }
+    if (!config_ok(config) || work == NULL || work_size < LINNEDecoder_CalculateWorkSize(config)) {
+        if (own) free(work);
+        return NULL;
+    }
+    dec = (struct LINNEDecoder *)LNB_ROUNDUP((uintptr_t)work, LNB_ALIGNMENT);
+    memset(dec, 0, sizeof(*dec));
+    dec->work = work;
+    dec->max_num_channels = config->max_num_channels;
+    dec->max_num_layers = config->max_num_layers;
+    dec->max_num_parameters_per_layer = config->max_num_parameters_per_layer;
+    if (own) dec->flags |= DEC_FLAG_OWN_WORK;
+    if (config->check_crc == 1) dec->flags |= DEC_FLAG_CHECK_CRC;
+    if (lnb_shim_open(&dec->dev, -1) != 0) {
+        fprintf(stderr, "linne_b200: no usable CUDA device -- the decoder has no CPU fallback\n");
+        if (own) free(work);
+        return NULL;
+    }
+    return dec;
+}
+
+/* reference linne_decoder.c:299-306 */
+void LINNEDecoder_Destroy(struct LINNEDecoder *dec)
+{
+    if (dec == NULL) return;
+    if (dec->dev) {
+        lnb_buf_release_device(dec->dev, &dec->d_stream);
+        lnb_buf_release_device(dec->dev, &dec->d_blocks);
+        lnb_buf_release_device(dec->dev, &dec->d_params);
+        lnb_buf_release_device(dec->dev, &dec->d_pcm);
+        lnb_buf_release_host(&dec->h_blocks);
+        lnb_shim_close(dec->dev);
+        dec->dev = NULL;
+    }
+    if (dec->flags & DEC_FLAG_OWN_WORK) free(dec->work);
+}
+
+/* reference linne_decoder.c:309-354 */
+LINNEApiResult LINNEDecoder_SetHeader(struct LINNEDecoder *dec, const struct LINNEHeader *header)
+{
+    const LnbPreset *ps;
+    int i;
+    if (dec == NULL || header == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (!lnb_header_fields_valid(header)) return LINNE_APIRESULT_INVALID_FORMAT;
+    if (dec->max_num_channels < header->num_channels) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    ps = &g_lnb_presets[header->preset];
+    if (dec->max_num_layers < (uint32_t)ps->num_layers) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    for (i = 0; i < ps->num_layers; i++)
+        if (dec->max_num_parameters_per_layer < (uint32_t)ps->layer_params[i]) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    if (header->num_channels > LINNE_MAX_NUM_CHANNELS) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    dec->header = *header;
+    dec->flags |= DEC_FLAG_HEADER_SET;
+    return LINNE_APIRESULT_OK;
+}
+
+/* ----------------------------------------------------------------------------------------------
+ * Block table: hop over the size fields (serial by nature, a few ns per block).
+ * Per block the reference checks, in this order (linne_decoder.c:604-653):
+ *   sync (INVALID_FORMAT) -> size (INSUFFICIENT_DATA) -> CRC (DETECT_DATA_CORRUPTION)
+ *   -> sample count vs buffer (INSUFFICIENT_BUFFER) -> type (INVALID_FORMAT, :651)
+ *   -> raw payload size (INSUFFICIENT_DATA, :383)
+ * Sync and size stop the hop; the later ones are recorded as the terminal block's `post_crc_error`
+ * because a CRC mismatch (known only after the GPU pass) outranks them.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t num_blocks;          /* blocks entered in the table (the terminal block included if its CRC can be checked) */
+    uint32_t num_decodable;       /* blocks that can be decoded (terminal block with a post-CRC error excluded) */
+    LINNEApiResult framing_error; /* error that ends the stream after num_blocks blocks (or OK) */
+    LINNEApiResult post_crc_error;/* error of block num_decodable (only when num_blocks == num_decodable + 1) */
+    uint32_t total_samples;
+    uint32_t end_offset;
+} BlockScan;
+
+static int scan_blocks(const struct LINNEHeader *h, const uint8_t *data, uint32_t data_size,
+                       uint32_t start_offset, uint32_t max_samples, uint32_t sample_limit, int single,
+                       LnbBlockDesc *table, uint32_t table_cap, BlockScan *out)
+{
+    uint32_t off = start_offset, progress = 0, nb = 0;
+    memset(out, 0, sizeof(*out));
+    out->framing_error = LINNE_APIRESULT_OK;
+    out->post_crc_error = LINNE_APIRESULT_OK;
+    while (progress < sample_limit && off < data_size) {
+        const uint8_t *p = data + off;
+        const uint32_t remain = data_size - off;
+        uint32_t size32, type, ns, consumed;
+        LnbBlockDesc *d;
+        if (nb >= table_cap) return 1;                         /* caller grows the table and retries */
+        if (remain < 2 || lnb_rd_be(p, 2) != LNB_SYNC_CODE) {
+            out->framing_error = (remain < 2) ? LINNE_APIRESULT_INSUFFICIENT_DATA : LINNE_APIRESULT_INVALID_FORMAT;
+            break;
+        }
+        if (remain < 6) { out->framing_error = LINNE_APIRESULT_INSUFFICIENT_DATA; break; }
+        size32 = lnb_rd_be(p + 2, 4);
+        if ((uint64_t)size32 + 6u > remain) { out->framing_error = LINNE_APIRESULT_INSUFFICIENT_DATA; break; }
+        if (size32 < 5u) { out->framing_error = LINNE_APIRESULT_INVALID_FORMAT; break; }   /* cannot hold crc+type+count */
+        type = p[8];
+        ns = lnb_rd_be(p + 9, 2);
+        d = &table[nb];
+        memset(d, 0, sizeof(*d));
+        d->smp_off = progress; d->nsmp = ns; d->byte_off = off; d->byte_size = size32 + 6u; d->type = type;
+        nb++;
+        if (ns > max_samples - progress) { out->post_crc_error = LINNE_APIRESULT_INSUFFICIENT_BUFFER; break; }
+        if (type > LNB_BLOCK_RAW) { out->post_crc_error = LINNE_APIRESULT_INVALID_FORMAT; break; }
+        if (type == LNB_BLOCK_RAW) {
+            const uint32_t need = (h->bits_per_sample * ns * h->num_channels) / 8u;
+            if (remain - LNB_BLOCK_HEADER_SIZE < need) { out->post_crc_error = LINNE_APIRESULT_INSUFFICIENT_DATA; break; }
+            consumed = LNB_BLOCK_HEADER_SIZE + (h->bits_per_sample / 8u) * ns * h->num_channels;
+        } else if (type == LNB_BLOCK_SILENT) {
+            consumed = LNB_BLOCK_HEADER_SIZE;
+        } else {
+            consumed = size32 + 6u;                            /* == 11 + ceil(bits/8) for any stream an encoder wrote */
+        }
+        out->num_decodable = nb;
+        progress += ns;
+        off += consumed;
+        if (single) break;
+    }
+    out->num_blocks = nb;
+    out->total_samples = progress;
+    out->end_offset = off;
+    return 0;
+}
+
+/* shared by DecodeBlock (single = 1) and DecodeWhole */
+static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
+                                   uint32_t start_offset, int32_t **buffer, uint32_t buffer_num_samples,
+                                   uint32_t sample_limit, int single,
+                                   uint32_t *consumed_bytes, uint32_t *decoded_samples)
+{
+    const struct LINNEHeader *h = &dec->header;
+    const uint32_t C = h->num_channels;
+    LnbDecodeBatch batch;
+    BlockScan scan;
+    LnbBlockDesc *blocks;
+    uint32_t guess, first_bad, ok_samples, c, i;
+    size_t padded;
+    LINNEApiResult result;
+
+    /* block table in pinned host memory; grow until the hop fits */
+    guess = single ? 1u : (uint32_t)((uint64_t)(data_size - start_offset) / 64u + 16u);
+    if (!single && h->num_samples_per_block) {
+        const uint32_t by_samples = sample_limit / h->num_samples_per_block + 16u;
+        if (by_samples < guess) guess = by_samples * 2u;
+    }
+    for (;;) {
+        if (lnb_buf_reserve_host(&dec->h_blocks, (size_t)guess * sizeof(LnbBlockDesc))) return LINNE_APIRESULT_NG;
+        blocks = (LnbBlockDesc *)dec->h_blocks.ptr;
+        if (scan_blocks(h, data, data_size, start_offset, buffer_num_samples, sample_limit, single,
+                        blocks, guess, &scan) == 0) break;
+        guess *= 2u;
+    }
+
+    if (consumed_bytes) *consumed_bytes = 0;
+    if (decoded_samples) *decoded_samples = 0;
+    if (scan.num_blocks == 0) return scan.framing_error;      /* OK when there was simply nothing to do */
+
+    /* device buffers */
+    padded = LNB_ROUNDUP((size_t)data_size + 16u, 16u);
+    lnb_fill_stream_cfg(&batch.cfg, h);
+    batch.cfg.pcm_stride = (uint32_t)LNB_ROUNDUP((size_t)scan.total_samples + 4u, 4u);
+    {   /* the terminal block (post-CRC error) may not fit the PCM planes: park it inside the stride */
+        uint32_t worst = scan.total_samples;
+        if (scan.num_blocks > scan.num_decodable) worst += blocks[scan.num_blocks - 1].nsmp;
+        batch.cfg.pcm_stride = (uint32_t)LNB_ROUNDUP((size_t)worst + 4u, 4u);
+    }
+    batch.cfg.work_stride = 0;
+    batch.cfg.check_crc = (dec->flags & DEC_FLAG_CHECK_CRC) ? 1u : 0u;
+    if (lnb_buf_reserve_device(dec->dev, &dec->d_stream, padded)
+        || lnb_buf_reserve_device(dec->dev, &dec->d_blocks, (size_t)scan.num_blocks * sizeof(LnbBlockDesc))
+        || lnb_buf_reserve_device(dec->dev, &dec->d_params, (size_t)scan.num_blocks * C * sizeof(LnbChanParams))
+        || lnb_buf_reserve_device(dec->dev, &dec->d_pcm, (size_t)batch.cfg.pcm_stride * C * sizeof(int32_t)))
+        return LINNE_APIRESULT_NG;
+
+    /* a terminal block with a post-CRC error takes part in the CRC pass only */
+    for (i = scan.num_decodable; i < scan.num_blocks; i++) blocks[i].type = 0xFFu;
+
+    batch.tab = *lnb_shim_tables(dec->dev);
+    batch.stream = (const uint8_t *)dec->d_stream.ptr;
+    batch.stream_size = data_size;
+    batch.blocks = (LnbBlockDesc *)dec->d_blocks.ptr;
+    batch.num_blocks = scan.num_blocks;
+    batch.params = (LnbChanParams *)dec->d_params.ptr;
+    batch.pcm = (int32_t *)dec->d_pcm.ptr;
+
+    lnb_shim_memset(dec->dev, (uint8_t *)dec->d_stream.ptr + (padded - 16u), 0, 16u);
+    lnb_shim_h2d(dec->dev, dec->d_stream.ptr, data, data_size);
+    lnb_shim_h2d(dec->dev, dec->d_blocks.ptr, blocks, (size_t)scan.num_blocks * sizeof(LnbBlockDesc));
+    if (lnb_shim_decode(dec->dev, &batch)) return LINNE_APIRESULT_NG;
+    lnb_shim_d2h(dec->dev, blocks, dec->d_blocks.ptr, (size_t)scan.num_blocks * sizeof(LnbBlockDesc));
+    if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+
+    /* first block (stream order) whose CRC failed outranks everything after it */
+    first_bad = scan.num_blocks;
+    if (dec->flags & DEC_FLAG_CHECK_CRC)
+        for (i = 0; i < scan.num_blocks; i++) if (blocks[i].status & LNB_ST_CRC_MISMATCH) { first_bad = i; break; }
+
+    if (first_bad < scan.num_blocks) {
+        result = LINNE_APIRESULT_DETECT_DATA_CORRUPTION;
+        ok_samples = blocks[first_bad].smp_off;
+    } else if (scan.num_blocks > scan.num_decodable) {
+        result = scan.post_crc_error;
+        ok_samples = scan.total_samples;
+        first_bad = scan.num_decodable;
+    } else {
+        result = scan.framing_error;
+        ok_samples = scan.total_samples;
+    }
+
+    /* hand back every sample the reference would have produced before stopping */
+    for (c = 0; c < C; c++)
+        lnb_shim_d2h(dec->dev, buffer[c], (int32_t *)dec->d_pcm.ptr + (size_t)c * batch.cfg.pcm_stride,
+                     (size_t)ok_samples * sizeof(int32_t));
+    if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+
+    if (single && result == LINNE_APIRESULT_OK) {
+        if (consumed_bytes) *consumed_bytes = LNB_BLOCK_HEADER_SIZE + blocks[0].na;
+        if (decoded_samples) *decoded_samples = blocks[0].nsmp;
+    } else {
+        if (consumed_bytes) *consumed_bytes = scan.end_offset - start_offset;
+        if (decoded_samples) *decoded_samples = ok_samples;
+    }
+    return result;
+}
+
+/* reference linne_decoder.c:564-668 */
+LINNEApiResult LINNEDecoder_DecodeBlock(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
+        int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples,
+        uint32_t *decode_size, uint32_t *num_decode_samples)
+{
+    uint32_t c;
+    if (dec == NULL || data == NULL || buffer == NULL || decode_size == NULL || num_decode_samples == NULL)
+        return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (!(dec->flags & DEC_FLAG_HEADER_SET)) return LINNE_APIRESULT_PARAMETER_NOT_SET;
+    if (buffer_num_channels < dec->header.num_channels) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    for (c = 0; c < dec->header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (data_size == 0) return LINNE_APIRESULT_INSUFFICIENT_DATA;
+    return decode_range(dec, data, data_size, 0, buffer, buffer_num_samples, 0xFFFFFFFFu, 1,
+                        decode_size, num_decode_samples);
+}
+
+/* reference linne_decoder.c:671-730 */
+LINNEApiResult LINNEDecoder_DecodeWhole(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
+        int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples)
+{
+    struct LINNEHeader header;
+    LINNEApiResult ret;
+    uint32_t c;
+    if (dec == NULL || data == NULL || buffer == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if ((ret = LINNEDecoder_DecodeHeader(data, data_size, &header)) != LINNE_APIRESULT_OK) return ret;
+    if ((ret = LINNEDecoder_SetHeader(dec, &header)) != LINNE_APIRESULT_OK) return ret;
+    if (buffer_num_channels < header.num_channels || buffer_num_samples < header.num_samples)
+        return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    for (c = 0; c < header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, buffer, buffer_num_samples,
+                        header.num_samples, 0, NULL, NULL);
+}
+
+LnbDevice *lnb_decoder_device(const struct LINNEDecoder *dec) { return dec->dev; }

@@ -1,0 +1,300 @@
+/* linne_encoder_host.c -- LINNEEncoder_* entry points (include/linne_encoder.h) on top of the CUDA shim.
+ *
+ * Replaces reference libs/linne_encoder/src/linne_encoder.c.  Host side: argument / parameter
+ * validation, the 30-byte header, cutting the stream into blocks, chunking the batch so the
+ * analysis scratch fits, and copying the packed chunk back.  All signal processing, analysis,
+ * coding and bit packing of every block x channel runs on the GPU.
+ */
+#include "linne_encoder.h"
+#include "lnb_host_util.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct LINNEEncoder {
+    struct LINNEHeader header;
+    uint32_t max_num_channels, max_num_samples_per_block, max_num_layers, max_num_parameters_per_layer;
+    uint8_t set_parameter, enable_learning, num_afmethod_iterations, own_work;
+    void *work;
+    LnbDevice *dev;
+    size_t scratch_budget;                 /* bytes of analysis scratch per chunk */
+    LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_win, d_cand, d_unit_loss,
+           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total;
+    LnbBuf h_blocks, h_welch, h_total;
+};
+
+/* reference linne_encoder.c:53-138 */
+LINNEApiResult LINNEEncoder_EncodeHeader(const struct LINNEHeader *header, uint8_t *data, uint32_t data_size)
+{
+    LINNEApiResult r;
+    if (header == NULL || data == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (data_size < LINNE_HEADER_SIZE) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    if ((r = lnb_header_check_for_encode(header)) != LINNE_APIRESULT_OK) return r;
+    lnb_header_write(header, data);
+    return LINNE_APIRESULT_OK;
+}
+
+static int config_ok(const struct LINNEEncoderConfig *c)
+{
+    return c && c->max_num_samples_per_block && c->max_num_channels && c->max_num_layers
+        && c->max_num_parameters_per_layer && c->max_num_parameters_per_layer <= c->max_num_samples_per_block;
+}
+
+/* reference linne_encoder.c:201-265 */
+int32_t LINNEEncoder_CalculateWorkSize(const struct LINNEEncoderConfig *config)
+{
+    if (!config_ok(config)) return -1;
+    return (int32_t)(sizeof(struct LINNEEncoder) + LNB_ALIGNMENT);
+}
+
+/* reference linne_encoder.c:268-396 */
+struct LINNEEncoder *LINNEEncoder_Create(const struct LINNEEncoderConfig *config, void *work, int32_t work_size)
+{
+    struct LINNEEncoder *enc;
+    int own = 0;
+    const char *budget;
+    if (work == NULL && work_size == 0) {
+        if ((work_size = LINNEEncoder_CalculateWorkSize(config)) < 0) return NULL;
+        work = malloc((size_t)work_size);
+        own = 1;
+    }
+    if (!config_ok(config) || work == NULL || work_size < LINNEEncoder_CalculateWorkSize(config)) {
+        if (own) free(work);
+        return NULL;
+    }
+    enc = (struct LINNEEncoder *)LNB_ROUNDUP((uintptr_t)work, LNB_ALIGNMENT);
+    memset(enc, 0, sizeof(*enc));
+    enc->work = work;
+    enc->own_work = (uint8_t)own;
+    enc->max_num_channels = config->max_num_channels;
+    enc->max_num_samples_per_block = config->max_num_samples_per_block;
+    enc->max_num_layers = config->max_num_layers;
+    enc->max_num_parameters_per_layer = config->max_num_parameters_per_layer;
+    enc->scratch_budget = (size_t)8 << 30;
+    if ((budget = getenv("LINNE_B200_SCRATCH_MB")) != NULL && atol(budget) > 0) enc->scratch_budget = (size_t)atol(budget) << 20;
+    if (lnb_shim_open(&enc->dev, -1) != 0) {
+        fprintf(stderr, "linne_b200: no usable CUDA device -- the encoder has no CPU fallback\n");
+        if (own) free(work);
+        return NULL;
+    }
+    return enc;
+}
+
+/* reference linne_encoder.c:399-407 */
+void LINNEEncoder_Destroy(struct LINNEEncoder *enc)
+{
+    if (enc == NULL) return;
+    if (enc->dev) {
+        LnbBuf *dbufs[] = { &enc->d_pcm, &enc->d_blocks, &enc->d_params, &enc->d_est, &enc->d_work, &enc->d_sig_a,
+                            &enc->d_sig_b, &enc->d_win, &enc->d_cand, &enc->d_unit_loss, &enc->d_chosen_w,
+                            &enc->d_chosen_u, &enc->d_final_sum, &enc->d_welch, &enc->d_plans, &enc->d_plan_mean,
+                            &enc->d_out, &enc->d_total };
+        size_t i;
+        for (i = 0; i < sizeof(dbufs) / sizeof(dbufs[0]); i++) lnb_buf_release_device(enc->dev, dbufs[i]);
+        lnb_buf_release_host(&enc->h_blocks);
+        lnb_buf_release_host(&enc->h_welch);
+        lnb_buf_release_host(&enc->h_total);
+        lnb_shim_close(enc->dev);
+        enc->dev = NULL;
+    }
+    if (enc->own_work) free(enc->work);
+}
+
+/* reference linne_encoder.c:141-198 (validation) and :410-477 */
+LINNEApiResult LINNEEncoder_SetEncodeParameter(struct LINNEEncoder *enc, const struct LINNEEncodeParameter *prm)
+{
+    const LnbPreset *ps;
+    int l;
+    if (enc == NULL || prm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (prm->num_channels == 0 || prm->bits_per_sample == 0 || prm->sampling_rate == 0
+        || prm->num_samples_per_block == 0 || prm->preset >= LINNE_NUM_PARAMETER_PRESETS
+        || (unsigned)prm->ch_process_method >= (unsigned)LINNE_CH_PROCESS_METHOD_INVALID)
+        return LINNE_APIRESULT_INVALID_FORMAT;
+    ps = &g_lnb_presets[prm->preset];
+    for (l = 0; l < ps->num_layers; l++)
+        if (prm->num_samples_per_block <= (uint32_t)ps->layer_params[l]) return LINNE_APIRESULT_INVALID_FORMAT;
+    if (enc->max_num_samples_per_block < prm->num_samples_per_block || enc->max_num_channels < prm->num_channels)
+        return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    if (enc->max_num_layers < (uint32_t)ps->num_layers) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    for (l = 0; l < ps->num_layers; l++)
+        if (enc->max_num_parameters_per_layer < (uint32_t)ps->layer_params[l]) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    if (prm->num_channels > LINNE_MAX_NUM_CHANNELS) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+
+    memset(&enc->header, 0, sizeof(enc->header));
+    enc->header.format_version = LINNE_FORMAT_VERSION;
+    enc->header.codec_version = LINNE_CODEC_VERSION;
+    enc->header.num_channels = prm->num_channels;
+    enc->header.sampling_rate = prm->sampling_rate;
+    enc->header.bits_per_sample = prm->bits_per_sample;
+    enc->header.num_samples_per_block = prm->num_samples_per_block;
+    enc->header.preset = prm->preset;
+    enc->header.ch_process_method = prm->ch_process_method;
+    enc->enable_learning = prm->enable_learning;
+    enc->num_afmethod_iterations = prm->num_afmethod_iterations;
+    enc->set_parameter = 1;
+    return LINNE_APIRESULT_OK;
+}
+
+/* samples the analysis looks at: reference linne_encoder.c:644-655 */
+static uint32_t analysis_length(const LnbStreamCfg *cfg, uint32_t n)
+{
+    uint32_t maxp = 0, na, l;
+    for (l = 0; l < cfg->num_layers; l++) if (maxp < cfg->layer_params[l]) maxp = cfg->layer_params[l];
+    na = LNB_ROUNDUP(n, 8u);
+    if (na < maxp) na = maxp;
+    if (na > cfg->block_size) na = cfg->block_size;
+    return na;
+}
+
+/* Encode the blocks covering samples [first_sample, first_sample + num_samples) of the device PCM
+ * planes into data[0..data_size); blocks are cut every header.num_samples_per_block samples. */
+static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_samples,
+                                    uint8_t *data, uint32_t data_size, uint32_t *written)
+{
+    const struct LINNEHeader *h = &enc->header;
+    const uint32_t C = h->num_channels, NB = h->num_samples_per_block;
+    const uint32_t total_blocks = (uint32_t)(((uint64_t)num_samples + NB - 1u) / NB);
+    LnbEncodeBatch batch;
+    uint32_t lambdas, slots_per_block, chunk_blocks, first, out_off = 0, i, lvl;
+    size_t per_block;
+
+    memset(&batch, 0, sizeof(batch));
+    lnb_fill_stream_cfg(&batch.cfg, h);
+    batch.cfg.pcm_stride = (uint32_t)LNB_ROUNDUP((size_t)num_samples + 4u, 4u);
+    batch.cfg.work_stride = (uint32_t)LNB_ROUNDUP((size_t)NB, 4u);
+    batch.tab = *lnb_shim_tables(enc->dev);
+    batch.pcm = (const int32_t *)enc->d_pcm.ptr;
+    lambdas = batch.cfg.num_lambdas;
+    slots_per_block = C * lambdas;
+
+    /* chunk so the double-precision analysis scratch stays inside the budget */
+    per_block = (size_t)slots_per_block * batch.cfg.work_stride * sizeof(double) * (2u + LNB_MAX_LEVELS)
+              + (size_t)C * batch.cfg.work_stride * sizeof(int32_t);
+    chunk_blocks = (uint32_t)(enc->scratch_budget / per_block);
+    if (chunk_blocks < 1u) chunk_blocks = 1u;
+    if (chunk_blocks > total_blocks) chunk_blocks = total_blocks;
+    while ((uint64_t)chunk_blocks * slots_per_block * batch.cfg.work_stride >= 0x7FFFFFFFull && chunk_blocks > 1u) chunk_blocks /= 2u;
+
+    {
+        const size_t S = (size_t)chunk_blocks * slots_per_block, BC = (size_t)chunk_blocks * C;
+        const size_t ws = batch.cfg.work_stride;
+        if (lnb_buf_reserve_host(&enc->h_blocks, chunk_blocks * sizeof(LnbBlockDesc))
+            || lnb_buf_reserve_host(&enc->h_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
+            || lnb_buf_reserve_host(&enc->h_total, 64)
+            || lnb_buf_reserve_device(enc->dev, &enc->d_blocks, chunk_blocks * sizeof(LnbBlockDesc))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_params, BC * sizeof(LnbChanParams))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_est, BC * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_work, BC * ws * sizeof(int32_t))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_sig_a, S * ws * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_sig_b, S * ws * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_win, S * LNB_MAX_LEVELS * ws * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_cand, S * LNB_MAX_LEVELS * LNB_MAX_PARAMS * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_unit_loss, S * LNB_MAX_LEVELS * LNB_MAX_UNITS * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_chosen_w, S * LNB_MAX_LAYERS * LNB_MAX_PARAMS * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_chosen_u, S * LNB_MAX_LAYERS)
+            || lnb_buf_reserve_device(enc->dev, &enc->d_final_sum, S * LNB_MAX_UNITS * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_plans, BC * sizeof(LnbCoderPlan))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_plan_mean, BC * 2u * LNB_MAX_PARTITIONS * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_total, 64))
+            return LINNE_APIRESULT_NG;
+    }
+    batch.blocks = (LnbBlockDesc *)enc->d_blocks.ptr;
+    batch.params = (LnbChanParams *)enc->d_params.ptr;
+    batch.est = (double *)enc->d_est.ptr;
+    batch.work = (int32_t *)enc->d_work.ptr;
+    batch.sig_a = (double *)enc->d_sig_a.ptr;
+    batch.sig_b = (double *)enc->d_sig_b.ptr;
+    batch.win = (double *)enc->d_win.ptr;
+    batch.cand = (double *)enc->d_cand.ptr;
+    batch.unit_loss = (double *)enc->d_unit_loss.ptr;
+    batch.chosen_w = (double *)enc->d_chosen_w.ptr;
+    batch.chosen_log2u = (uint8_t *)enc->d_chosen_u.ptr;
+    batch.final_sum = (double *)enc->d_final_sum.ptr;
+    batch.welch = (const double *)enc->d_welch.ptr;
+    batch.plans = (LnbCoderPlan *)enc->d_plans.ptr;
+    batch.plan_mean = (double *)enc->d_plan_mean.ptr;
+    batch.total_size = (uint32_t *)enc->d_total.ptr;
+    batch.out_base = 0;
+
+    for (first = 0; first < total_blocks; first += chunk_blocks) {
+        const uint32_t nb = (total_blocks - first < chunk_blocks) ? total_blocks - first : chunk_blocks;
+        LnbBlockDesc *hb = (LnbBlockDesc *)enc->h_blocks.ptr;
+        double *hw = (double *)enc->h_welch.ptr;
+        uint32_t chunk_bytes;
+        for (i = 0; i < nb; i++) {
+            const uint32_t start = (first + i) * NB;
+            const uint32_t n = (num_samples - start < NB) ? num_samples - start : NB;
+            memset(&hb[i], 0, sizeof(hb[i]));
+            hb[i].smp_off = start; hb[i].nsmp = n; hb[i].na = analysis_length(&batch.cfg, n);
+            for (lvl = 0; lvl < LNB_MAX_LEVELS; lvl++) {
+                const uint32_t m = hb[i].na >> lvl;
+                hw[(size_t)i * LNB_MAX_LEVELS + lvl] = (m >= 2u) ? lnb_welch_scale(m) : 0.0;
+            }
+        }
+        batch.num_blocks = nb;
+        lnb_shim_h2d(enc->dev, enc->d_blocks.ptr, hb, nb * sizeof(LnbBlockDesc));
+        lnb_shim_h2d(enc->dev, enc->d_welch.ptr, hw, (size_t)nb * LNB_MAX_LEVELS * sizeof(double));
+        if (lnb_shim_encode_analyze(enc->dev, &batch)) return LINNE_APIRESULT_NG;
+        lnb_shim_d2h(enc->dev, enc->h_total.ptr, enc->d_total.ptr, sizeof(uint32_t));
+        if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
+        chunk_bytes = *(uint32_t *)enc->h_total.ptr;
+        if ((uint64_t)out_off + chunk_bytes > data_size) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+        if (lnb_buf_reserve_device(enc->dev, &enc->d_out, (size_t)chunk_bytes + 64u)) return LINNE_APIRESULT_NG;
+        batch.out = (uint8_t *)enc->d_out.ptr;
+        if (lnb_shim_encode_pack(enc->dev, &batch, chunk_bytes)) return LINNE_APIRESULT_NG;
+        lnb_shim_d2h(enc->dev, data + out_off, enc->d_out.ptr, chunk_bytes);
+        if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
+        out_off += chunk_bytes;
+    }
+    *written = out_off;
+    return LINNE_APIRESULT_OK;
+}
+
+static LINNEApiResult upload_and_encode(struct LINNEEncoder *enc, const int32_t *const *input, uint32_t num_samples,
+                                        uint8_t *data, uint32_t data_size, uint32_t *written)
+{
+    const uint32_t C = enc->header.num_channels;
+    const size_t stride = LNB_ROUNDUP((size_t)num_samples + 4u, 4u);
+    uint32_t c;
+    if (enc->enable_learning || enc->num_afmethod_iterations) {
+        fprintf(stderr, "linne_b200: enable_learning / num_afmethod_iterations are not implemented on the device yet\n");
+        return LINNE_APIRESULT_NG;
+    }
+    if (lnb_buf_reserve_device(enc->dev, &enc->d_pcm, stride * C * sizeof(int32_t))) return LINNE_APIRESULT_NG;
+    for (c = 0; c < C; c++) {
+        if (input[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+        lnb_shim_h2d(enc->dev, (int32_t *)enc->d_pcm.ptr + c * stride, input[c], (size_t)num_samples * sizeof(int32_t));
+    }
+    return encode_blocks(enc, num_samples, data, data_size, written);
+}
+
+/* reference linne_encoder.c:774-862 */
+LINNEApiResult LINNEEncoder_EncodeBlock(struct LINNEEncoder *enc, const int32_t *const *input, uint32_t num_samples,
+        uint8_t *data, uint32_t data_size, uint32_t *output_size)
+{
+    if (enc == NULL || input == NULL || num_samples == 0 || data == NULL || data_size == 0 || output_size == NULL)
+        return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
+    if (num_samples > enc->header.num_samples_per_block) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    return upload_and_encode(enc, input, num_samples, data, data_size, output_size);
+}
+
+/* reference linne_encoder.c:865-932 */
+LINNEApiResult LINNEEncoder_EncodeWhole(struct LINNEEncoder *enc, const int32_t *const *input, uint32_t num_samples,
+        uint8_t *data, uint32_t data_size, uint32_t *output_size)
+{
+    LINNEApiResult ret;
+    uint32_t written = 0;
+    if (enc == NULL || input == NULL || data == NULL || output_size == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
+    enc->header.num_samples = num_samples;
+    if ((ret = LINNEEncoder_EncodeHeader(&enc->header, data, data_size)) != LINNE_APIRESULT_OK) return ret;
+    ret = upload_and_encode(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, &written);
+    if (ret != LINNE_APIRESULT_OK) return ret;
+    *output_size = LINNE_HEADER_SIZE + written;
+    return LINNE_APIRESULT_OK;
+}
+
+LnbDevice *lnb_encoder_device(const struct LINNEEncoder *enc) { return enc->dev; }

@@ -1,0 +1,31 @@
+/* lnb_host_util.h -- small helpers shared by the encoder and decoder host code (plain C). */
+#ifndef LNB_HOST_UTIL_H
+#define LNB_HOST_UTIL_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include "linne.h"
+#include "lnb_shim.h"
+
+#define LNB_ALIGNMENT 16
+#define LNB_ROUNDUP(v, n) ((((v) + ((n) - 1)) / (n)) * (n))
+
+/* grow-only device / host buffers owned by a handle */
+typedef struct LnbBuf { void *ptr; size_t cap; } LnbBuf;
+
+int  lnb_buf_reserve_device(LnbDevice *dev, LnbBuf *buf, size_t bytes);
+void lnb_buf_release_device(LnbDevice *dev, LnbBuf *buf);
+int  lnb_buf_reserve_host(LnbBuf *buf, size_t bytes);       /* pinned */
+void lnb_buf_release_host(LnbBuf *buf);
+
+/* 30-byte stream header (big-endian fields) */
+LINNEApiResult lnb_header_check_for_encode(const struct LINNEHeader *h);
+int  lnb_header_fields_valid(const struct LINNEHeader *h);  /* decoder-side validation */
+void lnb_header_write(const struct LINNEHeader *h, uint8_t *dst);
+void lnb_header_read(const uint8_t *src, struct LINNEHeader *h);
+
+static inline uint32_t lnb_rd_be(const uint8_t *p, int n) { uint32_t v = 0; int i; for (i = 0; i < n; i++) v = (v << 8) | p[i]; return v; }
+
+void lnb_fill_stream_cfg(LnbStreamCfg *cfg, const struct LINNEHeader *h);
+
+#endif

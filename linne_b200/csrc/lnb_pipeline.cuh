@@ -1,0 +1,350 @@
+/* lnb_pipeline.cuh -- the batch pipelines: which work-item functor runs over which index space,
+ * in which order.  Templated on an executor so the same sequence is
+ *   - launched as CUDA kernels on a stream by the product (lnb_kernels.cu), and
+ *   - stepped through as plain loops by tests/hostsim (CPU-only CI; not part of the product).
+ *
+ * An executor provides:  template<class F> void run(const char *name, uint32_t n_items, const F &f);
+ */
+#pragma once
+#include "lnb_common.cuh"
+#include "lnb_decode_core.cuh"
+#include "lnb_encode_core.cuh"
+
+#define LNB_ITEMS_PER_SLOT 255u          /* units over all unit-count levels: 1 + 2 + ... + 128 */
+
+/* =============================================================================================
+ * Decode
+ * ============================================================================================= */
+
+/* D0: CRC16 of every block body (type, sample count, payload) vs the transmitted field.
+ * reference linne_decoder.c:617-625 */
+struct LnbItemCrc {
+    LnbDecodeBatch b;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        LnbBlockDesc &blk = b.blocks[i];
+        const uint8_t *p = b.stream + blk.byte_off;
+        const uint16_t crc = lnb_crc16_serial(b.tab.crc_table, p + 8, blk.byte_size - 8u);
+        blk.crc = crc;
+        if (b.cfg.check_crc && crc != (uint16_t)lnb_get_be(p + 6, 2)) blk.status |= LNB_ST_CRC_MISMATCH;
+    }
+};
+
+/* D1: side information + entropy decode, one block per item */
+struct LnbItemEntropy {
+    LnbDecodeBatch b;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        lnb_decode_block_payload(b.cfg, b.tab, b.stream, b.stream_size, b.blocks[i],
+                                 b.params + (size_t)i * b.cfg.num_channels, b.pcm);
+    }
+};
+
+/* D2: synthesis of one layer; item = (block, channel, unit slot) */
+struct LnbItemSynth {
+    LnbDecodeBatch b;
+    uint32_t layer;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t u = i % LNB_MAX_UNITS, bc = i / LNB_MAX_UNITS;
+        const uint32_t blk_i = bc / b.cfg.num_channels, c = bc % b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED || blk.status) return;
+        const LnbChanParams &prm = b.params[bc];
+        const uint32_t P = b.cfg.layer_params[layer];
+        uint32_t U = 1u << prm.log2_units[layer];
+        if (u >= U || U > P) return;
+        const uint32_t p = P / U, m = blk.nsmp / U;
+        int32_t *x = b.pcm + (size_t)c * b.cfg.pcm_stride + blk.smp_off + (size_t)u * m;
+        lnb_synthesize_unit(x, m, prm.coef + layer * LNB_MAX_PARAMS + u * p, p, prm.rshift[layer]);
+    }
+};
+
+/* D3: de-emphasis; item = (block, channel) */
+struct LnbItemDeemph {
+    LnbDecodeBatch b;
+    LNB_HDM void operator()(uint32_t bc) const
+    {
+        const uint32_t blk_i = bc / b.cfg.num_channels, c = bc % b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED || blk.status) return;
+        const LnbChanParams &prm = b.params[bc];
+        lnb_deemphasis(b.pcm + (size_t)c * b.cfg.pcm_stride + blk.smp_off, blk.nsmp, prm.preem_prev, prm.preem_coef);
+    }
+};
+
+/* D4: M/S -> L/R; item = (block, sample) */
+struct LnbItemMsInverse {
+    LnbDecodeBatch b;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t blk_i = i / b.cfg.block_size, s = i % b.cfg.block_size;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED || blk.status || s >= blk.nsmp) return;
+        int32_t *l = b.pcm + blk.smp_off + s;
+        lnb_ms_to_lr(l[0], l[b.cfg.pcm_stride]);
+    }
+};
+
+template <class Exec>
+void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
+{
+    const uint32_t B = b.num_blocks, C = b.cfg.num_channels;
+    if (B == 0) return;
+    ex.run("crc", B, LnbItemCrc{b});
+    ex.run("entropy", B, LnbItemEntropy{b});
+    for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)
+        ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l});
+    ex.run("deemph", B * C, LnbItemDeemph{b});
+    if (b.cfg.ms && C >= 2u) ex.run("ms_inverse", B * b.cfg.block_size, LnbItemMsInverse{b});
+}
+
+/* =============================================================================================
+ * Encode
+ * ============================================================================================= */
+
+LNB_HD bool lnb_level_valid(uint32_t level, uint32_t P, uint32_t na)
+{
+    const uint32_t U = 1u << level;
+    return U <= P && U <= LNB_MAX_UNITS && (P % U) == 0u && (na % U) == 0u && na >= U;
+}
+
+struct LnbItemEstimate {            /* E0: (block, channel) */
+    LnbEncodeBatch b;
+    LNB_HDM void operator()(uint32_t bc) const
+    {
+        const uint32_t blk_i = bc / b.cfg.num_channels, c = bc % b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        b.est[bc] = lnb_estimate_bits(b.pcm + (size_t)c * b.cfg.pcm_stride + blk.smp_off, blk.nsmp,
+                                      b.cfg.bits_per_sample, b.cfg.layer_params[0]);
+    }
+};
+
+struct LnbItemPrepare {             /* E1: (block) */
+    LnbEncodeBatch b;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t C = b.cfg.num_channels;
+        lnb_prepare_block(b.cfg, b.blocks[i], b.est + (size_t)i * C, b.pcm,
+                          b.work + (size_t)i * C * b.cfg.work_stride, b.params + (size_t)i * C);
+    }
+};
+
+struct LnbItemToDouble {            /* (slot, sample): normalised copy of the work signal */
+    LnbEncodeBatch b;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t s = i / b.cfg.work_stride, t = i % b.cfg.work_stride;
+        const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        const double norm = ldexp(1.0, -(int)(b.cfg.bits_per_sample - 1u));
+        b.sig_a[(size_t)s * b.cfg.work_stride + t] =
+            (t < blk.na) ? (double)b.work[(size_t)bc * b.cfg.work_stride + t] * norm : 0.0;
+    }
+};
+
+struct LnbItemSearch {              /* E2: (slot, level, unit) */
+    LnbEncodeBatch b;
+    uint32_t layer;
+    const double *sig;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t s = i / LNB_ITEMS_PER_SLOT, id = i % LNB_ITEMS_PER_SLOT + 1u;
+        const uint32_t level = 31u - lnb_clz32(id), u = id - (1u << level);
+        const uint32_t bc = s / b.cfg.num_lambdas, lam = s % b.cfg.num_lambdas;
+        const uint32_t blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        const uint32_t P = b.cfg.layer_params[layer];
+        if (!lnb_level_valid(level, P, blk.na)) return;
+        const uint32_t U = 1u << level, p = P / U, m = blk.na / U;
+        const size_t ws = b.cfg.work_stride;
+        const double loss = lnb_search_unit(
+            sig + (size_t)s * ws, u, m, p, b.cfg.lambdas[lam], b.welch[(size_t)blk_i * LNB_MAX_LEVELS + level],
+            b.win + ((size_t)s * LNB_MAX_LEVELS + level) * ws + (size_t)u * m,
+            b.cand + ((size_t)s * LNB_MAX_LEVELS + level) * LNB_MAX_PARAMS + (size_t)u * p);
+        b.unit_loss[((size_t)s * LNB_MAX_LEVELS + level) * LNB_MAX_UNITS + u] = loss;
+    }
+};
+
+struct LnbItemSelect {              /* E3: (slot): first minimum over the unit counts (linne_network.c:337-341) */
+    LnbEncodeBatch b;
+    uint32_t layer;
+    LNB_HDM void operator()(uint32_t s) const
+    {
+        const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        const uint32_t P = b.cfg.layer_params[layer];
+        double best_loss = (double)FLT_MAX;
+        uint32_t best = 0;
+        bool found = false;
+        for (uint32_t level = 0; level < LNB_MAX_LEVELS; level++) {
+            if (!lnb_level_valid(level, P, blk.na)) continue;
+            const double *ul = b.unit_loss + ((size_t)s * LNB_MAX_LEVELS + level) * LNB_MAX_UNITS;
+            double loss = 0.0;
+            for (uint32_t u = 0; u < (1u << level); u++) loss += ul[u];
+            loss /= (double)blk.na;
+            if (loss < best_loss) { best_loss = loss; best = level; found = true; }
+        }
+        if (!found) best = 0;
+        b.chosen_log2u[(size_t)s * LNB_MAX_LAYERS + layer] = (uint8_t)best;
+        const double *src = b.cand + ((size_t)s * LNB_MAX_LEVELS + best) * LNB_MAX_PARAMS;
+        double *dst = b.chosen_w + ((size_t)s * LNB_MAX_LAYERS + layer) * LNB_MAX_PARAMS;
+        for (uint32_t k = 0; k < P; k++) dst[k] = src[k];
+    }
+};
+
+struct LnbItemForward {             /* E4: (slot, unit) */
+    LnbEncodeBatch b;
+    uint32_t layer;
+    const double *sig_in;
+    double *sig_out;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t s = i / LNB_MAX_UNITS, u = i % LNB_MAX_UNITS;
+        const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        const uint32_t U = 1u << b.chosen_log2u[(size_t)s * LNB_MAX_LAYERS + layer];
+        if (u >= U) return;
+        const uint32_t P = b.cfg.layer_params[layer], p = P / U, m = blk.na / U;
+        const size_t ws = b.cfg.work_stride;
+        const double sum = lnb_forward_unit(
+            sig_in + (size_t)s * ws, sig_out + (size_t)s * ws, u, m, p,
+            b.chosen_w + ((size_t)s * LNB_MAX_LAYERS + layer) * LNB_MAX_PARAMS + (size_t)u * p);
+        b.final_sum[(size_t)s * LNB_MAX_UNITS + u] = sum;
+    }
+};
+
+struct LnbItemFinish {              /* E5: (block, channel): best regulariser, quantise (linne_network.c:618-629) */
+    LnbEncodeBatch b;
+    LNB_HDM void operator()(uint32_t bc) const
+    {
+        const uint32_t blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        const uint32_t last = b.cfg.num_layers - 1u;
+        double best_loss = (double)FLT_MAX;
+        uint32_t best = 0;
+        for (uint32_t lam = 0; lam < b.cfg.num_lambdas; lam++) {
+            const size_t s = (size_t)bc * b.cfg.num_lambdas + lam;
+            const uint32_t U = 1u << b.chosen_log2u[s * LNB_MAX_LAYERS + last];
+            double sum = 0.0;
+            for (uint32_t u = 0; u < U; u++) sum += b.final_sum[s * LNB_MAX_UNITS + u];
+            const double loss = sum / (double)blk.na;
+            if (loss < best_loss) { best_loss = loss; best = lam; }
+        }
+        const size_t s = (size_t)bc * b.cfg.num_lambdas + best;
+        LnbChanParams &prm = b.params[bc];
+        for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
+            prm.log2_units[l] = b.chosen_log2u[s * LNB_MAX_LAYERS + l];
+            lnb_quantize_layer(b.chosen_w + (s * LNB_MAX_LAYERS + l) * LNB_MAX_PARAMS, b.cfg.layer_params[l],
+                               prm.coef + l * LNB_MAX_PARAMS, &prm.rshift[l]);
+        }
+    }
+};
+
+struct LnbItemPredict {             /* E6: (block, channel, unit slot), one layer */
+    LnbEncodeBatch b;
+    uint32_t layer;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t u = i % LNB_MAX_UNITS, bc = i / LNB_MAX_UNITS;
+        const uint32_t blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        const LnbChanParams &prm = b.params[bc];
+        const uint32_t P = b.cfg.layer_params[layer], U = 1u << prm.log2_units[layer];
+        if (u >= U || U > P) return;
+        const uint32_t p = P / U, m = blk.nsmp / U;
+        lnb_predict_unit_inplace(b.work + (size_t)bc * b.cfg.work_stride + (size_t)u * m, m,
+                                 prm.coef + layer * LNB_MAX_PARAMS + u * p, p, prm.rshift[layer]);
+    }
+};
+
+struct LnbItemPlan {                /* E7: (block, channel) */
+    LnbEncodeBatch b;
+    LNB_HDM void operator()(uint32_t bc) const
+    {
+        const uint32_t blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        lnb_coder_plan(b.tab.k2_threshold, b.work + (size_t)bc * b.cfg.work_stride, blk.nsmp,
+                       b.plan_mean + (size_t)bc * 2u * LNB_MAX_PARTITIONS, b.plans[bc]);
+    }
+};
+
+struct LnbItemSize {                /* E8a: (block) */
+    LnbEncodeBatch b;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        LnbBlockDesc &blk = b.blocks[i];
+        const uint32_t C = b.cfg.num_channels;
+        uint32_t payload = 0;
+        if (blk.type == LNB_BLOCK_RAW) payload = (b.cfg.bits_per_sample >> 3) * blk.nsmp * C;
+        else if (blk.type == LNB_BLOCK_COMPRESSED) {
+            uint64_t bits = lnb_side_info_bits(b.cfg, b.tab, b.params + (size_t)i * C);
+            for (uint32_t c = 0; c < C; c++) bits += b.plans[(size_t)i * C + c].bits;
+            payload = (uint32_t)((bits + 7u) >> 3);
+        }
+        blk.byte_size = LNB_BLOCK_HEADER_SIZE + payload;
+    }
+};
+
+struct LnbItemScan {                /* E8b: single item: exclusive scan of the block sizes */
+    LnbEncodeBatch b;
+    LNB_HDM void operator()(uint32_t) const
+    {
+        uint32_t off = b.out_base;
+        for (uint32_t i = 0; i < b.num_blocks; i++) { b.blocks[i].byte_off = off; off += b.blocks[i].byte_size; }
+        *b.total_size = off - b.out_base;
+    }
+};
+
+struct LnbItemPack {                /* E9: (block) */
+    LnbEncodeBatch b;
+    uint32_t out_capacity;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const LnbBlockDesc &blk = b.blocks[i];
+        const uint32_t C = b.cfg.num_channels;
+        if ((uint64_t)blk.byte_off + blk.byte_size > out_capacity) return;      /* host reports INSUFFICIENT_BUFFER */
+        lnb_pack_block(b.cfg, b.tab, blk, b.params + (size_t)i * C, b.plans + (size_t)i * C, b.pcm,
+                       b.work + (size_t)i * C * b.cfg.work_stride, b.out + blk.byte_off);
+    }
+};
+
+/* Stages E0..E8: everything up to (and including) the size scan.  Packing is a separate call so the
+ * host can check the output capacity (and place the batch) in between. */
+template <class Exec>
+void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
+{
+    const uint32_t B = b.num_blocks, C = b.cfg.num_channels;
+    if (B == 0) return;
+    const uint32_t S = B * C * b.cfg.num_lambdas;
+    ex.run("estimate", B * C, LnbItemEstimate{b});
+    ex.run("prepare", B, LnbItemPrepare{b});
+    ex.run("to_double", S * b.cfg.work_stride, LnbItemToDouble{b});
+    double *cur = b.sig_a, *nxt = b.sig_b;
+    for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
+        ex.run("search", S * LNB_ITEMS_PER_SLOT, LnbItemSearch{b, l, cur});
+        ex.run("select", S, LnbItemSelect{b, l});
+        ex.run("forward", S * LNB_MAX_UNITS, LnbItemForward{b, l, cur, nxt});
+        double *t = cur; cur = nxt; nxt = t;
+    }
+    ex.run("finish", B * C, LnbItemFinish{b});
+    for (uint32_t l = 0; l < b.cfg.num_layers; l++)
+        ex.run("predict", B * C * LNB_MAX_UNITS, LnbItemPredict{b, l});
+    ex.run("plan", B * C, LnbItemPlan{b});
+    ex.run("size", B, LnbItemSize{b});
+    ex.run("scan", 1, LnbItemScan{b});
+}
+
+template <class Exec>
+void lnb_encode_pack_pipeline(Exec &ex, const LnbEncodeBatch &b, uint32_t out_capacity)
+{
+    if (b.num_blocks == 0) return;
+    ex.run("pack", b.num_blocks, LnbItemPack{b, out_capacity});
+}

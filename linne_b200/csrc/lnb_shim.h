@@ -1,0 +1,49 @@
+/* lnb_shim.h -- the thin C-ABI shim between the host code (plain C) and the CUDA side.
+ *
+ * The host code (linne_encoder_host.c / linne_decoder_host.c) sees ONLY these functions: device
+ * memory, copies, stream synchronisation and the three batch pipelines.  lnb_shim_cuda.cu
+ * implements them with CUDA runtime calls and sm_100a kernels.  (tests/hostsim links the same host
+ * code against a loop-based stand-in to exercise host logic and kernel bodies in CPU-only CI; that
+ * stand-in is test infrastructure and is never part of liblinne_b200.so.)
+ */
+#ifndef LNB_SHIM_H
+#define LNB_SHIM_H
+
+#include "lnb_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LnbDevice LnbDevice;      /* one CUDA stream + the uploaded constant tables */
+
+/* Returns 0 and a device context, or non-zero when no usable CUDA device exists (callers then fail:
+ * there is no CPU fallback).  `device_ordinal` < 0 keeps the current device. */
+int  lnb_shim_open(LnbDevice **dev, int device_ordinal);
+void lnb_shim_close(LnbDevice *dev);
+const LnbDevTables *lnb_shim_tables(const LnbDevice *dev);
+/* Launch on an externally owned stream (cudaStream_t as void*) instead of the context's own. */
+void lnb_shim_use_stream(LnbDevice *dev, void *cuda_stream);
+const char *lnb_shim_backend(void);      /* "cuda-sm_100a" for the product */
+
+void *lnb_shim_alloc(LnbDevice *dev, size_t bytes);
+void  lnb_shim_free(LnbDevice *dev, void *ptr);
+void *lnb_shim_alloc_pinned(size_t bytes);
+void  lnb_shim_free_pinned(void *ptr);
+int   lnb_shim_h2d(LnbDevice *dev, void *dst, const void *src, size_t bytes);      /* async on the stream */
+int   lnb_shim_d2h(LnbDevice *dev, void *dst, const void *src, size_t bytes);      /* async on the stream */
+int   lnb_shim_memset(LnbDevice *dev, void *dst, int value, size_t bytes);
+int   lnb_shim_sync(LnbDevice *dev);     /* 0 on success; non-zero reports a CUDA error */
+
+/* the batch pipelines (enqueue only; results are valid after lnb_shim_sync) */
+int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *batch);
+int lnb_shim_encode_analyze(LnbDevice *dev, const LnbEncodeBatch *batch);
+int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *batch, uint32_t out_capacity);
+
+/* number of kernels launched through this context since it was opened (bench.py's gpu_launches) */
+uint64_t lnb_shim_launch_count(const LnbDevice *dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -12,184 +12,19 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from linne_b200.api import (LINNEHeader, LINNEEncodeParameter, LINNEEncoderConfig, LINNEDecoderConfig,  # noqa: E402
+                            bind_linne_api, LinneApi, _chan_ptrs, PRESET_LAYERS)
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "liblinne_ref.so")
 ORACLE_SO = os.path.join(ROOT, "oracle", "liblinne_oracle.so")
 
 OK, INVALID_ARGUMENT, INVALID_FORMAT, INSUFFICIENT_BUFFER, INSUFFICIENT_DATA, \
     PARAMETER_NOT_SET, DATA_CORRUPTION, NG = range(8)
-
-PRESET_LAYERS = {0: (2, 32), 1: (2, 32), 2: (4, 64, 8), 3: (4, 64, 8), 4: (4, 64, 8),
-                 5: (4, 128, 16), 6: (4, 128, 16), 7: (4, 128, 16)}
-
-
-# ----------------------------------------------------------------------------------------------
-# ctypes mirrors of the public structs (include/linne.h, linne_encoder.h, linne_decoder.h)
-# ----------------------------------------------------------------------------------------------
-class LINNEHeader(C.Structure):
-    _fields_ = [("format_version", C.c_uint32), ("codec_version", C.c_uint32),
-                ("num_channels", C.c_uint16), ("num_samples", C.c_uint32),
-                ("sampling_rate", C.c_uint32), ("bits_per_sample", C.c_uint16),
-                ("num_samples_per_block", C.c_uint32), ("preset", C.c_uint8),
-                ("ch_process_method", C.c_int)]
-
-
-class LINNEEncodeParameter(C.Structure):
-    _fields_ = [("num_channels", C.c_uint16), ("bits_per_sample", C.c_uint16),
-                ("sampling_rate", C.c_uint32), ("num_samples_per_block", C.c_uint16),
-                ("preset", C.c_uint8), ("ch_process_method", C.c_int),
-                ("enable_learning", C.c_uint8), ("num_afmethod_iterations", C.c_uint8)]
-
-
-class LINNEEncoderConfig(C.Structure):
-    _fields_ = [("max_num_channels", C.c_uint32), ("max_num_samples_per_block", C.c_uint32),
-                ("max_num_layers", C.c_uint32), ("max_num_parameters_per_layer", C.c_uint32)]
-
-
-class LINNEDecoderConfig(C.Structure):
-    _fields_ = [("max_num_channels", C.c_uint32), ("max_num_layers", C.c_uint32),
-                ("max_num_parameters_per_layer", C.c_uint32), ("check_crc", C.c_uint8)]
-
-
-def bind_linne_api(lib):
-    """Declare argtypes/restype of the 14 public entry points on a loaded library."""
-    u8p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
-    i32pp = C.POINTER(C.POINTER(C.c_int32))
-    lib.LINNEEncoder_EncodeHeader.argtypes = [C.POINTER(LINNEHeader), u8p, C.c_uint32]
-    lib.LINNEEncoder_EncodeHeader.restype = C.c_int
-    lib.LINNEEncoder_CalculateWorkSize.argtypes = [C.POINTER(LINNEEncoderConfig)]
-    lib.LINNEEncoder_CalculateWorkSize.restype = C.c_int32
-    lib.LINNEEncoder_Create.argtypes = [C.POINTER(LINNEEncoderConfig), C.c_void_p, C.c_int32]
-    lib.LINNEEncoder_Create.restype = C.c_void_p
-    lib.LINNEEncoder_Destroy.argtypes = [C.c_void_p]
-    lib.LINNEEncoder_Destroy.restype = None
-    lib.LINNEEncoder_SetEncodeParameter.argtypes = [C.c_void_p, C.POINTER(LINNEEncodeParameter)]
-    lib.LINNEEncoder_SetEncodeParameter.restype = C.c_int
-    for name in ("LINNEEncoder_EncodeBlock", "LINNEEncoder_EncodeWhole"):
-        f = getattr(lib, name)
-        f.argtypes = [C.c_void_p, i32pp, C.c_uint32, u8p, C.c_uint32, u32p]
-        f.restype = C.c_int
-    lib.LINNEDecoder_DecodeHeader.argtypes = [u8p, C.c_uint32, C.POINTER(LINNEHeader)]
-    lib.LINNEDecoder_DecodeHeader.restype = C.c_int
-    lib.LINNEDecoder_CalculateWorkSize.argtypes = [C.POINTER(LINNEDecoderConfig)]
-    lib.LINNEDecoder_CalculateWorkSize.restype = C.c_int32
-    lib.LINNEDecoder_Create.argtypes = [C.POINTER(LINNEDecoderConfig), C.c_void_p, C.c_int32]
-    lib.LINNEDecoder_Create.restype = C.c_void_p
-    lib.LINNEDecoder_Destroy.argtypes = [C.c_void_p]
-    lib.LINNEDecoder_Destroy.restype = None
-    lib.LINNEDecoder_SetHeader.argtypes = [C.c_void_p, C.POINTER(LINNEHeader)]
-    lib.LINNEDecoder_SetHeader.restype = C.c_int
-    lib.LINNEDecoder_DecodeBlock.argtypes = [C.c_void_p, u8p, C.c_uint32, i32pp, C.c_uint32,
-                                             C.c_uint32, u32p, u32p]
-    lib.LINNEDecoder_DecodeBlock.restype = C.c_int
-    lib.LINNEDecoder_DecodeWhole.argtypes = [C.c_void_p, u8p, C.c_uint32, i32pp, C.c_uint32, C.c_uint32]
-    lib.LINNEDecoder_DecodeWhole.restype = C.c_int
-    return lib
-
-
-def _chan_ptrs(pcm: np.ndarray):
-    """pcm: int32 [C][n] C-contiguous -> (int32**) array of row pointers (keeps pcm alive by ref)."""
-    assert pcm.dtype == np.int32 and pcm.ndim == 2 and pcm.flags["C_CONTIGUOUS"]
-    arr = (C.POINTER(C.c_int32) * pcm.shape[0])()
-    for c in range(pcm.shape[0]):
-        arr[c] = pcm[c].ctypes.data_as(C.POINTER(C.c_int32))
-    return arr
-
-
-class LinneApi:
-    """Drives any library exporting the LINNE public C API (reference or product)."""
-
-    def __init__(self, lib):
-        self.lib = bind_linne_api(lib)
-
-    # -- encode ---------------------------------------------------------------------------------
-    def make_encoder(self, channels, block, layers=3, params=128):
-        cfg = LINNEEncoderConfig(channels, block, layers, params)
-        h = self.lib.LINNEEncoder_Create(C.byref(cfg), None, 0)
-        if not h:
-            raise RuntimeError("LINNEEncoder_Create failed")
-        return h
-
-    def encode(self, pcm, bits=16, rate=44100, block=10240, preset=0, ms=None, learning=0, af=0,
-               max_block=None, cap=None, whole=True, return_code=False):
-        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
-        nch, n = pcm.shape
-        if ms is None:
-            ms = 1 if nch >= 2 else 0
-        enc = self.make_encoder(nch, max_block or block)
-        try:
-            prm = LINNEEncodeParameter(nch, bits, rate, block, preset, ms, learning, af)
-            rc = self.lib.LINNEEncoder_SetEncodeParameter(enc, C.byref(prm))
-            if rc != OK:
-                if return_code:
-                    return rc, b""
-                raise RuntimeError(f"SetEncodeParameter rc={rc}")
-            if cap is None:
-                cap = 30 + 2 * nch * n * 4 + 1024 * (n // block + 2)
-            out = np.zeros(cap + 64, dtype=np.uint8)
-            size = C.c_uint32(0)
-            ptrs = _chan_ptrs(pcm)
-            if whole:
-                rc = self.lib.LINNEEncoder_EncodeWhole(enc, ptrs, n, out.ctypes.data_as(C.POINTER(C.c_uint8)),
-                                                       cap, C.byref(size))
-            else:  # the CLI's loop: header + EncodeBlock per block (tools/linne_codec/linne_codec.c:123-161)
-                hdr = LINNEHeader(1, 2, nch, n, rate, bits, block, preset, ms)
-                rc = self.lib.LINNEEncoder_EncodeHeader(C.byref(hdr), out.ctypes.data_as(C.POINTER(C.c_uint8)), cap)
-                off, done = 30, 0
-                while rc == OK and done < n:
-                    m = min(block, n - done)
-                    sub = (C.POINTER(C.c_int32) * nch)()
-                    for c in range(nch):
-                        sub[c] = C.cast(pcm[c].ctypes.data + 4 * done, C.POINTER(C.c_int32))
-                    rc = self.lib.LINNEEncoder_EncodeBlock(
-                        enc, sub, m, C.cast(out.ctypes.data + off, C.POINTER(C.c_uint8)), cap - off, C.byref(size))
-                    off += size.value
-                    done += m
-                size = C.c_uint32(off)
-            if return_code:
-                return rc, out[:size.value].tobytes() if rc == OK else b""
-            if rc != OK:
-                raise RuntimeError(f"encode rc={rc}")
-            return out[:size.value].tobytes()
-        finally:
-            self.lib.LINNEEncoder_Destroy(enc)
-
-    # -- decode ---------------------------------------------------------------------------------
-    def decode_header(self, data: bytes):
-        buf = np.frombuffer(data, dtype=np.uint8)
-        hdr = LINNEHeader()
-        rc = self.lib.LINNEDecoder_DecodeHeader(buf.ctypes.data_as(C.POINTER(C.c_uint8)), len(data), C.byref(hdr))
-        return rc, hdr
-
-    def decode(self, data: bytes, check_crc=1, return_code=False, out_channels=None, out_samples=None,
-               fill=0):
-        rc, hdr = self.decode_header(data)
-        if rc != OK:
-            if return_code:
-                return rc, None
-            raise RuntimeError(f"DecodeHeader rc={rc}")
-        nch = out_channels if out_channels is not None else hdr.num_channels
-        n = out_samples if out_samples is not None else hdr.num_samples
-        cfg = LINNEDecoderConfig(max(nch, hdr.num_channels, 1), 3, 128, check_crc)
-        dec = self.lib.LINNEDecoder_Create(C.byref(cfg), None, 0)
-        if not dec:
-            raise RuntimeError("LINNEDecoder_Create failed")
-        try:
-            # pad the stream: the reference's reader may touch up to 3 bytes past the end (SURVEY A11)
-            buf = np.zeros(len(data) + 16, dtype=np.uint8)
-            buf[:len(data)] = np.frombuffer(data, dtype=np.uint8)
-            out = np.full((max(nch, 1), max(n, 1)), fill, dtype=np.int32)
-            rc = self.lib.LINNEDecoder_DecodeWhole(dec, buf.ctypes.data_as(C.POINTER(C.c_uint8)), len(data),
-                                                   _chan_ptrs(out), nch, n)
-            if return_code:
-                return rc, out
-            if rc != OK:
-                raise RuntimeError(f"decode rc={rc}")
-            return out
-        finally:
-            self.lib.LINNEDecoder_Destroy(dec)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -464,3 +299,19 @@ def tile_stream(stream: bytes, times: int, block: int) -> bytes:
     hdr = bytearray(stream[:30])
     hdr[14:18] = total.to_bytes(4, "big")
     return bytes(hdr) + body * times
+
+
+# ----------------------------------------------------------------------------------------------
+# Host simulator: the product's host C code + kernel bodies compiled for the CPU (tests/hostsim).
+# TEST INFRASTRUCTURE for the CPU-only suite; the linne_b200 package never loads it.
+# ----------------------------------------------------------------------------------------------
+HOSTSIM_SO = os.path.join(ROOT, "tests", "hostsim", "liblinne_hostsim.so")
+
+
+def have_hostsim() -> bool:
+    return os.path.exists(HOSTSIM_SO)
+
+
+class HostSim(LinneApi):
+    def __init__(self):
+        super().__init__(C.CDLL(HOSTSIM_SO, mode=getattr(os, "RTLD_LOCAL", 0)))

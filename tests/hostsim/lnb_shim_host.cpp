@@ -1,0 +1,50 @@
+/* lnb_shim_host.cpp -- TEST INFRASTRUCTURE: a loop-based stand-in for the CUDA shim.
+ *
+ * Implements lnb_shim.h with malloc/memcpy and a sequential executor so the CPU-only CI
+ * (pytest -m "not gpu") can exercise the host-side C code and the very same kernel bodies
+ * (lnb_*_core.cuh / lnb_pipeline.cuh, compiled here as plain host C++).  It is built into
+ * tests/hostsim/liblinne_hostsim.so only; liblinne_b200.so never contains or loads it.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "lnb_shim.h"
+#include "lnb_pipeline.cuh"
+
+struct LnbDevice { LnbDevTables tables; uint64_t launches; };
+
+struct LoopExec {
+    LnbDevice *dev;
+    template <class F> void run(const char *, uint32_t n, const F &f)
+    {
+        for (uint32_t i = 0; i < n; i++) f(i);
+        dev->launches++;
+    }
+};
+
+extern "C" {
+const char *lnb_shim_backend(void) { return "hostsim"; }
+int lnb_shim_open(LnbDevice **out, int)
+{
+    LnbDevice *dev = (LnbDevice *)calloc(1, sizeof(LnbDevice));
+    const LnbHostTables *ht = lnb_tables_get();
+    dev->tables.huff_lut = ht->huff_lut; dev->tables.huff_code = ht->huff_code; dev->tables.huff_len = ht->huff_len;
+    dev->tables.k2_threshold = ht->k2_threshold; dev->tables.crc_table = ht->crc_table;
+    *out = dev;
+    return 0;
+}
+void lnb_shim_close(LnbDevice *dev) { free(dev); }
+const LnbDevTables *lnb_shim_tables(const LnbDevice *dev) { return &dev->tables; }
+void lnb_shim_use_stream(LnbDevice *, void *) {}
+void *lnb_shim_alloc(LnbDevice *, size_t bytes) { return calloc(1, bytes ? bytes : 16); }
+void lnb_shim_free(LnbDevice *, void *p) { free(p); }
+void *lnb_shim_alloc_pinned(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
+void lnb_shim_free_pinned(void *p) { free(p); }
+int lnb_shim_h2d(LnbDevice *, void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
+int lnb_shim_d2h(LnbDevice *, void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
+int lnb_shim_memset(LnbDevice *, void *d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
+int lnb_shim_sync(LnbDevice *) { return 0; }
+int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *b) { LoopExec ex{dev}; lnb_decode_pipeline(ex, *b); return 0; }
+int lnb_shim_encode_analyze(LnbDevice *dev, const LnbEncodeBatch *b) { LoopExec ex{dev}; lnb_encode_analyze_pipeline(ex, *b); return 0; }
+int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *b, uint32_t cap) { LoopExec ex{dev}; lnb_encode_pack_pipeline(ex, *b, cap); return 0; }
+uint64_t lnb_shim_launch_count(const LnbDevice *dev) { return dev->launches; }
+}
