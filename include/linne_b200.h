@@ -30,6 +30,44 @@ uint64_t LINNEB200_DecoderLaunchCount(const struct LINNEDecoder *decoder);
 void LINNEB200_EncoderUseStream(struct LINNEEncoder *encoder, void *cuda_stream);
 void LINNEB200_DecoderUseStream(struct LINNEDecoder *decoder, void *cuda_stream);
 
+/* ---- device-resident entry points: bulk data stays in HBM -------------------------------------
+ * EncodeWholeResident: `d_pcm` = device int32 planes [C][pcm_stride]; the stream is written to the
+ * device buffer `d_data`.  DecodeWholeResident: `d_data` = device copy of the stream padded with
+ * >= 16 zero bytes (`data` = the host copy, needed only to hop over the block size fields);
+ * PCM is left in the device planes `d_pcm` [C][pcm_stride].  Same result codes as the host calls. */
+LINNEApiResult LINNEB200_EncodeWholeResident(struct LINNEEncoder *encoder,
+        const int32_t *d_pcm, uint32_t pcm_stride, uint32_t num_samples,
+        uint8_t *d_data, uint32_t data_size, uint32_t *output_size);
+LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *decoder,
+        const uint8_t *data, const uint8_t *d_data, uint32_t data_size,
+        int32_t *d_pcm, uint32_t pcm_stride, uint32_t buffer_num_channels, uint32_t buffer_num_samples);
+
+/* ---- encode with externally supplied analysis results ------------------------------------------
+ * One record per (block, channel), block-major.  Used to show that identical quantised
+ * coefficients yield byte-identical residuals and coded bits (north star, parity leg 3). */
+struct LINNEB200ChannelParams {
+    uint8_t log2_units[3];
+    uint8_t rshift[3];
+    int8_t  coef[3][128];
+};
+LINNEApiResult LINNEB200_EncodeWholeWithParams(struct LINNEEncoder *encoder,
+        const int32_t *const *input, uint32_t num_samples,
+        const struct LINNEB200ChannelParams *params, uint32_t num_param_blocks,
+        uint8_t *data, uint32_t data_size, uint32_t *output_size);
+
+/* ---- per-stage device timing (CUDA events around every kernel of a handle) ---------------------- */
+struct LINNEB200StageStat { char name[24]; uint64_t launches; double total_ms; };
+void LINNEB200_EncoderSetProfiling(struct LINNEEncoder *encoder, int on);
+void LINNEB200_DecoderSetProfiling(struct LINNEDecoder *decoder, int on);
+void LINNEB200_EncoderResetStageStats(struct LINNEEncoder *encoder);
+void LINNEB200_DecoderResetStageStats(struct LINNEDecoder *decoder);
+int  LINNEB200_EncoderGetStageStats(struct LINNEEncoder *encoder, struct LINNEB200StageStat *out, int max_stages);
+int  LINNEB200_DecoderGetStageStats(struct LINNEDecoder *decoder, struct LINNEB200StageStat *out, int max_stages);
+
+/* Sustained FP64 FMA throughput (TFLOP/s) of the current device: roofline denominator of the
+ * encoder's analysis kernels.  Returns 0 without a device. */
+double LINNEB200_MeasureFp64Tflops(void);
+
 #ifdef __cplusplus
 }
 #endif

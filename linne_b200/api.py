@@ -189,6 +189,36 @@ class LinneApi:
 
 
 
+def bind_ext_api(lib):
+    """Declare the LINNEB200_* extension entry points (include/linne_b200.h)."""
+    lib.LINNEB200_Backend.restype = C.c_char_p
+    lib.LINNEB200_DeviceAvailable.restype = C.c_int
+    lib.LINNEB200_EncoderLaunchCount.argtypes = [C.c_void_p]
+    lib.LINNEB200_EncoderLaunchCount.restype = C.c_uint64
+    lib.LINNEB200_DecoderLaunchCount.argtypes = [C.c_void_p]
+    lib.LINNEB200_DecoderLaunchCount.restype = C.c_uint64
+    lib.LINNEB200_EncoderUseStream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.LINNEB200_DecoderUseStream.argtypes = [C.c_void_p, C.c_void_p]
+    u8p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+    lib.LINNEB200_EncodeWholeResident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                                  C.c_void_p, C.c_uint32, u32p]
+    lib.LINNEB200_EncodeWholeResident.restype = C.c_int
+    lib.LINNEB200_DecodeWholeResident.argtypes = [C.c_void_p, u8p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                  C.c_uint32, C.c_uint32, C.c_uint32]
+    lib.LINNEB200_DecodeWholeResident.restype = C.c_int
+    lib.LINNEB200_EncodeWholeWithParams.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.c_uint32,
+                                                    C.POINTER(ChannelParams), C.c_uint32, u8p, C.c_uint32, u32p]
+    lib.LINNEB200_EncodeWholeWithParams.restype = C.c_int
+    for side in ("Encoder", "Decoder"):
+        getattr(lib, f"LINNEB200_{side}SetProfiling").argtypes = [C.c_void_p, C.c_int]
+        getattr(lib, f"LINNEB200_{side}ResetStageStats").argtypes = [C.c_void_p]
+        f = getattr(lib, f"LINNEB200_{side}GetStageStats")
+        f.argtypes = [C.c_void_p, C.POINTER(StageStat), C.c_int]
+        f.restype = C.c_int
+    lib.LINNEB200_MeasureFp64Tflops.restype = C.c_double
+    return lib
+
+
 _lib = None
 
 
@@ -202,16 +232,112 @@ def load_library():
                 "linne_b200 has no CPU fallback.")
         lib = C.CDLL(PRODUCT_SO, mode=getattr(os, "RTLD_LOCAL", 0))
         bind_linne_api(lib)
-        lib.LINNEB200_Backend.restype = C.c_char_p
-        lib.LINNEB200_DeviceAvailable.restype = C.c_int
-        lib.LINNEB200_EncoderLaunchCount.argtypes = [C.c_void_p]
-        lib.LINNEB200_EncoderLaunchCount.restype = C.c_uint64
-        lib.LINNEB200_DecoderLaunchCount.argtypes = [C.c_void_p]
-        lib.LINNEB200_DecoderLaunchCount.restype = C.c_uint64
-        lib.LINNEB200_EncoderUseStream.argtypes = [C.c_void_p, C.c_void_p]
-        lib.LINNEB200_DecoderUseStream.argtypes = [C.c_void_p, C.c_void_p]
+        bind_ext_api(lib)
         _lib = lib
     return _lib
+
+
+class StageStat(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("total_ms", C.c_double)]
+
+
+class ChannelParams(C.Structure):
+    """struct LINNEB200ChannelParams (include/linne_b200.h)"""
+    _fields_ = [("log2_units", C.c_uint8 * 3), ("rshift", C.c_uint8 * 3), ("coef", (C.c_int8 * 128) * 3)]
+
+
+class _Session:
+    """A long-lived encoder or decoder handle (what a server keeps per stream/worker)."""
+    _side = ""
+
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, handle
+
+    def use_stream(self, cuda_stream_ptr):
+        getattr(self.lib, f"LINNEB200_{self._side}UseStream")(self.h, C.c_void_p(cuda_stream_ptr))
+
+    def set_profiling(self, on=True):
+        getattr(self.lib, f"LINNEB200_{self._side}SetProfiling")(self.h, 1 if on else 0)
+
+    def reset_stage_stats(self):
+        getattr(self.lib, f"LINNEB200_{self._side}ResetStageStats")(self.h)
+
+    def stage_stats(self):
+        buf = (StageStat * 32)()
+        n = getattr(self.lib, f"LINNEB200_{self._side}GetStageStats")(self.h, buf, 32)
+        return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n)}
+
+    def launch_count(self):
+        return int(getattr(self.lib, f"LINNEB200_{self._side}LaunchCount")(self.h))
+
+    def close(self):
+        if self.h:
+            getattr(self.lib, f"LINNE{self._side}_Destroy")(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EncoderSession(_Session):
+    _side = "Encoder"
+
+    def __init__(self, channels, bits=16, rate=44100, block=10240, preset=0, ms=None, learning=0, af=0,
+                 max_block=None, lib=None):
+        lib = lib or load_library()
+        cfg = LINNEEncoderConfig(channels, max_block or block, 3, 128)
+        h = lib.LINNEEncoder_Create(C.byref(cfg), None, 0)
+        if not h:
+            raise RuntimeError("LINNEEncoder_Create failed (no CUDA device? linne_b200 has no CPU fallback)")
+        super().__init__(lib, h)
+        if ms is None:
+            ms = 1 if channels >= 2 else 0
+        prm = LINNEEncodeParameter(channels, bits, rate, block, preset, ms, learning, af)
+        rc = lib.LINNEEncoder_SetEncodeParameter(h, C.byref(prm))
+        if rc != OK:
+            raise RuntimeError(f"SetEncodeParameter rc={rc}")
+        self.channels = channels
+
+    def encode_whole(self, chan_ptrs, n, out_ptr, cap):
+        """chan_ptrs: (int32*)[C] ctypes array of host pointers; out_ptr: host address. Returns bytes written."""
+        size = C.c_uint32(0)
+        rc = self.lib.LINNEEncoder_EncodeWhole(self.h, chan_ptrs, n, C.cast(out_ptr, C.POINTER(C.c_uint8)), cap, C.byref(size))
+        if rc != OK:
+            raise RuntimeError(f"EncodeWhole rc={rc}")
+        return size.value
+
+    def encode_whole_resident(self, d_pcm_ptr, stride, n, d_out_ptr, cap):
+        size = C.c_uint32(0)
+        rc = self.lib.LINNEB200_EncodeWholeResident(self.h, C.c_void_p(d_pcm_ptr), stride, n, C.c_void_p(d_out_ptr), cap, C.byref(size))
+        if rc != OK:
+            raise RuntimeError(f"EncodeWholeResident rc={rc}")
+        return size.value
+
+
+class DecoderSession(_Session):
+    _side = "Decoder"
+
+    def __init__(self, channels=8, check_crc=1, lib=None):
+        lib = lib or load_library()
+        cfg = LINNEDecoderConfig(channels, 3, 128, check_crc)
+        h = lib.LINNEDecoder_Create(C.byref(cfg), None, 0)
+        if not h:
+            raise RuntimeError("LINNEDecoder_Create failed (no CUDA device? linne_b200 has no CPU fallback)")
+        super().__init__(lib, h)
+
+    def decode_whole(self, data_ptr, size, chan_ptrs, channels, n):
+        rc = self.lib.LINNEDecoder_DecodeWhole(self.h, C.cast(data_ptr, C.POINTER(C.c_uint8)), size, chan_ptrs, channels, n)
+        if rc != OK:
+            raise RuntimeError(f"DecodeWhole rc={rc}")
+
+    def decode_whole_resident(self, data_ptr, d_data_ptr, size, d_pcm_ptr, stride, channels, n):
+        rc = self.lib.LINNEB200_DecodeWholeResident(self.h, C.cast(data_ptr, C.POINTER(C.c_uint8)), C.c_void_p(d_data_ptr),
+                                                    size, C.c_void_p(d_pcm_ptr), stride, channels, n)
+        if rc != OK:
+            raise RuntimeError(f"DecodeWholeResident rc={rc}")
 
 
 class Product(LinneApi):
@@ -224,3 +350,23 @@ class Product(LinneApi):
 
     def device_available(self) -> bool:
         return bool(self.lib.LINNEB200_DeviceAvailable())
+
+    def measure_fp64_tflops(self) -> float:
+        return float(self.lib.LINNEB200_MeasureFp64Tflops())
+
+    def encode_with_params(self, pcm, params, bits=16, rate=44100, block=10240, preset=0, ms=None):
+        """params: ctypes array of ChannelParams, one per (block, channel), block-major."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        nch, n = pcm.shape
+        sess = EncoderSession(nch, bits=bits, rate=rate, block=block, preset=preset, ms=ms, lib=self.lib)
+        try:
+            cap = 30 + 2 * nch * n * 4 + 4096
+            out = np.zeros(cap, dtype=np.uint8)
+            size = C.c_uint32(0)
+            rc = self.lib.LINNEB200_EncodeWholeWithParams(sess.h, _chan_ptrs(pcm), n, params, len(params) // nch,
+                                                          out.ctypes.data_as(C.POINTER(C.c_uint8)), cap, C.byref(size))
+            if rc != OK:
+                raise RuntimeError(f"EncodeWholeWithParams rc={rc}")
+            return out[:size.value].tobytes()
+        finally:
+            sess.close()

@@ -21,3 +21,25 @@ uint64_t LINNEB200_EncoderLaunchCount(const struct LINNEEncoder *e) { return e ?
 uint64_t LINNEB200_DecoderLaunchCount(const struct LINNEDecoder *d) { return d ? lnb_shim_launch_count(lnb_decoder_device(d)) : 0; }
 void LINNEB200_EncoderUseStream(struct LINNEEncoder *e, void *s) { if (e) lnb_shim_use_stream(lnb_encoder_device(e), s); }
 void LINNEB200_DecoderUseStream(struct LINNEDecoder *d, void *s) { if (d) lnb_shim_use_stream(lnb_decoder_device(d), s); }
+
+void LINNEB200_EncoderSetProfiling(struct LINNEEncoder *e, int on) { if (e) lnb_shim_profile_enable(lnb_encoder_device(e), on); }
+void LINNEB200_DecoderSetProfiling(struct LINNEDecoder *d, int on) { if (d) lnb_shim_profile_enable(lnb_decoder_device(d), on); }
+void LINNEB200_EncoderResetStageStats(struct LINNEEncoder *e) { if (e) lnb_shim_profile_reset(lnb_encoder_device(e)); }
+void LINNEB200_DecoderResetStageStats(struct LINNEDecoder *d) { if (d) lnb_shim_profile_reset(lnb_decoder_device(d)); }
+int LINNEB200_EncoderGetStageStats(struct LINNEEncoder *e, struct LINNEB200StageStat *out, int n)
+{
+    return e ? lnb_shim_profile_get(lnb_encoder_device(e), (LnbStageStat *)out, n) : 0;
+}
+int LINNEB200_DecoderGetStageStats(struct LINNEDecoder *d, struct LINNEB200StageStat *out, int n)
+{
+    return d ? lnb_shim_profile_get(lnb_decoder_device(d), (LnbStageStat *)out, n) : 0;
+}
+double LINNEB200_MeasureFp64Tflops(void)
+{
+    LnbDevice *dev = NULL;
+    double t;
+    if (lnb_shim_open(&dev, -1) != 0) return 0.0;
+    t = lnb_shim_measure_fp64_tflops(dev);
+    lnb_shim_close(dev);
+    return t;
+}

@@ -181,10 +181,14 @@ static int scan_blocks(const struct LINNEHeader *h, const uint8_t *data, uint32_
 }
 
 /* shared by DecodeBlock (single = 1) and DecodeWhole */
+/* Resident mode (d_stream_ext / d_pcm_ext non-NULL): the stream image and/or the PCM planes already
+ * live on the device, so the corresponding bulk copy is skipped; `data` (host) is still needed for
+ * the block hop. */
 static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
                                    uint32_t start_offset, int32_t **buffer, uint32_t buffer_num_samples,
                                    uint32_t sample_limit, int single,
-                                   uint32_t *consumed_bytes, uint32_t *decoded_samples)
+                                   uint32_t *consumed_bytes, uint32_t *decoded_samples,
+                                   const uint8_t *d_stream_ext, int32_t *d_pcm_ext, uint32_t pcm_stride_ext)
 {
     const struct LINNEHeader *h = &dec->header;
     const uint32_t C = h->num_channels;
@@ -224,25 +228,28 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
     }
     batch.cfg.work_stride = 0;
     batch.cfg.check_crc = (dec->flags & DEC_FLAG_CHECK_CRC) ? 1u : 0u;
-    if (lnb_buf_reserve_device(dec->dev, &dec->d_stream, padded)
+    if (d_pcm_ext) batch.cfg.pcm_stride = pcm_stride_ext;
+    if ((!d_stream_ext && lnb_buf_reserve_device(dec->dev, &dec->d_stream, padded))
         || lnb_buf_reserve_device(dec->dev, &dec->d_blocks, (size_t)scan.num_blocks * sizeof(LnbBlockDesc))
         || lnb_buf_reserve_device(dec->dev, &dec->d_params, (size_t)scan.num_blocks * C * sizeof(LnbChanParams))
-        || lnb_buf_reserve_device(dec->dev, &dec->d_pcm, (size_t)batch.cfg.pcm_stride * C * sizeof(int32_t)))
+        || (!d_pcm_ext && lnb_buf_reserve_device(dec->dev, &dec->d_pcm, (size_t)batch.cfg.pcm_stride * C * sizeof(int32_t))))
         return LINNE_APIRESULT_NG;
 
     /* a terminal block with a post-CRC error takes part in the CRC pass only */
     for (i = scan.num_decodable; i < scan.num_blocks; i++) blocks[i].type = 0xFFu;
 
     batch.tab = *lnb_shim_tables(dec->dev);
-    batch.stream = (const uint8_t *)dec->d_stream.ptr;
+    batch.stream = d_stream_ext ? d_stream_ext : (const uint8_t *)dec->d_stream.ptr;
     batch.stream_size = data_size;
     batch.blocks = (LnbBlockDesc *)dec->d_blocks.ptr;
     batch.num_blocks = scan.num_blocks;
     batch.params = (LnbChanParams *)dec->d_params.ptr;
-    batch.pcm = (int32_t *)dec->d_pcm.ptr;
+    batch.pcm = d_pcm_ext ? d_pcm_ext : (int32_t *)dec->d_pcm.ptr;
 
-    lnb_shim_memset(dec->dev, (uint8_t *)dec->d_stream.ptr + (padded - 16u), 0, 16u);
-    lnb_shim_h2d(dec->dev, dec->d_stream.ptr, data, data_size);
+    if (!d_stream_ext) {
+        lnb_shim_memset(dec->dev, (uint8_t *)dec->d_stream.ptr + (padded - 16u), 0, 16u);
+        lnb_shim_h2d(dec->dev, dec->d_stream.ptr, data, data_size);
+    }
     lnb_shim_h2d(dec->dev, dec->d_blocks.ptr, blocks, (size_t)scan.num_blocks * sizeof(LnbBlockDesc));
     if (lnb_shim_decode(dec->dev, &batch)) return LINNE_APIRESULT_NG;
     lnb_shim_d2h(dec->dev, blocks, dec->d_blocks.ptr, (size_t)scan.num_blocks * sizeof(LnbBlockDesc));
@@ -266,10 +273,12 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
     }
 
     /* hand back every sample the reference would have produced before stopping */
-    for (c = 0; c < C; c++)
-        lnb_shim_d2h(dec->dev, buffer[c], (int32_t *)dec->d_pcm.ptr + (size_t)c * batch.cfg.pcm_stride,
-                     (size_t)ok_samples * sizeof(int32_t));
-    if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+    if (!d_pcm_ext) {
+        for (c = 0; c < C; c++)
+            lnb_shim_d2h(dec->dev, buffer[c], (int32_t *)dec->d_pcm.ptr + (size_t)c * batch.cfg.pcm_stride,
+                         (size_t)ok_samples * sizeof(int32_t));
+        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+    }
 
     if (single && result == LINNE_APIRESULT_OK) {
         if (consumed_bytes) *consumed_bytes = LNB_BLOCK_HEADER_SIZE + blocks[0].na;
@@ -294,7 +303,7 @@ LINNEApiResult LINNEDecoder_DecodeBlock(struct LINNEDecoder *dec, const uint8_t 
     for (c = 0; c < dec->header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     if (data_size == 0) return LINNE_APIRESULT_INSUFFICIENT_DATA;
     return decode_range(dec, data, data_size, 0, buffer, buffer_num_samples, 0xFFFFFFFFu, 1,
-                        decode_size, num_decode_samples);
+                        decode_size, num_decode_samples, NULL, NULL, 0);
 }
 
 /* reference linne_decoder.c:671-730 */
@@ -311,7 +320,24 @@ LINNEApiResult LINNEDecoder_DecodeWhole(struct LINNEDecoder *dec, const uint8_t 
         return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     for (c = 0; c < header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, buffer, buffer_num_samples,
-                        header.num_samples, 0, NULL, NULL);
+                        header.num_samples, 0, NULL, NULL, NULL, NULL, 0);
 }
 
 LnbDevice *lnb_decoder_device(const struct LINNEDecoder *dec) { return dec->dev; }
+
+/* ---- extension entry point (include/linne_b200.h) ---- */
+#include "linne_b200.h"
+
+LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uint8_t *data, const uint8_t *d_data,
+        uint32_t data_size, int32_t *d_pcm, uint32_t pcm_stride, uint32_t buffer_num_channels, uint32_t buffer_num_samples)
+{
+    struct LINNEHeader header;
+    LINNEApiResult ret;
+    if (dec == NULL || data == NULL || d_data == NULL || d_pcm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if ((ret = LINNEDecoder_DecodeHeader(data, data_size, &header)) != LINNE_APIRESULT_OK) return ret;
+    if ((ret = LINNEDecoder_SetHeader(dec, &header)) != LINNE_APIRESULT_OK) return ret;
+    if (buffer_num_channels < header.num_channels || buffer_num_samples < header.num_samples
+        || pcm_stride < buffer_num_samples) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, NULL, buffer_num_samples,
+                        header.num_samples, 0, NULL, NULL, d_data, d_pcm, pcm_stride);
+}

@@ -22,6 +22,8 @@ struct LINNEEncoder {
     LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_win, d_cand, d_unit_loss,
            d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total;
     LnbBuf h_blocks, h_welch, h_total;
+    const int32_t *cur_pcm;                /* device PCM planes of the call in flight */
+    uint32_t cur_pcm_stride;
 };
 
 /* reference linne_encoder.c:53-138 */
@@ -149,8 +151,11 @@ static uint32_t analysis_length(const LnbStreamCfg *cfg, uint32_t n)
 
 /* Encode the blocks covering samples [first_sample, first_sample + num_samples) of the device PCM
  * planes into data[0..data_size); blocks are cut every header.num_samples_per_block samples. */
+/* `data` is a host buffer unless `data_on_device` is set; `forced` (optional, host memory,
+ * [total_blocks * C]) supplies unit counts / shifts / coefficients and skips the analysis. */
 static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_samples,
-                                    uint8_t *data, uint32_t data_size, uint32_t *written)
+                                    uint8_t *data, uint32_t data_size, int data_on_device,
+                                    const LnbChanParams *forced, uint32_t *written)
 {
     const struct LINNEHeader *h = &enc->header;
     const uint32_t C = h->num_channels, NB = h->num_samples_per_block;
@@ -161,10 +166,10 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
 
     memset(&batch, 0, sizeof(batch));
     lnb_fill_stream_cfg(&batch.cfg, h);
-    batch.cfg.pcm_stride = (uint32_t)LNB_ROUNDUP((size_t)num_samples + 4u, 4u);
+    batch.cfg.pcm_stride = enc->cur_pcm_stride;
     batch.cfg.work_stride = (uint32_t)LNB_ROUNDUP((size_t)NB, 4u);
     batch.tab = *lnb_shim_tables(enc->dev);
-    batch.pcm = (const int32_t *)enc->d_pcm.ptr;
+    batch.pcm = enc->cur_pcm;
     lambdas = batch.cfg.num_lambdas;
     slots_per_block = C * lambdas;
 
@@ -234,6 +239,8 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
             }
         }
         batch.num_blocks = nb;
+        batch.forced_params = forced ? 1u : 0u;
+        if (forced) lnb_shim_h2d(enc->dev, enc->d_params.ptr, forced + (size_t)first * C, (size_t)nb * C * sizeof(LnbChanParams));
         lnb_shim_h2d(enc->dev, enc->d_blocks.ptr, hb, nb * sizeof(LnbBlockDesc));
         lnb_shim_h2d(enc->dev, enc->d_welch.ptr, hw, (size_t)nb * LNB_MAX_LEVELS * sizeof(double));
         if (lnb_shim_encode_analyze(enc->dev, &batch)) return LINNE_APIRESULT_NG;
@@ -241,10 +248,16 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
         if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
         chunk_bytes = *(uint32_t *)enc->h_total.ptr;
         if ((uint64_t)out_off + chunk_bytes > data_size) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
-        if (lnb_buf_reserve_device(enc->dev, &enc->d_out, (size_t)chunk_bytes + 64u)) return LINNE_APIRESULT_NG;
-        batch.out = (uint8_t *)enc->d_out.ptr;
-        if (lnb_shim_encode_pack(enc->dev, &batch, chunk_bytes)) return LINNE_APIRESULT_NG;
-        lnb_shim_d2h(enc->dev, data + out_off, enc->d_out.ptr, chunk_bytes);
+        if (data_on_device) {
+            /* block offsets from the scan are relative to the chunk: pack straight into the caller's device buffer */
+            batch.out = data + out_off;
+            if (lnb_shim_encode_pack(enc->dev, &batch, chunk_bytes)) return LINNE_APIRESULT_NG;
+        } else {
+            if (lnb_buf_reserve_device(enc->dev, &enc->d_out, (size_t)chunk_bytes + 64u)) return LINNE_APIRESULT_NG;
+            batch.out = (uint8_t *)enc->d_out.ptr;
+            if (lnb_shim_encode_pack(enc->dev, &batch, chunk_bytes)) return LINNE_APIRESULT_NG;
+            lnb_shim_d2h(enc->dev, data + out_off, enc->d_out.ptr, chunk_bytes);
+        }
         if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
         out_off += chunk_bytes;
     }
@@ -252,22 +265,30 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     return LINNE_APIRESULT_OK;
 }
 
+static int unsupported_analysis(const struct LINNEEncoder *enc)
+{
+    if (enc->enable_learning || enc->num_afmethod_iterations) {
+        fprintf(stderr, "linne_b200: enable_learning / num_afmethod_iterations are not implemented on the device yet\n");
+        return 1;
+    }
+    return 0;
+}
+
 static LINNEApiResult upload_and_encode(struct LINNEEncoder *enc, const int32_t *const *input, uint32_t num_samples,
-                                        uint8_t *data, uint32_t data_size, uint32_t *written)
+                                        uint8_t *data, uint32_t data_size, const LnbChanParams *forced, uint32_t *written)
 {
     const uint32_t C = enc->header.num_channels;
     const size_t stride = LNB_ROUNDUP((size_t)num_samples + 4u, 4u);
     uint32_t c;
-    if (enc->enable_learning || enc->num_afmethod_iterations) {
-        fprintf(stderr, "linne_b200: enable_learning / num_afmethod_iterations are not implemented on the device yet\n");
-        return LINNE_APIRESULT_NG;
-    }
+    if (!forced && unsupported_analysis(enc)) return LINNE_APIRESULT_NG;
     if (lnb_buf_reserve_device(enc->dev, &enc->d_pcm, stride * C * sizeof(int32_t))) return LINNE_APIRESULT_NG;
     for (c = 0; c < C; c++) {
         if (input[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
         lnb_shim_h2d(enc->dev, (int32_t *)enc->d_pcm.ptr + c * stride, input[c], (size_t)num_samples * sizeof(int32_t));
     }
-    return encode_blocks(enc, num_samples, data, data_size, written);
+    enc->cur_pcm = (const int32_t *)enc->d_pcm.ptr;
+    enc->cur_pcm_stride = (uint32_t)stride;
+    return encode_blocks(enc, num_samples, data, data_size, 0, forced, written);
 }
 
 /* reference linne_encoder.c:774-862 */
@@ -278,7 +299,7 @@ LINNEApiResult LINNEEncoder_EncodeBlock(struct LINNEEncoder *enc, const int32_t 
         return LINNE_APIRESULT_INVALID_ARGUMENT;
     if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
     if (num_samples > enc->header.num_samples_per_block) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
-    return upload_and_encode(enc, input, num_samples, data, data_size, output_size);
+    return upload_and_encode(enc, input, num_samples, data, data_size, NULL, output_size);
 }
 
 /* reference linne_encoder.c:865-932 */
@@ -291,10 +312,65 @@ LINNEApiResult LINNEEncoder_EncodeWhole(struct LINNEEncoder *enc, const int32_t 
     if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
     enc->header.num_samples = num_samples;
     if ((ret = LINNEEncoder_EncodeHeader(&enc->header, data, data_size)) != LINNE_APIRESULT_OK) return ret;
-    ret = upload_and_encode(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, &written);
+    ret = upload_and_encode(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, NULL, &written);
     if (ret != LINNE_APIRESULT_OK) return ret;
     *output_size = LINNE_HEADER_SIZE + written;
     return LINNE_APIRESULT_OK;
 }
 
 LnbDevice *lnb_encoder_device(const struct LINNEEncoder *enc) { return enc->dev; }
+
+/* ---- extension entry points (include/linne_b200.h) ---- */
+#include "linne_b200.h"
+
+LINNEApiResult LINNEB200_EncodeWholeWithParams(struct LINNEEncoder *enc, const int32_t *const *input,
+        uint32_t num_samples, const struct LINNEB200ChannelParams *params, uint32_t num_param_blocks,
+        uint8_t *data, uint32_t data_size, uint32_t *output_size)
+{
+    LINNEApiResult ret;
+    LnbChanParams *forced;
+    uint32_t written = 0, blocks, i, l, C;
+    if (enc == NULL || input == NULL || params == NULL || data == NULL || output_size == NULL)
+        return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
+    C = enc->header.num_channels;
+    blocks = (num_samples + enc->header.num_samples_per_block - 1u) / enc->header.num_samples_per_block;
+    if (num_param_blocks < blocks) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    enc->header.num_samples = num_samples;
+    if ((ret = LINNEEncoder_EncodeHeader(&enc->header, data, data_size)) != LINNE_APIRESULT_OK) return ret;
+    forced = (LnbChanParams *)calloc((size_t)blocks * C, sizeof(LnbChanParams));
+    if (!forced) return LINNE_APIRESULT_NG;
+    for (i = 0; i < blocks * C; i++)
+        for (l = 0; l < LNB_MAX_LAYERS; l++) {
+            forced[i].log2_units[l] = params[i].log2_units[l];
+            forced[i].rshift[l] = params[i].rshift[l];
+            memcpy(forced[i].coef + l * LNB_MAX_PARAMS, params[i].coef[l], LNB_MAX_PARAMS);
+        }
+    ret = upload_and_encode(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, forced, &written);
+    free(forced);
+    if (ret != LINNE_APIRESULT_OK) return ret;
+    *output_size = LINNE_HEADER_SIZE + written;
+    return LINNE_APIRESULT_OK;
+}
+
+LINNEApiResult LINNEB200_EncodeWholeResident(struct LINNEEncoder *enc, const int32_t *d_pcm, uint32_t pcm_stride,
+        uint32_t num_samples, uint8_t *d_data, uint32_t data_size, uint32_t *output_size)
+{
+    uint8_t hdr[LINNE_HEADER_SIZE];
+    LINNEApiResult ret;
+    uint32_t written = 0;
+    if (enc == NULL || d_pcm == NULL || d_data == NULL || output_size == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
+    if (pcm_stride < num_samples) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (unsupported_analysis(enc)) return LINNE_APIRESULT_NG;
+    enc->header.num_samples = num_samples;
+    if (data_size < LINNE_HEADER_SIZE) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    if ((ret = LINNEEncoder_EncodeHeader(&enc->header, hdr, sizeof(hdr))) != LINNE_APIRESULT_OK) return ret;
+    lnb_shim_h2d(enc->dev, d_data, hdr, LINNE_HEADER_SIZE);
+    enc->cur_pcm = d_pcm;
+    enc->cur_pcm_stride = pcm_stride;
+    ret = encode_blocks(enc, num_samples, d_data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, 1, NULL, &written);
+    if (ret != LINNE_APIRESULT_OK) return ret;
+    *output_size = LINNE_HEADER_SIZE + written;
+    return LINNE_APIRESULT_OK;
+}

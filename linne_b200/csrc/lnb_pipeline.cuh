@@ -326,15 +326,17 @@ void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
     const uint32_t S = B * C * b.cfg.num_lambdas;
     ex.run("estimate", B * C, LnbItemEstimate{b});
     ex.run("prepare", B, LnbItemPrepare{b});
-    ex.run("to_double", S * b.cfg.work_stride, LnbItemToDouble{b});
-    double *cur = b.sig_a, *nxt = b.sig_b;
-    for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
-        ex.run("search", S * LNB_ITEMS_PER_SLOT, LnbItemSearch{b, l, cur});
-        ex.run("select", S, LnbItemSelect{b, l});
-        ex.run("forward", S * LNB_MAX_UNITS, LnbItemForward{b, l, cur, nxt});
-        double *t = cur; cur = nxt; nxt = t;
+    if (!b.forced_params) {
+        ex.run("to_double", S * b.cfg.work_stride, LnbItemToDouble{b});
+        double *cur = b.sig_a, *nxt = b.sig_b;
+        for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
+            ex.run("search", S * LNB_ITEMS_PER_SLOT, LnbItemSearch{b, l, cur});
+            ex.run("select", S, LnbItemSelect{b, l});
+            ex.run("forward", S * LNB_MAX_UNITS, LnbItemForward{b, l, cur, nxt});
+            double *t = cur; cur = nxt; nxt = t;
+        }
+        ex.run("finish", B * C, LnbItemFinish{b});
     }
-    ex.run("finish", B * C, LnbItemFinish{b});
     for (uint32_t l = 0; l < b.cfg.num_layers; l++)
         ex.run("predict", B * C * LNB_MAX_UNITS, LnbItemPredict{b, l});
     ex.run("plan", B * C, LnbItemPlan{b});

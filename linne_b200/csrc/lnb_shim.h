@@ -43,6 +43,17 @@ int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *batch, uint32_t o
 /* number of kernels launched through this context since it was opened (bench.py's gpu_launches) */
 uint64_t lnb_shim_launch_count(const LnbDevice *dev);
 
+/* Per-stage device timing (CUDA events on the launching stream around every kernel).  Off by default.
+ * Stats accumulate until reset; `get` returns the number of stages filled in. */
+typedef struct LnbStageStat { char name[24]; uint64_t launches; double total_ms; } LnbStageStat;
+void lnb_shim_profile_enable(LnbDevice *dev, int on);
+void lnb_shim_profile_reset(LnbDevice *dev);
+int  lnb_shim_profile_get(LnbDevice *dev, LnbStageStat *out, int max_stages);
+
+/* Sustained FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), measured with a
+ * register-resident microbenchmark: the roofline denominator of the analysis kernels. */
+double lnb_shim_measure_fp64_tflops(LnbDevice *dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,9 @@
 #include "lnb_shim.h"
 #include "lnb_pipeline.cuh"
 
+#define LNB_MAX_STAGES 32
+#define LNB_MAX_PENDING 8192
+
 struct LnbDevice {
     cudaStream_t stream;
     int owns_stream;
@@ -20,7 +23,37 @@ struct LnbDevice {
     void *table_mem;
     uint64_t launches;
     cudaError_t last_error;
+    /* optional per-stage timing */
+    int profiling;
+    int num_stages;
+    LnbStageStat stages[LNB_MAX_STAGES];
+    int num_pending;
+    cudaEvent_t ev_begin[LNB_MAX_PENDING], ev_end[LNB_MAX_PENDING];
+    int pending_stage[LNB_MAX_PENDING];
+    int events_created;
 };
+
+static int stage_index(LnbDevice *dev, const char *name)
+{
+    for (int i = 0; i < dev->num_stages; i++) if (strcmp(dev->stages[i].name, name) == 0) return i;
+    if (dev->num_stages >= LNB_MAX_STAGES) return LNB_MAX_STAGES - 1;
+    LnbStageStat *s = &dev->stages[dev->num_stages];
+    memset(s, 0, sizeof(*s));
+    strncpy(s->name, name, sizeof(s->name) - 1);
+    return dev->num_stages++;
+}
+
+static void drain_profile(LnbDevice *dev)
+{
+    for (int i = 0; i < dev->num_pending; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, dev->ev_begin[i], dev->ev_end[i]) == cudaSuccess) {
+            dev->stages[dev->pending_stage[i]].total_ms += ms;
+            dev->stages[dev->pending_stage[i]].launches += 1;
+        }
+    }
+    dev->num_pending = 0;
+}
 
 template <class F>
 __global__ void __launch_bounds__(128) lnb_items_kernel(uint32_t n, F f)
@@ -31,12 +64,20 @@ __global__ void __launch_bounds__(128) lnb_items_kernel(uint32_t n, F f)
 
 struct CudaExec {
     LnbDevice *dev;
-    template <class F> void run(const char *, uint32_t n, const F &f)
+    template <class F> void run(const char *name, uint32_t n, const F &f)
     {
         if (n == 0) return;
         const uint32_t threads = 128;
         const uint32_t grid = (n + threads - 1) / threads;
+        int slot = -1;
+        if (dev->profiling) {
+            if (dev->num_pending >= LNB_MAX_PENDING) { cudaStreamSynchronize(dev->stream); drain_profile(dev); }
+            slot = dev->num_pending++;
+            dev->pending_stage[slot] = stage_index(dev, name);
+            cudaEventRecord(dev->ev_begin[slot], dev->stream);
+        }
         lnb_items_kernel<F><<<grid, threads, 0, dev->stream>>>(n, f);
+        if (slot >= 0) cudaEventRecord(dev->ev_end[slot], dev->stream);
         dev->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess && dev->last_error == cudaSuccess) dev->last_error = e;
@@ -83,6 +124,8 @@ void lnb_shim_close(LnbDevice *dev)
 {
     if (!dev) return;
     cudaStreamSynchronize(dev->stream);
+    if (dev->events_created)
+        for (int i = 0; i < LNB_MAX_PENDING; i++) { cudaEventDestroy(dev->ev_begin[i]); cudaEventDestroy(dev->ev_end[i]); }
     cudaFree(dev->table_mem);
     if (dev->owns_stream) cudaStreamDestroy(dev->stream);
     free(dev);
@@ -133,6 +176,7 @@ int lnb_shim_memset(LnbDevice *dev, void *dst, int value, size_t bytes)
 int lnb_shim_sync(LnbDevice *dev)
 {
     cudaError_t e = cudaStreamSynchronize(dev->stream);
+    if (e == cudaSuccess && dev->profiling) drain_profile(dev);
     if (e == cudaSuccess) e = dev->last_error;
     if (e != cudaSuccess) {
         fprintf(stderr, "linne_b200: CUDA error: %s\n", cudaGetErrorString(e));
@@ -163,5 +207,66 @@ int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *batch, uint32_t o
 }
 
 uint64_t lnb_shim_launch_count(const LnbDevice *dev) { return dev->launches; }
+
+void lnb_shim_profile_enable(LnbDevice *dev, int on)
+{
+    if (on && !dev->events_created) {
+        for (int i = 0; i < LNB_MAX_PENDING; i++) { cudaEventCreate(&dev->ev_begin[i]); cudaEventCreate(&dev->ev_end[i]); }
+        dev->events_created = 1;
+    }
+    cudaStreamSynchronize(dev->stream);
+    drain_profile(dev);
+    dev->profiling = on ? 1 : 0;
+}
+void lnb_shim_profile_reset(LnbDevice *dev)
+{
+    cudaStreamSynchronize(dev->stream);
+    drain_profile(dev);
+    for (int i = 0; i < dev->num_stages; i++) { dev->stages[i].launches = 0; dev->stages[i].total_ms = 0.0; }
+}
+int lnb_shim_profile_get(LnbDevice *dev, LnbStageStat *out, int max_stages)
+{
+    cudaStreamSynchronize(dev->stream);
+    drain_profile(dev);
+    int n = dev->num_stages < max_stages ? dev->num_stages : max_stages;
+    for (int i = 0; i < n; i++) out[i] = dev->stages[i];
+    return n;
+}
+
+/* 8 independent DFMA chains per thread, 2048 x 8 DFMA each; grid fills every SM several times over */
+__global__ void __launch_bounds__(256) lnb_fp64_peak_kernel(double *sink, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 16
+    for (int i = 0; i < 2048; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678) sink[0] = s;
+}
+
+double lnb_shim_measure_fp64_tflops(LnbDevice *dev)
+{
+    double *sink = NULL;
+    cudaEvent_t e0, e1;
+    const int grid = 148 * 16, threads = 256, reps = 5;
+    float best = 1e30f;
+    if (cudaMalloc(&sink, 64) != cudaSuccess) return 0.0;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    lnb_fp64_peak_kernel<<<grid, threads, 0, dev->stream>>>(sink, 0.999999, 1e-9);
+    for (int r = 0; r < reps; r++) {
+        float ms = 0.f;
+        cudaEventRecord(e0, dev->stream);
+        lnb_fp64_peak_kernel<<<grid, threads, 0, dev->stream>>>(sink, 0.999999, 1e-9);
+        cudaEventRecord(e1, dev->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    const double flops = 2.0 * 8.0 * 2048.0 * (double)grid * threads;
+    return flops / (best * 1e-3) / 1e12;
+}
 
 }  /* extern "C" */

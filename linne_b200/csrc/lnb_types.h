@@ -100,6 +100,7 @@ typedef struct LnbEncodeBatch {
     uint8_t *out;                   /* device image of the output stream */
     uint32_t *total_size;           /* device scalar: bytes of all blocks of this batch */
     uint32_t out_base;              /* byte offset of the first block of this batch in `out` */
+    uint32_t forced_params;         /* 1: `params` already hold units/shift/coefficients -- skip the analysis stages */
 } LnbEncodeBatch;
 
 #endif

@@ -314,4 +314,31 @@ def have_hostsim() -> bool:
 
 class HostSim(LinneApi):
     def __init__(self):
-        super().__init__(C.CDLL(HOSTSIM_SO, mode=getattr(os, "RTLD_LOCAL", 0)))
+        from linne_b200.api import bind_ext_api, Product
+        super().__init__(bind_ext_api(C.CDLL(HOSTSIM_SO, mode=getattr(os, "RTLD_LOCAL", 0))))
+        assert self.lib.LINNEB200_Backend() == b"hostsim"
+        self.encode_with_params = Product.encode_with_params.__get__(self)
+
+
+def params_from_golden(g):
+    """ChannelParams array (block-major) from a tests/golden fixture."""
+    from linne_b200.api import ChannelParams
+    nb, nch = g["units"].shape[:2]
+    arr = (ChannelParams * (nb * nch))()
+    for b in range(nb):
+        for c in range(nch):
+            p = arr[b * nch + c]
+            for l in range(3):
+                u = int(g["units"][b, c, l])
+                p.log2_units[l] = max(u, 1).bit_length() - 1
+                p.rshift[l] = int(g["rshift"][b, c, l])
+                for i in range(128):
+                    p.coef[l][i] = int(g["coef"][b, c, l, i])
+    return arr
+
+
+def load_golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+
+GOLDEN_CASES = ["stereo16_m0", "stereo16_m4", "stereo16_m7", "mono8_m7", "eightch24_m7", "mono24_m2"]

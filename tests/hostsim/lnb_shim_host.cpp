@@ -47,4 +47,8 @@ int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *b) { LoopExec ex{dev};
 int lnb_shim_encode_analyze(LnbDevice *dev, const LnbEncodeBatch *b) { LoopExec ex{dev}; lnb_encode_analyze_pipeline(ex, *b); return 0; }
 int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *b, uint32_t cap) { LoopExec ex{dev}; lnb_encode_pack_pipeline(ex, *b, cap); return 0; }
 uint64_t lnb_shim_launch_count(const LnbDevice *dev) { return dev->launches; }
+void lnb_shim_profile_enable(LnbDevice *, int) {}
+void lnb_shim_profile_reset(LnbDevice *) {}
+int lnb_shim_profile_get(LnbDevice *, LnbStageStat *, int) { return 0; }
+double lnb_shim_measure_fp64_tflops(LnbDevice *) { return 0.0; }
 }
