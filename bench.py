@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- LINNE block encode/decode throughput on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], "C2"): the synthetic 10 s / 44.1 kHz / 16-bit / stereo clip
+(sinusoid mixture + coloured noise + transients), encoded AND decoded at every
+preset -m 0..7.  One step = the whole sweep: 8 x (EncodeWhole + DecodeWhole).  Samples are counted
+once per preset (a sample that went through encode and decode counts once), so
+
+    value [MSamples/s] = 8 presets x 882 000 samples x n_gpus / (ms_per_step / 1000) / 1e6.
+
+  value : inputs resident in HBM (PCM planes and .lnn image on the device, LINNEB200_*Resident)
+  e2e   : the reference-facing C-ABI with HOST buffers (pinned), H2D/D2H inside the timed region
+
+Multi-GPU: blocks/files are independent, so ranks run the same sweep on their own copy of the clip
+with no data-path collective ("weak"); time = max over ranks.
+
+--impl reference times the unmodified reference (oracle/_ref/liblinne_ref.so, its own CPU code)
+on the host cores, one thread per preset, same sweep.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+CLIP_SECONDS, RATE, BITS, CHANNELS, BLOCK = 10.0, 44100, 16, 2, 10240
+PRESETS = list(range(8))
+# algorithmic MACs per input sample of the default analysis, per preset
+MAC_PER_SAMPLE = {0: 420, 1: 630, 2: 934, 3: 1401, 4: 2335, 5: 1802, 6: 2703, 7: 4505}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_clip():
+    import harness
+    return harness.synth_pcm(seconds=CLIP_SECONDS, sr=RATE, channels=CHANNELS, bits=BITS, seed=1)
+
+
+# =================================================================================================
+# reference arm
+# =================================================================================================
+def run_reference(args, rank, world):
+    import harness
+    if rank != 0:
+        return
+    if harness.have_ref():
+        impl, kind = harness.Ref(), "reference"
+    else:
+        impl, kind = harness.Oracle(), "port"
+    pcm = make_clip()
+    n_samples = pcm.shape[0] * pcm.shape[1]
+    ncpu = os.cpu_count() or 1
+    # Blocks are independent (a fresh handle per block reproduces EncodeWhole byte
+    # for byte), so the fairest multi-core use of the single-threaded reference is one handle per
+    # (preset, contiguous block range): tasks = 8 presets x `parts` ranges, run on all host cores.
+    total_blocks = (pcm.shape[1] + BLOCK - 1) // BLOCK
+    parts = max(1, min(total_blocks, ncpu // len(PRESETS)))
+    per = (total_blocks + parts - 1) // parts
+    ranges = [(b * BLOCK, min((b + per) * BLOCK, pcm.shape[1])) for b in range(0, total_blocks, per)]
+    cores = min(ncpu, len(PRESETS) * len(ranges))
+
+    def one_task(m, lo, hi, out):
+        sub = np.ascontiguousarray(pcm[:, lo:hi])
+        t0 = time.perf_counter(); s = impl.encode(sub, preset=m); t1 = time.perf_counter()
+        d = impl.decode(s); t2 = time.perf_counter()
+        out[(m, lo)] = (t1 - t0, t2 - t1, len(s) - 30, bool(np.array_equal(d, sub)))
+
+    def sweep():
+        res = {}
+        pending = [(m, lo, hi) for m in PRESETS[::-1] for lo, hi in ranges]      # longest presets first
+        lock = threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    if not pending:
+                        return
+                    m, lo, hi = pending.pop(0)
+                one_task(m, lo, hi, res)
+        threads = [threading.Thread(target=worker) for _ in range(cores)]
+        t0 = time.perf_counter()
+        for t in threads: t.start()
+        for t in threads: t.join()
+        per_preset = {}
+        for (m, _), v in res.items():
+            a = per_preset.setdefault(m, [0.0, 0.0, 30, True])
+            a[0] += v[0]; a[1] += v[1]; a[2] += v[2]; a[3] = a[3] and v[3]
+        return time.perf_counter() - t0, per_preset
+
+    for _ in range(args.warmup):
+        sweep()
+    times, last = [], None
+    for _ in range(args.steps):
+        dt, last = sweep()
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = len(PRESETS) * n_samples / (ms / 1e3) / 1e6
+    line = {
+        "impl": "reference", "metric": "encode+decode MSamples/s over the -m 0..7 sweep", "value": round(value, 4),
+        "unit": "MSamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": "C2: 10 s 44.1 kHz 16-bit stereo synthetic clip, -m 0..7 sweep, encode+decode",
+                   "block": BLOCK, "ms": 1, "presets": PRESETS},
+        "cpu_baseline": {"value": round(value, 4), "unit": "MSamples/s", "cores": cores, "kind": kind,
+                         "sample": f"the full sweep (8 presets x 882000 samples) as {len(PRESETS) * len(ranges)} independent "
+                                   f"(preset, block-range) tasks on {cores} threads"},
+        "e2e": {"value": round(value, 4), "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "detail": {str(m): {"enc_s": round(v[0], 4), "dec_s": round(v[1], 4), "bytes": v[2], "lossless": v[3]}
+                   for m, v in sorted(last.items())},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =================================================================================================
+# our arm
+# =================================================================================================
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import harness
+    from linne_b200 import EncoderSession, DecoderSession, Product
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- linne_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    product = Product()
+    hbm_peak, peak_src = load_peaks()
+
+    pcm = make_clip()
+    nch, n = pcm.shape
+    n_samples = nch * n
+    stride = (n + 4 + 3) // 4 * 4
+    cap = 30 + 2 * nch * n * 4 + 65536
+
+    # host (pinned) and device buffers
+    h_pcm = torch.from_numpy(pcm.copy()).pin_memory()
+    h_out = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    h_back = torch.zeros((nch, n), dtype=torch.int32).pin_memory()
+    d_pcm = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+    d_pcm[:, :n].copy_(h_pcm)
+    d_out = [torch.zeros(cap + 64, dtype=torch.uint8, device=dev) for _ in PRESETS]
+    d_back = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    stream_ptr = torch.cuda.current_stream().cuda_stream
+    encs = {m: EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=m) for m in PRESETS}
+    decs = {m: DecoderSession(channels=nch) for m in PRESETS}
+    for s in list(encs.values()) + list(decs.values()):
+        s.use_stream(stream_ptr)
+
+    chan_in = (C.POINTER(C.c_int32) * nch)(*[C.cast(h_pcm[c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
+    chan_out = (C.POINTER(C.c_int32) * nch)(*[C.cast(h_back[c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
+    sizes = {}
+    host_streams = {}
+
+    def step_e2e():
+        for m in PRESETS:
+            sz = encs[m].encode_whole(chan_in, n, h_out.data_ptr(), cap)
+            sizes[m] = sz
+            decs[m].decode_whole(h_out.data_ptr(), sz, chan_out, nch, n)
+
+    def step_resident():
+        for m in PRESETS:
+            sz = encs[m].encode_whole_resident(d_pcm.data_ptr(), stride, n, d_out[m].data_ptr(), cap)
+            sizes[m] = sz
+            # the decoder hops over block headers on the host: it needs the (small) stream image there too;
+            # it is the encoder's output, so copy it back once outside the sweep's device work
+            host_streams[m] = d_out[m][:sz].cpu().numpy()
+            decs[m].decode_whole_resident(host_streams[m].ctypes.data, d_out[m].data_ptr(), sz,
+                                          d_back.data_ptr(), stride, nch, n)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        if profile:
+            for s in list(encs.values()) + list(decs.values()):
+                s.set_profiling(True); s.reset_stage_stats()
+        launches0 = sum(s.launch_count() for s in list(encs.values()) + list(decs.values()))
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            l2_flush.fill_(1)                       # flush L2 between timed iterations
+            fn()
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1) / steps
+        launches = sum(s.launch_count() for s in list(encs.values()) + list(decs.values())) - launches0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches // steps
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res, launches = timed(step_resident, args.steps, args.warmup, profile=True)
+    sampler.stop_flag.set(); sampler.join(timeout=3)
+
+    # correctness of what was just timed (outside the timed region)
+    torch.cuda.synchronize()
+    ok_resident = bool(torch.equal(d_back[:, :n].cpu(), h_pcm))
+    stage = {}
+    for sess in list(encs.values()) + list(decs.values()):
+        for name, (cnt, ms) in sess.stage_stats().items():
+            a = stage.setdefault(name, [0, 0.0]); a[0] += cnt; a[1] += ms
+        sess.set_profiling(False)
+
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    ok_e2e = bool(np.array_equal(h_back.numpy(), pcm))
+    comp_bytes = dict(sizes)
+
+    value = len(PRESETS) * n_samples * world / (ms_res / 1e3) / 1e6
+    e2e_value = len(PRESETS) * n_samples * world / (ms_e2e / 1e3) / 1e6
+    h2d = sum(4 * n_samples + comp_bytes[m] for m in PRESETS)     # PCM up for encode, stream up for decode
+    d2h = sum(comp_bytes[m] + 4 * n_samples for m in PRESETS)     # stream down from encode, PCM down from decode
+
+    # ---- roofline of the dominant kernel, from the CUDA events recorded inside the timed region ----
+    dom = max(stage.items(), key=lambda kv: kv[1][1]) if stage else ("none", [1, 1.0])
+    dom_name, (dom_cnt, dom_ms) = dom[0], dom[1]
+    fp64_peak = product.measure_fp64_tflops() if rank == 0 else 0.0
+    total_comp = sum(comp_bytes.values())
+    hbm_bytes_per_sample = 4.0 + total_comp / (len(PRESETS) * n_samples)      # int32 PCM + compressed bytes
+    analysis_kernels = {"search", "forward", "select", "to_double", "finish"}
+    steps_profiled = args.steps
+    if dom_name in analysis_kernels:
+        flops = 2.0 * sum(MAC_PER_SAMPLE[m] for m in PRESETS) * n_samples * steps_profiled
+        an_ms = sum(v[1] for k, v in stage.items() if k in analysis_kernels)
+        achieved = flops / (an_ms / 1e3) / 1e12
+        roofline = {"bound": "fp64", "kernel": dom_name, "achieved": round(achieved, 4), "peak": round(fp64_peak, 3),
+                    "unit": "TFLOP/s", "frac": round(achieved / fp64_peak, 5) if fp64_peak else None, "traffic": None,
+                    "note": "encoder analysis is FP64-pipe bound (SURVEY 8d): algorithmic FLOPs = 2 x MAC/sample table "
+                            "(un-deduplicated) over the analysis kernels' summed event time; peak = DFMA microbenchmark "
+                            "on this GPU"}
+    else:
+        by = hbm_bytes_per_sample * len(PRESETS) * n_samples * steps_profiled
+        achieved = by / (dom_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 3), "peak": hbm_peak,
+                    "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src}
+    # decode-side HBM roofline (sum of the decode kernels), always reported
+    dec_kernels = {"crc", "entropy", "synth", "deemph", "ms_inverse"}
+    dec_ms = sum(v[1] for k, v in stage.items() if k in dec_kernels)
+    by = hbm_bytes_per_sample * len(PRESETS) * n_samples * steps_profiled
+    roofline_decode = {"bound": "hbm", "kernels": sorted(dec_kernels), "achieved": round(by / (dec_ms / 1e3) / 1e9, 3) if dec_ms else None,
+                       "peak": hbm_peak, "unit": "GB/s", "frac": round(by / (dec_ms / 1e3) / 1e9 / hbm_peak, 5) if dec_ms else None,
+                       "peak_source": peak_src, "bytes_per_sample": round(hbm_bytes_per_sample, 3)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it: the unmodified reference, one thread, bounded sample ----
+    cpu_baseline = None
+    try:
+        impl, kind = (harness.Ref(), "reference") if harness.have_ref() else (harness.Oracle(), "port")
+        sample_presets = [0, 4, 7]
+        sub = pcm[:, :5 * BLOCK * 4]           # 20 full blocks = 4.64 s of the clip
+        t0 = time.perf_counter()
+        ref_sizes = {}
+        for m in sample_presets:
+            s = impl.encode(sub, preset=m); impl.decode(s); ref_sizes[m] = len(s)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": round(len(sample_presets) * sub.size / dt / 1e6, 4), "unit": "MSamples/s", "cores": 1,
+                        "kind": kind, "sample": f"first {sub.shape[1]} frames of the clip, presets {sample_presets}, "
+                                                f"encode+decode, {dt:.1f} s of CPU work"}
+    except Exception as e:  # pragma: no cover
+        cpu_baseline = {"value": None, "unit": "MSamples/s", "cores": 1, "kind": "unavailable", "sample": str(e)}
+
+    line = {
+        "metric": "encode+decode MSamples/s over the -m 0..7 sweep", "value": round(value, 3), "unit": "MSamples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": "C2: 10 s 44.1 kHz 16-bit stereo synthetic clip, -m 0..7 sweep, encode+decode",
+                   "block": BLOCK, "ms": 1, "presets": PRESETS, "l2": "256 MiB flush write between timed iterations",
+                   "per_rank": "each rank runs the whole sweep on its own clip"},
+        "e2e": {"value": round(e2e_value, 3), "unit": "MSamples/s", "ms_per_step": round(ms_e2e, 3),
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_decode": roofline_decode,
+        "cpu_baseline": cpu_baseline,
+        "clocks": sampler.summary(),
+        "stages_ms_per_step": {k: round(v[1] / steps_profiled, 3) for k, v in sorted(stage.items(), key=lambda kv: -kv[1][1])},
+        "compressed_bytes": {str(m): int(comp_bytes[m]) for m in PRESETS},
+        "lossless": {"resident": ok_resident, "e2e": ok_e2e},
+        "fp64_peak_tflops": round(fp64_peak, 3),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
