@@ -137,7 +137,7 @@ struct LnbItemToDouble {            /* (slot, sample): normalised copy of the wo
         const uint32_t s = i / b.cfg.work_stride, t = i % b.cfg.work_stride;
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
         const double norm = ldexp(1.0, -(int)(b.cfg.bits_per_sample - 1u));
         b.sig_a[(size_t)s * b.cfg.work_stride + t] =
             (t < blk.na) ? (double)b.work[(size_t)bc * b.cfg.work_stride + t] * norm : 0.0;
@@ -155,7 +155,7 @@ struct LnbItemSearch {              /* E2: (slot, level, unit) */
         const uint32_t bc = s / b.cfg.num_lambdas, lam = s % b.cfg.num_lambdas;
         const uint32_t blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
         const uint32_t P = b.cfg.layer_params[layer];
         if (!lnb_level_valid(level, P, blk.na)) return;
         const uint32_t U = 1u << level, p = P / U, m = blk.na / U;
@@ -175,7 +175,7 @@ struct LnbItemSelect {              /* E3: (slot): first minimum over the unit c
     {
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
         const uint32_t P = b.cfg.layer_params[layer];
         double best_loss = (double)FLT_MAX;
         uint32_t best = 0;
@@ -206,7 +206,7 @@ struct LnbItemForward {             /* E4: (slot, unit) */
         const uint32_t s = i / LNB_MAX_UNITS, u = i % LNB_MAX_UNITS;
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
         const uint32_t U = 1u << b.chosen_log2u[(size_t)s * LNB_MAX_LAYERS + layer];
         if (u >= U) return;
         const uint32_t P = b.cfg.layer_params[layer], p = P / U, m = blk.na / U;
@@ -327,13 +327,16 @@ void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
     ex.run("estimate", B * C, LnbItemEstimate{b});
     ex.run("prepare", B, LnbItemPrepare{b});
     if (!b.forced_params) {
-        ex.run("to_double", S * b.cfg.work_stride, LnbItemToDouble{b});
-        double *cur = b.sig_a, *nxt = b.sig_b;
-        for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
-            ex.run("search", S * LNB_ITEMS_PER_SLOT, LnbItemSearch{b, l, cur});
-            ex.run("select", S, LnbItemSelect{b, l});
-            ex.run("forward", S * LNB_MAX_UNITS, LnbItemForward{b, l, cur, nxt});
-            double *t = cur; cur = nxt; nxt = t;
+        if (b.num_fast_blocks) ex.analyze_cooperative(b);        /* one CTA per slot, signal in shared memory */
+        if (b.num_slow_blocks) {                                  /* shapes the cooperative kernel does not take */
+            ex.run("to_double", S * b.cfg.work_stride, LnbItemToDouble{b});
+            double *cur = b.sig_a, *nxt = b.sig_b;
+            for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
+                ex.run("search", S * LNB_ITEMS_PER_SLOT, LnbItemSearch{b, l, cur});
+                ex.run("select", S, LnbItemSelect{b, l});
+                ex.run("forward", S * LNB_MAX_UNITS, LnbItemForward{b, l, cur, nxt});
+                double *t = cur; cur = nxt; nxt = t;
+            }
         }
         ex.run("finish", B * C, LnbItemFinish{b});
     }

@@ -25,6 +25,8 @@ const LnbDevTables *lnb_shim_tables(const LnbDevice *dev);
 /* Launch on an externally owned stream (cudaStream_t as void*) instead of the context's own. */
 void lnb_shim_use_stream(LnbDevice *dev, void *cuda_stream);
 const char *lnb_shim_backend(void);      /* "cuda-sm_100a" for the product */
+/* Largest analysis length the cooperative (shared-memory) encoder kernels take; 0 = none. */
+uint32_t lnb_shim_fast_max_na(void);
 
 void *lnb_shim_alloc(LnbDevice *dev, size_t bytes);
 void  lnb_shim_free(LnbDevice *dev, void *ptr);

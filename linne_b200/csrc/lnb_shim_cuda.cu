@@ -11,6 +11,7 @@
 
 #include "lnb_shim.h"
 #include "lnb_pipeline.cuh"
+#include "lnb_analyze_v2.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -64,6 +65,36 @@ __global__ void __launch_bounds__(128) lnb_items_kernel(uint32_t n, F f)
 
 struct CudaExec {
     LnbDevice *dev;
+    int begin_stage(const char *name)
+    {
+        if (!dev->profiling) return -1;
+        if (dev->num_pending >= LNB_MAX_PENDING) { cudaStreamSynchronize(dev->stream); drain_profile(dev); }
+        const int slot = dev->num_pending++;
+        dev->pending_stage[slot] = stage_index(dev, name);
+        cudaEventRecord(dev->ev_begin[slot], dev->stream);
+        return slot;
+    }
+    void end_stage(int slot)
+    {
+        if (slot >= 0) cudaEventRecord(dev->ev_end[slot], dev->stream);
+        dev->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && dev->last_error == cudaSuccess) dev->last_error = e;
+    }
+    void analyze_cooperative(const LnbEncodeBatch &b)
+    {
+        const uint32_t S = b.num_blocks * b.cfg.num_channels * b.cfg.num_lambdas;
+        const uint32_t na_max = b.cfg.block_size < LNB_AN_MAX_NA ? b.cfg.block_size : LNB_AN_MAX_NA;
+        const size_t smem = lnb_an_smem_doubles(na_max) * sizeof(double);
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(lnb_analyze_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        const int slot = begin_stage("analyze_v2");
+        lnb_analyze_v2_kernel<<<S, LNB_AN_THREADS, smem, dev->stream>>>(b, na_max);
+        end_stage(slot);
+    }
     template <class F> void run(const char *name, uint32_t n, const F &f)
     {
         if (n == 0) return;
@@ -87,6 +118,7 @@ struct CudaExec {
 extern "C" {
 
 const char *lnb_shim_backend(void) { return "cuda-sm_100a"; }
+uint32_t lnb_shim_fast_max_na(void) { return LNB_AN_MAX_NA; }
 
 int lnb_shim_open(LnbDevice **out, int device_ordinal)
 {

@@ -36,6 +36,9 @@ typedef struct LnbBlockDesc {
     uint32_t crc;                 /* decoder: CRC16 computed over the block body */
 } LnbBlockDesc;
 
+/* encoder-side use of LnbBlockDesc.status: the block takes the cooperative (shared-memory) kernels */
+#define LNB_ENC_FLAG_FAST 1u
+
 enum { LNB_ST_OK = 0, LNB_ST_CRC_MISMATCH = 1, LNB_ST_OVERRUN = 2, LNB_ST_BAD_TYPE = 4 };
 
 /* ---- analysis result / parsed side information of one (block, channel) ---- */
@@ -100,6 +103,8 @@ typedef struct LnbEncodeBatch {
     uint8_t *out;                   /* device image of the output stream */
     uint32_t *total_size;           /* device scalar: bytes of all blocks of this batch */
     uint32_t out_base;              /* byte offset of the first block of this batch in `out` */
+    uint32_t num_fast_blocks;       /* blocks flagged LNB_ENC_FLAG_FAST (0: skip the cooperative launch) */
+    uint32_t num_slow_blocks;       /* compressed-candidate blocks left to the flat kernels */
     uint32_t forced_params;         /* 1: `params` already hold units/shift/coefficients -- skip the analysis stages */
 } LnbEncodeBatch;
 

@@ -19,10 +19,12 @@ struct LoopExec {
         for (uint32_t i = 0; i < n; i++) f(i);
         dev->launches++;
     }
+    void analyze_cooperative(const LnbEncodeBatch &) {}       /* CUDA only; the host never flags blocks for it */
 };
 
 extern "C" {
 const char *lnb_shim_backend(void) { return "hostsim"; }
+uint32_t lnb_shim_fast_max_na(void) { return 0; }
 int lnb_shim_open(LnbDevice **out, int)
 {
     LnbDevice *dev = (LnbDevice *)calloc(1, sizeof(LnbDevice));
