@@ -227,20 +227,22 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
         const uint32_t nb = (total_blocks - first < chunk_blocks) ? total_blocks - first : chunk_blocks;
         LnbBlockDesc *hb = (LnbBlockDesc *)enc->h_blocks.ptr;
         double *hw = (double *)enc->h_welch.ptr;
-        uint32_t chunk_bytes, num_fast = 0;
-        const uint32_t fast_max_na = lnb_shim_fast_max_na();
+        uint32_t chunk_bytes, num_fast = 0, num_coop = 0;
+        const uint32_t fast_max_na = lnb_shim_fast_max_na(), coop_max_n = lnb_shim_coop_max_n();
         for (i = 0; i < nb; i++) {
             const uint32_t start = (first + i) * NB;
             const uint32_t n = (num_samples - start < NB) ? num_samples - start : NB;
             memset(&hb[i], 0, sizeof(hb[i]));
             hb[i].smp_off = start; hb[i].nsmp = n; hb[i].na = analysis_length(&batch.cfg, n);
-            if (hb[i].na <= fast_max_na && (hb[i].na % 2048u) == 0u) { hb[i].status = LNB_ENC_FLAG_FAST; num_fast++; }
+            if (hb[i].na <= fast_max_na && (hb[i].na % 2048u) == 0u) { hb[i].status |= LNB_ENC_FLAG_FAST; num_fast++; }
+            if (n <= coop_max_n && NB <= coop_max_n) { hb[i].status |= LNB_ENC_FLAG_COOP; num_coop++; }
             for (lvl = 0; lvl < LNB_MAX_LEVELS; lvl++) {
                 const uint32_t m = hb[i].na >> lvl;
                 hw[(size_t)i * LNB_MAX_LEVELS + lvl] = (m >= 2u) ? lnb_welch_scale(m) : 0.0;
             }
         }
         batch.num_blocks = nb;
+        batch.num_coop_blocks = num_coop;
         batch.num_fast_blocks = num_fast;
         batch.num_slow_blocks = nb - num_fast;
         batch.forced_params = forced ? 1u : 0u;

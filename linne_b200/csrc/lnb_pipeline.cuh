@@ -115,6 +115,7 @@ struct LnbItemEstimate {            /* E0: (block, channel) */
     {
         const uint32_t blk_i = bc / b.cfg.num_channels, c = bc % b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.status & LNB_ENC_FLAG_COOP) return;
         b.est[bc] = lnb_estimate_bits(b.pcm + (size_t)c * b.cfg.pcm_stride + blk.smp_off, blk.nsmp,
                                       b.cfg.bits_per_sample, b.cfg.layer_params[0]);
     }
@@ -125,6 +126,7 @@ struct LnbItemPrepare {             /* E1: (block) */
     LNB_HDM void operator()(uint32_t i) const
     {
         const uint32_t C = b.cfg.num_channels;
+        if (b.blocks[i].status & LNB_ENC_FLAG_COOP) return;
         lnb_prepare_block(b.cfg, b.blocks[i], b.est + (size_t)i * C, b.pcm,
                           b.work + (size_t)i * C * b.cfg.work_stride, b.params + (size_t)i * C);
     }
@@ -254,7 +256,7 @@ struct LnbItemPredict {             /* E6: (block, channel, unit slot), one laye
         const uint32_t u = i % LNB_MAX_UNITS, bc = i / LNB_MAX_UNITS;
         const uint32_t blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_COOP)) return;
         const LnbChanParams &prm = b.params[bc];
         const uint32_t P = b.cfg.layer_params[layer], U = 1u << prm.log2_units[layer];
         if (u >= U || U > P) return;
@@ -270,7 +272,7 @@ struct LnbItemPlan {                /* E7: (block, channel) */
     {
         const uint32_t blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_COOP)) return;
         lnb_coder_plan(b.tab.k2_threshold, b.work + (size_t)bc * b.cfg.work_stride, blk.nsmp,
                        b.plan_mean + (size_t)bc * 2u * LNB_MAX_PARTITIONS, b.plans[bc]);
     }
@@ -311,6 +313,7 @@ struct LnbItemPack {                /* E9: (block) */
         const LnbBlockDesc &blk = b.blocks[i];
         const uint32_t C = b.cfg.num_channels;
         if ((uint64_t)blk.byte_off + blk.byte_size > out_capacity) return;      /* host reports INSUFFICIENT_BUFFER */
+        if (blk.status & LNB_ENC_FLAG_PACKED) return;                           /* done by the cooperative packer */
         lnb_pack_block(b.cfg, b.tab, blk, b.params + (size_t)i * C, b.plans + (size_t)i * C, b.pcm,
                        b.work + (size_t)i * C * b.cfg.work_stride, b.out + blk.byte_off);
     }
@@ -324,8 +327,12 @@ void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
     const uint32_t B = b.num_blocks, C = b.cfg.num_channels;
     if (B == 0) return;
     const uint32_t S = B * C * b.cfg.num_lambdas;
-    ex.run("estimate", B * C, LnbItemEstimate{b});
-    ex.run("prepare", B, LnbItemPrepare{b});
+    const bool flat = b.num_coop_blocks < B;                /* some blocks are too long for the cooperative kernels */
+    if (b.num_coop_blocks) ex.prepare_cooperative(b);
+    if (flat) {
+        ex.run("estimate", B * C, LnbItemEstimate{b});
+        ex.run("prepare", B, LnbItemPrepare{b});
+    }
     if (!b.forced_params) {
         if (b.num_fast_blocks) ex.analyze_cooperative(b);        /* one CTA per slot, signal in shared memory */
         if (b.num_slow_blocks) {                                  /* shapes the cooperative kernel does not take */
@@ -340,9 +347,12 @@ void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
         }
         ex.run("finish", B * C, LnbItemFinish{b});
     }
-    for (uint32_t l = 0; l < b.cfg.num_layers; l++)
-        ex.run("predict", B * C * LNB_MAX_UNITS, LnbItemPredict{b, l});
-    ex.run("plan", B * C, LnbItemPlan{b});
+    if (b.num_coop_blocks) ex.predict_plan_cooperative(b);
+    if (flat) {
+        for (uint32_t l = 0; l < b.cfg.num_layers; l++)
+            ex.run("predict", B * C * LNB_MAX_UNITS, LnbItemPredict{b, l});
+        ex.run("plan", B * C, LnbItemPlan{b});
+    }
     ex.run("size", B, LnbItemSize{b});
     ex.run("scan", 1, LnbItemScan{b});
 }
@@ -351,5 +361,6 @@ template <class Exec>
 void lnb_encode_pack_pipeline(Exec &ex, const LnbEncodeBatch &b, uint32_t out_capacity)
 {
     if (b.num_blocks == 0) return;
+    ex.pack_cooperative(b, out_capacity);                 /* one CTA per block; skips images too large for shared memory */
     ex.run("pack", b.num_blocks, LnbItemPack{b, out_capacity});
 }

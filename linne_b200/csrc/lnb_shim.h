@@ -27,6 +27,8 @@ void lnb_shim_use_stream(LnbDevice *dev, void *cuda_stream);
 const char *lnb_shim_backend(void);      /* "cuda-sm_100a" for the product */
 /* Largest analysis length the cooperative (shared-memory) encoder kernels take; 0 = none. */
 uint32_t lnb_shim_fast_max_na(void);
+/* Longest block (samples per channel) the cooperative prepare / predict+plan kernels take; 0 = none. */
+uint32_t lnb_shim_coop_max_n(void);
 
 void *lnb_shim_alloc(LnbDevice *dev, size_t bytes);
 void  lnb_shim_free(LnbDevice *dev, void *ptr);

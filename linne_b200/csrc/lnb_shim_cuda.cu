@@ -12,6 +12,8 @@
 #include "lnb_shim.h"
 #include "lnb_pipeline.cuh"
 #include "lnb_analyze_v2.cuh"
+#include "lnb_pack_v2.cuh"
+#include "lnb_front_v2.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -81,6 +83,42 @@ struct CudaExec {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess && dev->last_error == cudaSuccess) dev->last_error = e;
     }
+    void prepare_cooperative(const LnbEncodeBatch &b)
+    {
+        const int slot = begin_stage("prepare_v2");
+        lnb_prepare_v2_kernel<<<b.num_blocks, LNB_FR_THREADS, 0, dev->stream>>>(b);
+        end_stage(slot);
+    }
+    void predict_plan_cooperative(const LnbEncodeBatch &b)
+    {
+        uint32_t n_max = b.cfg.block_size < LNB_FR_MAX_N ? b.cfg.block_size : LNB_FR_MAX_N;
+        n_max = (n_max + 3u) & ~3u;
+        const size_t smem = (size_t)2 * n_max * sizeof(int32_t) + sizeof(LnbPlanSmem);
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(lnb_predict_plan_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        const int slot = begin_stage("predict_plan_v2");
+        lnb_predict_plan_v2_kernel<<<b.num_blocks * b.cfg.num_channels, LNB_FR_THREADS, smem, dev->stream>>>(b, n_max);
+        end_stage(slot);
+    }
+    void pack_cooperative(const LnbEncodeBatch &b, uint32_t out_capacity)
+    {
+        /* staging buffer: the raw-block size bound of this stream format plus slack, capped by the SM */
+        size_t bytes = 64 + LNB_BLOCK_HEADER_SIZE + (size_t)b.cfg.block_size * b.cfg.num_channels * ((b.cfg.bits_per_sample + 7u) / 8u);
+        bytes += bytes / 8;
+        if (bytes > 220u * 1024u) bytes = 220u * 1024u;
+        const uint32_t img_words = (uint32_t)((bytes + 3) / 4);
+        static size_t configured = 0;
+        if ((size_t)img_words * 4 > configured) {
+            cudaFuncSetAttribute(lnb_pack_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(img_words * 4));
+            configured = (size_t)img_words * 4;
+        }
+        const int slot = begin_stage("pack_v2");
+        lnb_pack_v2_kernel<<<b.num_blocks, LNB_PK_THREADS, (size_t)img_words * 4, dev->stream>>>(b, out_capacity, img_words);
+        end_stage(slot);
+    }
     void analyze_cooperative(const LnbEncodeBatch &b)
     {
         const uint32_t S = b.num_blocks * b.cfg.num_channels * b.cfg.num_lambdas;
@@ -119,6 +157,7 @@ extern "C" {
 
 const char *lnb_shim_backend(void) { return "cuda-sm_100a"; }
 uint32_t lnb_shim_fast_max_na(void) { return LNB_AN_MAX_NA; }
+uint32_t lnb_shim_coop_max_n(void) { return LNB_FR_MAX_N; }
 
 int lnb_shim_open(LnbDevice **out, int device_ordinal)
 {

@@ -38,6 +38,10 @@ typedef struct LnbBlockDesc {
 
 /* encoder-side use of LnbBlockDesc.status: the block takes the cooperative (shared-memory) kernels */
 #define LNB_ENC_FLAG_FAST 1u
+/* encoder-side: the block image has already been written by the cooperative packer */
+#define LNB_ENC_FLAG_PACKED 2u
+/* encoder-side: block short enough for the cooperative prepare / predict+plan kernels */
+#define LNB_ENC_FLAG_COOP 4u
 
 enum { LNB_ST_OK = 0, LNB_ST_CRC_MISMATCH = 1, LNB_ST_OVERRUN = 2, LNB_ST_BAD_TYPE = 4 };
 
@@ -103,6 +107,7 @@ typedef struct LnbEncodeBatch {
     uint8_t *out;                   /* device image of the output stream */
     uint32_t *total_size;           /* device scalar: bytes of all blocks of this batch */
     uint32_t out_base;              /* byte offset of the first block of this batch in `out` */
+    uint32_t num_coop_blocks;       /* blocks flagged LNB_ENC_FLAG_COOP */
     uint32_t num_fast_blocks;       /* blocks flagged LNB_ENC_FLAG_FAST (0: skip the cooperative launch) */
     uint32_t num_slow_blocks;       /* compressed-candidate blocks left to the flat kernels */
     uint32_t forced_params;         /* 1: `params` already hold units/shift/coefficients -- skip the analysis stages */
