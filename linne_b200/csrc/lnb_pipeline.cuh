@@ -91,11 +91,17 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
 {
     const uint32_t B = b.num_blocks, C = b.cfg.num_channels;
     if (B == 0) return;
-    ex.run("crc", B, LnbItemCrc{b});
-    ex.run("entropy", B, LnbItemEntropy{b});
-    for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)
-        ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l});
-    ex.run("deemph", B * C, LnbItemDeemph{b});
+    if (Exec::cooperative) {
+        ex.crc_cooperative(b);                            /* one CTA per block, chunk CRCs combined in GF(2) */
+        ex.run_per_warp("entropy", B, LnbItemEntropy{b}); /* serial chain: one block per warp, no divergence */
+        ex.synth_cooperative(b);                          /* one warp per (block, channel): systolic synthesis + de-emphasis */
+    } else {
+        ex.run("crc", B, LnbItemCrc{b});
+        ex.run("entropy", B, LnbItemEntropy{b});
+        for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)
+            ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l});
+        ex.run("deemph", B * C, LnbItemDeemph{b});
+    }
     if (b.cfg.ms && C >= 2u) ex.run("ms_inverse", B * b.cfg.block_size, LnbItemMsInverse{b});
 }
 

@@ -14,6 +14,8 @@
 #include "lnb_analyze_v2.cuh"
 #include "lnb_pack_v2.cuh"
 #include "lnb_front_v2.cuh"
+#include "lnb_synth_v2.cuh"
+#include "lnb_crc_v2.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -65,8 +67,38 @@ __global__ void __launch_bounds__(128) lnb_items_kernel(uint32_t n, F f)
     if (i < n) f(i);
 }
 
+/* one work item per WARP (lane 0 runs it): for strictly serial items such as the entropy decode of a
+ * block, where lanes of one warp would otherwise serialise each other's divergent paths */
+template <class F>
+__global__ void __launch_bounds__(128) lnb_items_per_warp_kernel(uint32_t n, F f)
+{
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i < n && (threadIdx.x & 31u) == 0u) f(i);
+}
+
 struct CudaExec {
+    static constexpr bool cooperative = true;
     LnbDevice *dev;
+    template <class F> void run_per_warp(const char *name, uint32_t n, const F &f)
+    {
+        if (n == 0) return;
+        const int slot = begin_stage(name);
+        lnb_items_per_warp_kernel<F><<<(n + 3u) / 4u, 128, 0, dev->stream>>>(n, f);
+        end_stage(slot);
+    }
+    void crc_cooperative(const LnbDecodeBatch &b)
+    {
+        const int slot = begin_stage("crc_v2");
+        lnb_crc_v2_kernel<<<b.num_blocks, LNB_CRC_THREADS, 0, dev->stream>>>(b);
+        end_stage(slot);
+    }
+    void synth_cooperative(const LnbDecodeBatch &b)
+    {
+        const uint32_t items = b.num_blocks * b.cfg.num_channels;
+        const int slot = begin_stage("synth_v2");
+        lnb_synth_v2_kernel<<<(items + LNB_SY_WARPS - 1) / LNB_SY_WARPS, LNB_SY_THREADS, 0, dev->stream>>>(b);
+        end_stage(slot);
+    }
     int begin_stage(const char *name)
     {
         if (!dev->profiling) return -1;

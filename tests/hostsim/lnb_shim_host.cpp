@@ -13,7 +13,11 @@
 struct LnbDevice { LnbDevTables tables; uint64_t launches; };
 
 struct LoopExec {
+    static constexpr bool cooperative = false;
     LnbDevice *dev;
+    void crc_cooperative(const LnbDecodeBatch &) {}
+    void synth_cooperative(const LnbDecodeBatch &) {}
+    template <class F> void run_per_warp(const char *n, uint32_t c, const F &f) { run(n, c, f); }
     template <class F> void run(const char *, uint32_t n, const F &f)
     {
         for (uint32_t i = 0; i < n; i++) f(i);
