@@ -188,40 +188,59 @@ def run_b200(args, rank, world, local_rank):
 
     # host (pinned) and device buffers
     h_pcm = torch.from_numpy(pcm.copy()).pin_memory()
-    h_out = torch.zeros(cap, dtype=torch.uint8).pin_memory()
-    h_back = torch.zeros((nch, n), dtype=torch.int32).pin_memory()
     d_pcm = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
     d_pcm[:, :n].copy_(h_pcm)
     d_out = [torch.zeros(cap + 64, dtype=torch.uint8, device=dev) for _ in PRESETS]
-    d_back = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    stream_ptr = torch.cuda.current_stream().cuda_stream
+    # one encoder + one decoder handle per preset, each with its own CUDA stream: the sweep's eight
+    # presets are independent streams of work, so a server would run them side by side
     encs = {m: EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=m) for m in PRESETS}
     decs = {m: DecoderSession(channels=nch) for m in PRESETS}
-    for s in list(encs.values()) + list(decs.values()):
-        s.use_stream(stream_ptr)
+    h_outs = {m: torch.zeros(cap, dtype=torch.uint8).pin_memory() for m in PRESETS}
+    h_backs = {m: torch.zeros((nch, n), dtype=torch.int32).pin_memory() for m in PRESETS}
+    d_backs = {m: torch.zeros((nch, stride), dtype=torch.int32, device=dev) for m in PRESETS}
+    chan_outs = {m: (C.POINTER(C.c_int32) * nch)(*[C.cast(h_backs[m][c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
+                 for m in PRESETS}
 
     chan_in = (C.POINTER(C.c_int32) * nch)(*[C.cast(h_pcm[c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
-    chan_out = (C.POINTER(C.c_int32) * nch)(*[C.cast(h_back[c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
     sizes = {}
-    host_streams = {}
+
+    def one_e2e(m):
+        sz = encs[m].encode_whole(chan_in, n, h_outs[m].data_ptr(), cap)
+        sizes[m] = sz
+        decs[m].decode_whole(h_outs[m].data_ptr(), sz, chan_outs[m], nch, n)
+
+    def one_resident(m):
+        sz = encs[m].encode_whole_resident(d_pcm.data_ptr(), stride, n, d_out[m].data_ptr(), cap)
+        sizes[m] = sz
+        # host image = None: the decoder fetches the (1 MB) stream image itself to hop over the block
+        # size fields -- inside the timed region
+        decs[m].decode_whole_resident(None, d_out[m].data_ptr(), sz, d_backs[m].data_ptr(), stride, nch, n)
+
+    def run_sweep(one):
+        if args.serial:
+            for m in PRESETS:
+                one(m)
+            return
+        errs = []
+
+        def guarded(m):
+            try:
+                one(m)
+            except Exception as e:      # pragma: no cover
+                errs.append(e)
+        threads = [threading.Thread(target=guarded, args=(m,)) for m in PRESETS[::-1]]   # longest presets first
+        for t in threads: t.start()
+        for t in threads: t.join()
+        if errs:
+            raise errs[0]
 
     def step_e2e():
-        for m in PRESETS:
-            sz = encs[m].encode_whole(chan_in, n, h_out.data_ptr(), cap)
-            sizes[m] = sz
-            decs[m].decode_whole(h_out.data_ptr(), sz, chan_out, nch, n)
+        run_sweep(one_e2e)
 
     def step_resident():
-        for m in PRESETS:
-            sz = encs[m].encode_whole_resident(d_pcm.data_ptr(), stride, n, d_out[m].data_ptr(), cap)
-            sizes[m] = sz
-            # the decoder hops over block headers on the host: it needs the (small) stream image there too;
-            # it is the encoder's output, so copy it back once outside the sweep's device work
-            host_streams[m] = d_out[m][:sz].cpu().numpy()
-            decs[m].decode_whole_resident(host_streams[m].ctypes.data, d_out[m].data_ptr(), sz,
-                                          d_back.data_ptr(), stride, nch, n)
+        run_sweep(one_resident)
 
     def barrier():
         if world > 1:
@@ -240,7 +259,8 @@ def run_b200(args, rank, world, local_rank):
         t0.record()
         for _ in range(steps):
             l2_flush.fill_(1)                       # flush L2 between timed iterations
-            fn()
+            torch.cuda.current_stream().synchronize()
+            fn()                                    # every API call is synchronous: all its device work is done on return
         t1.record()
         barrier()
         ms = t0.elapsed_time(t1) / steps
@@ -258,7 +278,7 @@ def run_b200(args, rank, world, local_rank):
 
     # correctness of what was just timed (outside the timed region)
     torch.cuda.synchronize()
-    ok_resident = bool(torch.equal(d_back[:, :n].cpu(), h_pcm))
+    ok_resident = all(bool(torch.equal(d_backs[m][:, :n].cpu(), h_pcm)) for m in PRESETS)
     stage = {}
     for sess in list(encs.values()) + list(decs.values()):
         for name, (cnt, ms) in sess.stage_stats().items():
@@ -266,7 +286,7 @@ def run_b200(args, rank, world, local_rank):
         sess.set_profiling(False)
 
     ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
-    ok_e2e = bool(np.array_equal(h_back.numpy(), pcm))
+    ok_e2e = all(bool(np.array_equal(h_backs[m].numpy(), pcm)) for m in PRESETS)
     comp_bytes = dict(sizes)
 
     value = len(PRESETS) * n_samples * world / (ms_res / 1e3) / 1e6
@@ -332,7 +352,8 @@ def run_b200(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
         "config": {"workload": "C2: 10 s 44.1 kHz 16-bit stereo synthetic clip, -m 0..7 sweep, encode+decode",
                    "block": BLOCK, "ms": 1, "presets": PRESETS, "l2": "256 MiB flush write between timed iterations",
-                   "per_rank": "each rank runs the whole sweep on its own clip"},
+                   "per_rank": "each rank runs the whole sweep on its own clip",
+                   "concurrency": "serial" if args.serial else "8 presets on 8 host threads / CUDA streams"},
         "e2e": {"value": round(e2e_value, 3), "unit": "MSamples/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
@@ -355,6 +376,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--serial", action="store_true", help="run the eight presets one after the other (one stream)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -33,7 +33,8 @@ void LINNEB200_DecoderUseStream(struct LINNEDecoder *decoder, void *cuda_stream)
 /* ---- device-resident entry points: bulk data stays in HBM -------------------------------------
  * EncodeWholeResident: `d_pcm` = device int32 planes [C][pcm_stride]; the stream is written to the
  * device buffer `d_data`.  DecodeWholeResident: `d_data` = device copy of the stream padded with
- * >= 16 zero bytes (`data` = the host copy, needed only to hop over the block size fields);
+ * >= 16 zero bytes (`data` = the host copy, needed only to hop over the block size fields; pass NULL
+ * and the library fetches the image from the device itself);
  * PCM is left in the device planes `d_pcm` [C][pcm_stride].  Same result codes as the host calls. */
 LINNEApiResult LINNEB200_EncodeWholeResident(struct LINNEEncoder *encoder,
         const int32_t *d_pcm, uint32_t pcm_stride, uint32_t num_samples,

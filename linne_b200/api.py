@@ -334,7 +334,8 @@ class DecoderSession(_Session):
             raise RuntimeError(f"DecodeWhole rc={rc}")
 
     def decode_whole_resident(self, data_ptr, d_data_ptr, size, d_pcm_ptr, stride, channels, n):
-        rc = self.lib.LINNEB200_DecodeWholeResident(self.h, C.cast(data_ptr, C.POINTER(C.c_uint8)), C.c_void_p(d_data_ptr),
+        host = C.cast(data_ptr, C.POINTER(C.c_uint8)) if data_ptr else None
+        rc = self.lib.LINNEB200_DecodeWholeResident(self.h, host, C.c_void_p(d_data_ptr),
                                                     size, C.c_void_p(d_pcm_ptr), stride, channels, n)
         if rc != OK:
             raise RuntimeError(f"DecodeWholeResident rc={rc}")

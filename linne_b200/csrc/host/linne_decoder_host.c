@@ -24,6 +24,7 @@ struct LINNEDecoder {
     LnbDevice *dev;
     LnbBuf d_stream, d_blocks, d_params, d_pcm;
     LnbBuf h_blocks;                       /* pinned LnbBlockDesc[] */
+    LnbBuf h_stream;                       /* pinned copy of a device-resident stream (block hop) */
 };
 
 /* reference linne_decoder.c:60-131 */
@@ -88,6 +89,7 @@ void LINNEDecoder_Destroy(struct LINNEDecoder *dec)
         lnb_buf_release_device(dec->dev, &dec->d_params);
         lnb_buf_release_device(dec->dev, &dec->d_pcm);
         lnb_buf_release_host(&dec->h_blocks);
+        lnb_buf_release_host(&dec->h_stream);
         lnb_shim_close(dec->dev);
         dec->dev = NULL;
     }
@@ -333,7 +335,14 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uin
 {
     struct LINNEHeader header;
     LINNEApiResult ret;
-    if (dec == NULL || data == NULL || d_data == NULL || d_pcm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (dec == NULL || d_data == NULL || d_pcm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (data == NULL) {
+        /* no host copy supplied: fetch the image once for the block hop (it is ~4x smaller than the PCM) */
+        if (lnb_buf_reserve_host(&dec->h_stream, (size_t)data_size + 16u)) return LINNE_APIRESULT_NG;
+        lnb_shim_d2h(dec->dev, dec->h_stream.ptr, d_data, data_size);
+        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+        data = (const uint8_t *)dec->h_stream.ptr;
+    }
     if ((ret = LINNEDecoder_DecodeHeader(data, data_size, &header)) != LINNE_APIRESULT_OK) return ret;
     if ((ret = LINNEDecoder_SetHeader(dec, &header)) != LINNE_APIRESULT_OK) return ret;
     if (buffer_num_channels < header.num_channels || buffer_num_samples < header.num_samples

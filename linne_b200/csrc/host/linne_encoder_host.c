@@ -19,7 +19,7 @@ struct LINNEEncoder {
     void *work;
     LnbDevice *dev;
     size_t scratch_budget;                 /* bytes of analysis scratch per chunk */
-    LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_win, d_cand, d_unit_loss,
+    LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_acorr, d_cand, d_unit_loss,
            d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total;
     LnbBuf h_blocks, h_welch, h_total;
     const int32_t *cur_pcm;                /* device PCM planes of the call in flight */
@@ -89,7 +89,7 @@ void LINNEEncoder_Destroy(struct LINNEEncoder *enc)
     if (enc == NULL) return;
     if (enc->dev) {
         LnbBuf *dbufs[] = { &enc->d_pcm, &enc->d_blocks, &enc->d_params, &enc->d_est, &enc->d_work, &enc->d_sig_a,
-                            &enc->d_sig_b, &enc->d_win, &enc->d_cand, &enc->d_unit_loss, &enc->d_chosen_w,
+                            &enc->d_sig_b, &enc->d_acorr, &enc->d_cand, &enc->d_unit_loss, &enc->d_chosen_w,
                             &enc->d_chosen_u, &enc->d_final_sum, &enc->d_welch, &enc->d_plans, &enc->d_plan_mean,
                             &enc->d_out, &enc->d_total };
         size_t i;
@@ -174,8 +174,8 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     slots_per_block = C * lambdas;
 
     /* chunk so the double-precision analysis scratch stays inside the budget */
-    per_block = (size_t)slots_per_block * batch.cfg.work_stride * sizeof(double) * (2u + LNB_MAX_LEVELS)
-              + (size_t)C * batch.cfg.work_stride * sizeof(int32_t);
+    per_block = (size_t)slots_per_block * (batch.cfg.work_stride * sizeof(double) * 2u + 64u * 1024u)
+              + (size_t)C * (batch.cfg.work_stride * sizeof(int32_t) + 32u * 1024u);
     chunk_blocks = (uint32_t)(enc->scratch_budget / per_block);
     if (chunk_blocks < 1u) chunk_blocks = 1u;
     if (chunk_blocks > total_blocks) chunk_blocks = total_blocks;
@@ -184,6 +184,7 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     {
         const size_t S = (size_t)chunk_blocks * slots_per_block, BC = (size_t)chunk_blocks * C;
         const size_t ws = batch.cfg.work_stride;
+        const size_t chunks = (ws + 63u) / 64u;
         if (lnb_buf_reserve_host(&enc->h_blocks, chunk_blocks * sizeof(LnbBlockDesc))
             || lnb_buf_reserve_host(&enc->h_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
             || lnb_buf_reserve_host(&enc->h_total, 64)
@@ -193,12 +194,12 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
             || lnb_buf_reserve_device(enc->dev, &enc->d_work, BC * ws * sizeof(int32_t))
             || lnb_buf_reserve_device(enc->dev, &enc->d_sig_a, S * ws * sizeof(double))
             || lnb_buf_reserve_device(enc->dev, &enc->d_sig_b, S * ws * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_win, S * LNB_MAX_LEVELS * ws * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_acorr, S * LNB_MAX_LEVELS * ws * sizeof(double))
             || lnb_buf_reserve_device(enc->dev, &enc->d_cand, S * LNB_MAX_LEVELS * LNB_MAX_PARAMS * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_unit_loss, S * LNB_MAX_LEVELS * LNB_MAX_UNITS * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_unit_loss, S * LNB_MAX_LEVELS * chunks * sizeof(double))
             || lnb_buf_reserve_device(enc->dev, &enc->d_chosen_w, S * LNB_MAX_LAYERS * LNB_MAX_PARAMS * sizeof(double))
             || lnb_buf_reserve_device(enc->dev, &enc->d_chosen_u, S * LNB_MAX_LAYERS)
-            || lnb_buf_reserve_device(enc->dev, &enc->d_final_sum, S * LNB_MAX_UNITS * sizeof(double))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_final_sum, S * chunks * sizeof(double))
             || lnb_buf_reserve_device(enc->dev, &enc->d_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
             || lnb_buf_reserve_device(enc->dev, &enc->d_plans, BC * sizeof(LnbCoderPlan))
             || lnb_buf_reserve_device(enc->dev, &enc->d_plan_mean, BC * 2u * LNB_MAX_PARTITIONS * sizeof(double))
@@ -211,7 +212,7 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     batch.work = (int32_t *)enc->d_work.ptr;
     batch.sig_a = (double *)enc->d_sig_a.ptr;
     batch.sig_b = (double *)enc->d_sig_b.ptr;
-    batch.win = (double *)enc->d_win.ptr;
+    batch.acorr = (double *)enc->d_acorr.ptr;
     batch.cand = (double *)enc->d_cand.ptr;
     batch.unit_loss = (double *)enc->d_unit_loss.ptr;
     batch.chosen_w = (double *)enc->d_chosen_w.ptr;

@@ -363,5 +363,8 @@ __global__ void __launch_bounds__(LNB_AN_THREADS, 1) lnb_analyze_v2_kernel(LnbEn
         double *t = cx.A; cx.A = cx.B; cx.B = t;
     }
     /* total |residual| of the cascade: what picks the regulariser (linne_network.c:618-626) */
-    if (c < LNB_MAX_UNITS) b.final_sum[(size_t)s * LNB_MAX_UNITS + c] = (c == 0) ? final_loss : 0.0;
+    {   /* the finish stage sums ceil(na/64) chunk slots of this analysis slot: total in slot 0, zeros after */
+        const uint32_t chunks_per_slot = (b.cfg.work_stride + 63u) / 64u, nch = (na + 63u) / 64u;
+        if (c < nch) b.final_sum[(size_t)s * chunks_per_slot + c] = (c == 0) ? final_loss : 0.0;
+    }
 }

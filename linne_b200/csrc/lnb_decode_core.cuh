@@ -96,33 +96,116 @@ LNB_HD uint32_t lnb_br_bytes_consumed(const LnbBitReader &br)
 }
 
 /* ------------------------------------------------------------------------------------------
- * Elias-gamma and recursive Rice symbol decode: reference linne_coder.c:106-127, :150-169
+ * Residual reader: the hot loop of the decoder.  Two big-endian words + one prefetched word in
+ * registers; a 32-bit window at the current bit position comes from one funnel shift, the unary
+ * part from one clz, and in the common case (code <= 32 bits) the binary part from the same window.
+ * Bit semantics: reference bit_stream.h:305-394; codes: linne_coder.c:106-127 (gamma), :150-169 (Rice).
  * ------------------------------------------------------------------------------------------ */
-LNB_HD uint32_t lnb_get_gamma(LnbBitReader &br)
+struct LnbFastReader {
+    const uint32_t *words;
+    uint32_t idx, end_word;      /* word index of w0; words at or past end_word read as zero */
+    uint32_t w0, w1, pre;        /* words idx, idx+1, idx+2 (stream byte order = big-endian) */
+    uint32_t bitpos;             /* 0..31: bits of w0 already consumed */
+    uint32_t overrun;
+};
+
+LNB_HD uint32_t lnb_fr_word(const LnbFastReader &r, uint32_t i)
 {
-    const uint32_t nd = lnb_br_zero_run(br) + 1u;
+    return (i < r.end_word) ? lnb_bswap32(r.words[i]) : 0u;
+}
+LNB_HD void lnb_fr_open(LnbFastReader &r, const uint32_t *words, uint64_t bit_position, uint32_t end_word)
+{
+    r.words = words; r.end_word = end_word; r.overrun = 0;
+    r.idx = (uint32_t)(bit_position >> 5); r.bitpos = (uint32_t)(bit_position & 31u);
+    r.w0 = lnb_fr_word(r, r.idx); r.w1 = lnb_fr_word(r, r.idx + 1u); r.pre = lnb_fr_word(r, r.idx + 2u);
+}
+LNB_HD uint32_t lnb_fr_peek32(const LnbFastReader &r)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(r.w1, r.w0, r.bitpos);
+#else
+    return (uint32_t)((((uint64_t)r.w0 << 32) | r.w1) >> (32u - r.bitpos));
+#endif
+}
+LNB_HD void lnb_fr_skip(LnbFastReader &r, uint32_t n)           /* n <= 32 */
+{
+    r.bitpos += n;
+    if (r.bitpos >= 32u) {
+        r.bitpos -= 32u;
+        r.w0 = r.w1; r.w1 = r.pre; r.idx++;
+        r.pre = lnb_fr_word(r, r.idx + 2u);
+        if (r.idx > r.end_word) r.overrun = 1;
+    }
+}
+LNB_HD uint32_t lnb_fr_get(LnbFastReader &r, uint32_t n)         /* 0 <= n <= 32 */
+{
+    if (n == 0) return 0;
+    const uint32_t v = lnb_fr_peek32(r) >> (32u - n);
+    lnb_fr_skip(r, n);
+    return v;
+}
+/* zeros up to the next one bit; the one is consumed */
+LNB_HD uint32_t lnb_fr_zero_run(LnbFastReader &r)
+{
+    uint32_t run = 0;
+    for (;;) {
+        const uint32_t win = lnb_fr_peek32(r);
+        if (win != 0u) {
+            const uint32_t lz = lnb_clz32(win);
+            lnb_fr_skip(r, lz + 1u);
+            return run + lz;
+        }
+        run += 32u;
+        lnb_fr_skip(r, 32u);
+        if (r.overrun) return run;
+    }
+}
+LNB_HD uint64_t lnb_fr_position(const LnbFastReader &r) { return (uint64_t)r.idx * 32u + r.bitpos; }
+
+LNB_HD uint32_t lnb_get_gamma(LnbFastReader &r)
+{
+    const uint32_t nd = lnb_fr_zero_run(r) + 1u;
     if (nd == 1u) return 0;
-    if (nd > 32u) { br.overrun = 1; return 0; }
-    return (uint32_t)(((uint64_t)1 << (nd - 1u)) + lnb_br_get(br, nd - 1u) - 1u);
+    if (nd > 32u) { r.overrun = 1; return 0; }
+    return (uint32_t)(((uint64_t)1 << (nd - 1u)) + lnb_fr_get(r, nd - 1u) - 1u);
 }
 
-LNB_HD uint32_t lnb_get_rice(LnbBitReader &br, uint32_t k1, uint32_t k2)
+/* one recursive-Rice symbol, k1 = k2 + 1, 0 <= k2 <= 30 */
+LNB_HD uint32_t lnb_get_rice(LnbFastReader &r, uint32_t k1, uint32_t k2)
 {
-    const uint32_t q = lnb_br_zero_run(br);
-    if (q == 0) return lnb_br_get(br, k1);
-    return lnb_br_get(br, k2) + (1u << k1) + ((q - 1u) << k2);
+    const uint32_t win = lnb_fr_peek32(r);
+    if (win & 0x80000000u) {                                   /* '1' + k1 bits */
+        const uint32_t u = (win << 1) >> (32u - k1);
+        lnb_fr_skip(r, 1u + k1);
+        return u;
+    }
+    if (win != 0u) {
+        const uint32_t lz = lnb_clz32(win);                    /* 1..31 zeros, then the terminating one */
+        const uint32_t total = lz + 1u + k2;
+        uint32_t low = 0;
+        if (total <= 32u) {
+            if (k2) low = (win << (lz + 1u)) >> (32u - k2);
+            lnb_fr_skip(r, total);
+        } else {
+            lnb_fr_skip(r, lz + 1u);
+            low = lnb_fr_get(r, k2);
+        }
+        return low + (1u << k1) + ((lz - 1u) << k2);
+    }
+    const uint32_t q = lnb_fr_zero_run(r);                     /* 32 or more zeros: rare */
+    return lnb_fr_get(r, k2) + (1u << k1) + ((q - 1u) << k2);
 }
 
 /* residual of one channel: reference linne_coder.c:306-327 */
-LNB_HD void lnb_decode_residual(LnbBitReader &br, int32_t *out, uint32_t n)
+LNB_HD void lnb_decode_residual(LnbFastReader &br, int32_t *out, uint32_t n)
 {
-    const uint32_t porder = lnb_br_get(br, 10);
+    const uint32_t porder = lnb_fr_get(br, 10);
     const uint32_t len = (porder < 32u) ? (n >> porder) : 0u;
     const uint32_t parts = (porder <= LNB_MAX_PORDER) ? (1u << porder) : 0u;
     uint32_t k2 = 0;
     if (porder > LNB_MAX_PORDER) { br.overrun = 1; }
     for (uint32_t part = 0; part < parts; part++) {
-        if (part == 0) k2 = lnb_br_get(br, 5);
+        if (part == 0) k2 = lnb_fr_get(br, 5);
         else k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(lnb_get_gamma(br)));
         if (k2 > 30u) { br.overrun = 1; k2 = 30u; }           /* never produced by a valid encoder */
         const uint32_t k1 = k2 + 1u;
@@ -190,10 +273,13 @@ LNB_HD void lnb_decode_block_payload(const LnbStreamCfg &cfg, const LnbDevTables
                 q[i] = (int8_t)lnb_zz_dec(e >> 4);
             }
         }
+    LnbFastReader fr;
+    lnb_fr_open(fr, (const uint32_t *)stream, (uint64_t)br.next_word * 32u - br.nbits, (end_byte + 3u) >> 2);
     for (uint32_t c = 0; c < C; c++)
-        lnb_decode_residual(br, pcm + (size_t)c * cfg.pcm_stride + blk.smp_off, n);
-    blk.na = lnb_br_bytes_consumed(br);        /* payload bytes consumed (reference Flush + Tell) */
-    if (br.overrun || payload_off + blk.na > end_byte) blk.status |= LNB_ST_OVERRUN;
+        lnb_decode_residual(fr, pcm + (size_t)c * cfg.pcm_stride + blk.smp_off, n);
+    /* payload bytes consumed, rounded up (reference Flush + Tell, bit_stream.h:402-406) */
+    blk.na = (uint32_t)((lnb_fr_position(fr) - (uint64_t)payload_off * 8u + 7u) >> 3);
+    if (br.overrun || fr.overrun || payload_off + blk.na > end_byte) blk.status |= LNB_ST_OVERRUN;
 }
 
 /* ------------------------------------------------------------------------------------------

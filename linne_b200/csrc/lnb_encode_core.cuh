@@ -3,9 +3,11 @@
  * Stage order for a batch of blocks (every stage is one kernel over all blocks of the batch):
  *   E0 estimate     (block, channel)               entropy estimate for the raw/compressed decision
  *   E1 prepare      (block)                        block type, copy + M/S + 2x pre-emphasis
- *   E2 search       (block, ch, lambda, level, unit)  LPC fit + L1 loss of every unit of every unit count
+ *   E2 acorr        (block, ch, lambda, level, unit, lag)   windowed autocorrelation, one lag per item
+ *      solve        (block, ch, lambda, level, unit)        Levinson-Durbin per unit
+ *      loss         (block, ch, lambda, level, chunk)       L1 loss of every unit count
  *   E3 select       (block, ch, lambda)            argmin unit count, latch its coefficients
- *   E4 forward      (block, ch, lambda, unit)      residual of the layer = next layer's input
+ *   E4 forward      (block, ch, lambda, chunk)     residual of the layer = next layer's input
  *      (E2..E4 repeat per layer)
  *   E5 finish       (block, ch)                    pick the regulariser, quantise coefficients
  *   E6 predict      (block, ch)                    integer predictor cascade -> residual
@@ -171,85 +173,80 @@ LNB_HD void lnb_prepare_block(const LnbStreamCfg &cfg, LnbBlockDesc &blk, const 
 }
 
 /* ------------------------------------------------------------------------------------------
- * E2: one unit of one unit-count level.  Welch window -> autocorrelation (p+1 lags) ->
- * regularise -> Levinson -> reversed coefficients -> L1 loss of the unit.
- * reference libs/linne_network/src/linne_network.c:297-336 with lpc.c:196-205, :215-249, :327-366.
- *   x        layer input of the whole block-channel (double), unit u covers x[u*m .. u*m+m)
- *   win      scratch for the windowed unit (m doubles)
- *   out_w    reversed coefficients of the unit (p doubles): out_w[j] multiplies x[t-p+j]
- * Returns the unit's sum of |residual| (unit 0 uses the ramp-in rule and skips t = 0).
- * The centre sample of an odd-length unit gets the window's true centre weight; the reference
- * leaves a stale value there.
+ * E2 (flat path): the unit-count search of reference libs/linne_network/src/linne_network.c:268-347
+ * cut into independent work items so that no single thread walks a whole block:
+ *   lnb_acorr_lag      one autocorrelation lag of one unit (Welch window applied on the fly;
+ *                      lpc.c:196-205, :215-249).  A lag is summed in ascending sample order, exactly
+ *                      like the reference, so with LNB_EXACT_FP the value is bit-identical.
+ *   lnb_solve_unit     regularise + Levinson-Durbin + coefficient reversal (lpc.c:358, :252-324,
+ *                      linne_network.c:312-316)
+ *   lnb_loss_chunk     sum of |residual| over a run of samples (linne_network.c:318-335)
+ * The centre sample of an odd-length unit gets the window's true centre weight; the reference leaves
+ * a stale value there.
  * ------------------------------------------------------------------------------------------ */
-LNB_HD double lnb_search_unit(const double *x, uint32_t u, uint32_t m, uint32_t p, double lambda,
-                              double welch_scale, double *win, double *out_w)
+LNB_HD double lnb_welch_weight(double scale, uint32_t pos, uint32_t m)
 {
-    const double *xs = x + (size_t)u * m;
-    double r[LNB_MAX_PARAMS + 1], a[LNB_MAX_PARAMS + 2], coef[LNB_MAX_PARAMS];
+    const uint32_t q = (pos < m - 1u - pos) ? pos : (m - 1u - pos);
+    return lnb_mul_rn(lnb_mul_rn(scale, (double)q), (double)(m - 1u - q));
+}
 
-    for (uint32_t i = 0; i < (m >> 1); i++) {
-        const double wgt = lnb_mul_rn(lnb_mul_rn(welch_scale, (double)i), (double)(m - 1u - i));
-        win[i] = lnb_mul_rn(xs[i], wgt);
-        win[m - 1u - i] = lnb_mul_rn(xs[m - 1u - i], wgt);
+LNB_HD double lnb_acorr_lag(const double *xs, uint32_t m, uint32_t lag, double scale)
+{
+    double s = 0.0;
+    if (lag >= m) return 0.0;
+    for (uint32_t i = 0; i + lag < m; i++) {
+        const double a = lnb_mul_rn(xs[i], lnb_welch_weight(scale, i, m));
+        const double b = lnb_mul_rn(xs[i + lag], lnb_welch_weight(scale, i + lag, m));
+        s = lnb_mac(a, b, s);
     }
-    if (m & 1u) {
-        const uint32_t c = m >> 1;
-        win[c] = lnb_mul_rn(xs[c], lnb_mul_rn(lnb_mul_rn(welch_scale, (double)c), (double)(m - 1u - c)));
-    }
-    for (uint32_t lag = 0; lag <= p; lag++) {
-        double s = 0.0;
-        if (lag < m) for (uint32_t i = 0; i + lag < m; i++) s = lnb_mac(win[i], win[i + lag], s);
-        r[lag] = s;
-    }
+    return s;
+}
+
+LNB_HD void lnb_solve_unit(const double *r_in, uint32_t p, uint32_t m, double lambda, double *out_w)
+{
+    double r[LNB_MAX_PARAMS + 1], a[LNB_MAX_PARAMS + 2], coef[LNB_MAX_PARAMS];
     if (m < p) {
         for (uint32_t i = 0; i < p; i++) coef[i] = 0.0;
     } else {
+        for (uint32_t k = 0; k <= p; k++) r[k] = r_in[k];
         r[0] = lnb_mul_rn(r[0], lnb_add_rn(1.0, lambda));
         lnb_levinson(r, p, a, coef, (double *)0);
     }
     for (uint32_t j = 0; j < p; j++) out_w[j] = coef[p - 1u - j];
+}
 
+/* residual at sample t of the block-channel for the layer split into units of m samples, p taps each;
+ * `w_all` = reversed coefficients of every unit, unit u at w_all + u*p.  History before the block is
+ * zero (unit 0 ramp-in); later units reach back into the previous unit. */
+LNB_HD double lnb_residual_at(const double *x, uint32_t t, uint32_t m, uint32_t p, const double *w_all, double init)
+{
+    const uint32_t u = t / m;
+    const double *w = w_all + (size_t)u * p;
+    double acc = init;
+    const uint32_t first = (t >= p) ? 0u : p - t;            /* taps that would read before sample 0 are dropped */
+    const double *h = x + t - p;
+    for (uint32_t k = first; k < p; k++) acc = lnb_mac(w[k], h[k], acc);
+    return acc;
+}
+
+LNB_HD double lnb_loss_chunk(const double *x, uint32_t t0, uint32_t t1, uint32_t m, uint32_t p, const double *w_all)
+{
     double loss = 0.0;
-    uint32_t t = 0;
-    if (u == 0) {
-        for (t = 1; t < p && t < m; t++) {
-            double res = xs[t];
-            for (uint32_t k = 0; k < t; k++) res = lnb_mac(out_w[p - t + k], xs[k], res);
-            loss += fabs(res);
-        }
-        if (t < 1u) t = 1u;
-    }
-    for (; t < m; t++) {
-        double res = xs[t];
-        const double *h = xs + t - p;          /* units > 0 reach back into the previous unit */
-        for (uint32_t k = 0; k < p; k++) res = lnb_mac(out_w[k], h[k], res);
-        loss += fabs(res);
-    }
+    for (uint32_t t = (t0 == 0u) ? 1u : t0; t < t1; t++)     /* sample 0 is not counted (linne_network.c:319-321) */
+        loss += fabs(lnb_residual_at(x, t, m, p, w_all, x[t]));
     return loss;
 }
 
-/* E4: residual of one unit given the chosen coefficients (out of place).
- * reference linne_network.c:165-210.  Returns the unit's sum of |residual|. */
-LNB_HD double lnb_forward_unit(const double *x, double *y, uint32_t u, uint32_t m, uint32_t p, const double *w)
+/* E4 (flat path): residual of a run of samples given the chosen coefficients, out of place.
+ * reference linne_network.c:165-210 (the prediction is summed from zero, then added).  Returns sum |y|. */
+LNB_HD double lnb_forward_chunk(const double *x, double *y, uint32_t t0, uint32_t t1, uint32_t m, uint32_t p,
+                                const double *w_all)
 {
-    const double *xs = x + (size_t)u * m;
-    double *ys = y + (size_t)u * m;
     double sum = 0.0;
-    uint32_t t = 0;
-    if (u == 0) {
-        ys[0] = xs[0]; sum += fabs(xs[0]);
-        for (t = 1; t < p && t < m; t++) {
-            double acc = 0.0;
-            for (uint32_t k = 0; k < t; k++) acc = lnb_mac(w[p - t + k], xs[k], acc);
-            ys[t] = xs[t] + acc; sum += fabs(ys[t]);
-        }
-        if (t < 1u) t = 1u;
-    }
-    for (; t < m; t++) {
-        double acc = 0.0;
-        const double *h = xs + t - p;
-        for (uint32_t k = 0; k < p; k++) acc = lnb_mac(w[k], h[k], acc);
-        ys[t] = xs[t] + acc; sum += fabs(ys[t]);
+    for (uint32_t t = t0; t < t1; t++) {
+        const double v = (t == 0u) ? x[0] : x[t] + lnb_residual_at(x, t, m, p, w_all, 0.0);
+        y[t] = v;
+        sum += fabs(v);
     }
     return sum;
 }

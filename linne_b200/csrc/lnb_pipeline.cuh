@@ -44,12 +44,13 @@ struct LnbItemEntropy {
 struct LnbItemSynth {
     LnbDecodeBatch b;
     uint32_t layer;
+    uint32_t skip_upto;             /* block-channels of at most this many samples were done cooperatively */
     LNB_HDM void operator()(uint32_t i) const
     {
         const uint32_t u = i % LNB_MAX_UNITS, bc = i / LNB_MAX_UNITS;
         const uint32_t blk_i = bc / b.cfg.num_channels, c = bc % b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED || blk.status) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || blk.status || blk.nsmp <= skip_upto) return;
         const LnbChanParams &prm = b.params[bc];
         const uint32_t P = b.cfg.layer_params[layer];
         uint32_t U = 1u << prm.log2_units[layer];
@@ -63,11 +64,12 @@ struct LnbItemSynth {
 /* D3: de-emphasis; item = (block, channel) */
 struct LnbItemDeemph {
     LnbDecodeBatch b;
+    uint32_t skip_upto;
     LNB_HDM void operator()(uint32_t bc) const
     {
         const uint32_t blk_i = bc / b.cfg.num_channels, c = bc % b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED || blk.status) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || blk.status || blk.nsmp <= skip_upto) return;
         const LnbChanParams &prm = b.params[bc];
         lnb_deemphasis(b.pcm + (size_t)c * b.cfg.pcm_stride + blk.smp_off, blk.nsmp, prm.preem_prev, prm.preem_coef);
     }
@@ -95,12 +97,17 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
         ex.crc_cooperative(b);                            /* one CTA per block, chunk CRCs combined in GF(2) */
         ex.run_per_warp("entropy", B, LnbItemEntropy{b}); /* serial chain: one block per warp, no divergence */
         ex.synth_cooperative(b);                          /* one warp per (block, channel): systolic synthesis + de-emphasis */
+        if (b.cfg.block_size > ex.synth_max_n()) {        /* longer block-channels: flat kernels (they skip the short ones) */
+            for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)
+                ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l, ex.synth_max_n()});
+            ex.run("deemph", B * C, LnbItemDeemph{b, ex.synth_max_n()});
+        }
     } else {
         ex.run("crc", B, LnbItemCrc{b});
         ex.run("entropy", B, LnbItemEntropy{b});
         for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)
-            ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l});
-        ex.run("deemph", B * C, LnbItemDeemph{b});
+            ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l, 0u});
+        ex.run("deemph", B * C, LnbItemDeemph{b, 0u});
     }
     if (b.cfg.ms && C >= 2u) ex.run("ms_inverse", B * b.cfg.block_size, LnbItemMsInverse{b});
 }
@@ -152,10 +159,35 @@ struct LnbItemToDouble {            /* (slot, sample): normalised copy of the wo
     }
 };
 
-struct LnbItemSearch {              /* E2: (slot, level, unit) */
+#define LNB_CHUNK 64u                       /* samples per loss / forward work item of the flat path */
+
+LNB_HDM uint32_t lnb_num_chunks(uint32_t na) { return (na + LNB_CHUNK - 1u) / LNB_CHUNK; }
+
+struct LnbItemAcorr {               /* E2a: (slot, level, unit, lag) -- 256 (unit, lag) cells per level */
     LnbEncodeBatch b;
     uint32_t layer;
     const double *sig;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t s = i / (LNB_MAX_LEVELS * 256u), cell = i % (LNB_MAX_LEVELS * 256u);
+        const uint32_t level = cell / 256u, r = cell % 256u;
+        const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        const uint32_t P = b.cfg.layer_params[layer];
+        if (!lnb_level_valid(level, P, blk.na)) return;
+        const uint32_t U = 1u << level, p = P / U, m = blk.na / U;
+        if (r >= U * (p + 1u)) return;
+        const uint32_t u = r / (p + 1u), lag = r % (p + 1u);
+        b.acorr[(size_t)s * LNB_MAX_LEVELS * 256u + cell] =
+            lnb_acorr_lag(sig + (size_t)s * b.cfg.work_stride + (size_t)u * m, m, lag,
+                          b.welch[(size_t)blk_i * LNB_MAX_LEVELS + level]);
+    }
+};
+
+struct LnbItemSolve {               /* E2b: (slot, level, unit) */
+    LnbEncodeBatch b;
+    uint32_t layer;
     LNB_HDM void operator()(uint32_t i) const
     {
         const uint32_t s = i / LNB_ITEMS_PER_SLOT, id = i % LNB_ITEMS_PER_SLOT + 1u;
@@ -167,36 +199,57 @@ struct LnbItemSearch {              /* E2: (slot, level, unit) */
         const uint32_t P = b.cfg.layer_params[layer];
         if (!lnb_level_valid(level, P, blk.na)) return;
         const uint32_t U = 1u << level, p = P / U, m = blk.na / U;
-        const size_t ws = b.cfg.work_stride;
-        const double loss = lnb_search_unit(
-            sig + (size_t)s * ws, u, m, p, b.cfg.lambdas[lam], b.welch[(size_t)blk_i * LNB_MAX_LEVELS + level],
-            b.win + ((size_t)s * LNB_MAX_LEVELS + level) * ws + (size_t)u * m,
-            b.cand + ((size_t)s * LNB_MAX_LEVELS + level) * LNB_MAX_PARAMS + (size_t)u * p);
-        b.unit_loss[((size_t)s * LNB_MAX_LEVELS + level) * LNB_MAX_UNITS + u] = loss;
+        lnb_solve_unit(b.acorr + ((size_t)s * LNB_MAX_LEVELS + level) * 256u + (size_t)u * (p + 1u), p, m,
+                       b.cfg.lambdas[lam],
+                       b.cand + ((size_t)s * LNB_MAX_LEVELS + level) * LNB_MAX_PARAMS + (size_t)u * p);
+    }
+};
+
+struct LnbItemLoss {                /* E2c: (slot, level, chunk) */
+    LnbEncodeBatch b;
+    uint32_t layer;
+    const double *sig;
+    uint32_t chunks_per_slot;       /* lnb_num_chunks(work_stride) */
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint32_t per_slot = LNB_MAX_LEVELS * chunks_per_slot;
+        const uint32_t s = i / per_slot, level = (i % per_slot) / chunks_per_slot, g = i % chunks_per_slot;
+        const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
+        const LnbBlockDesc &blk = b.blocks[blk_i];
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        const uint32_t P = b.cfg.layer_params[layer];
+        if (!lnb_level_valid(level, P, blk.na)) return;
+        const uint32_t t0 = g * LNB_CHUNK;
+        if (t0 >= blk.na) return;
+        const uint32_t t1 = (t0 + LNB_CHUNK < blk.na) ? t0 + LNB_CHUNK : blk.na;
+        const uint32_t U = 1u << level, p = P / U, m = blk.na / U;
+        b.unit_loss[((size_t)s * LNB_MAX_LEVELS + level) * chunks_per_slot + g] =
+            lnb_loss_chunk(sig + (size_t)s * b.cfg.work_stride, t0, t1, m, p,
+                           b.cand + ((size_t)s * LNB_MAX_LEVELS + level) * LNB_MAX_PARAMS);
     }
 };
 
 struct LnbItemSelect {              /* E3: (slot): first minimum over the unit counts (linne_network.c:337-341) */
     LnbEncodeBatch b;
     uint32_t layer;
+    uint32_t chunks_per_slot;
     LNB_HDM void operator()(uint32_t s) const
     {
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
         if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
         const uint32_t P = b.cfg.layer_params[layer];
+        const uint32_t nch = lnb_num_chunks(blk.na);
         double best_loss = (double)FLT_MAX;
         uint32_t best = 0;
-        bool found = false;
         for (uint32_t level = 0; level < LNB_MAX_LEVELS; level++) {
             if (!lnb_level_valid(level, P, blk.na)) continue;
-            const double *ul = b.unit_loss + ((size_t)s * LNB_MAX_LEVELS + level) * LNB_MAX_UNITS;
+            const double *ul = b.unit_loss + ((size_t)s * LNB_MAX_LEVELS + level) * chunks_per_slot;
             double loss = 0.0;
-            for (uint32_t u = 0; u < (1u << level); u++) loss += ul[u];
+            for (uint32_t g = 0; g < nch; g++) loss += ul[g];
             loss /= (double)blk.na;
-            if (loss < best_loss) { best_loss = loss; best = level; found = true; }
+            if (loss < best_loss) { best_loss = loss; best = level; }
         }
-        if (!found) best = 0;
         b.chosen_log2u[(size_t)s * LNB_MAX_LAYERS + layer] = (uint8_t)best;
         const double *src = b.cand + ((size_t)s * LNB_MAX_LEVELS + best) * LNB_MAX_PARAMS;
         double *dst = b.chosen_w + ((size_t)s * LNB_MAX_LAYERS + layer) * LNB_MAX_PARAMS;
@@ -204,43 +257,45 @@ struct LnbItemSelect {              /* E3: (slot): first minimum over the unit c
     }
 };
 
-struct LnbItemForward {             /* E4: (slot, unit) */
+struct LnbItemForward {             /* E4: (slot, chunk) */
     LnbEncodeBatch b;
     uint32_t layer;
     const double *sig_in;
     double *sig_out;
+    uint32_t chunks_per_slot;
     LNB_HDM void operator()(uint32_t i) const
     {
-        const uint32_t s = i / LNB_MAX_UNITS, u = i % LNB_MAX_UNITS;
+        const uint32_t s = i / chunks_per_slot, g = i % chunks_per_slot;
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
         if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        double *fs = b.final_sum + (size_t)s * chunks_per_slot + g;
+        const uint32_t t0 = g * LNB_CHUNK;
+        if (t0 >= blk.na) { *fs = 0.0; return; }
+        const uint32_t t1 = (t0 + LNB_CHUNK < blk.na) ? t0 + LNB_CHUNK : blk.na;
         const uint32_t U = 1u << b.chosen_log2u[(size_t)s * LNB_MAX_LAYERS + layer];
-        if (u >= U) return;
         const uint32_t P = b.cfg.layer_params[layer], p = P / U, m = blk.na / U;
         const size_t ws = b.cfg.work_stride;
-        const double sum = lnb_forward_unit(
-            sig_in + (size_t)s * ws, sig_out + (size_t)s * ws, u, m, p,
-            b.chosen_w + ((size_t)s * LNB_MAX_LAYERS + layer) * LNB_MAX_PARAMS + (size_t)u * p);
-        b.final_sum[(size_t)s * LNB_MAX_UNITS + u] = sum;
+        *fs = lnb_forward_chunk(sig_in + (size_t)s * ws, sig_out + (size_t)s * ws, t0, t1, m, p,
+                                b.chosen_w + ((size_t)s * LNB_MAX_LAYERS + layer) * LNB_MAX_PARAMS);
     }
 };
 
 struct LnbItemFinish {              /* E5: (block, channel): best regulariser, quantise (linne_network.c:618-629) */
     LnbEncodeBatch b;
+    uint32_t chunks_per_slot;
     LNB_HDM void operator()(uint32_t bc) const
     {
         const uint32_t blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
         if (blk.type != LNB_BLOCK_COMPRESSED) return;
-        const uint32_t last = b.cfg.num_layers - 1u;
+        const uint32_t nch = lnb_num_chunks(blk.na);
         double best_loss = (double)FLT_MAX;
         uint32_t best = 0;
         for (uint32_t lam = 0; lam < b.cfg.num_lambdas; lam++) {
             const size_t s = (size_t)bc * b.cfg.num_lambdas + lam;
-            const uint32_t U = 1u << b.chosen_log2u[s * LNB_MAX_LAYERS + last];
             double sum = 0.0;
-            for (uint32_t u = 0; u < U; u++) sum += b.final_sum[s * LNB_MAX_UNITS + u];
+            for (uint32_t g = 0; g < nch; g++) sum += b.final_sum[s * chunks_per_slot + g];
             const double loss = sum / (double)blk.na;
             if (loss < best_loss) { best_loss = loss; best = lam; }
         }
@@ -333,6 +388,7 @@ void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
     const uint32_t B = b.num_blocks, C = b.cfg.num_channels;
     if (B == 0) return;
     const uint32_t S = B * C * b.cfg.num_lambdas;
+    const uint32_t CH = lnb_num_chunks(b.cfg.work_stride);    /* chunk slots per analysis slot */
     const bool flat = b.num_coop_blocks < B;                /* some blocks are too long for the cooperative kernels */
     if (b.num_coop_blocks) ex.prepare_cooperative(b);
     if (flat) {
@@ -345,13 +401,15 @@ void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
             ex.run("to_double", S * b.cfg.work_stride, LnbItemToDouble{b});
             double *cur = b.sig_a, *nxt = b.sig_b;
             for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
-                ex.run("search", S * LNB_ITEMS_PER_SLOT, LnbItemSearch{b, l, cur});
-                ex.run("select", S, LnbItemSelect{b, l});
-                ex.run("forward", S * LNB_MAX_UNITS, LnbItemForward{b, l, cur, nxt});
+                ex.run("acorr", S * LNB_MAX_LEVELS * 256u, LnbItemAcorr{b, l, cur});
+                ex.run("solve", S * LNB_ITEMS_PER_SLOT, LnbItemSolve{b, l});
+                ex.run("loss", S * LNB_MAX_LEVELS * CH, LnbItemLoss{b, l, cur, CH});
+                ex.run("select", S, LnbItemSelect{b, l, CH});
+                ex.run("forward", S * CH, LnbItemForward{b, l, cur, nxt, CH});
                 double *t = cur; cur = nxt; nxt = t;
             }
         }
-        ex.run("finish", B * C, LnbItemFinish{b});
+        ex.run("finish", B * C, LnbItemFinish{b, CH});
     }
     if (b.num_coop_blocks) ex.predict_plan_cooperative(b);
     if (flat) {

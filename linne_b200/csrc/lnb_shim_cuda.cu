@@ -92,11 +92,20 @@ struct CudaExec {
         lnb_crc_v2_kernel<<<b.num_blocks, LNB_CRC_THREADS, 0, dev->stream>>>(b);
         end_stage(slot);
     }
+    uint32_t synth_max_n() const { return LNB_SY_MAX_N; }
     void synth_cooperative(const LnbDecodeBatch &b)
     {
         const uint32_t items = b.num_blocks * b.cfg.num_channels;
+        uint32_t n_max = b.cfg.block_size < LNB_SY_MAX_N ? b.cfg.block_size : LNB_SY_MAX_N;
+        n_max = (n_max + 3u) & ~3u;
+        const size_t smem = (size_t)LNB_SY_WARPS * n_max * sizeof(int32_t);
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(lnb_synth_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
         const int slot = begin_stage("synth_v2");
-        lnb_synth_v2_kernel<<<(items + LNB_SY_WARPS - 1) / LNB_SY_WARPS, LNB_SY_THREADS, 0, dev->stream>>>(b);
+        lnb_synth_v2_kernel<<<(items + LNB_SY_WARPS - 1) / LNB_SY_WARPS, LNB_SY_THREADS, smem, dev->stream>>>(b, n_max);
         end_stage(slot);
     }
     int begin_stage(const char *name)

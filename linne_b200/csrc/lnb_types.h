@@ -95,12 +95,12 @@ typedef struct LnbEncodeBatch {
     int32_t *work;                  /* [B*C][work_stride] */
     /* analysis scratch; slot s = (block*C + ch)*num_lambdas + lambda */
     double *sig_a, *sig_b;          /* [S][work_stride] ping-pong layer signal */
-    double *win;                    /* [S][LNB_MAX_LEVELS][work_stride] windowed units */
+    double *acorr;                  /* [S][LNB_MAX_LEVELS][256] autocorrelations: U*(p+1) <= 256 cells per level */
     double *cand;                   /* [S][LNB_MAX_LEVELS][LNB_MAX_PARAMS] candidate coefficients */
-    double *unit_loss;              /* [S][LNB_MAX_LEVELS][LNB_MAX_UNITS] */
+    double *unit_loss;              /* [S][LNB_MAX_LEVELS][chunks] partial L1 losses, chunks = ceil(work_stride/64) */
     double *chosen_w;               /* [S][LNB_MAX_LAYERS][LNB_MAX_PARAMS] */
     uint8_t *chosen_log2u;          /* [S][LNB_MAX_LAYERS] */
-    double *final_sum;              /* [S][LNB_MAX_UNITS] |residual| sums of the last layer */
+    double *final_sum;              /* [S][chunks] partial |residual| sums of the last layer */
     const double *welch;            /* [B][LNB_MAX_LEVELS] window scale per unit-count level */
     LnbCoderPlan *plans;            /* [B*C] */
     double *plan_mean;              /* [B*C][2*LNB_MAX_PARTITIONS] */
