@@ -103,38 +103,34 @@ __device__ void lnb_an_autocorr(const LnbAnCtx &cx, uint32_t U, uint32_t p, doub
 #pragma unroll
             for (int k = 0; k < LNB_AN_LAGS - 1; k++) wv[k] = wv[k + 8];
         }
-        /* fixed-order reduction of the chunk partials */
+        /* fixed-order reduction of the chunk partials: warp w sums lags 2w and 2w+1; lanes read
+         * consecutive words (conflict-free), then an xor-butterfly inside each unit's lane segment */
 #pragma unroll
         for (int k = 0; k < LNB_AN_LAGS; k++) cx.part[k * LNB_AN_THREADS + c] = acc[k];
         __syncthreads();
         {
-            const uint32_t k = c / 16u, sgm = c % 16u;          /* 16 lags x 16 segments of 16 chunks */
-            const double *row = cx.part + k * LNB_AN_THREADS + sgm * 16u;
-            if (cpu >= 16u) {
-                double s = 0.0;
-                for (uint32_t i = 0; i < 16u; i++) s += row[i];
-                cx.seg[k * 16u + sgm] = s;
-            } else {
-                const uint32_t per = 16u / cpu;                 /* units inside this segment */
-                for (uint32_t uu = 0; uu < per; uu++) {
-                    double s = 0.0;
-                    for (uint32_t i = 0; i < cpu; i++) s += row[uu * cpu + i];
-                    const uint32_t u = sgm * per + uu;
-                    if (k0 + k <= p) acorr_lvl[u * (p + 1u) + k0 + k] = s;
+            const uint32_t warp = c >> 5, lane = c & 31u;
+            for (uint32_t kk = 0; kk < 2u; kk++) {
+                const uint32_t k = 2u * warp + kk;
+                const double *row = cx.part + k * LNB_AN_THREADS;
+                if (cpu >= 32u) {
+                    for (uint32_t u = 0; u < U; u++) {
+                        double v = 0.0;
+                        for (uint32_t q = 0; q < cpu; q += 32u) v += row[u * cpu + q + lane];
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                        if (lane == 0 && k0 + k <= p) acorr_lvl[u * (p + 1u) + k0 + k] = v;
+                    }
+                } else {
+                    for (uint32_t q = 0; q < LNB_AN_THREADS; q += 32u) {
+                        double v = row[q + lane];
+                        for (uint32_t off = cpu >> 1; off > 0u; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, (int)off);
+                        if ((lane & (cpu - 1u)) == 0u && k0 + k <= p) acorr_lvl[((q + lane) / cpu) * (p + 1u) + k0 + k] = v;
+                    }
                 }
             }
         }
         __syncthreads();
-        if (cpu >= 16u) {
-            const uint32_t spu = cpu / 16u;                     /* segments per unit */
-            if (c < LNB_AN_LAGS * U) {
-                const uint32_t k = c / U, u = c % U;
-                double s = 0.0;
-                for (uint32_t i = 0; i < spu; i++) s += cx.seg[k * 16u + u * spu + i];
-                if (k0 + k <= p) acorr_lvl[u * (p + 1u) + k0 + k] = s;
-            }
-            __syncthreads();
-        }
     }
 }
 

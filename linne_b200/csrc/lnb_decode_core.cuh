@@ -96,16 +96,19 @@ LNB_HD uint32_t lnb_br_bytes_consumed(const LnbBitReader &br)
 }
 
 /* ------------------------------------------------------------------------------------------
- * Residual reader: the hot loop of the decoder.  Two big-endian words + one prefetched word in
- * registers; a 32-bit window at the current bit position comes from one funnel shift, the unary
- * part from one clz, and in the common case (code <= 32 bits) the binary part from the same window.
+ * Residual reader: the hot loop of the decoder (one thread walks a block's payload: the format
+ * concatenates channels and delta-codes the Rice parameters inline, so there is no second entry
+ * point into a block).  What matters is the length of the dependent instruction chain per symbol.
+ * State: a 64-bit MSB-aligned window (hi:lo) with `nbits` valid bits (>= 32 between symbols) and one
+ * prefetched word.  A symbol costs clz(hi) -> code length -> one funnel shift on the chain; the
+ * refill (every ~3 symbols) ORs a prefetched word in.
  * Bit semantics: reference bit_stream.h:305-394; codes: linne_coder.c:106-127 (gamma), :150-169 (Rice).
  * ------------------------------------------------------------------------------------------ */
 struct LnbFastReader {
     const uint32_t *words;
-    uint32_t idx, end_word;      /* word index of w0; words at or past end_word read as zero */
-    uint32_t w0, w1, pre;        /* words idx, idx+1, idx+2 (stream byte order = big-endian) */
-    uint32_t bitpos;             /* 0..31: bits of w0 already consumed */
+    uint32_t next, end_word;     /* index of the word held in `pre`; words at or past end_word read as zero */
+    uint32_t hi, lo, pre;
+    uint32_t nbits;              /* valid bits in hi:lo, 32..64 between symbols */
     uint32_t overrun;
 };
 
@@ -113,34 +116,62 @@ LNB_HD uint32_t lnb_fr_word(const LnbFastReader &r, uint32_t i)
 {
     return (i < r.end_word) ? lnb_bswap32(r.words[i]) : 0u;
 }
+/* (hi:lo) << n for 0 <= n <= 32: new high / low words */
+LNB_HD uint32_t lnb_shl64_hi(uint32_t hi, uint32_t lo, uint32_t n)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(lo, hi, n);
+#else
+    return (n >= 32u) ? lo : (uint32_t)((((uint64_t)hi << 32) | lo) >> (32u - n));
+#endif
+}
+LNB_HD uint32_t lnb_shl32_clamped(uint32_t x, uint32_t n)      /* x << n, 0 for n >= 32 */
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_lc(0u, x, n);
+#else
+    return (n >= 32u) ? 0u : x << n;
+#endif
+}
+LNB_HD uint32_t lnb_shr32_clamped(uint32_t x, uint32_t n)      /* x >> n, 0 for n >= 32 */
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(x, 0u, n);
+#else
+    return (n >= 32u) ? 0u : x >> n;
+#endif
+}
+LNB_HD void lnb_fr_refill(LnbFastReader &r)                     /* call when nbits < 32 */
+{
+    const uint32_t w = r.pre;
+    r.hi |= lnb_shr32_clamped(w, r.nbits);
+    r.lo = lnb_shl32_clamped(w, 32u - r.nbits);
+    r.nbits += 32u;
+    r.next++;
+    r.pre = lnb_fr_word(r, r.next);
+    if (r.next > r.end_word + 2u) r.overrun = 1;
+}
 LNB_HD void lnb_fr_open(LnbFastReader &r, const uint32_t *words, uint64_t bit_position, uint32_t end_word)
 {
     r.words = words; r.end_word = end_word; r.overrun = 0;
-    r.idx = (uint32_t)(bit_position >> 5); r.bitpos = (uint32_t)(bit_position & 31u);
-    r.w0 = lnb_fr_word(r, r.idx); r.w1 = lnb_fr_word(r, r.idx + 1u); r.pre = lnb_fr_word(r, r.idx + 2u);
-}
-LNB_HD uint32_t lnb_fr_peek32(const LnbFastReader &r)
-{
-#if defined(__CUDA_ARCH__)
-    return __funnelshift_l(r.w1, r.w0, r.bitpos);
-#else
-    return (uint32_t)((((uint64_t)r.w0 << 32) | r.w1) >> (32u - r.bitpos));
-#endif
+    const uint32_t idx = (uint32_t)(bit_position >> 5), s = (uint32_t)(bit_position & 31u);
+    const uint32_t w0 = lnb_fr_word(r, idx), w1 = lnb_fr_word(r, idx + 1u);
+    r.hi = lnb_shl64_hi(w0, w1, s);
+    r.lo = lnb_shl32_clamped(w1, s);
+    r.nbits = 64u - s;
+    r.next = idx + 2u;
+    r.pre = lnb_fr_word(r, r.next);
 }
 LNB_HD void lnb_fr_skip(LnbFastReader &r, uint32_t n)           /* n <= 32 */
 {
-    r.bitpos += n;
-    if (r.bitpos >= 32u) {
-        r.bitpos -= 32u;
-        r.w0 = r.w1; r.w1 = r.pre; r.idx++;
-        r.pre = lnb_fr_word(r, r.idx + 2u);
-        if (r.idx > r.end_word) r.overrun = 1;
-    }
+    r.hi = lnb_shl64_hi(r.hi, r.lo, n);
+    r.lo = lnb_shl32_clamped(r.lo, n);
+    r.nbits -= n;
+    if (r.nbits < 32u) lnb_fr_refill(r);
 }
 LNB_HD uint32_t lnb_fr_get(LnbFastReader &r, uint32_t n)         /* 0 <= n <= 32 */
 {
-    if (n == 0) return 0;
-    const uint32_t v = lnb_fr_peek32(r) >> (32u - n);
+    const uint32_t v = lnb_shr32_clamped(r.hi, 32u - n);
     lnb_fr_skip(r, n);
     return v;
 }
@@ -149,9 +180,8 @@ LNB_HD uint32_t lnb_fr_zero_run(LnbFastReader &r)
 {
     uint32_t run = 0;
     for (;;) {
-        const uint32_t win = lnb_fr_peek32(r);
-        if (win != 0u) {
-            const uint32_t lz = lnb_clz32(win);
+        if (r.hi != 0u) {
+            const uint32_t lz = lnb_clz32(r.hi);
             lnb_fr_skip(r, lz + 1u);
             return run + lz;
         }
@@ -160,7 +190,7 @@ LNB_HD uint32_t lnb_fr_zero_run(LnbFastReader &r)
         if (r.overrun) return run;
     }
 }
-LNB_HD uint64_t lnb_fr_position(const LnbFastReader &r) { return (uint64_t)r.idx * 32u + r.bitpos; }
+LNB_HD uint64_t lnb_fr_position(const LnbFastReader &r) { return (uint64_t)r.next * 32u - r.nbits; }
 
 LNB_HD uint32_t lnb_get_gamma(LnbFastReader &r)
 {
@@ -170,29 +200,22 @@ LNB_HD uint32_t lnb_get_gamma(LnbFastReader &r)
     return (uint32_t)(((uint64_t)1 << (nd - 1u)) + lnb_fr_get(r, nd - 1u) - 1u);
 }
 
-/* one recursive-Rice symbol, k1 = k2 + 1, 0 <= k2 <= 30 */
+/* one recursive-Rice symbol, k1 = k2 + 1, 0 <= k2 <= 30.  Straight-line for codes of <= 32 bits:
+ *   lz = leading zeros (0 -> '1' + k1 bits; lz >= 1 -> lz zeros, '1', k2 bits) */
 LNB_HD uint32_t lnb_get_rice(LnbFastReader &r, uint32_t k1, uint32_t k2)
 {
-    const uint32_t win = lnb_fr_peek32(r);
-    if (win & 0x80000000u) {                                   /* '1' + k1 bits */
-        const uint32_t u = (win << 1) >> (32u - k1);
-        lnb_fr_skip(r, 1u + k1);
-        return u;
+    const uint32_t hi = r.hi;
+    const uint32_t lz = lnb_clz32(hi);
+    const uint32_t kk = lz ? k2 : k1;
+    const uint32_t total = lz + 1u + kk;
+    if (total <= 32u) {                                          /* also implies hi != 0 */
+        const uint32_t low = ((hi << lz) << 1 >> 1) >> (31u - kk);
+        const uint32_t base = lz ? ((1u << k1) + ((lz - 1u) << k2)) : 0u;
+        lnb_fr_skip(r, total);
+        return low + base;
     }
-    if (win != 0u) {
-        const uint32_t lz = lnb_clz32(win);                    /* 1..31 zeros, then the terminating one */
-        const uint32_t total = lz + 1u + k2;
-        uint32_t low = 0;
-        if (total <= 32u) {
-            if (k2) low = (win << (lz + 1u)) >> (32u - k2);
-            lnb_fr_skip(r, total);
-        } else {
-            lnb_fr_skip(r, lz + 1u);
-            low = lnb_fr_get(r, k2);
-        }
-        return low + (1u << k1) + ((lz - 1u) << k2);
-    }
-    const uint32_t q = lnb_fr_zero_run(r);                     /* 32 or more zeros: rare */
+    const uint32_t q = lnb_fr_zero_run(r);                       /* long code: zero run, then k2 bits */
+    if (q == 0u) return lnb_fr_get(r, k1);
     return lnb_fr_get(r, k2) + (1u << k1) + ((q - 1u) << k2);
 }
 
@@ -203,14 +226,14 @@ LNB_HD void lnb_decode_residual(LnbFastReader &br, int32_t *out, uint32_t n)
     const uint32_t len = (porder < 32u) ? (n >> porder) : 0u;
     const uint32_t parts = (porder <= LNB_MAX_PORDER) ? (1u << porder) : 0u;
     uint32_t k2 = 0;
+    int32_t *dst = out;
     if (porder > LNB_MAX_PORDER) { br.overrun = 1; }
     for (uint32_t part = 0; part < parts; part++) {
         if (part == 0) k2 = lnb_fr_get(br, 5);
         else k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(lnb_get_gamma(br)));
         if (k2 > 30u) { br.overrun = 1; k2 = 30u; }           /* never produced by a valid encoder */
         const uint32_t k1 = k2 + 1u;
-        int32_t *dst = out + part * len;
-        for (uint32_t s = 0; s < len; s++) dst[s] = lnb_zz_dec(lnb_get_rice(br, k1, k2));
+        for (uint32_t s = 0; s < len; s++) *dst++ = lnb_zz_dec(lnb_get_rice(br, k1, k2));
         if (br.overrun) break;
     }
     /* samples a broken porder leaves uncovered */

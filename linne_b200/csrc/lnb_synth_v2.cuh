@@ -23,50 +23,102 @@
 #define LNB_SY_THREADS (32 * LNB_SY_WARPS)
 #define LNB_SY_MAX_N   10240               /* samples per block-channel staged in shared memory per warp */
 
-/* One round of one layer on the shared-memory copy `x` of the block-channel: up to 32/G units side
- * by side, G lanes per unit, TT taps per lane.  The last lane of a group reads d[j+1] two steps ahead
- * and writes y[j+1] straight back (shared memory: no cache-line ping-pong between loads and stores). */
+/* One round of one layer on the shared-memory copy `x` of the block-channel, single-lane form:
+ * up to 32 units side by side, one lane per unit, TT <= 4 taps (no shuffles at all). */
 template <int TT>
-__device__ __forceinline__ void lnb_sy_round(int32_t *x, uint32_t m, uint32_t p, uint32_t G, uint32_t unit0,
-                                             uint32_t units_in_round, const int8_t *coef, uint32_t rs)
+__device__ __forceinline__ void lnb_sy_round_lane(int32_t *x, uint32_t m, uint32_t p, uint32_t unit0,
+                                                  uint32_t units_in_round, const int8_t *coef, uint32_t rs)
 {
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool active = lane < units_in_round;
+    const uint32_t u = unit0 + (active ? lane : 0u);
+    const int32_t half = rs ? (int32_t)(1u << (rs - 1u)) : 0;
+    int32_t *xu = x + (size_t)u * m;
+    int32_t c[TT], acc[TT];
+#pragma unroll
+    for (int s = 0; s < TT; s++) { c[s] = active ? (int32_t)coef[u * p + s] : 0; acc[s] = half; }
+    int32_t y = active ? xu[0] : 0;
+    int32_t d1 = (active && 1u < m) ? xu[1] : 0, d2 = (active && 2u < m) ? xu[2] : 0;
+    for (uint32_t j = 0; j + 1u < m; j += TT) {
+#pragma unroll
+        for (int jj = 0; jj < TT; jj++) {
+            const uint32_t js = j + (uint32_t)jj;
+            if (js + 1u < m) {
+                const int32_t d3 = (active && js + 3u < m) ? xu[js + 3u] : 0;
+#pragma unroll
+                for (int r = 0; r < TT; r++)
+                    acc[r] = (int32_t)((uint32_t)acc[r] + (uint32_t)c[(r + jj) % TT] * (uint32_t)y);
+                const int rc = (TT - 1 - jj + TT) % TT;
+                const int32_t done = acc[rc];
+                acc[rc] = half;
+                const uint32_t jn = js + 1u;
+                y = (jn >= p) ? (int32_t)((uint32_t)d1 - (uint32_t)(done >> rs)) : d1;
+                if (active) xu[jn] = y;
+                d1 = d2; d2 = d3;
+            }
+        }
+    }
+}
+
+/* Systolic form for long filters: G >= 2 lanes per unit, 4 taps per lane, up to 32/G units side by side.
+ * Software-pipelined so that neither shuffle sits on the sample-to-sample dependency chain:
+ *   - the lane that owns the unit's stream (last lane of the group) finishes output j+1 from its own
+ *     registers:  done = acc[last tap] + c_last * y_j   -- no broadcast needed for that;
+ *   - y_j is broadcast right away; the other taps consume the broadcast value a little later;
+ *   - a partial sum handed over from the previous lane (shuffle-up) is merged only three steps after
+ *     it was sent, when its register reaches the third tap -- until then the register accumulates from
+ *     zero (addition commutes), so the shuffle latency is hidden. */
+__device__ __forceinline__ void lnb_sy_round_group(int32_t *x, uint32_t m, uint32_t p, uint32_t G, uint32_t unit0,
+                                                   uint32_t units_in_round, const int8_t *coef, uint32_t rs)
+{
+    constexpr int TT = 4;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gl = lane & (G - 1u), ug = lane / G;
     const bool active = ug < units_in_round;
     const uint32_t u = unit0 + (active ? ug : 0u);
-    const bool is_last = gl == G - 1u, is_first = gl == 0u;
-    const bool io = active && is_last;                       /* lane that owns the unit's input/output stream */
+    const bool is_first = gl == 0u;
+    const bool io = active && (gl == G - 1u);
     const int32_t half = rs ? (int32_t)(1u << (rs - 1u)) : 0;
     int32_t *xu = x + (size_t)u * m;
 
-    int32_t c[TT], acc[TT];
+    int32_t c[TT], acc[TT], late[TT];
 #pragma unroll
     for (int s = 0; s < TT; s++) {
         c[s] = active ? (int32_t)coef[u * p + gl * TT + s] : 0;
-        acc[s] = half;
+        acc[s] = half; late[s] = 0;
     }
     int32_t y = io ? xu[0] : 0;                              /* y[0] = d[0] */
-    int32_t d1 = (io && 1u < m) ? xu[1] : 0;                 /* d[j+1] */
-    int32_t d2 = (io && 2u < m) ? xu[2] : 0;                 /* d[j+2] */
+    int32_t d1 = (io && 1u < m) ? xu[1] : 0, d2 = (io && 2u < m) ? xu[2] : 0;
+    int32_t yb = __shfl_sync(0xffffffffu, y, (int)(G - 1u), (int)G);
 
     for (uint32_t j = 0; j + 1u < m; j += TT) {
 #pragma unroll
         for (int jj = 0; jj < TT; jj++) {
-            const uint32_t js = j + (uint32_t)jj;             /* sample being consumed */
+            const uint32_t js = j + (uint32_t)jj;             /* sample being consumed: y = y[js], yb = its broadcast */
             if (js + 1u < m) {
+                const int rc = (TT - 1 - jj + TT) % TT;       /* register at this lane's last tap in this step */
+                const int32_t c_last = c[TT - 1];
+                /* fast chain (stream-owning lane): next output from local state only */
                 const int32_t d3 = (io && js + 3u < m) ? xu[js + 3u] : 0;
-                const int32_t yb = (G > 1u) ? __shfl_sync(0xffffffffu, y, (int)(G - 1u), (int)G) : y;
-                /* physical register r sits at tap (r + jj) % TT of this lane in this step */
-#pragma unroll
-                for (int r = 0; r < TT; r++)
-                    acc[r] = (int32_t)((uint32_t)acc[r] + (uint32_t)c[(r + jj) % TT] * (uint32_t)yb);
-                const int rc = (TT - 1 - jj + TT) % TT;       /* register that just passed its last tap */
-                const int32_t done = acc[rc];
-                const int32_t incoming = (G > 1u) ? __shfl_up_sync(0xffffffffu, done, 1, (int)G) : half;
-                acc[rc] = is_first ? half : incoming;
+                const int32_t done = (int32_t)((uint32_t)acc[rc] + (uint32_t)c_last * (uint32_t)y);
                 const uint32_t jn = js + 1u;
-                y = (jn >= p) ? (int32_t)((uint32_t)d1 - (uint32_t)(done >> rs)) : d1;
-                if (io) xu[jn] = y;
+                const int32_t y_next = (jn >= p) ? (int32_t)((uint32_t)d1 - (uint32_t)(done >> rs)) : d1;
+                if (io) xu[jn] = y_next;
+                const int32_t yb_next = __shfl_sync(0xffffffffu, y_next, (int)(G - 1u), (int)G);
+                /* slow part: every tap consumes the broadcast sample */
+                const int32_t upd = (int32_t)((uint32_t)acc[rc] + (uint32_t)c_last * (uint32_t)yb);
+#pragma unroll
+                for (int r = 0; r < TT; r++) {
+                    if (r != rc) {
+                        const int tap = (r + jj) % TT;
+                        if (tap == TT - 2) acc[r] = (int32_t)((uint32_t)acc[r] + (uint32_t)late[r]);   /* merge the handed-over sum */
+                        acc[r] = (int32_t)((uint32_t)acc[r] + (uint32_t)c[tap] * (uint32_t)yb);
+                    }
+                }
+                const int32_t handed = __shfl_up_sync(0xffffffffu, upd, 1, (int)G);
+                acc[rc] = is_first ? half : 0;                /* fresh partial sum enters at tap 0 next step */
+                late[rc] = is_first ? 0 : handed;
+                y = y_next; yb = yb_next;
                 d1 = d2; d2 = d3;
             }
         }
@@ -84,9 +136,10 @@ __device__ __forceinline__ void lnb_sy_layer(int32_t *x, uint32_t n, uint32_t P,
     const uint32_t per_round = 32u / G;
     for (uint32_t u0 = 0; u0 < U; u0 += per_round) {
         const uint32_t cnt = (U - u0 < per_round) ? U - u0 : per_round;
-        if (TT == 1u) lnb_sy_round<1>(x, m, p, G, u0, cnt, coef, rs);
-        else if (TT == 2u) lnb_sy_round<2>(x, m, p, G, u0, cnt, coef, rs);
-        else lnb_sy_round<4>(x, m, p, G, u0, cnt, coef, rs);
+        if (G > 1u) lnb_sy_round_group(x, m, p, G, u0, cnt, coef, rs);
+        else if (TT == 1u) lnb_sy_round_lane<1>(x, m, p, u0, cnt, coef, rs);
+        else if (TT == 2u) lnb_sy_round_lane<2>(x, m, p, u0, cnt, coef, rs);
+        else lnb_sy_round_lane<4>(x, m, p, u0, cnt, coef, rs);
         __syncwarp();
     }
 }

@@ -73,3 +73,84 @@ def test_crc_corruption_detected(gpu, oracle, clip):
     stream[-1] ^= 0x01
     rc, _ = gpu.decode(bytes(stream), return_code=True)
     assert rc == harness.DATA_CORRUPTION
+
+
+# ---- the reference's own round-trip matrix: 9 generators x {1,2,8} ch x {8,16,24} bit x preset {0,7} ----
+# test/linne_encode_decode/main.cpp:341-521 (8192 samples, block 1024, M/S for >= 2 channels)
+@pytest.mark.parametrize("gen_name", sorted(harness.reference_test_generators()))
+def test_reference_roundtrip_matrix(gpu, oracle, gen_name):
+    gen = harness.reference_test_generators()[gen_name]
+    for channels in (1, 2, 8):
+        for bits in (8, 16, 24):
+            pcm = harness.to_fixed(gen(channels, 8192), bits)
+            for preset in (0, 7):
+                stream = gpu.encode(pcm, bits=bits, rate=8000, block=1024, preset=preset)
+                assert np.array_equal(gpu.decode(stream), pcm), (gen_name, channels, bits, preset)
+                assert np.array_equal(oracle.decode(stream), pcm), (gen_name, channels, bits, preset)
+
+
+@pytest.mark.parametrize("name", harness.GOLDEN_CASES + ["mixed_types_m5"])
+def test_golden_decode_bit_exact(gpu, name):
+    g = harness.load_golden(name)
+    assert np.array_equal(gpu.decode(g["stream"].tobytes()), g["pcm"])
+
+
+@pytest.mark.parametrize("name", harness.GOLDEN_CASES)
+def test_golden_coefficients_give_identical_bytes(gpu, name):
+    # north star leg 3: identical quantised coefficients -> identical residuals and coded bits
+    g = harness.load_golden(name)
+    got = gpu.encode_with_params(g["pcm"], harness.params_from_golden(g), bits=int(g["bits"]),
+                                 block=int(g["block"]), preset=int(g["preset"]))
+    assert got == g["stream"].tobytes()
+
+
+def test_block_sizes_on_both_kernel_paths(gpu, oracle):
+    # 2048/4096/8192/10240 take the cooperative kernels, 1024/3000/12000 the flat ones; all must agree with the oracle
+    for block in (1024, 2048, 3000, 4096, 8192, 10240, 12000):
+        pcm = harness.synth_pcm(n=block * 2 + block // 3, channels=2, bits=16, seed=block)
+        for preset in (1, 6):
+            got = gpu.encode(pcm, preset=preset, block=block)
+            want = oracle.encode(pcm, preset=preset, block=block)
+            assert np.array_equal(oracle.decode(got), pcm), (block, preset)
+            assert np.array_equal(gpu.decode(want), pcm), (block, preset)
+            assert abs(len(got) - len(want)) <= max(2, SIZE_TOLERANCE * len(want)), (block, preset, len(got), len(want))
+
+
+def test_config_c4_24bit_96k_8ch(gpu, oracle):
+    # BASELINE.json configs[3]: 24-bit / 96 kHz / 8 channels at -m 7 (long-order predictor, multichannel path)
+    pcm = harness.synth_pcm(seconds=1.0, sr=96000, channels=8, bits=24, seed=44)
+    got = gpu.encode(pcm, bits=24, rate=96000, preset=7)
+    want = oracle.encode(pcm, bits=24, rate=96000, preset=7)
+    assert np.array_equal(oracle.decode(got), pcm)
+    assert np.array_equal(gpu.decode(want), pcm)
+    assert abs(len(got) - len(want)) <= SIZE_TOLERANCE * len(want)
+
+
+def test_config_c3_long_stream_decode(gpu, oracle):
+    # BASELINE.json configs[2] shape: a long -m 7 stream built by tiling the blocks of a verified short one
+    # (legal because blocks are self-contained); property: decode == tiled PCM
+    pcm = harness.synth_pcm(n=10240 * 12, channels=2, bits=16, seed=55)
+    base = gpu.encode(pcm, preset=7)
+    assert np.array_equal(oracle.decode(base), pcm)
+    times = 40                                     # 480 blocks, ~111 s of audio
+    long_stream = harness.tile_stream(base, times, 10240)
+    out = gpu.decode(long_stream)
+    assert out.shape[1] == pcm.shape[1] * times
+    assert np.array_equal(out, np.tile(pcm, (1, times)))
+
+
+def test_config_c5_block_range_shards(gpu):
+    # BASELINE.json configs[4] property: encoding contiguous block ranges separately and concatenating them
+    # equals the single-call stream byte for byte, so ranks can take block ranges with no exchange but the gather
+    from linne_b200 import shard
+    pcm = harness.synth_pcm(n=10240 * 9 + 4000, channels=2, bits=16, seed=66)
+    whole = gpu.encode(pcm, preset=4)
+    for world in (2, 4, 8):
+        parts = [shard.encode_shard(gpu, pcm, r, world, 10240, preset=4) for r in range(world)]
+        assert shard.assemble(parts[0][0], [p[1] for p in parts]) == whole
+        out = np.zeros_like(pcm)
+        for r in range(world):
+            first, got = shard.decode_shard(gpu, whole, r, world)
+            if got is not None:
+                out[:, first:first + got.shape[1]] = got
+        assert np.array_equal(out, pcm)
