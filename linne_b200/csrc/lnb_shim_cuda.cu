@@ -16,6 +16,7 @@
 #include "lnb_front_v2.cuh"
 #include "lnb_synth_v2.cuh"
 #include "lnb_crc_v2.cuh"
+#include "lnb_entropy_v2.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -84,6 +85,12 @@ struct CudaExec {
         if (n == 0) return;
         const int slot = begin_stage(name);
         lnb_items_per_warp_kernel<F><<<(n + 3u) / 4u, 128, 0, dev->stream>>>(n, f);
+        end_stage(slot);
+    }
+    void entropy_cooperative(const LnbDecodeBatch &b)
+    {
+        const int slot = begin_stage("entropy_v2");
+        lnb_entropy_v2_kernel<<<(b.num_blocks + LNB_EN_WARPS - 1) / LNB_EN_WARPS, LNB_EN_THREADS, 0, dev->stream>>>(b);
         end_stage(slot);
     }
     void crc_cooperative(const LnbDecodeBatch &b)

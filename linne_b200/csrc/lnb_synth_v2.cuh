@@ -23,8 +23,26 @@
 #define LNB_SY_THREADS (32 * LNB_SY_WARPS)
 #define LNB_SY_MAX_N   10240               /* samples per block-channel staged in shared memory per warp */
 
-/* One round of one layer on the shared-memory copy `x` of the block-channel, single-lane form:
- * up to 32 units side by side, one lane per unit, TT <= 4 taps (no shuffles at all). */
+/* One step of the single-lane form (one lane per unit, TT <= 4 taps, no shuffles). */
+template <int TT, int JJ, bool GUARD>
+__device__ __forceinline__ void lnb_sy_lane_step(int32_t *xu, uint32_t js, uint32_t m, uint32_t p, uint32_t rs, int32_t half,
+                                                 bool active, const int32_t (&c)[TT], int32_t (&acc)[TT],
+                                                 int32_t &y, int32_t &d1, int32_t &d2)
+{
+    if (GUARD && !(js + 1u < m)) return;
+    const int32_t d3 = (active && (!GUARD || js + 3u < m)) ? xu[js + 3u] : 0;
+#pragma unroll
+    for (int r = 0; r < TT; r++)
+        acc[r] = (int32_t)((uint32_t)acc[r] + (uint32_t)c[(r + JJ) % TT] * (uint32_t)y);
+    constexpr int rc = (TT - 1 - JJ + TT) % TT;          /* register that just passed its last tap */
+    const int32_t done = acc[rc];
+    acc[rc] = half;
+    const uint32_t jn = js + 1u;
+    y = (jn >= p) ? (int32_t)((uint32_t)d1 - (uint32_t)(done >> rs)) : d1;
+    if (active) xu[jn] = y;
+    d1 = d2; d2 = d3;
+}
+
 template <int TT>
 __device__ __forceinline__ void lnb_sy_round_lane(int32_t *x, uint32_t m, uint32_t p, uint32_t unit0,
                                                   uint32_t units_in_round, const int8_t *coef, uint32_t rs)
@@ -39,24 +57,18 @@ __device__ __forceinline__ void lnb_sy_round_lane(int32_t *x, uint32_t m, uint32
     for (int s = 0; s < TT; s++) { c[s] = active ? (int32_t)coef[u * p + s] : 0; acc[s] = half; }
     int32_t y = active ? xu[0] : 0;
     int32_t d1 = (active && 1u < m) ? xu[1] : 0, d2 = (active && 2u < m) ? xu[2] : 0;
-    for (uint32_t j = 0; j + 1u < m; j += TT) {
-#pragma unroll
-        for (int jj = 0; jj < TT; jj++) {
-            const uint32_t js = j + (uint32_t)jj;
-            if (js + 1u < m) {
-                const int32_t d3 = (active && js + 3u < m) ? xu[js + 3u] : 0;
-#pragma unroll
-                for (int r = 0; r < TT; r++)
-                    acc[r] = (int32_t)((uint32_t)acc[r] + (uint32_t)c[(r + jj) % TT] * (uint32_t)y);
-                const int rc = (TT - 1 - jj + TT) % TT;
-                const int32_t done = acc[rc];
-                acc[rc] = half;
-                const uint32_t jn = js + 1u;
-                y = (jn >= p) ? (int32_t)((uint32_t)d1 - (uint32_t)(done >> rs)) : d1;
-                if (active) xu[jn] = y;
-                d1 = d2; d2 = d3;
-            }
-        }
+    uint32_t j = 0;
+    for (; j + TT + 3u < m; j += TT) {                       /* whole groups, no bounds checks */
+        lnb_sy_lane_step<TT, 0, false>(xu, j, m, p, rs, half, active, c, acc, y, d1, d2);
+        if (TT > 1) lnb_sy_lane_step<TT, 1 % TT, false>(xu, j + 1u, m, p, rs, half, active, c, acc, y, d1, d2);
+        if (TT > 2) lnb_sy_lane_step<TT, 2 % TT, false>(xu, j + 2u, m, p, rs, half, active, c, acc, y, d1, d2);
+        if (TT > 2) lnb_sy_lane_step<TT, 3 % TT, false>(xu, j + 3u, m, p, rs, half, active, c, acc, y, d1, d2);
+    }
+    for (; j + 1u < m; j += TT) {                            /* ragged end */
+        lnb_sy_lane_step<TT, 0, true>(xu, j, m, p, rs, half, active, c, acc, y, d1, d2);
+        if (TT > 1) lnb_sy_lane_step<TT, 1 % TT, true>(xu, j + 1u, m, p, rs, half, active, c, acc, y, d1, d2);
+        if (TT > 2) lnb_sy_lane_step<TT, 2 % TT, true>(xu, j + 2u, m, p, rs, half, active, c, acc, y, d1, d2);
+        if (TT > 2) lnb_sy_lane_step<TT, 3 % TT, true>(xu, j + 3u, m, p, rs, half, active, c, acc, y, d1, d2);
     }
 }
 
@@ -68,6 +80,44 @@ __device__ __forceinline__ void lnb_sy_round_lane(int32_t *x, uint32_t m, uint32
  *   - a partial sum handed over from the previous lane (shuffle-up) is merged only three steps after
  *     it was sent, when its register reaches the third tap -- until then the register accumulates from
  *     zero (addition commutes), so the shuffle latency is hidden. */
+struct LnbSyGroupState {
+    int32_t c[4], acc[4], late[4];
+    int32_t y, yb, d1, d2;
+};
+
+template <int JJ, bool GUARD>
+__device__ __forceinline__ void lnb_sy_group_step(int32_t *xu, uint32_t js, uint32_t m, uint32_t p, uint32_t rs, int32_t half,
+                                                  uint32_t G, bool io, bool is_first, LnbSyGroupState &st)
+{
+    constexpr int TT = 4;
+    if (GUARD && !(js + 1u < m)) return;
+    constexpr int rc = (TT - 1 - JJ + TT) % TT;          /* register at this lane's last tap in this step */
+    const int32_t c_last = st.c[TT - 1];
+    /* fast chain (stream-owning lane): next output from local state only */
+    const int32_t d3 = (io && (!GUARD || js + 3u < m)) ? xu[js + 3u] : 0;
+    const int32_t done = (int32_t)((uint32_t)st.acc[rc] + (uint32_t)c_last * (uint32_t)st.y);
+    const uint32_t jn = js + 1u;
+    const int32_t y_next = (jn >= p) ? (int32_t)((uint32_t)st.d1 - (uint32_t)(done >> rs)) : st.d1;
+    if (io) xu[jn] = y_next;
+    const int32_t yb_next = __shfl_sync(0xffffffffu, y_next, (int)(G - 1u), (int)G);
+    /* slow part: every tap consumes the broadcast sample */
+    const int32_t upd = (int32_t)((uint32_t)st.acc[rc] + (uint32_t)c_last * (uint32_t)st.yb);
+#pragma unroll
+    for (int r = 0; r < TT; r++) {
+        if (r != rc) {
+            constexpr int dummy = 0; (void)dummy;
+            const int tap = (r + JJ) % TT;
+            if (tap == TT - 2)                               /* merge the handed-over sum (first lane of a group: none) */
+                st.acc[r] = (int32_t)((uint32_t)st.acc[r] + (uint32_t)(is_first ? 0 : st.late[r]));
+            st.acc[r] = (int32_t)((uint32_t)st.acc[r] + (uint32_t)st.c[tap] * (uint32_t)st.yb);
+        }
+    }
+    st.late[rc] = __shfl_up_sync(0xffffffffu, upd, 1, (int)G);   /* consumed three steps from now */
+    st.acc[rc] = is_first ? half : 0;                             /* fresh partial sum enters at tap 0 next step */
+    st.y = y_next; st.yb = yb_next;
+    st.d1 = st.d2; st.d2 = d3;
+}
+
 __device__ __forceinline__ void lnb_sy_round_group(int32_t *x, uint32_t m, uint32_t p, uint32_t G, uint32_t unit0,
                                                    uint32_t units_in_round, const int8_t *coef, uint32_t rs)
 {
@@ -81,47 +131,28 @@ __device__ __forceinline__ void lnb_sy_round_group(int32_t *x, uint32_t m, uint3
     const int32_t half = rs ? (int32_t)(1u << (rs - 1u)) : 0;
     int32_t *xu = x + (size_t)u * m;
 
-    int32_t c[TT], acc[TT], late[TT];
+    LnbSyGroupState st;
 #pragma unroll
     for (int s = 0; s < TT; s++) {
-        c[s] = active ? (int32_t)coef[u * p + gl * TT + s] : 0;
-        acc[s] = half; late[s] = 0;
+        st.c[s] = active ? (int32_t)coef[u * p + gl * TT + s] : 0;
+        st.acc[s] = half; st.late[s] = 0;
     }
-    int32_t y = io ? xu[0] : 0;                              /* y[0] = d[0] */
-    int32_t d1 = (io && 1u < m) ? xu[1] : 0, d2 = (io && 2u < m) ? xu[2] : 0;
-    int32_t yb = __shfl_sync(0xffffffffu, y, (int)(G - 1u), (int)G);
+    st.y = io ? xu[0] : 0;                                   /* y[0] = d[0] */
+    st.d1 = (io && 1u < m) ? xu[1] : 0; st.d2 = (io && 2u < m) ? xu[2] : 0;
+    st.yb = __shfl_sync(0xffffffffu, st.y, (int)(G - 1u), (int)G);
 
-    for (uint32_t j = 0; j + 1u < m; j += TT) {
-#pragma unroll
-        for (int jj = 0; jj < TT; jj++) {
-            const uint32_t js = j + (uint32_t)jj;             /* sample being consumed: y = y[js], yb = its broadcast */
-            if (js + 1u < m) {
-                const int rc = (TT - 1 - jj + TT) % TT;       /* register at this lane's last tap in this step */
-                const int32_t c_last = c[TT - 1];
-                /* fast chain (stream-owning lane): next output from local state only */
-                const int32_t d3 = (io && js + 3u < m) ? xu[js + 3u] : 0;
-                const int32_t done = (int32_t)((uint32_t)acc[rc] + (uint32_t)c_last * (uint32_t)y);
-                const uint32_t jn = js + 1u;
-                const int32_t y_next = (jn >= p) ? (int32_t)((uint32_t)d1 - (uint32_t)(done >> rs)) : d1;
-                if (io) xu[jn] = y_next;
-                const int32_t yb_next = __shfl_sync(0xffffffffu, y_next, (int)(G - 1u), (int)G);
-                /* slow part: every tap consumes the broadcast sample */
-                const int32_t upd = (int32_t)((uint32_t)acc[rc] + (uint32_t)c_last * (uint32_t)yb);
-#pragma unroll
-                for (int r = 0; r < TT; r++) {
-                    if (r != rc) {
-                        const int tap = (r + jj) % TT;
-                        if (tap == TT - 2) acc[r] = (int32_t)((uint32_t)acc[r] + (uint32_t)late[r]);   /* merge the handed-over sum */
-                        acc[r] = (int32_t)((uint32_t)acc[r] + (uint32_t)c[tap] * (uint32_t)yb);
-                    }
-                }
-                const int32_t handed = __shfl_up_sync(0xffffffffu, upd, 1, (int)G);
-                acc[rc] = is_first ? half : 0;                /* fresh partial sum enters at tap 0 next step */
-                late[rc] = is_first ? 0 : handed;
-                y = y_next; yb = yb_next;
-                d1 = d2; d2 = d3;
-            }
-        }
+    uint32_t j = 0;
+    for (; j + TT + 3u < m; j += TT) {                       /* whole groups of four steps, no bounds checks */
+        lnb_sy_group_step<0, false>(xu, j, m, p, rs, half, G, io, is_first, st);
+        lnb_sy_group_step<1, false>(xu, j + 1u, m, p, rs, half, G, io, is_first, st);
+        lnb_sy_group_step<2, false>(xu, j + 2u, m, p, rs, half, G, io, is_first, st);
+        lnb_sy_group_step<3, false>(xu, j + 3u, m, p, rs, half, G, io, is_first, st);
+    }
+    for (; j + 1u < m; j += TT) {                            /* ragged end */
+        lnb_sy_group_step<0, true>(xu, j, m, p, rs, half, G, io, is_first, st);
+        lnb_sy_group_step<1, true>(xu, j + 1u, m, p, rs, half, G, io, is_first, st);
+        lnb_sy_group_step<2, true>(xu, j + 2u, m, p, rs, half, G, io, is_first, st);
+        lnb_sy_group_step<3, true>(xu, j + 3u, m, p, rs, half, G, io, is_first, st);
     }
 }
 

@@ -16,6 +16,7 @@ struct LoopExec {
     static constexpr bool cooperative = false;
     LnbDevice *dev;
     void crc_cooperative(const LnbDecodeBatch &) {}
+    void entropy_cooperative(const LnbDecodeBatch &) {}
     void synth_cooperative(const LnbDecodeBatch &) {}
     uint32_t synth_max_n() const { return 0; }
     template <class F> void run_per_warp(const char *n, uint32_t c, const F &f) { run(n, c, f); }
