@@ -80,23 +80,26 @@ __device__ void lnb_an_autocorr(const LnbAnCtx &cx, uint32_t U, uint32_t p, doub
         double wv[LNB_AN_LAGS + 7];
 #pragma unroll
         for (int k = 0; k < LNB_AN_LAGS; k++) acc[k] = 0.0;
-        /* running cursor of the window's next element: unit-local position q, physical (ew, cw) */
-        uint32_t q = pos0 + k0;
-        uint32_t cw = c + k0 / T, ew = k0 % T;
+        /* Cursor of the window's next element.  Its logical offset r from the chunk start is the same in
+         * every thread, so the wrap logic (r -> element ew of chunk c + dq) runs on warp-uniform values;
+         * per thread only the address add and the unit-end test (r < lim) remain. */
+        const uint32_t lim = m - pos0;                       /* offsets at or past the unit end read as zero */
+        const double *Bc = cx.B + c;
+        uint32_t r = k0, ew = k0 % T, dq = k0 / T;
 #pragma unroll
         for (int k = 0; k < LNB_AN_LAGS - 1; k++) {
-            wv[k] = (q < m) ? cx.B[ew * LNB_AN_THREADS + cw] : 0.0;
-            q++; if (++ew == T) { ew = 0; cw++; }
+            wv[k] = (r < lim) ? Bc[ew * LNB_AN_THREADS + dq] : 0.0;
+            r++; if (++ew == T) { ew = 0; dq++; }
         }
         for (uint32_t e0 = 0; e0 < T; e0 += 8u) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                wv[LNB_AN_LAGS - 1 + k] = (q < m) ? cx.B[ew * LNB_AN_THREADS + cw] : 0.0;
-                q++; if (++ew == T) { ew = 0; cw++; }
+                wv[LNB_AN_LAGS - 1 + k] = (r < lim) ? Bc[ew * LNB_AN_THREADS + dq] : 0.0;
+                r++; if (++ew == T) { ew = 0; dq++; }
             }
 #pragma unroll
             for (int o = 0; o < 8; o++) {
-                const double w = cx.B[(e0 + o) * LNB_AN_THREADS + c];
+                const double w = Bc[(e0 + o) * LNB_AN_THREADS];
 #pragma unroll
                 for (int k = 0; k < LNB_AN_LAGS; k++) acc[k] = lnb_mac(w, wv[o + k], acc[k]);
             }
@@ -180,20 +183,22 @@ __device__ double lnb_an_fir(const LnbAnCtx &cx, const double *X, double *Y, uin
     const uint32_t cpu = LNB_AN_THREADS / U, u = c / cpu;
     const double *w = cand_lvl + u * p;
     double loss = 0.0;
+    const double *Xc = X + c;
+    const int32_t first_valid = -(int32_t)(c * T);          /* chunk-relative offsets below this lie before the block: zero */
     for (uint32_t e0 = 0; e0 < T; e0 += 8u) {
         const uint32_t t0 = c * T + e0;
         double acc[8], xw[15];
 #pragma unroll
-        for (int o = 0; o < 8; o++) acc[o] = (MODE == 0) ? X[(e0 + o) * LNB_AN_THREADS + c] : 0.0;
-        /* cursor over x starting at logical index t0 - p (negative = before the block = 0) */
-        int32_t li = (int32_t)t0 - (int32_t)p;
-        uint32_t cw = 0, ew = 0;
-        if (li >= 0) { cw = (uint32_t)li / T; ew = (uint32_t)li % T; }
+        for (int o = 0; o < 8; o++) acc[o] = (MODE == 0) ? Xc[(e0 + o) * LNB_AN_THREADS] : 0.0;
+        /* cursor over x starting at chunk-relative offset rr = e0 - p (same in every thread): element ew of
+         * chunk c + dq, with floor division for negative offsets */
+        int32_t rr = (int32_t)e0 - (int32_t)p;
+        int32_t dq = (rr >= 0) ? rr / (int32_t)T : -(((int32_t)T - 1 - rr) / (int32_t)T);
+        int32_t ew = rr - dq * (int32_t)T;
 #pragma unroll
         for (int k = 0; k < 7; k++) {
-            xw[k] = (li >= 0) ? X[ew * LNB_AN_THREADS + cw] : 0.0;
-            if (li >= 0) { if (++ew == T) { ew = 0; cw++; } }
-            li++;
+            xw[k] = (rr >= first_valid) ? Xc[ew * LNB_AN_THREADS + dq] : 0.0;
+            rr++; if (++ew == (int32_t)T) { ew = 0; dq++; }
         }
         for (uint32_t j0 = 0; j0 < p; j0 += 8u) {
             const uint32_t nj = (p - j0 < 8u) ? p - j0 : 8u;
@@ -201,8 +206,8 @@ __device__ double lnb_an_fir(const LnbAnCtx &cx, const double *X, double *Y, uin
             for (int k = 0; k < 8; k++) {
                 /* element t0 - p + j0 + 7 + k; never read past t0 + 7 */
                 const bool need = (uint32_t)k < nj;
-                xw[7 + k] = (need && li >= 0) ? X[ew * LNB_AN_THREADS + cw] : 0.0;
-                if (need) { if (li >= 0) { if (++ew == T) { ew = 0; cw++; } } li++; }
+                xw[7 + k] = (need && rr >= first_valid) ? Xc[ew * LNB_AN_THREADS + dq] : 0.0;
+                if (need) { rr++; if (++ew == (int32_t)T) { ew = 0; dq++; } }
             }
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {

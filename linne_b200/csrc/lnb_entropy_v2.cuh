@@ -118,25 +118,50 @@ __global__ void __launch_bounds__(LNB_EN_THREADS) lnb_entropy_v2_kernel(LnbDecod
             for (uint32_t s0 = 0; s0 < len; s0 += 32u) {
                 const uint32_t cnt = (len - s0 < 32u) ? len - s0 : 32u;
                 if (lane == 0) {
-                    /* measure: start bit of each of the next `cnt` code words */
-                    uint32_t position = (uint32_t)lnb_fr_position(fr);
-                    for (uint32_t i = 0; i < cnt; i++) {
-                        const uint32_t lz = lnb_clz32(fr.hi);
-                        if (lz + k2 > 31u) {                     /* code longer than 32 bits (or a zero run past the window) */
-                            const uint32_t q = lnb_fr_zero_run(fr);
-                            val[i] = (q == 0u) ? lnb_fr_get(fr, k1) : lnb_fr_get(fr, k2) + (1u << k1) + ((q - 1u) << k2);
-                            pos[i] = LNB_EN_DIRECT;
-                            position = (uint32_t)lnb_fr_position(fr);
-                            continue;
+                    /* measure: start bit of each of the next `cnt` code words.  Straight-line, predicated
+                     * body (taken branches cost a lone warp ~15 cycles each); a code longer than 32 bits only
+                     * raises a flag, and the run is redone from that symbol on the general path. */
+                    uint32_t i = 0;
+                    while (i < cnt) {
+                        uint32_t hi = fr.hi, lo = fr.lo, nbits = fr.nbits, nxt = fr.next, pre = fr.pre;
+                        uint32_t position = nxt * 32u - nbits;
+                        uint32_t first_long = cnt;
+                        const uint32_t kc = k2 + 1u;
+#pragma unroll 4
+                        for (uint32_t j = i; j < cnt; j++) {
+                            const uint32_t lz = lnb_clz32(hi);
+                            const uint32_t ml = (lz > 1u) ? lz : 1u;
+                            const uint32_t L = kc + ml;              /* k1 = k2 + 1: both code forms have this length */
+                            first_long = (lz + k2 > 31u && j < first_long) ? j : first_long;
+                            pos[j] = position;
+                            position += L;
+                            hi = lnb_shl64_hi(hi, lo, L);
+                            lo = lnb_shl32_clamped(lo, L);
+                            nbits -= L;
+                            const bool need = nbits < 32u;           /* refill from the prefetched word */
+                            hi |= need ? lnb_shr32_clamped(pre, nbits) : 0u;
+                            lo = need ? lnb_shl32_clamped(pre, 32u - nbits) : lo;
+                            nbits += need ? 32u : 0u;
+                            nxt += need ? 1u : 0u;
+                            if (need) pre = (nxt < end_word) ? lnb_bswap32(words[nxt]) : 0u;
                         }
-                        const uint32_t ml = (lz > 1u) ? lz : 1u;
-                        const uint32_t L = k2 + 1u + ml;          /* k1 = k2 + 1: both code forms have this length */
-                        pos[i] = position;
-                        position += L;
-                        fr.hi = lnb_shl64_hi(fr.hi, fr.lo, L);
-                        fr.lo = lnb_shl32_clamped(fr.lo, L);
-                        fr.nbits -= L;
-                        if (fr.nbits < 32u) lnb_fr_refill(fr);
+                        if (first_long >= cnt) {                     /* common case: the whole run was short codes */
+                            fr.hi = hi; fr.lo = lo; fr.nbits = nbits; fr.next = nxt; fr.pre = pre;
+                            if (nxt > end_word + 2u) fr.overrun = 1;
+                            break;
+                        }
+                        /* re-synchronise at the long code word, decode it on the general path, go on after it */
+                        lnb_fr_open(fr, words, pos[first_long], end_word);
+                        {
+                            const uint32_t q = lnb_fr_zero_run(fr);
+                            val[first_long] = (q == 0u) ? lnb_fr_get(fr, k1) : lnb_fr_get(fr, k2) + (1u << k1) + ((q - 1u) << k2);
+                            pos[first_long] = LNB_EN_DIRECT;
+                        }
+                        if (fr.overrun) {                            /* corrupt data: fill the rest of the run and stop measuring */
+                            for (uint32_t j = first_long + 1u; j < cnt; j++) { val[j] = 0; pos[j] = LNB_EN_DIRECT; }
+                            break;
+                        }
+                        i = first_long + 1u;
                     }
                 }
                 __syncwarp();
