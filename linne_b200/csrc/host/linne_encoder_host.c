@@ -20,7 +20,7 @@ struct LINNEEncoder {
     LnbDevice *dev;
     size_t scratch_budget;                 /* bytes of analysis scratch per chunk */
     LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_acorr, d_cand, d_unit_loss,
-           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total;
+           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train;
     LnbBuf h_blocks, h_welch, h_total;
     const int32_t *cur_pcm;                /* device PCM planes of the call in flight */
     uint32_t cur_pcm_stride;
@@ -91,7 +91,7 @@ void LINNEEncoder_Destroy(struct LINNEEncoder *enc)
         LnbBuf *dbufs[] = { &enc->d_pcm, &enc->d_blocks, &enc->d_params, &enc->d_est, &enc->d_work, &enc->d_sig_a,
                             &enc->d_sig_b, &enc->d_acorr, &enc->d_cand, &enc->d_unit_loss, &enc->d_chosen_w,
                             &enc->d_chosen_u, &enc->d_final_sum, &enc->d_welch, &enc->d_plans, &enc->d_plan_mean,
-                            &enc->d_out, &enc->d_total };
+                            &enc->d_out, &enc->d_total, &enc->d_train };
         size_t i;
         for (i = 0; i < sizeof(dbufs) / sizeof(dbufs[0]); i++) lnb_buf_release_device(enc->dev, dbufs[i]);
         lnb_buf_release_host(&enc->h_blocks);
@@ -175,7 +175,8 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
 
     /* chunk so the double-precision analysis scratch stays inside the budget */
     per_block = (size_t)slots_per_block * (batch.cfg.work_stride * sizeof(double) * 2u + 64u * 1024u)
-              + (size_t)C * (batch.cfg.work_stride * sizeof(int32_t) + 32u * 1024u);
+              + (size_t)C * (batch.cfg.work_stride * sizeof(int32_t) + 32u * 1024u)
+              + (enc->enable_learning ? (size_t)C * (2u * LNB_MAX_LAYERS + 1u) * batch.cfg.work_stride * sizeof(double) : 0u);
     chunk_blocks = (uint32_t)(enc->scratch_budget / per_block);
     if (chunk_blocks < 1u) chunk_blocks = 1u;
     if (chunk_blocks > total_blocks) chunk_blocks = total_blocks;
@@ -203,7 +204,9 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
             || lnb_buf_reserve_device(enc->dev, &enc->d_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
             || lnb_buf_reserve_device(enc->dev, &enc->d_plans, BC * sizeof(LnbCoderPlan))
             || lnb_buf_reserve_device(enc->dev, &enc->d_plan_mean, BC * 2u * LNB_MAX_PARTITIONS * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_total, 64))
+            || lnb_buf_reserve_device(enc->dev, &enc->d_total, 64)
+            || (enc->enable_learning && !forced
+                && lnb_buf_reserve_device(enc->dev, &enc->d_train, BC * (2u * LNB_MAX_LAYERS + 1u) * ws * sizeof(double))))
             return LINNE_APIRESULT_NG;
     }
     batch.blocks = (LnbBlockDesc *)enc->d_blocks.ptr;
@@ -222,6 +225,9 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     batch.plans = (LnbCoderPlan *)enc->d_plans.ptr;
     batch.plan_mean = (double *)enc->d_plan_mean.ptr;
     batch.total_size = (uint32_t *)enc->d_total.ptr;
+    batch.af_iterations = forced ? 0u : enc->num_afmethod_iterations;
+    batch.enable_learning = forced ? 0u : (enc->enable_learning ? 1u : 0u);
+    batch.train_scratch = (double *)enc->d_train.ptr;
     batch.out_base = 0;
 
     for (first = 0; first < total_blocks; first += chunk_blocks) {
@@ -274,8 +280,10 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
 
 static int unsupported_analysis(const struct LINNEEncoder *enc)
 {
-    if (enc->enable_learning || enc->num_afmethod_iterations) {
-        fprintf(stderr, "linne_b200: enable_learning / num_afmethod_iterations are not implemented on the device yet\n");
+    if ((enc->enable_learning || enc->num_afmethod_iterations)
+        && enc->header.num_samples_per_block > lnb_shim_refine_max_na()) {
+        fprintf(stderr, "linne_b200: enable_learning / num_afmethod_iterations need blocks of at most %u samples\n",
+                (unsigned)lnb_shim_refine_max_na());
         return 1;
     }
     return 0;

@@ -409,6 +409,7 @@ void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
                 double *t = cur; cur = nxt; nxt = t;
             }
         }
+        if (b.af_iterations || b.enable_learning) ex.refine_cooperative(b, CH);   /* IRLS / SGD final pass (rows a14, a15) */
         ex.run("finish", B * C, LnbItemFinish{b, CH});
     }
     if (b.num_coop_blocks) ex.predict_plan_cooperative(b);

@@ -17,6 +17,7 @@
 #include "lnb_synth_v2.cuh"
 #include "lnb_crc_v2.cuh"
 #include "lnb_entropy_v2.cuh"
+#include "lnb_refine_v2.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -131,6 +132,25 @@ struct CudaExec {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess && dev->last_error == cudaSuccess) dev->last_error = e;
     }
+    void refine_cooperative(const LnbEncodeBatch &b, uint32_t chunks_per_slot)
+    {
+        uint32_t na_max = b.cfg.block_size < LNB_RF_MAX_NA ? b.cfg.block_size : LNB_RF_MAX_NA;
+        uint32_t max_p = 0;
+        for (uint32_t l = 0; l < b.cfg.num_layers; l++) if (b.cfg.layer_params[l] > max_p) max_p = b.cfg.layer_params[l];
+        const uint32_t tri = max_p * (max_p + 1u) / 2u;          /* the signal buffers double as the packed Gram matrix */
+        if (b.af_iterations && na_max < tri) na_max = tri;
+        na_max = (na_max + 7u) & ~7u;
+        const size_t smem = (size_t)2 * (na_max + LNB_RF_HIST) * sizeof(double) + sizeof(LnbRefineSmem);
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(lnb_refine_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        const int slot = begin_stage("refine_v2");
+        lnb_refine_v2_kernel<<<b.num_blocks * b.cfg.num_channels, LNB_RF_THREADS, smem, dev->stream>>>(
+            b, na_max, b.af_iterations, b.enable_learning, b.train_scratch, chunks_per_slot);
+        end_stage(slot);
+    }
     void prepare_cooperative(const LnbEncodeBatch &b)
     {
         const int slot = begin_stage("prepare_v2");
@@ -206,6 +226,7 @@ extern "C" {
 const char *lnb_shim_backend(void) { return "cuda-sm_100a"; }
 uint32_t lnb_shim_fast_max_na(void) { return LNB_AN_MAX_NA; }
 uint32_t lnb_shim_coop_max_n(void) { return LNB_FR_MAX_N; }
+uint32_t lnb_shim_refine_max_na(void) { return LNB_RF_MAX_NA; }
 
 int lnb_shim_open(LnbDevice **out, int device_ordinal)
 {

@@ -110,6 +110,9 @@ typedef struct LnbEncodeBatch {
     uint32_t num_coop_blocks;       /* blocks flagged LNB_ENC_FLAG_COOP */
     uint32_t num_fast_blocks;       /* blocks flagged LNB_ENC_FLAG_FAST (0: skip the cooperative launch) */
     uint32_t num_slow_blocks;       /* compressed-candidate blocks left to the flat kernels */
+    uint32_t af_iterations;         /* IRLS iterations of the final pass (0 = off) */
+    uint32_t enable_learning;       /* 1: momentum-SGD refinement of the final coefficients */
+    double *train_scratch;          /* [B*C][2*layers+1][work_stride], only when enable_learning */
     uint32_t forced_params;         /* 1: `params` already hold units/shift/coefficients -- skip the analysis stages */
 } LnbEncodeBatch;
 

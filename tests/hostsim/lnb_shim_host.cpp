@@ -28,6 +28,7 @@ struct LoopExec {
     void analyze_cooperative(const LnbEncodeBatch &) {}       /* CUDA only; the host never flags blocks for it */
     void pack_cooperative(const LnbEncodeBatch &, uint32_t) {}
     void prepare_cooperative(const LnbEncodeBatch &) {}
+    void refine_cooperative(const LnbEncodeBatch &, uint32_t) {}
     void predict_plan_cooperative(const LnbEncodeBatch &) {}
 };
 
@@ -35,6 +36,7 @@ extern "C" {
 const char *lnb_shim_backend(void) { return "hostsim"; }
 uint32_t lnb_shim_fast_max_na(void) { return 0; }
 uint32_t lnb_shim_coop_max_n(void) { return 0; }
+uint32_t lnb_shim_refine_max_na(void) { return 0; }
 int lnb_shim_open(LnbDevice **out, int)
 {
     LnbDevice *dev = (LnbDevice *)calloc(1, sizeof(LnbDevice));

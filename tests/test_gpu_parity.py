@@ -154,3 +154,25 @@ def test_config_c5_block_range_shards(gpu):
             if got is not None:
                 out[:, first:first + got.shape[1]] = got
         assert np.array_equal(out, pcm)
+
+
+# ---- non-default analysis paths: CLI -a N and -l ----
+@pytest.mark.parametrize("preset,block", [(0, 4096), (2, 4096), (5, 1024)])
+def test_irls_refinement_path(gpu, oracle, preset, block):
+    pcm = harness.synth_pcm(n=block * 2 + block // 2, channels=2, bits=16, seed=91 + preset)
+    got = gpu.encode(pcm, preset=preset, block=block, af=2)
+    want = oracle.encode(pcm, preset=preset, block=block, af=2)
+    assert np.array_equal(oracle.decode(got), pcm)
+    assert abs(len(got) - len(want)) <= max(2, SIZE_TOLERANCE * len(want)), (len(got), len(want))
+    plain = gpu.encode(pcm, preset=preset, block=block)
+    assert got != plain                      # the refinement really ran
+
+
+def test_sgd_training_path(gpu, oracle):
+    pcm = harness.synth_pcm(n=2048 * 2, channels=2, bits=16, seed=97)
+    got = gpu.encode(pcm, preset=0, block=2048, learning=1)
+    want = oracle.encode(pcm, preset=0, block=2048, learning=1)
+    assert np.array_equal(oracle.decode(got), pcm)
+    # 2000 chaotic gradient steps amplify last-bit differences of the summation order: allow 0.5 % here
+    assert abs(len(got) - len(want)) <= 0.005 * len(want), (len(got), len(want))
+    assert got != gpu.encode(pcm, preset=0, block=2048)
