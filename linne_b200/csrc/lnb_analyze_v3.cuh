@@ -1,0 +1,450 @@
+/* lnb_analyze_v3.cuh -- cooperative analysis kernel: one CTA per slot (block, channel, regulariser).
+ *
+ * Runs the whole layer cascade of one slot with the signal resident in shared memory.  Covers
+ * reference rows a7-a13: libs/linne_network/src/linne_network.c:268-347
+ * (unit-count search), :350-376 (set parameter), :165-210 (forward), :50-63 (L1 loss),
+ * libs/lpc/src/lpc.c:196-205 (Welch window), :215-249 (autocorrelation), :252-324 (Levinson-Durbin),
+ * :327-366 (regularised solve).  Blocks whose analysis length is a multiple of 1024 and at most 10240
+ * samples (the CLI default block) take this kernel; other shapes (in practice a file's tail block)
+ * keep the flat kernels of lnb_pipeline.cuh.
+ *
+ * Design (what bounds it: the FP64 pipe, SURVEY 8d -- everything here exists to keep DFMA issuing)
+ *   - Layout.  A signal is stored in GROUPS of 8 samples padded to 9 doubles: sample i lives at
+ *     FRONT + i + (i >> 3).  A thread always works on whole groups and lanes of a warp on consecutive
+ *     groups, so lanes are 9 doubles apart: every LDS.64 is bank-conflict free, and because all tile
+ *     shapes are multiples of 8 every window element sits at a COMPILE-TIME offset from the group base
+ *     (no cursor arithmetic, no bounds predicates: the arrays carry zeroed pads in front and behind).
+ *   - Autocorrelation.  Work item = (unit, group of 16 lags[, sample split]) per warp.  A lane takes
+ *     8 samples x L lags (L = 16, or 17 for the group holding lag p): 8 + L+7 loads feed 8*L DFMA.
+ *     Lane partials are reduced once per work item (xor butterfly, fixed order => deterministic).
+ *     Window elements past the end of a unit are masked only in the warp iterations that reach it.
+ *   - Residual evaluation / forward filter.  A lane takes 8 consecutive outputs and slides an
+ *     8-tap x 15-sample register window over the unit's taps: 8 + 8 loads feed 64 DFMA.
+ *   - Levinson-Durbin.  Orders <= 16: one thread per unit in the reference's operation order.
+ *     Orders 32..128: one warp per unit, coefficients in registers, the update of step k fused with the
+ *     dot product of step k+1, reciprocal of the error off the critical path.
+ *   - Signal loops use fused multiply-add (results differ from the unfused CPU reference in the last
+ *     bits only; the 8-bit quantiser absorbs that -- tests/test_gpu_parity.py checks byte identity).
+ */
+#pragma once
+#include "lnb_common.cuh"
+#include "lnb_encode_core.cuh"
+
+#define LNB_A3_THREADS  256
+#define LNB_A3_WARPS    8
+#define LNB_A3_MAX_NA   10240
+#define LNB_A3_FRONT    160          /* zeroed doubles in front of sample 0 (>= 9 * 128 / 8 + window) */
+#define LNB_A3_BACK     176          /* zeroed doubles behind the last sample (>= 9 * (128 + 24) / 8) */
+#define LNB_A3_PART     24           /* doubles per work-item partial (>= 17 lags) */
+
+__host__ __device__ inline uint32_t lnb_a3_array_doubles(uint32_t na_max)
+{
+    return LNB_A3_FRONT + na_max / 8u * 9u + LNB_A3_BACK;
+}
+__host__ __device__ inline size_t lnb_a3_smem_doubles(uint32_t na_max)
+{
+    return (size_t)2 * lnb_a3_array_doubles(na_max)
+         + (size_t)LNB_MAX_LEVELS * LNB_MAX_PARAMS        /* candidate coefficients per level */
+         + (size_t)LNB_MAX_LEVELS * 256                   /* autocorrelations per level: U*(p+1) = P+U <= 256 */
+         + (size_t)LNB_A3_WARPS * LNB_A3_PART             /* work-item partials */
+         + 64;                                            /* level losses, block-sum scratch */
+}
+
+struct LnbA3Ctx {
+    double *A, *B;               /* point at sample 0 (front pad lies below) */
+    double *cand, *acorr, *part, *misc;
+    uint32_t na, ng;             /* samples, groups of 8 */
+};
+
+/* ---- Welch-windowed copy A -> B for unit length m (lpc.c:196-205), one group of 8 at a time ---- */
+__device__ __forceinline__ void lnb_a3_window(const LnbA3Ctx &cx, uint32_t m, double scale)
+{
+    const uint32_t mg = m >> 3;
+    for (uint32_t G = threadIdx.x; G < cx.ng; G += LNB_A3_THREADS) {
+        const uint32_t pos0 = (G % mg) * 8u;
+        const double *src = cx.A + G * 9u;
+        double *dst = cx.B + G * 9u;
+#pragma unroll
+        for (uint32_t e = 0; e < 8u; e++) {
+            const uint32_t pos = pos0 + e;
+            const uint32_t q = (pos < m - 1u - pos) ? pos : (m - 1u - pos);
+            const double w = __dmul_rn(__dmul_rn(scale, (double)q), (double)(m - 1u - q));
+            dst[e] = __dmul_rn(src[e], w);
+        }
+    }
+}
+
+/* ---- one 8-sample x L-lag tile: acc[k] += sum_o B[8g+o] * B[8g+o+k0+k] ----
+ * Bg = address of the group's first sample, qoff = padded offset of lag k0 (= 18 * k0/16),
+ * lim = number of window elements (from lag k0 of sample 0 on) that still lie inside the unit. */
+template <int L, bool MASK>
+__device__ __forceinline__ void lnb_a3_tile(const double *Bg, uint32_t qoff, int32_t lim, double (&acc)[L])
+{
+    double s[8], wv[L + 7];
+#pragma unroll
+    for (int o = 0; o < 8; o++) s[o] = Bg[o];
+#pragma unroll
+    for (int t = 0; t < L + 7; t++) {
+        const double v = (!MASK || t < lim) ? Bg[qoff + t + (t >> 3)] : 0.0;
+        wv[t] = v;
+    }
+#pragma unroll
+    for (int o = 0; o < 8; o++)
+#pragma unroll
+        for (int k = 0; k < L; k++) acc[k] = fma(s[o], wv[o + k], acc[k]);
+}
+
+/* one work item: lags [16q, 16q+L) of unit u over the groups [g_lo, g_hi) of that unit */
+template <int L>
+__device__ __forceinline__ void lnb_a3_autocorr_item(const LnbA3Ctx &cx, uint32_t u, uint32_t q, uint32_t m, bool last_unit,
+                                                     uint32_t g_lo, uint32_t g_hi, double *out /* L sums, lane 0 writes */)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t mg = m >> 3;
+    double acc[L];
+#pragma unroll
+    for (int k = 0; k < L; k++) acc[k] = 0.0;
+    const double *Bu = cx.B + (size_t)u * mg * 9u;
+    const uint32_t qoff = 18u * q;
+    for (uint32_t g0 = g_lo; g0 < g_hi; g0 += 32u) {                /* warp-uniform trip count */
+        const uint32_t g = g0 + lane;
+        const bool active = g < g_hi;
+        const uint32_t gg = active ? g : g_lo;
+        const int32_t lim = (int32_t)m - (int32_t)(8u * gg + 16u * q);
+        const bool need_mask = !last_unit && lim < L + 7;
+        if (__any_sync(0xffffffffu, need_mask)) {
+            double tmp[L];
+#pragma unroll
+            for (int k = 0; k < L; k++) tmp[k] = 0.0;
+            lnb_a3_tile<L, true>(Bu + gg * 9u, qoff, last_unit ? (int32_t)(L + 7) : lim, tmp);
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < L; k++) acc[k] += tmp[k];
+            }
+        } else if (active) {
+            lnb_a3_tile<L, false>(Bu + gg * 9u, qoff, 0, acc);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < L; k++) {
+        double v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) out[k] = v;
+    }
+}
+
+/* ---- autocorrelation of every unit of one level: r[u][0..p] into acorr_lvl[u*(p+1) + lag] ---- */
+__device__ void lnb_a3_autocorr(const LnbA3Ctx &cx, uint32_t U, uint32_t p, double *acorr_lvl)
+{
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t m = cx.na / U, mg = m >> 3;
+    const uint32_t nq = (p >= 16u) ? p / 16u : 1u;                   /* lag groups per unit */
+    const uint32_t tasks = U * nq;
+    const uint32_t S = (tasks >= LNB_A3_WARPS) ? 1u : LNB_A3_WARPS / tasks;   /* sample splits per task */
+    const uint32_t items = tasks * S;
+    const uint32_t per = (mg + S - 1u) / S;
+    for (uint32_t wi = warp; wi < items; wi += LNB_A3_WARPS) {
+        const uint32_t task = wi / S, split = wi % S;
+        const uint32_t u = task / nq, q = task % nq;
+        const uint32_t g_lo = split * per, g_hi = (g_lo + per < mg) ? g_lo + per : mg;
+        const bool last_unit = (u + 1u == U);
+        double *out = (S == 1u) ? acorr_lvl + u * (p + 1u) + 16u * q : cx.part + wi * LNB_A3_PART;
+        if (p >= 16u) {
+            if (q + 1u < nq) lnb_a3_autocorr_item<16>(cx, u, q, m, last_unit, g_lo, g_hi, out);
+            else             lnb_a3_autocorr_item<17>(cx, u, q, m, last_unit, g_lo, g_hi, out);
+        } else if (p == 8u)  lnb_a3_autocorr_item<9>(cx, u, q, m, last_unit, g_lo, g_hi, out);
+        else if (p == 4u)    lnb_a3_autocorr_item<5>(cx, u, q, m, last_unit, g_lo, g_hi, out);
+        else if (p == 2u)    lnb_a3_autocorr_item<3>(cx, u, q, m, last_unit, g_lo, g_hi, out);
+        else                 lnb_a3_autocorr_item<2>(cx, u, q, m, last_unit, g_lo, g_hi, out);
+    }
+    if (S > 1u) {                                                    /* sum the sample splits in a fixed order */
+        __syncthreads();
+        const uint32_t L_last = (p >= 16u) ? 17u : p + 1u;
+        for (uint32_t i = threadIdx.x; i < tasks * 17u; i += LNB_A3_THREADS) {
+            const uint32_t task = i / 17u, k = i % 17u;
+            const uint32_t u = task / nq, q = task % nq;
+            const uint32_t Lq = (q + 1u == nq) ? L_last : 16u;
+            if (k >= Lq) continue;
+            double v = 0.0;
+            for (uint32_t s = 0; s < S; s++) v += cx.part[(task * S + s) * LNB_A3_PART + k];
+            acorr_lvl[u * (p + 1u) + 16u * q + k] = v;
+        }
+    }
+}
+
+/* ---- Levinson-Durbin by one warp (orders 32..128); reversed coefficients into out_w[0..p) ----
+ * Lane l keeps a[l], a[l+32], ..., a[l+128] in registers; a shared-memory mirror serves the reversed
+ * reads a[k+1-i].  The loop body updates a (step k) and accumulates the dot product of step k+1 in one
+ * pass; 1/err is computed while the butterfly of the dot product is in flight. */
+__device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lambda, double *mirror /* p + 2 */, double *out_w)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const double r0 = __dmul_rn(r_in[0], __dadd_rn(1.0, lambda));
+    if (fabs(r0) < (double)FLT_EPSILON) {
+        for (uint32_t i = lane; i < p; i += 32u) out_w[i] = 0.0;
+        return;
+    }
+    double a[5];                                                     /* a[s] = coefficient lane + 32 s (0 .. p <= 128) */
+#pragma unroll
+    for (int s = 0; s < 5; s++) a[s] = 0.0;
+    const double a1 = -r_in[1] / r0;
+    if (lane == 0) a[0] = 1.0;
+    if (lane == 1) a[0] = a1;
+    double err = __dadd_rn(r0, __dmul_rn(r_in[1], a1));
+    for (uint32_t i = lane; i < p + 2u; i += 32u) mirror[i] = (i == 0u) ? 1.0 : (i == 1u) ? a1 : 0.0;
+    __syncwarp();
+    /* dot product for k = 1: sum_{i=0..1} a[i] r[2-i] */
+    double part = 0.0;
+    if (lane < 2u) part = a[0] * ((lane == 0u) ? r_in[2] : r_in[1]);
+    for (uint32_t k = 1; k < p; k++) {
+        const double rinv = 1.0 / -err;                              /* independent of the butterfly below */
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        const double gamma = part * rinv;
+        err = __dmul_rn(err, __dadd_rn(1.0, -__dmul_rn(gamma, gamma)));
+        /* a_new[i] = a[i] + gamma * a[k+1-i] (i = 1..k), a_new[k+1] = gamma; then the next dot product */
+        double np = 0.0;
+        const uint32_t kn = k + 2u;                                  /* next step pairs a_new[i] with r[k+2-i] */
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const uint32_t i = lane + 32u * (uint32_t)s;
+            if (i <= k + 1u && i <= p) {
+                double v = a[s];
+                if (i >= 1u && i <= k) v = fma(gamma, mirror[k + 1u - i], v);
+                else if (i == k + 1u) v = gamma;
+                a[s] = v;
+                if (k + 1u < p) {
+                    const uint32_t ri = kn - i;                      /* 1 .. k+2 */
+                    np = fma(v, r_in[ri], np);
+                }
+            }
+        }
+        __syncwarp();                                                /* all reversed reads done before the mirror changes */
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const uint32_t i = lane + 32u * (uint32_t)s;
+            if (i >= 1u && i <= k + 1u && i <= p) mirror[i] = a[s];
+        }
+        __syncwarp();
+        part = np;
+    }
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const uint32_t i = lane + 32u * (uint32_t)s;                 /* a[i], i = 1..p -> out_w[p - i] */
+        if (i >= 1u && i <= p) out_w[p - i] = a[s];
+    }
+    __syncwarp();
+}
+
+/* ---- FIR over whole groups: res[t] = init + sum_j w[j] * x[t-p+j]  (x[<0] = 0) ----
+ * MODE 0: search loss (init = x[t], sample 0 not counted)          linne_network.c:318-335
+ * MODE 1: forward (y = x[t] + sum, written to Y, all samples counted)   linne_network.c:183-208
+ * PS = 0: p is a multiple of 8; PS = 1, 2, 4: p = PS. */
+template <int MODE, int PS>
+__device__ __forceinline__ double lnb_a3_fir(const LnbA3Ctx &cx, const double *X, double *Y, uint32_t p, uint32_t m,
+                                             const double *cand_lvl)
+{
+    const uint32_t mg = m >> 3;
+    double loss = 0.0;
+    for (uint32_t G = threadIdx.x; G < cx.ng; G += LNB_A3_THREADS) {
+        const uint32_t u = G / mg;
+        const double *w = cand_lvl + u * p;
+        const double *Xg = X + G * 9u;
+        double acc[8];
+#pragma unroll
+        for (int o = 0; o < 8; o++) acc[o] = (MODE == 0) ? Xg[o] : 0.0;
+        if (PS == 0) {
+            const double *base = Xg - (p >> 3) * 9u;                 /* sample 8G - p */
+            double xw[15];
+#pragma unroll
+            for (int k = 0; k < 7; k++) xw[k] = base[k];
+            for (uint32_t j0 = 0; j0 < p; j0 += 8u) {
+#pragma unroll
+                for (int k = 7; k < 15; k++) xw[k] = base[k + (k >> 3)];   /* window samples 7..14 (the pad slot is skipped) */
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const double wj = w[j0 + jj];
+#pragma unroll
+                    for (int o = 0; o < 8; o++) acc[o] = fma(wj, xw[jj + o], acc[o]);
+                }
+#pragma unroll
+                for (int k = 0; k < 7; k++) xw[k] = xw[k + 8];
+                base += 9;
+            }
+        } else {
+            double xw[PS + 7];
+#pragma unroll
+            for (int t = 0; t < PS + 7; t++) xw[t] = (t < PS) ? Xg[t - 1 - PS] : Xg[t - PS];
+#pragma unroll
+            for (int jj = 0; jj < PS; jj++) {
+                const double wj = w[jj];
+#pragma unroll
+                for (int o = 0; o < 8; o++) acc[o] = fma(wj, xw[jj + o], acc[o]);
+            }
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int o = 0; o < 8; o++) if (!(G == 0u && o == 0)) loss += fabs(acc[o]);
+        } else {
+            double *Yg = Y + G * 9u;
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                const double y = Xg[o] + acc[o];
+                Yg[o] = y;
+                loss += fabs(y);
+            }
+        }
+    }
+    return loss;
+}
+
+template <int MODE>
+__device__ double lnb_a3_fir_any(const LnbA3Ctx &cx, const double *X, double *Y, uint32_t p, uint32_t m, const double *cand_lvl)
+{
+    if (p >= 8u) return lnb_a3_fir<MODE, 0>(cx, X, Y, p, m, cand_lvl);
+    if (p == 4u) return lnb_a3_fir<MODE, 4>(cx, X, Y, p, m, cand_lvl);
+    if (p == 2u) return lnb_a3_fir<MODE, 2>(cx, X, Y, p, m, cand_lvl);
+    return lnb_a3_fir<MODE, 1>(cx, X, Y, p, m, cand_lvl);
+}
+
+/* block-wide sum in a fixed order; result valid in every thread */
+__device__ double lnb_a3_block_sum(double v, double *scratch /* >= 9 doubles */)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31u) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < LNB_A3_WARPS; w++) s += scratch[w];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEncodeBatch b, uint32_t na_max)
+{
+    extern __shared__ __align__(16) double lnb_a3_smem[];
+    const uint32_t s = blockIdx.x, c = threadIdx.x;
+    const uint32_t bc = s / b.cfg.num_lambdas, lam = s % b.cfg.num_lambdas;
+    const uint32_t blk_i = bc / b.cfg.num_channels;
+    const LnbBlockDesc blk = b.blocks[blk_i];
+    if (blk.type != LNB_BLOCK_COMPRESSED || !(blk.status & LNB_ENC_FLAG_FAST)) return;
+
+    const uint32_t arr = lnb_a3_array_doubles(na_max);
+    LnbA3Ctx cx;
+    cx.na = blk.na; cx.ng = blk.na >> 3;
+    cx.A = lnb_a3_smem + LNB_A3_FRONT;
+    cx.B = lnb_a3_smem + arr + LNB_A3_FRONT;
+    cx.cand = lnb_a3_smem + 2u * arr;
+    cx.acorr = cx.cand + LNB_MAX_LEVELS * LNB_MAX_PARAMS;
+    cx.part = cx.acorr + LNB_MAX_LEVELS * 256;
+    cx.misc = cx.part + LNB_A3_WARPS * LNB_A3_PART;
+    const uint32_t na = cx.na;
+    const double lambda = b.cfg.lambdas[lam];
+
+    /* zero pads of both arrays (everything outside the samples), then the layer-0 input:
+     * normalised work signal (linne_encoder.c:661-663) */
+    {
+        const uint32_t data = cx.ng * 9u;
+        for (uint32_t i = c; i < LNB_A3_FRONT; i += LNB_A3_THREADS) { lnb_a3_smem[i] = 0.0; lnb_a3_smem[arr + i] = 0.0; }
+        for (uint32_t i = LNB_A3_FRONT + data + c; i < arr; i += LNB_A3_THREADS) { lnb_a3_smem[i] = 0.0; lnb_a3_smem[arr + i] = 0.0; }
+        const int32_t *src = b.work + (size_t)bc * b.cfg.work_stride;
+        const double norm = ldexp(1.0, -(int)(b.cfg.bits_per_sample - 1u));
+        for (uint32_t G = c; G < cx.ng; G += LNB_A3_THREADS) {
+            const int4 v0 = *(const int4 *)(src + 8u * G), v1 = *(const int4 *)(src + 8u * G + 4u);
+            double *dst = cx.A + G * 9u;
+            dst[0] = (double)v0.x * norm; dst[1] = (double)v0.y * norm; dst[2] = (double)v0.z * norm; dst[3] = (double)v0.w * norm;
+            dst[4] = (double)v1.x * norm; dst[5] = (double)v1.y * norm; dst[6] = (double)v1.z * norm; dst[7] = (double)v1.w * norm;
+            dst[8] = 0.0;
+            cx.B[G * 9u + 8u] = 0.0;
+        }
+    }
+    __syncthreads();
+
+    double final_loss = 0.0;
+    for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
+        const uint32_t P = b.cfg.layer_params[l];
+        uint32_t nlev = 0;
+        while (nlev < LNB_MAX_LEVELS && (1u << nlev) <= P) nlev++;        /* U = 1 .. min(128, P) */
+
+        /* ---- autocorrelation of every unit of every level ---- */
+        for (uint32_t lv = 0; lv < nlev; lv++) {
+            const uint32_t U = 1u << lv, p = P / U, m = na / U;
+            lnb_a3_window(cx, m, b.welch[(size_t)blk_i * LNB_MAX_LEVELS + lv]);
+            __syncthreads();
+            lnb_a3_autocorr(cx, U, p, cx.acorr + lv * 256);
+            __syncthreads();
+        }
+
+        /* ---- Levinson-Durbin: thread-serial for p <= 16, warp-cooperative above (B is free: scratch) ---- */
+        {
+            uint32_t task = c;
+            for (uint32_t lv = 0; lv < nlev; lv++) {
+                const uint32_t U = 1u << lv, p = P / U;
+                if (p > 16u) continue;
+                if (task < U) {
+                    double r[17], a[18], coef[16];
+                    const double *src = cx.acorr + lv * 256 + task * (p + 1u);
+                    for (uint32_t k = 0; k <= p; k++) r[k] = src[k];
+                    r[0] = __dmul_rn(r[0], __dadd_rn(1.0, lambda));
+                    lnb_levinson(r, p, a, coef, (double *)0);
+                    double *dst = cx.cand + lv * LNB_MAX_PARAMS + task * p;
+                    for (uint32_t j = 0; j < p; j++) dst[j] = coef[p - 1u - j];
+                    task = 0xFFFFFFFFu;
+                } else if (task != 0xFFFFFFFFu) {
+                    task -= U;
+                }
+            }
+            const uint32_t warp = c >> 5;
+            uint32_t wt = warp;
+            for (uint32_t lv = 0; lv < nlev; lv++) {
+                const uint32_t U = 1u << lv, p = P / U;
+                if (p <= 16u) continue;
+                if (wt < U) {
+                    lnb_a3_levinson_warp(cx.acorr + lv * 256 + wt * (p + 1u), p, lambda,
+                                         cx.B + warp * (LNB_MAX_PARAMS + 8), cx.cand + lv * LNB_MAX_PARAMS + wt * p);
+                    wt = 0xFFFFFFFFu;
+                } else if (wt != 0xFFFFFFFFu) {
+                    wt -= U;
+                }
+            }
+        }
+        __syncthreads();
+
+        /* ---- L1 loss of every level, first minimum wins (linne_network.c:337-341) ---- */
+        for (uint32_t lv = 0; lv < nlev; lv++) {
+            const uint32_t U = 1u << lv, p = P / U;
+            const double part = lnb_a3_fir_any<0>(cx, cx.A, (double *)0, p, na / U, cx.cand + lv * LNB_MAX_PARAMS);
+            const double tot = lnb_a3_block_sum(part, cx.misc + 16);
+            if (c == 0) cx.misc[lv] = tot / (double)na;
+        }
+        __syncthreads();
+        uint32_t best = 0;
+        {
+            double best_loss = (double)FLT_MAX;
+            for (uint32_t lv = 0; lv < nlev; lv++)
+                if (cx.misc[lv] < best_loss) { best_loss = cx.misc[lv]; best = lv; }
+        }
+        if (c == 0) b.chosen_log2u[(size_t)s * LNB_MAX_LAYERS + l] = (uint8_t)best;
+        {
+            double *dst = b.chosen_w + ((size_t)s * LNB_MAX_LAYERS + l) * LNB_MAX_PARAMS;
+            const double *src = cx.cand + best * LNB_MAX_PARAMS;
+            for (uint32_t k = c; k < P; k += LNB_A3_THREADS) dst[k] = src[k];
+        }
+
+        /* ---- forward: this layer's residual becomes the next layer's input ---- */
+        {
+            const uint32_t U = 1u << best, p = P / U;
+            const double part = lnb_a3_fir_any<1>(cx, cx.A, cx.B, p, na / U, cx.cand + best * LNB_MAX_PARAMS);
+            final_loss = lnb_a3_block_sum(part, cx.misc + 16);
+        }
+        __syncthreads();
+        double *t = cx.A; cx.A = cx.B; cx.B = t;
+    }
+    /* total |residual| of the cascade: what picks the regulariser (linne_network.c:618-626) */
+    {   /* the finish stage sums ceil(na/64) chunk slots of this analysis slot: total in slot 0, zeros after */
+        const uint32_t chunks_per_slot = (b.cfg.work_stride + 63u) / 64u, nch = (na + 63u) / 64u;
+        for (uint32_t i = c; i < nch; i += LNB_A3_THREADS) b.final_sum[(size_t)s * chunks_per_slot + i] = (i == 0) ? final_loss : 0.0;
+    }
+}

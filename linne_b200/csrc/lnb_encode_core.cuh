@@ -23,7 +23,7 @@
  * on the same inputs); LNB_EXACT_FP=0 uses one DFMA per term (half the FP64 pipe work; results
  * differ from the CPU reference in the last bits only, which the 8-bit quantiser absorbs). */
 #ifndef LNB_EXACT_FP
-#define LNB_EXACT_FP 1
+#define LNB_EXACT_FP 0
 #endif
 LNB_HD double lnb_mac(double a, double b, double acc)
 {

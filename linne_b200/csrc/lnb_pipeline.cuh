@@ -95,7 +95,7 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
     if (B == 0) return;
     if (Exec::cooperative) {
         ex.crc_cooperative(b);                            /* one CTA per block, chunk CRCs combined in GF(2) */
-        ex.entropy_cooperative(b);                        /* one warp per block: lane 0 measures code words, 32 lanes extract */
+        ex.entropy_cooperative(b);                        /* one warp per block: 32 speculative code-word starts per round */
         ex.synth_cooperative(b);                          /* one warp per (block, channel): systolic synthesis + de-emphasis */
         if (b.cfg.block_size > ex.synth_max_n()) {        /* longer block-channels: flat kernels (they skip the short ones) */
             for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)

@@ -11,12 +11,12 @@
 
 #include "lnb_shim.h"
 #include "lnb_pipeline.cuh"
-#include "lnb_analyze_v2.cuh"
+#include "lnb_analyze_v3.cuh"
 #include "lnb_pack_v2.cuh"
 #include "lnb_front_v2.cuh"
 #include "lnb_synth_v2.cuh"
 #include "lnb_crc_v2.cuh"
-#include "lnb_entropy_v2.cuh"
+#include "lnb_entropy_v3.cuh"
 #include "lnb_refine_v2.cuh"
 
 #define LNB_MAX_STAGES 32
@@ -39,6 +39,14 @@ struct LnbDevice {
     int pending_stage[LNB_MAX_PENDING];
     int events_created;
 };
+
+/* The CUDA "current device" is per host thread: a handle created on one thread (and device) may be
+ * driven from another, so every entry point re-binds the calling thread to the handle's device. */
+static inline void bind_device(const LnbDevice *dev)
+{
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != dev->ordinal) cudaSetDevice(dev->ordinal);
+}
 
 static int stage_index(LnbDevice *dev, const char *name)
 {
@@ -90,8 +98,8 @@ struct CudaExec {
     }
     void entropy_cooperative(const LnbDecodeBatch &b)
     {
-        const int slot = begin_stage("entropy_v2");
-        lnb_entropy_v2_kernel<<<(b.num_blocks + LNB_EN_WARPS - 1) / LNB_EN_WARPS, LNB_EN_THREADS, 0, dev->stream>>>(b);
+        const int slot = begin_stage("entropy_v3");
+        lnb_entropy_v3_kernel<<<(b.num_blocks + LNB_E3_WARPS - 1) / LNB_E3_WARPS, LNB_E3_THREADS, 0, dev->stream>>>(b);
         end_stage(slot);
     }
     void crc_cooperative(const LnbDecodeBatch &b)
@@ -190,15 +198,16 @@ struct CudaExec {
     void analyze_cooperative(const LnbEncodeBatch &b)
     {
         const uint32_t S = b.num_blocks * b.cfg.num_channels * b.cfg.num_lambdas;
-        const uint32_t na_max = b.cfg.block_size < LNB_AN_MAX_NA ? b.cfg.block_size : LNB_AN_MAX_NA;
-        const size_t smem = lnb_an_smem_doubles(na_max) * sizeof(double);
+        uint32_t na_max = b.cfg.block_size < LNB_A3_MAX_NA ? b.cfg.block_size : LNB_A3_MAX_NA;
+        na_max = (na_max + 7u) & ~7u;
+        const size_t smem = lnb_a3_smem_doubles(na_max) * sizeof(double);
         static size_t configured = 0;
         if (smem > configured) {
-            cudaFuncSetAttribute(lnb_analyze_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(lnb_analyze_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
-        const int slot = begin_stage("analyze_v2");
-        lnb_analyze_v2_kernel<<<S, LNB_AN_THREADS, smem, dev->stream>>>(b, na_max);
+        const int slot = begin_stage("analyze_v3");
+        lnb_analyze_v3_kernel<<<S, LNB_A3_THREADS, smem, dev->stream>>>(b, na_max);
         end_stage(slot);
     }
     template <class F> void run(const char *name, uint32_t n, const F &f)
@@ -224,7 +233,7 @@ struct CudaExec {
 extern "C" {
 
 const char *lnb_shim_backend(void) { return "cuda-sm_100a"; }
-uint32_t lnb_shim_fast_max_na(void) { return LNB_AN_MAX_NA; }
+uint32_t lnb_shim_fast_max_na(void) { return LNB_A3_MAX_NA; }
 uint32_t lnb_shim_coop_max_n(void) { return LNB_FR_MAX_N; }
 uint32_t lnb_shim_refine_max_na(void) { return LNB_RF_MAX_NA; }
 
@@ -262,6 +271,7 @@ int lnb_shim_open(LnbDevice **out, int device_ordinal)
 
 void lnb_shim_close(LnbDevice *dev)
 {
+    bind_device(dev);
     if (!dev) return;
     cudaStreamSynchronize(dev->stream);
     if (dev->events_created)
@@ -275,6 +285,7 @@ const LnbDevTables *lnb_shim_tables(const LnbDevice *dev) { return &dev->tables;
 
 void lnb_shim_use_stream(LnbDevice *dev, void *cuda_stream)
 {
+    bind_device(dev);
     if (dev->owns_stream) { cudaStreamSynchronize(dev->stream); cudaStreamDestroy(dev->stream); dev->owns_stream = 0; }
     dev->stream = (cudaStream_t)cuda_stream;
 }
@@ -282,12 +293,12 @@ void lnb_shim_use_stream(LnbDevice *dev, void *cuda_stream)
 void *lnb_shim_alloc(LnbDevice *dev, size_t bytes)
 {
     void *p = NULL;
-    (void)dev;
+    bind_device(dev);
     if (bytes == 0) bytes = 16;
     if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return NULL; }
     return p;
 }
-void lnb_shim_free(LnbDevice *dev, void *ptr) { (void)dev; if (ptr) cudaFree(ptr); }
+void lnb_shim_free(LnbDevice *dev, void *ptr) { bind_device(dev); if (ptr) cudaFree(ptr); }
 void *lnb_shim_alloc_pinned(size_t bytes)
 {
     void *p = NULL;
@@ -303,18 +314,22 @@ static int note(LnbDevice *dev, cudaError_t e)
 }
 int lnb_shim_h2d(LnbDevice *dev, void *dst, const void *src, size_t bytes)
 {
+    bind_device(dev);
     return bytes ? note(dev, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, dev->stream)) : 0;
 }
 int lnb_shim_d2h(LnbDevice *dev, void *dst, const void *src, size_t bytes)
 {
+    bind_device(dev);
     return bytes ? note(dev, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream)) : 0;
 }
 int lnb_shim_memset(LnbDevice *dev, void *dst, int value, size_t bytes)
 {
+    bind_device(dev);
     return bytes ? note(dev, cudaMemsetAsync(dst, value, bytes, dev->stream)) : 0;
 }
 int lnb_shim_sync(LnbDevice *dev)
 {
+    bind_device(dev);
     cudaError_t e = cudaStreamSynchronize(dev->stream);
     if (e == cudaSuccess && dev->profiling) drain_profile(dev);
     if (e == cudaSuccess) e = dev->last_error;
@@ -329,18 +344,21 @@ int lnb_shim_sync(LnbDevice *dev)
 
 int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *batch)
 {
+    bind_device(dev);
     CudaExec ex{dev};
     lnb_decode_pipeline(ex, *batch);
     return dev->last_error == cudaSuccess ? 0 : 1;
 }
 int lnb_shim_encode_analyze(LnbDevice *dev, const LnbEncodeBatch *batch)
 {
+    bind_device(dev);
     CudaExec ex{dev};
     lnb_encode_analyze_pipeline(ex, *batch);
     return dev->last_error == cudaSuccess ? 0 : 1;
 }
 int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *batch, uint32_t out_capacity)
 {
+    bind_device(dev);
     CudaExec ex{dev};
     lnb_encode_pack_pipeline(ex, *batch, out_capacity);
     return dev->last_error == cudaSuccess ? 0 : 1;
@@ -350,6 +368,7 @@ uint64_t lnb_shim_launch_count(const LnbDevice *dev) { return dev->launches; }
 
 void lnb_shim_profile_enable(LnbDevice *dev, int on)
 {
+    bind_device(dev);
     if (on && !dev->events_created) {
         for (int i = 0; i < LNB_MAX_PENDING; i++) { cudaEventCreate(&dev->ev_begin[i]); cudaEventCreate(&dev->ev_end[i]); }
         dev->events_created = 1;
@@ -360,12 +379,14 @@ void lnb_shim_profile_enable(LnbDevice *dev, int on)
 }
 void lnb_shim_profile_reset(LnbDevice *dev)
 {
+    bind_device(dev);
     cudaStreamSynchronize(dev->stream);
     drain_profile(dev);
     for (int i = 0; i < dev->num_stages; i++) { dev->stages[i].launches = 0; dev->stages[i].total_ms = 0.0; }
 }
 int lnb_shim_profile_get(LnbDevice *dev, LnbStageStat *out, int max_stages)
 {
+    bind_device(dev);
     cudaStreamSynchronize(dev->stream);
     drain_profile(dev);
     int n = dev->num_stages < max_stages ? dev->num_stages : max_stages;
@@ -388,6 +409,7 @@ __global__ void __launch_bounds__(256) lnb_fp64_peak_kernel(double *sink, double
 
 double lnb_shim_measure_fp64_tflops(LnbDevice *dev)
 {
+    bind_device(dev);
     double *sink = NULL;
     cudaEvent_t e0, e1;
     const int grid = 148 * 16, threads = 256, reps = 5;
