@@ -294,33 +294,61 @@ def run_b200(args, rank, world, local_rank):
     h2d = sum(4 * n_samples + comp_bytes[m] for m in PRESETS)     # PCM up for encode, stream up for decode
     d2h = sum(comp_bytes[m] + 4 * n_samples for m in PRESETS)     # stream down from encode, PCM down from decode
 
-    # ---- roofline of the dominant kernel, from the CUDA events recorded inside the timed region ----
-    dom = max(stage.items(), key=lambda kv: kv[1][1]) if stage else ("none", [1, 1.0])
-    dom_name, (dom_cnt, dom_ms) = dom[0], dom[1]
+    # ---- roofline of the dominant kernel ----
+    # Per-kernel durations come from CUDA events recorded on each launching stream.  In the timed region the
+    # eight presets overlap, so a kernel's event time there includes the other streams' kernels it shared the
+    # GPU with; the roofline therefore uses a SERIAL pass of the same step (same inputs, profiling on, kernels
+    # alone on the GPU) run right after the timed region.  Both sets of stage times are reported.
+    args_serial = args.serial
+    args.serial = True
+    for sess in list(encs.values()) + list(decs.values()):
+        sess.set_profiling(True); sess.reset_stage_stats()
+    serial_steps = max(1, min(args.steps, 3))
+    torch.cuda.synchronize()
+    for _ in range(serial_steps):
+        l2_flush.fill_(1); torch.cuda.current_stream().synchronize()
+        step_resident()
+    stage_serial = {}
+    for sess in list(encs.values()) + list(decs.values()):
+        for name, (cnt, ms) in sess.stage_stats().items():
+            a = stage_serial.setdefault(name, [0, 0.0]); a[0] += cnt; a[1] += ms
+        sess.set_profiling(False)
+    args.serial = args_serial
+
     fp64_peak = product.measure_fp64_tflops() if rank == 0 else 0.0
     total_comp = sum(comp_bytes.values())
     hbm_bytes_per_sample = 4.0 + total_comp / (len(PRESETS) * n_samples)      # int32 PCM + compressed bytes
-    analysis_kernels = {"search", "forward", "select", "to_double", "finish"}
-    steps_profiled = args.steps
+    analysis_kernels = {"analyze_v3", "to_double", "acorr", "solve", "loss", "select", "forward", "refine_v2"}
+    dec_kernels = {"crc_v2", "entropy_v3", "synth_v2", "crc", "entropy", "synth", "deemph", "ms_inverse"}
+    dom = max(stage_serial.items(), key=lambda kv: kv[1][1]) if stage_serial else ("none", [1, 1.0])
+    dom_name, (dom_cnt, dom_ms) = dom[0], dom[1]
+    samples_done = len(PRESETS) * n_samples * serial_steps
     if dom_name in analysis_kernels:
-        flops = 2.0 * sum(MAC_PER_SAMPLE[m] for m in PRESETS) * n_samples * steps_profiled
-        an_ms = sum(v[1] for k, v in stage.items() if k in analysis_kernels)
-        achieved = flops / (an_ms / 1e3) / 1e12
+        flops = 2.0 * sum(MAC_PER_SAMPLE[m] for m in PRESETS) * n_samples * serial_steps
+        achieved = flops / (dom_ms / 1e3) / 1e12
         roofline = {"bound": "fp64", "kernel": dom_name, "achieved": round(achieved, 4), "peak": round(fp64_peak, 3),
                     "unit": "TFLOP/s", "frac": round(achieved / fp64_peak, 5) if fp64_peak else None, "traffic": None,
+                    "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
                     "note": "encoder analysis is FP64-pipe bound (SURVEY 8d): algorithmic FLOPs = 2 x MAC/sample table "
-                            "(un-deduplicated) over the analysis kernels' summed event time; peak = DFMA microbenchmark "
-                            "on this GPU"}
+                            "(un-deduplicated) over this kernel's summed launch time; peak = DFMA microbenchmark on this GPU"}
     else:
-        by = hbm_bytes_per_sample * len(PRESETS) * n_samples * steps_profiled
+        by = hbm_bytes_per_sample * samples_done
         achieved = by / (dom_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 3), "peak": hbm_peak,
-                    "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src}
-    # decode-side HBM roofline (sum of the decode kernels), always reported
-    dec_kernels = {"crc", "entropy", "synth", "deemph", "ms_inverse"}
-    dec_ms = sum(v[1] for k, v in stage.items() if k in dec_kernels)
-    by = hbm_bytes_per_sample * len(PRESETS) * n_samples * steps_profiled
-    roofline_decode = {"bound": "hbm", "kernels": sorted(dec_kernels), "achieved": round(by / (dec_ms / 1e3) / 1e9, 3) if dec_ms else None,
+                    "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                    "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
+                    "bytes_per_sample": round(hbm_bytes_per_sample, 3),
+                    "note": "latency-bound at this batch size (44 blocks per launch): one warp per block / block-channel"}
+    # the other side of the path, always reported: encoder analysis against the FP64 pipe, decode against HBM
+    an_ms = sum(v[1] for k, v in stage_serial.items() if k in analysis_kernels)
+    flops = 2.0 * sum(MAC_PER_SAMPLE[m] for m in PRESETS) * n_samples * serial_steps
+    roofline_analysis = {"bound": "fp64", "kernels": sorted(k for k in stage_serial if k in analysis_kernels),
+                         "achieved": round(flops / (an_ms / 1e3) / 1e12, 4) if an_ms else None, "peak": round(fp64_peak, 3),
+                         "unit": "TFLOP/s", "frac": round(flops / (an_ms / 1e3) / 1e12 / fp64_peak, 5) if an_ms and fp64_peak else None}
+    dec_ms = sum(v[1] for k, v in stage_serial.items() if k in dec_kernels)
+    by = hbm_bytes_per_sample * samples_done
+    roofline_decode = {"bound": "hbm", "kernels": sorted(k for k in stage_serial if k in dec_kernels),
+                       "achieved": round(by / (dec_ms / 1e3) / 1e9, 3) if dec_ms else None,
                        "peak": hbm_peak, "unit": "GB/s", "frac": round(by / (dec_ms / 1e3) / 1e9 / hbm_peak, 5) if dec_ms else None,
                        "peak_source": peak_src, "bytes_per_sample": round(hbm_bytes_per_sample, 3)}
 
@@ -357,10 +385,11 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": round(e2e_value, 3), "unit": "MSamples/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
-        "roofline": roofline, "roofline_decode": roofline_decode,
+        "roofline": roofline, "roofline_analysis": roofline_analysis, "roofline_decode": roofline_decode,
         "cpu_baseline": cpu_baseline,
         "clocks": sampler.summary(),
-        "stages_ms_per_step": {k: round(v[1] / steps_profiled, 3) for k, v in sorted(stage.items(), key=lambda kv: -kv[1][1])},
+        "stages_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in sorted(stage.items(), key=lambda kv: -kv[1][1])},
+        "stages_ms_per_step_serial": {k: round(v[1] / serial_steps, 3) for k, v in sorted(stage_serial.items(), key=lambda kv: -kv[1][1])},
         "compressed_bytes": {str(m): int(comp_bytes[m]) for m in PRESETS},
         "lossless": {"resident": ok_resident, "e2e": ok_e2e},
         "fp64_peak_tflops": round(fp64_peak, 3),

@@ -241,7 +241,10 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
             const uint32_t n = (num_samples - start < NB) ? num_samples - start : NB;
             memset(&hb[i], 0, sizeof(hb[i]));
             hb[i].smp_off = start; hb[i].nsmp = n; hb[i].na = analysis_length(&batch.cfg, n);
-            if (hb[i].na <= fast_max_na && (hb[i].na % 1024u) == 0u) { hb[i].status |= LNB_ENC_FLAG_FAST; num_fast++; }
+            if (hb[i].na <= fast_max_na) {                      /* cooperative analysis: fast layout or generic path */
+                hb[i].status |= ((hb[i].na % 1024u) == 0u) ? LNB_ENC_FLAG_FAST : LNB_ENC_FLAG_GENERIC;
+                num_fast++;
+            }
             if (n <= coop_max_n && NB <= coop_max_n) { hb[i].status |= LNB_ENC_FLAG_COOP; num_coop++; }
             for (lvl = 0; lvl < LNB_MAX_LEVELS; lvl++) {
                 const uint32_t m = hb[i].na >> lvl;

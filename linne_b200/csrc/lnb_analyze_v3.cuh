@@ -322,6 +322,97 @@ __device__ double lnb_a3_block_sum(double v, double *scratch /* >= 9 doubles */)
     return s;
 }
 
+/* ---- any other shape up to LNB_A3_MAX_NA samples (a file's tail block): same cascade, plain layout ----
+ * One thread per autocorrelation cell / sample, work-item bodies shared with the flat kernels
+ * (lnb_encode_core.cuh), so the tail costs one CTA of the same launch instead of a chain of small ones. */
+__device__ void lnb_a3_generic(const LnbEncodeBatch &b, uint32_t s, uint32_t bc, uint32_t blk_i, uint32_t na,
+                               double lambda, uint32_t na_max, double *smem)
+{
+    const uint32_t c = threadIdx.x, warp = c >> 5;
+    const uint32_t arr = lnb_a3_array_doubles(na_max);
+    double *A = smem, *B = smem + arr;
+    double *cand = smem + 2u * arr, *acorr = cand + LNB_MAX_LEVELS * LNB_MAX_PARAMS;
+    double *misc = acorr + LNB_MAX_LEVELS * 256 + LNB_A3_WARPS * LNB_A3_PART;
+    {
+        const int32_t *src = b.work + (size_t)bc * b.cfg.work_stride;
+        const double norm = ldexp(1.0, -(int)(b.cfg.bits_per_sample - 1u));
+        for (uint32_t i = c; i < na; i += LNB_A3_THREADS) A[i] = (double)src[i] * norm;
+    }
+    __syncthreads();
+    double final_loss = 0.0;
+    for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
+        const uint32_t P = b.cfg.layer_params[l];
+        for (uint32_t lv = 0; lv < LNB_MAX_LEVELS; lv++) {           /* lpc.c:196-249, window applied on the fly */
+            if (!lnb_level_valid(lv, P, na)) continue;
+            const uint32_t U = 1u << lv, p = P / U, m = na / U;
+            const double scale = b.welch[(size_t)blk_i * LNB_MAX_LEVELS + lv];
+            for (uint32_t cell = c; cell < U * (p + 1u); cell += LNB_A3_THREADS)
+                acorr[lv * 256u + cell] = lnb_acorr_lag(A + (size_t)(cell / (p + 1u)) * m, m, cell % (p + 1u), scale);
+        }
+        __syncthreads();
+        {   /* regularised solve: threads take the short orders, warps the long ones (B is free: mirror scratch) */
+            uint32_t task = c, wt = warp;
+            for (uint32_t lv = 0; lv < LNB_MAX_LEVELS; lv++) {
+                if (!lnb_level_valid(lv, P, na)) continue;
+                const uint32_t U = 1u << lv, p = P / U, m = na / U;
+                if (p <= 16u) {
+                    if (task < U) {
+                        double r[17], a[18], coef[16];
+                        const double *src = acorr + lv * 256u + task * (p + 1u);
+                        for (uint32_t k = 0; k <= p; k++) r[k] = src[k];
+                        r[0] = __dmul_rn(r[0], __dadd_rn(1.0, lambda));
+                        if (m < p) { for (uint32_t k = 0; k < p; k++) coef[k] = 0.0; }
+                        else lnb_levinson(r, p, a, coef, (double *)0);
+                        double *dst = cand + lv * LNB_MAX_PARAMS + task * p;
+                        for (uint32_t j = 0; j < p; j++) dst[j] = coef[p - 1u - j];
+                        task = 0xFFFFFFFFu;
+                    } else if (task != 0xFFFFFFFFu) task -= U;
+                } else {
+                    if (wt < U) {
+                        double *dst = cand + lv * LNB_MAX_PARAMS + wt * p;
+                        if (m < p) { for (uint32_t j = c & 31u; j < p; j += 32u) dst[j] = 0.0; }
+                        else lnb_a3_levinson_warp(acorr + lv * 256u + wt * (p + 1u), p, lambda, B + warp * (LNB_MAX_PARAMS + 8), dst);
+                        wt = 0xFFFFFFFFu;
+                    } else if (wt != 0xFFFFFFFFu) wt -= U;
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t best = 0;
+        {   /* L1 loss of every valid level, first minimum wins (linne_network.c:318-341) */
+            double best_loss = (double)FLT_MAX;
+            for (uint32_t lv = 0; lv < LNB_MAX_LEVELS; lv++) {
+                if (!lnb_level_valid(lv, P, na)) continue;
+                const uint32_t U = 1u << lv, p = P / U, m = na / U;
+                double part = 0.0;
+                for (uint32_t t = c; t < na; t += LNB_A3_THREADS)
+                    if (t) part += fabs(lnb_residual_at(A, t, m, p, cand + lv * LNB_MAX_PARAMS, A[t]));
+                const double loss = lnb_a3_block_sum(part, misc + 16) / (double)na;
+                if (loss < best_loss) { best_loss = loss; best = lv; }
+            }
+        }
+        if (c == 0) b.chosen_log2u[(size_t)s * LNB_MAX_LAYERS + l] = (uint8_t)best;
+        {
+            double *dst = b.chosen_w + ((size_t)s * LNB_MAX_LAYERS + l) * LNB_MAX_PARAMS;
+            for (uint32_t k = c; k < P; k += LNB_A3_THREADS) dst[k] = cand[best * LNB_MAX_PARAMS + k];
+        }
+        {   /* forward (linne_network.c:165-210) */
+            const uint32_t U = 1u << best, p = P / U, m = na / U;
+            double part = 0.0;
+            for (uint32_t t = c; t < na; t += LNB_A3_THREADS) {
+                const double v = (t == 0u) ? A[0] : A[t] + lnb_residual_at(A, t, m, p, cand + best * LNB_MAX_PARAMS, 0.0);
+                B[t] = v;
+                part += fabs(v);
+            }
+            final_loss = lnb_a3_block_sum(part, misc + 16);
+        }
+        __syncthreads();
+        double *t = A; A = B; B = t;
+    }
+    const uint32_t chunks_per_slot = (b.cfg.work_stride + 63u) / 64u, nch = (na + 63u) / 64u;
+    for (uint32_t i = c; i < nch; i += LNB_A3_THREADS) b.final_sum[(size_t)s * chunks_per_slot + i] = (i == 0) ? final_loss : 0.0;
+}
+
 __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEncodeBatch b, uint32_t na_max)
 {
     extern __shared__ __align__(16) double lnb_a3_smem[];
@@ -329,7 +420,11 @@ __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEn
     const uint32_t bc = s / b.cfg.num_lambdas, lam = s % b.cfg.num_lambdas;
     const uint32_t blk_i = bc / b.cfg.num_channels;
     const LnbBlockDesc blk = b.blocks[blk_i];
-    if (blk.type != LNB_BLOCK_COMPRESSED || !(blk.status & LNB_ENC_FLAG_FAST)) return;
+    if (blk.type != LNB_BLOCK_COMPRESSED || !(blk.status & (LNB_ENC_FLAG_FAST | LNB_ENC_FLAG_GENERIC))) return;
+    if (!(blk.status & LNB_ENC_FLAG_FAST)) {
+        lnb_a3_generic(b, s, bc, blk_i, blk.na, b.cfg.lambdas[lam], na_max, lnb_a3_smem);
+        return;
+    }
 
     const uint32_t arr = lnb_a3_array_doubles(na_max);
     LnbA3Ctx cx;

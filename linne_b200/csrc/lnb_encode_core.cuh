@@ -34,6 +34,14 @@ LNB_HD double lnb_mac(double a, double b, double acc)
 #endif
 }
 
+/* a unit count 2^level takes part in the search of a layer with P parameters over na samples
+ * (reference linne_network.c:291-296) */
+LNB_HD bool lnb_level_valid(uint32_t level, uint32_t P, uint32_t na)
+{
+    const uint32_t U = 1u << level;
+    return U <= P && U <= LNB_MAX_UNITS && (P % U) == 0u && (na % U) == 0u && na >= U;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Levinson-Durbin on r[0..p] -> a[1..p] (returned in coef[0..p-1]); parcor optional.
  * reference libs/lpc/src/lpc.c:252-324 (same operation order, unfused arithmetic).

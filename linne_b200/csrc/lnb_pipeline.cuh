@@ -116,11 +116,6 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
  * Encode
  * ============================================================================================= */
 
-LNB_HD bool lnb_level_valid(uint32_t level, uint32_t P, uint32_t na)
-{
-    const uint32_t U = 1u << level;
-    return U <= P && U <= LNB_MAX_UNITS && (P % U) == 0u && (na % U) == 0u && na >= U;
-}
 
 struct LnbItemEstimate {            /* E0: (block, channel) */
     LnbEncodeBatch b;
@@ -152,7 +147,7 @@ struct LnbItemToDouble {            /* (slot, sample): normalised copy of the wo
         const uint32_t s = i / b.cfg.work_stride, t = i % b.cfg.work_stride;
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & (LNB_ENC_FLAG_FAST | LNB_ENC_FLAG_GENERIC))) return;
         const double norm = ldexp(1.0, -(int)(b.cfg.bits_per_sample - 1u));
         b.sig_a[(size_t)s * b.cfg.work_stride + t] =
             (t < blk.na) ? (double)b.work[(size_t)bc * b.cfg.work_stride + t] * norm : 0.0;
@@ -173,7 +168,7 @@ struct LnbItemAcorr {               /* E2a: (slot, level, unit, lag) -- 256 (uni
         const uint32_t level = cell / 256u, r = cell % 256u;
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & (LNB_ENC_FLAG_FAST | LNB_ENC_FLAG_GENERIC))) return;
         const uint32_t P = b.cfg.layer_params[layer];
         if (!lnb_level_valid(level, P, blk.na)) return;
         const uint32_t U = 1u << level, p = P / U, m = blk.na / U;
@@ -195,7 +190,7 @@ struct LnbItemSolve {               /* E2b: (slot, level, unit) */
         const uint32_t bc = s / b.cfg.num_lambdas, lam = s % b.cfg.num_lambdas;
         const uint32_t blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & (LNB_ENC_FLAG_FAST | LNB_ENC_FLAG_GENERIC))) return;
         const uint32_t P = b.cfg.layer_params[layer];
         if (!lnb_level_valid(level, P, blk.na)) return;
         const uint32_t U = 1u << level, p = P / U, m = blk.na / U;
@@ -216,7 +211,7 @@ struct LnbItemLoss {                /* E2c: (slot, level, chunk) */
         const uint32_t s = i / per_slot, level = (i % per_slot) / chunks_per_slot, g = i % chunks_per_slot;
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & (LNB_ENC_FLAG_FAST | LNB_ENC_FLAG_GENERIC))) return;
         const uint32_t P = b.cfg.layer_params[layer];
         if (!lnb_level_valid(level, P, blk.na)) return;
         const uint32_t t0 = g * LNB_CHUNK;
@@ -237,7 +232,7 @@ struct LnbItemSelect {              /* E3: (slot): first minimum over the unit c
     {
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & (LNB_ENC_FLAG_FAST | LNB_ENC_FLAG_GENERIC))) return;
         const uint32_t P = b.cfg.layer_params[layer];
         const uint32_t nch = lnb_num_chunks(blk.na);
         double best_loss = (double)FLT_MAX;
@@ -268,7 +263,7 @@ struct LnbItemForward {             /* E4: (slot, chunk) */
         const uint32_t s = i / chunks_per_slot, g = i % chunks_per_slot;
         const uint32_t bc = s / b.cfg.num_lambdas, blk_i = bc / b.cfg.num_channels;
         const LnbBlockDesc &blk = b.blocks[blk_i];
-        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & LNB_ENC_FLAG_FAST)) return;
+        if (blk.type != LNB_BLOCK_COMPRESSED || (blk.status & (LNB_ENC_FLAG_FAST | LNB_ENC_FLAG_GENERIC))) return;
         double *fs = b.final_sum + (size_t)s * chunks_per_slot + g;
         const uint32_t t0 = g * LNB_CHUNK;
         if (t0 >= blk.na) { *fs = 0.0; return; }
@@ -419,7 +414,8 @@ void lnb_encode_analyze_pipeline(Exec &ex, const LnbEncodeBatch &b)
         ex.run("plan", B * C, LnbItemPlan{b});
     }
     ex.run("size", B, LnbItemSize{b});
-    ex.run("scan", 1, LnbItemScan{b});
+    if (Exec::cooperative) ex.scan_cooperative(b);           /* one CTA: run sums -> scan -> offsets */
+    else ex.run("scan", 1, LnbItemScan{b});
 }
 
 template <class Exec>

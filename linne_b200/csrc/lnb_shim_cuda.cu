@@ -18,6 +18,7 @@
 #include "lnb_crc_v2.cuh"
 #include "lnb_entropy_v3.cuh"
 #include "lnb_refine_v2.cuh"
+#include "lnb_scan_v2.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -139,6 +140,12 @@ struct CudaExec {
         dev->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess && dev->last_error == cudaSuccess) dev->last_error = e;
+    }
+    void scan_cooperative(const LnbEncodeBatch &b)
+    {
+        const int slot = begin_stage("scan_v2");
+        lnb_scan_v2_kernel<<<1, LNB_SC_THREADS, 0, dev->stream>>>(b);
+        end_stage(slot);
     }
     void refine_cooperative(const LnbEncodeBatch &b, uint32_t chunks_per_slot)
     {

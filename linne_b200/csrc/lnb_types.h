@@ -42,6 +42,9 @@ typedef struct LnbBlockDesc {
 #define LNB_ENC_FLAG_PACKED 2u
 /* encoder-side: block short enough for the cooperative prepare / predict+plan kernels */
 #define LNB_ENC_FLAG_COOP 4u
+/* encoder-side: analysis length fits the cooperative analysis kernel but not its fast layout (any
+ * length up to its maximum, e.g. a tail block): the same launch runs it on the generic path */
+#define LNB_ENC_FLAG_GENERIC 8u
 
 enum { LNB_ST_OK = 0, LNB_ST_CRC_MISMATCH = 1, LNB_ST_OVERRUN = 2, LNB_ST_BAD_TYPE = 4 };
 

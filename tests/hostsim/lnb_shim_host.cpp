@@ -26,6 +26,7 @@ struct LoopExec {
         dev->launches++;
     }
     void analyze_cooperative(const LnbEncodeBatch &) {}       /* CUDA only; the host never flags blocks for it */
+    void scan_cooperative(const LnbEncodeBatch &) {}
     void pack_cooperative(const LnbEncodeBatch &, uint32_t) {}
     void prepare_cooperative(const LnbEncodeBatch &) {}
     void refine_cooperative(const LnbEncodeBatch &, uint32_t) {}
