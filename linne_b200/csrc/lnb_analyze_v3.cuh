@@ -39,6 +39,7 @@
 
 __host__ __device__ inline uint32_t lnb_a3_array_doubles(uint32_t na_max)
 {
+    if (na_max < 2048u) na_max = 2048u;            /* the sample area doubles as Levinson scratch: 8 warps x 2 mirrors */
     return LNB_A3_FRONT + na_max / 8u * 9u + LNB_A3_BACK;
 }
 __host__ __device__ inline size_t lnb_a3_smem_doubles(uint32_t na_max)
@@ -173,11 +174,27 @@ __device__ void lnb_a3_autocorr(const LnbA3Ctx &cx, uint32_t U, uint32_t p, doub
     }
 }
 
+/* reciprocal from a single-precision seed and three Newton steps: straight-line code (no slow-path call),
+ * within an ulp or two of 1/x -- used only where the operation order already differs from the reference */
+__device__ __forceinline__ double lnb_a3_rcp(double x)
+{
+    float seed;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"(__double2float_rn(x)));
+    double y = (double)seed;
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
+#define LNB_A3_MIRROR (LNB_MAX_PARAMS + 8)        /* doubles per mirror buffer; a warp task uses two */
+
 /* ---- Levinson-Durbin by one warp (orders 32..128); reversed coefficients into out_w[0..p) ----
- * Lane l keeps a[l], a[l+32], ..., a[l+128] in registers; a shared-memory mirror serves the reversed
- * reads a[k+1-i].  The loop body updates a (step k) and accumulates the dot product of step k+1 in one
- * pass; 1/err is computed while the butterfly of the dot product is in flight. */
-__device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lambda, double *mirror /* p + 2 */, double *out_w)
+ * Lane l keeps a[l], a[l+32], ..., a[l+128] in registers; a double-buffered shared-memory mirror serves
+ * the reversed reads a[k+1-i] (one warp barrier per step).  The body updates a (step k) and accumulates
+ * the dot product of step k+1 in one pass; the reciprocal of the next error is computed while the update
+ * is in flight.  Control flow is warp-uniform (slot count), per-lane cases are selects. */
+__device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lambda, double *mirror /* 2 * LNB_A3_MIRROR */, double *out_w)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const double r0 = __dmul_rn(r_in[0], __dadd_rn(1.0, lambda));
@@ -192,42 +209,42 @@ __device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lamb
     if (lane == 0) a[0] = 1.0;
     if (lane == 1) a[0] = a1;
     double err = __dadd_rn(r0, __dmul_rn(r_in[1], a1));
-    for (uint32_t i = lane; i < p + 2u; i += 32u) mirror[i] = (i == 0u) ? 1.0 : (i == 1u) ? a1 : 0.0;
+    double *cur = mirror, *nxt = mirror + LNB_A3_MIRROR;
+    for (uint32_t i = lane; i < LNB_A3_MIRROR; i += 32u) { cur[i] = (i == 0u) ? 1.0 : (i == 1u) ? a1 : 0.0; nxt[i] = 0.0; }
     __syncwarp();
     /* dot product for k = 1: sum_{i=0..1} a[i] r[2-i] */
     double part = 0.0;
     if (lane < 2u) part = a[0] * ((lane == 0u) ? r_in[2] : r_in[1]);
+    double rinv = lnb_a3_rcp(-err);
     for (uint32_t k = 1; k < p; k++) {
-        const double rinv = 1.0 / -err;                              /* independent of the butterfly below */
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
         const double gamma = part * rinv;
         err = __dmul_rn(err, __dadd_rn(1.0, -__dmul_rn(gamma, gamma)));
+        const double rinv_next = lnb_a3_rcp(-err);
         /* a_new[i] = a[i] + gamma * a[k+1-i] (i = 1..k), a_new[k+1] = gamma; then the next dot product */
+        const uint32_t ns = ((k + 1u) >> 5) + 1u;                    /* slots holding an index <= k+1 */
         double np = 0.0;
-        const uint32_t kn = k + 2u;                                  /* next step pairs a_new[i] with r[k+2-i] */
 #pragma unroll
         for (int s = 0; s < 5; s++) {
-            const uint32_t i = lane + 32u * (uint32_t)s;
-            if (i <= k + 1u && i <= p) {
+            if ((uint32_t)s < ns) {
+                const uint32_t i = lane + 32u * (uint32_t)s;
+                const bool inside = i <= k + 1u;
+                const double rev = cur[inside ? k + 1u - i : 0u];
                 double v = a[s];
-                if (i >= 1u && i <= k) v = fma(gamma, mirror[k + 1u - i], v);
-                else if (i == k + 1u) v = gamma;
+                if (i >= 1u && i <= k) v = fma(gamma, rev, v);
+                if (i == k + 1u) v = gamma;
                 a[s] = v;
-                if (k + 1u < p) {
-                    const uint32_t ri = kn - i;                      /* 1 .. k+2 */
-                    np = fma(v, r_in[ri], np);
-                }
+                if (i < LNB_A3_MIRROR) nxt[i] = v;
+                const uint32_t ri = k + 2u - i;                      /* next step pairs a_new[i] with r[k+2-i] */
+                const double rr = (inside && ri <= p) ? r_in[ri] : 0.0;
+                np = fma(v, rr, np);
             }
         }
-        __syncwarp();                                                /* all reversed reads done before the mirror changes */
-#pragma unroll
-        for (int s = 0; s < 5; s++) {
-            const uint32_t i = lane + 32u * (uint32_t)s;
-            if (i >= 1u && i <= k + 1u && i <= p) mirror[i] = a[s];
-        }
         __syncwarp();
+        double *t = cur; cur = nxt; nxt = t;
         part = np;
+        rinv = rinv_next;
     }
 #pragma unroll
     for (int s = 0; s < 5; s++) {
@@ -371,7 +388,7 @@ __device__ void lnb_a3_generic(const LnbEncodeBatch &b, uint32_t s, uint32_t bc,
                     if (wt < U) {
                         double *dst = cand + lv * LNB_MAX_PARAMS + wt * p;
                         if (m < p) { for (uint32_t j = c & 31u; j < p; j += 32u) dst[j] = 0.0; }
-                        else lnb_a3_levinson_warp(acorr + lv * 256u + wt * (p + 1u), p, lambda, B + warp * (LNB_MAX_PARAMS + 8), dst);
+                        else lnb_a3_levinson_warp(acorr + lv * 256u + wt * (p + 1u), p, lambda, B + warp * 2 * LNB_A3_MIRROR, dst);
                         wt = 0xFFFFFFFFu;
                     } else if (wt != 0xFFFFFFFFu) wt -= U;
                 }
@@ -498,7 +515,7 @@ __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEn
                 if (p <= 16u) continue;
                 if (wt < U) {
                     lnb_a3_levinson_warp(cx.acorr + lv * 256 + wt * (p + 1u), p, lambda,
-                                         cx.B + warp * (LNB_MAX_PARAMS + 8), cx.cand + lv * LNB_MAX_PARAMS + wt * p);
+                                         cx.B + warp * 2 * LNB_A3_MIRROR, cx.cand + lv * LNB_MAX_PARAMS + wt * p);
                     wt = 0xFFFFFFFFu;
                 } else if (wt != 0xFFFFFFFFu) {
                     wt -= U;
