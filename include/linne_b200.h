@@ -7,6 +7,7 @@
 #ifndef LINNE_B200_H_INCLUDED
 #define LINNE_B200_H_INCLUDED
 
+#include <stddef.h>
 #include "linne.h"
 #include "linne_encoder.h"
 #include "linne_decoder.h"
@@ -55,6 +56,21 @@ LINNEApiResult LINNEB200_EncodeWholeWithParams(struct LINNEEncoder *encoder,
         const int32_t *const *input, uint32_t num_samples,
         const struct LINNEB200ChannelParams *params, uint32_t num_param_blocks,
         uint8_t *data, uint32_t data_size, uint32_t *output_size);
+
+/* ---- device memory and peer mappings: multi-GPU sharding with one process per GPU ---------------
+ * A stream is sharded by contiguous block ranges (blocks are independent).  Every rank encodes its
+ * range into a local device buffer; after an exclusive scan of the shard byte counts each rank writes
+ * its shard straight into the destination buffer of rank 0 through a CUDA IPC peer mapping -- a
+ * device-to-device copy over NVLink, no collective.  All calls act on the calling thread's current
+ * CUDA device; copies are synchronous; int results are 0 on success. */
+void *LINNEB200_DeviceAlloc(size_t bytes);
+void  LINNEB200_DeviceFree(void *d_ptr);
+int   LINNEB200_IpcExport(const void *d_ptr, uint8_t handle[64]);      /* d_ptr from LINNEB200_DeviceAlloc */
+void *LINNEB200_IpcOpen(const uint8_t handle[64]);                     /* peer mapping in this process, NULL on failure */
+void  LINNEB200_IpcClose(void *d_peer_ptr);
+int   LINNEB200_DeviceCopy(void *d_dst, const void *d_src, size_t bytes);   /* either side may be a peer mapping */
+int   LINNEB200_CopyToDevice(void *d_dst, const void *h_src, size_t bytes);
+int   LINNEB200_CopyToHost(void *h_dst, const void *d_src, size_t bytes);
 
 /* ---- per-stage device timing (CUDA events around every kernel of a handle) ---------------------- */
 struct LINNEB200StageStat { char name[24]; uint64_t launches; double total_ms; };

@@ -216,6 +216,18 @@ def bind_ext_api(lib):
         f.argtypes = [C.c_void_p, C.POINTER(StageStat), C.c_int]
         f.restype = C.c_int
     lib.LINNEB200_MeasureFp64Tflops.restype = C.c_double
+    lib.LINNEB200_DeviceAlloc.argtypes = [C.c_size_t]
+    lib.LINNEB200_DeviceAlloc.restype = C.c_void_p
+    lib.LINNEB200_DeviceFree.argtypes = [C.c_void_p]
+    lib.LINNEB200_IpcExport.argtypes = [C.c_void_p, u8p]
+    lib.LINNEB200_IpcExport.restype = C.c_int
+    lib.LINNEB200_IpcOpen.argtypes = [u8p]
+    lib.LINNEB200_IpcOpen.restype = C.c_void_p
+    lib.LINNEB200_IpcClose.argtypes = [C.c_void_p]
+    for name in ("DeviceCopy", "CopyToDevice", "CopyToHost"):
+        f = getattr(lib, f"LINNEB200_{name}")
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        f.restype = C.c_int
     return lib
 
 
@@ -339,6 +351,73 @@ class DecoderSession(_Session):
                                                     size, C.c_void_p(d_pcm_ptr), stride, channels, n)
         if rc != OK:
             raise RuntimeError(f"DecodeWholeResident rc={rc}")
+
+
+class DeviceBuffer:
+    """Raw device memory of the current CUDA device (LINNEB200_DeviceAlloc): exportable to peer processes."""
+
+    def __init__(self, nbytes, lib=None):
+        self.lib = lib or load_library()
+        self.nbytes = int(nbytes)
+        self.ptr = self.lib.LINNEB200_DeviceAlloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(f"LINNEB200_DeviceAlloc({nbytes}) failed")
+
+    def ipc_handle(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        if self.lib.LINNEB200_IpcExport(C.c_void_p(self.ptr), h) != 0:
+            raise RuntimeError("LINNEB200_IpcExport failed")
+        return bytes(h)
+
+    def upload(self, data: bytes, offset=0):
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        if self.lib.LINNEB200_CopyToDevice(C.c_void_p(self.ptr + offset), buf, len(data)) != 0:
+            raise RuntimeError("LINNEB200_CopyToDevice failed")
+
+    def download(self, nbytes=None, offset=0) -> bytes:
+        n = self.nbytes - offset if nbytes is None else int(nbytes)
+        buf = (C.c_uint8 * n)()
+        if self.lib.LINNEB200_CopyToHost(buf, C.c_void_p(self.ptr + offset), n) != 0:
+            raise RuntimeError("LINNEB200_CopyToHost failed")
+        return bytes(buf)
+
+    def free(self):
+        if self.ptr:
+            self.lib.LINNEB200_DeviceFree(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PeerMapping:
+    """A peer process's DeviceBuffer mapped into this process (CUDA IPC; copies run over NVLink)."""
+
+    def __init__(self, handle: bytes, lib=None):
+        self.lib = lib or load_library()
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self.ptr = self.lib.LINNEB200_IpcOpen(h)
+        if not self.ptr:
+            raise RuntimeError("LINNEB200_IpcOpen failed (no peer access between these devices?)")
+
+    def put(self, offset, d_src_ptr, nbytes):
+        """device -> peer device copy of `nbytes` from local device address `d_src_ptr`."""
+        if self.lib.LINNEB200_DeviceCopy(C.c_void_p(self.ptr + offset), C.c_void_p(d_src_ptr), nbytes) != 0:
+            raise RuntimeError("LINNEB200_DeviceCopy to the peer failed")
+
+    def close(self):
+        if self.ptr:
+            self.lib.LINNEB200_IpcClose(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Product(LinneApi):

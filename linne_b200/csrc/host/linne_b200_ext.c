@@ -43,3 +43,13 @@ double LINNEB200_MeasureFp64Tflops(void)
     lnb_shim_close(dev);
     return t;
 }
+
+/* ---- device memory and peer mappings (multi-GPU sharding) ---- */
+void *LINNEB200_DeviceAlloc(size_t bytes) { return lnb_shim_device_alloc(bytes); }
+void LINNEB200_DeviceFree(void *d_ptr) { lnb_shim_device_free(d_ptr); }
+int LINNEB200_IpcExport(const void *d_ptr, uint8_t handle[64]) { return (d_ptr && handle) ? lnb_shim_ipc_export(d_ptr, handle) : 1; }
+void *LINNEB200_IpcOpen(const uint8_t handle[64]) { return handle ? lnb_shim_ipc_open(handle) : NULL; }
+void LINNEB200_IpcClose(void *d_peer_ptr) { lnb_shim_ipc_close(d_peer_ptr); }
+int LINNEB200_DeviceCopy(void *d_dst, const void *d_src, size_t bytes) { return lnb_shim_copy(d_dst, d_src, bytes, 0); }
+int LINNEB200_CopyToDevice(void *d_dst, const void *h_src, size_t bytes) { return lnb_shim_copy(d_dst, h_src, bytes, 1); }
+int LINNEB200_CopyToHost(void *h_dst, const void *d_src, size_t bytes) { return lnb_shim_copy(h_dst, d_src, bytes, 2); }

@@ -60,6 +60,16 @@ int  lnb_shim_profile_get(LnbDevice *dev, LnbStageStat *out, int max_stages);
  * register-resident microbenchmark: the roofline denominator of the analysis kernels. */
 double lnb_shim_measure_fp64_tflops(LnbDevice *dev);
 
+/* ---- raw device memory and cross-process peer mappings (multi-GPU sharding, one process per GPU) ----
+ * All act on the calling thread's current CUDA device.  `kind`: 0 device->device (either side may be a
+ * peer mapping: the copy then runs over NVLink), 1 host->device, 2 device->host.  Copies are synchronous. */
+void *lnb_shim_device_alloc(size_t bytes);
+void  lnb_shim_device_free(void *ptr);
+int   lnb_shim_ipc_export(const void *ptr, unsigned char handle[64]);     /* 0 on success */
+void *lnb_shim_ipc_open(const unsigned char handle[64]);                  /* NULL on failure */
+void  lnb_shim_ipc_close(void *peer_ptr);
+int   lnb_shim_copy(void *dst, const void *src, size_t bytes, int kind);  /* 0 on success */
+
 #ifdef __cplusplus
 }
 #endif

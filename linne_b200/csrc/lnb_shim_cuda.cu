@@ -438,4 +438,42 @@ double lnb_shim_measure_fp64_tflops(LnbDevice *dev)
     return flops / (best * 1e-3) / 1e12;
 }
 
+void *lnb_shim_device_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return NULL; }
+    return p;
+}
+void lnb_shim_device_free(void *ptr) { if (ptr) cudaFree(ptr); }
+int lnb_shim_ipc_export(const void *ptr, unsigned char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, (void *)ptr) != cudaSuccess) { cudaGetLastError(); return 1; }
+    memcpy(handle, &h, 64);
+    return 0;
+}
+void *lnb_shim_ipc_open(const unsigned char handle[64])
+{
+    cudaIpcMemHandle_t h;
+    void *p = NULL;
+    memcpy(&h, handle, 64);
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        fprintf(stderr, "linne_b200: cudaIpcOpenMemHandle: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return NULL;
+    }
+    return p;
+}
+void lnb_shim_ipc_close(void *peer_ptr) { if (peer_ptr) cudaIpcCloseMemHandle(peer_ptr); }
+int lnb_shim_copy(void *dst, const void *src, size_t bytes, int kind)
+{
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (bytes == 0) return 0;
+    if (cudaMemcpy(dst, src, bytes, k) != cudaSuccess) {
+        fprintf(stderr, "linne_b200: cudaMemcpy: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    return 0;
+}
+
 }  /* extern "C" */

@@ -10,9 +10,16 @@ CONTIGUOUS BLOCK RANGES with no data-path collective:
   decode: rank 0 hops over the block size fields, ranks take contiguous block ranges of the stream;
           outputs are disjoint sample ranges, so nothing is exchanged.
 
-`torch.distributed` carries the (tiny) size scan and the shard gather: NCCL on GPUs, gloo in the
-CPU-only tests.  The codec object is anything with `encode(pcm, ...) -> bytes` / `decode(bytes)`
-(the CUDA `Product`; the tests also drive the host simulator through the same code).
+Two gathers are provided:
+  encode_distributed      sizes and shard bytes through `torch.distributed` (gloo in the CPU-only tests,
+                          NCCL on GPUs): the portable baseline.
+  encode_distributed_p2p  the B200 path: shards stay in HBM; `torch.distributed` carries only the 8-byte
+                          shard sizes and the 64-byte CUDA IPC handle of rank 0's destination buffer (control
+                          plane); every rank then writes its shard into that buffer at its scanned offset
+                          with ONE device-to-device copy over NVLink (LINNEB200_DeviceCopy on a peer
+                          mapping).  No data-path collective.
+The codec object is anything with `encode(pcm, ...) -> bytes` / `decode(bytes)` (the CUDA `Product`; the
+tests also drive the host simulator through the same code).
 """
 from __future__ import annotations
 
@@ -111,3 +118,62 @@ def decode_shard(codec, stream: bytes, rank: int, world: int):
     count = sum(t[2] for t in table[b0:b1])
     sub = patch_num_samples(stream[:HEADER], count) + stream[table[b0][0]:table[b1 - 1][0] + table[b1 - 1][1]]
     return first, codec.decode(sub)
+
+
+def encode_distributed_p2p(pcm: np.ndarray, block: int, bits=16, rate=44100, preset=0, device=None, to_host=True):
+    """Collective: every rank encodes its contiguous block range ON ITS GPU and puts the shard into rank 0's
+    device buffer over NVLink.  Rank 0 returns (DeviceBuffer holding the whole stream, its size[, bytes]);
+    other ranks return None.  Needs the NCCL (or gloo) process group for the control messages only."""
+    import torch
+    import torch.distributed as dist
+    from .api import EncoderSession, DeviceBuffer, PeerMapping
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    nch, n = pcm.shape
+    lo, hi = block_ranges(n, block, world)[rank]
+    count = hi - lo
+    shard_size, d_shard = 0, None
+    if count > 0:
+        stride = (count + 4 + 3) // 4 * 4
+        d_pcm = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+        d_pcm[:, :count].copy_(torch.from_numpy(np.ascontiguousarray(pcm[:, lo:hi])))
+        cap = HEADER + 2 * nch * count * 4 + 65536
+        d_shard = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
+        enc = EncoderSession(nch, bits=bits, rate=rate, block=block, preset=preset)
+        try:
+            torch.cuda.synchronize(dev)
+            shard_size = enc.encode_whole_resident(d_pcm.data_ptr(), stride, count, d_shard.data_ptr(), cap) - HEADER
+        finally:
+            enc.close()
+    # control plane: shard sizes (exclusive scan on every rank) and the IPC handle of the destination
+    ctl_dev = dev if dist.get_backend() == "nccl" else torch.device("cpu")
+    sizes_t = [torch.zeros(1, dtype=torch.int64, device=ctl_dev) for _ in range(world)]
+    dist.all_gather(sizes_t, torch.tensor([shard_size], dtype=torch.int64, device=ctl_dev))
+    sizes = [int(t.item()) for t in sizes_t]
+    offsets, total = exclusive_scan(sizes)
+    handle_t = torch.zeros(64, dtype=torch.uint8, device=ctl_dev)
+    dest = None
+    if rank == 0:
+        dest = DeviceBuffer(HEADER + total + 64)
+        handle_t.copy_(torch.frombuffer(bytearray(dest.ipc_handle()), dtype=torch.uint8))
+    dist.broadcast(handle_t, src=0)
+    # data plane: one device-to-device copy per rank, straight into rank 0's HBM
+    if rank == 0:
+        if shard_size:
+            dest.lib.LINNEB200_DeviceCopy(dest.ptr + HEADER + offsets[0], d_shard.data_ptr() + HEADER, shard_size)
+            hdr = bytearray(d_shard[:HEADER].cpu().numpy().tobytes())
+        else:
+            hdr = bytearray(HEADER)
+        dest.upload(patch_num_samples(bytes(hdr), n), 0)
+    elif shard_size:
+        peer = PeerMapping(bytes(handle_t.cpu().numpy().tobytes()))
+        try:
+            peer.put(HEADER + offsets[rank], d_shard.data_ptr() + HEADER, shard_size)
+        finally:
+            peer.close()
+    dist.barrier()
+    if rank != 0:
+        return None
+    if to_host:
+        return dest, HEADER + total, dest.download(HEADER + total)
+    return dest, HEADER + total

@@ -66,4 +66,10 @@ void lnb_shim_profile_enable(LnbDevice *, int) {}
 void lnb_shim_profile_reset(LnbDevice *) {}
 int lnb_shim_profile_get(LnbDevice *, LnbStageStat *, int) { return 0; }
 double lnb_shim_measure_fp64_tflops(LnbDevice *) { return 0.0; }
+void *lnb_shim_device_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
+void lnb_shim_device_free(void *p) { free(p); }
+int lnb_shim_ipc_export(const void *, unsigned char *) { return 1; }          /* no peers on the CPU */
+void *lnb_shim_ipc_open(const unsigned char *) { return NULL; }
+void lnb_shim_ipc_close(void *) {}
+int lnb_shim_copy(void *d, const void *s, size_t n, int) { if (n) memcpy(d, s, n); return 0; }
 }
