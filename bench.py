@@ -162,6 +162,150 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+# =================================================================================================
+# at-scale legs (BASELINE.json configs[2] "C3" and the sharded-stream step of configs[4] "C5")
+# =================================================================================================
+def long_pcm(seconds):
+    clip = make_clip()
+    n = int(round(seconds * RATE))
+    reps = (n + clip.shape[1] - 1) // clip.shape[1]
+    return np.ascontiguousarray(np.tile(clip, (1, reps))[:, :n])
+
+
+def cut_stream(stream, max_blocks):
+    """header + the first `max_blocks` blocks of a stream, sample count patched (blocks are self-contained)."""
+    off, ns, k = 30, 0, 0
+    while off < len(stream) and k < max_blocks:
+        size = int.from_bytes(stream[off + 2:off + 6], "big") + 6
+        ns += int.from_bytes(stream[off + 9:off + 11], "big")
+        off += size; k += 1
+    hdr = bytearray(stream[:30]); hdr[14:18] = ns.to_bytes(4, "big")
+    return bytes(hdr) + bytes(stream[30:off]), ns
+
+
+def run_c3(args, dev, hbm_peak, fp64_peak):
+    """C3: decode-only throughput on a synthetic 1-hour 44.1 kHz 16-bit stereo stream at -m 7 (the stream is
+    built with the GPU encoder, whose m7 throughput is reported beside it)."""
+    import torch
+    import harness
+    from linne_b200 import EncoderSession, DecoderSession
+    pcm = long_pcm(args.c3_seconds)
+    nch, n = pcm.shape
+    stride = (n + 4 + 3) // 4 * 4
+    h_pcm = torch.from_numpy(pcm).pin_memory()
+    d_pcm = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+    d_pcm[:, :n].copy_(h_pcm)
+    cap = 30 + nch * n * 2 + 11 * (n // BLOCK + 2) + 65536
+    d_stream = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
+    enc = EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=7)
+    dec = DecoderSession(channels=nch)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_once(fn):
+        torch.cuda.synchronize()
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    size = [0]
+    def do_encode():
+        size[0] = enc.encode_whole_resident(d_pcm.data_ptr(), stride, n, d_stream.data_ptr(), cap)
+    do_encode()                                                  # warm-up: allocations
+    enc.set_profiling(True); enc.reset_stage_stats()
+    ms_enc = timed_once(do_encode)
+    enc_stages = {k: round(v[1], 3) for k, v in sorted(enc.stage_stats().items(), key=lambda kv: -kv[1][1])}
+    enc.set_profiling(False)
+    sz = size[0]
+    h_stream = torch.zeros(sz + 16, dtype=torch.uint8).pin_memory()
+    h_stream[:sz].copy_(d_stream[:sz])
+    d_back = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+    h_back = torch.zeros((nch, n), dtype=torch.int32).pin_memory()
+    chan_out = (C.POINTER(C.c_int32) * nch)(*[C.cast(h_back[c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
+
+    def dec_resident():          # stream and PCM stay in HBM; the host keeps a copy of the image for the block hop
+        dec.decode_whole_resident(h_stream.data_ptr(), d_stream.data_ptr(), sz, d_back.data_ptr(), stride, nch, n)
+    def dec_e2e():               # the reference call: host stream in, host PCM out
+        dec.decode_whole(h_stream.data_ptr(), sz, chan_out, nch, n)
+    dec_resident(); dec_e2e()                                    # warm-up
+    dec.set_profiling(True); dec.reset_stage_stats()
+    ms_res = min(timed_once(dec_resident) for _ in range(3))
+    stages = dec.stage_stats()
+    dec.set_profiling(False)
+    ms_e2e = min(timed_once(dec_e2e) for _ in range(2))
+    ok = bool(torch.equal(d_back[:, :n], d_pcm[:, :n])) and bool(np.array_equal(h_back.numpy(), pcm))
+    samples = nch * n
+    bytes_per_sample = 4.0 + sz / samples
+    dec_stage_ms = {k: round(v[1] / 3.0, 3) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][1])}
+    dom = max(dec_stage_ms.items(), key=lambda kv: kv[1])
+    out = {
+        "workload": f"C3: {args.c3_seconds:.0f} s 44.1 kHz 16-bit stereo, -m 7, {n // BLOCK + 1} blocks, decode-only",
+        "value": round(samples / (ms_res / 1e3) / 1e6, 1), "unit": "MSamples/s", "ms": round(ms_res, 3),
+        "e2e": {"value": round(samples / (ms_e2e / 1e3) / 1e6, 1), "ms": round(ms_e2e, 3),
+                "h2d_bytes": int(sz), "d2h_bytes": int(4 * samples)},
+        "stream_bytes": int(sz), "lossless": ok, "stages_ms": dec_stage_ms,
+        "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": round(bytes_per_sample * samples / (dom[1] / 1e3) / 1e9, 1),
+                     "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(bytes_per_sample * samples / (dom[1] / 1e3) / 1e9 / hbm_peak, 4),
+                     "bytes_per_sample": round(bytes_per_sample, 3), "traffic": None},
+        "encode_m7": {"value": round(samples / (ms_enc / 1e3) / 1e6, 1), "unit": "MSamples/s", "ms": round(ms_enc, 2),
+                      "stages_ms": enc_stages,
+                      "fp64_frac": round(2.0 * MAC_PER_SAMPLE[7] * samples / (enc_stages.get("analyze_v3", ms_enc) / 1e3) / 1e12
+                                         / fp64_peak, 4) if fp64_peak else None},
+    }
+    # the reference decoder on the first blocks of the same stream, one host core
+    try:
+        if harness.have_ref():
+            sub, ns = cut_stream(h_stream[:sz].numpy().tobytes(), 1024)
+            ref = harness.Ref()
+            t0 = time.perf_counter(); back = ref.decode(sub); dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": round(nch * ns / dt / 1e6, 3), "unit": "MSamples/s", "cores": 1, "kind": "reference",
+                                   "sample": f"reference decoder on the first 1024 blocks ({ns} frames), {dt:.1f} s",
+                                   "matches": bool(np.array_equal(back, pcm[:, :ns]))}
+    except Exception as e:  # pragma: no cover
+        out["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": str(e)}
+    enc.close(); dec.close()
+    del d_pcm, d_stream, d_back, h_pcm, h_back, h_stream
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sharded(args, dev, rank, world):
+    """One long stream sharded by contiguous block ranges over the ranks: every rank encodes its range
+    at -m 7, the shards meet in rank 0's HBM over NVLink (CUDA IPC peer put, no collective), then every rank
+    decodes its own block range of the gathered stream.  Time = max over ranks, CUDA events."""
+    import torch
+    import torch.distributed as dist
+    from linne_b200 import Product, shard
+    pcm = long_pcm(args.shard_seconds)
+    nch, n = pcm.shape
+    res = {}
+    for it in range(2):                                          # first pass warms allocations and the IPC path
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        out = shard.encode_distributed_p2p(pcm, BLOCK, bits=BITS, rate=RATE, preset=7, device=dev, to_host=True)
+        e1.record()
+        box = [out[2] if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)                  # decode input distribution (host bytes; not timed as codec work)
+        torch.cuda.synchronize(); dist.barrier()
+        e1b = torch.cuda.Event(enable_timing=True); e1b.record()
+        first, got = shard.decode_shard(Product(), box[0], rank, world)
+        e2.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1), e1b.elapsed_time(e2)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = torch.tensor([1 if (got is None or np.array_equal(got, pcm[:, first:first + got.shape[1]])) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        res = {"workload": f"{args.shard_seconds:.0f} s stereo stream, -m 7, sharded by contiguous block range over {world} GPUs",
+               "encode_gather_ms": round(float(t[0]), 2), "decode_ms": round(float(t[1]), 2),
+               "encode_MSamples_s": round(nch * n / (float(t[0]) / 1e3) / 1e6, 1),
+               "decode_MSamples_s": round(nch * n / (float(t[1]) / 1e3) / 1e6, 1),
+               "stream_bytes": (len(box[0]) if box[0] else None), "lossless": bool(int(ok.item())),
+               "exchange": "exclusive scan of shard byte counts + one CUDA-IPC device-to-device put per rank (NVLink); no collective",
+               "note": "API-level timing: includes each rank's host->device upload of its PCM range and the final device->host read on rank 0"}
+        if rank == 0 and out is not None:
+            out[0].free()
+    return res
+
 # =================================================================================================
 # our arm
 # =================================================================================================
@@ -176,6 +320,8 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     product = Product()
     hbm_peak, peak_src = load_peaks()
@@ -352,10 +498,27 @@ def run_b200(args, rank, world, local_rank):
                        "peak": hbm_peak, "unit": "GB/s", "frac": round(by / (dec_ms / 1e3) / 1e9 / hbm_peak, 5) if dec_ms else None,
                        "peak_source": peak_src, "bytes_per_sample": round(hbm_bytes_per_sample, 3)}
 
+    # ---- at-scale legs: free the sweep's buffers first ----
+    for sess in list(encs.values()) + list(decs.values()):
+        sess.close()
+    del d_out, d_backs, h_outs, h_backs, l2_flush
+    torch.cuda.empty_cache()
+    sharded = None
+    if world > 1 and args.shard_seconds > 0:
+        try:
+            sharded = run_sharded(args, dev, rank, world)
+        except Exception as e:      # pragma: no cover
+            sharded = {"error": repr(e)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    c3 = None
+    if world == 1 and args.c3_seconds > 0:
+        try:
+            c3 = run_c3(args, dev, hbm_peak, fp64_peak)
+        except Exception as e:      # pragma: no cover
+            c3 = {"error": repr(e)}
 
     # ---- CPU baseline beside it: the unmodified reference, one thread, bounded sample ----
     cpu_baseline = None
@@ -394,6 +557,10 @@ def run_b200(args, rank, world, local_rank):
         "lossless": {"resident": ok_resident, "e2e": ok_e2e},
         "fp64_peak_tflops": round(fp64_peak, 3),
     }
+    if c3 is not None:
+        line["c3_decode"] = c3
+    if sharded is not None:
+        line["sharded_stream"] = sharded
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -406,6 +573,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--serial", action="store_true", help="run the eight presets one after the other (one stream)")
+    ap.add_argument("--c3-seconds", type=float, default=3600.0,
+                    help="N=1: length of the C3 decode-only stream (BASELINE.json configs[2]); 0 = skip")
+    ap.add_argument("--shard-seconds", type=float, default=600.0,
+                    help="N>1: length of the stream sharded by block range over the ranks; 0 = skip")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

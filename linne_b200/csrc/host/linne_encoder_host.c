@@ -173,41 +173,50 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     lambdas = batch.cfg.num_lambdas;
     slots_per_block = C * lambdas;
 
-    /* chunk so the double-precision analysis scratch stays inside the budget */
-    per_block = (size_t)slots_per_block * (batch.cfg.work_stride * sizeof(double) * 2u + 64u * 1024u)
-              + (size_t)C * (batch.cfg.work_stride * sizeof(int32_t) + 32u * 1024u)
-              + (enc->enable_learning ? (size_t)C * (2u * LNB_MAX_LAYERS + 1u) * batch.cfg.work_stride * sizeof(double) : 0u);
-    chunk_blocks = (uint32_t)(enc->scratch_budget / per_block);
-    if (chunk_blocks < 1u) chunk_blocks = 1u;
-    if (chunk_blocks > total_blocks) chunk_blocks = total_blocks;
-    while ((uint64_t)chunk_blocks * slots_per_block * batch.cfg.work_stride >= 0x7FFFFFFFull && chunk_blocks > 1u) chunk_blocks /= 2u;
-
+    /* Chunk so the per-chunk scratch stays inside the budget.  Blocks of up to lnb_shim_fast_max_na()
+     * samples are analysed by the cooperative kernel (signal in shared memory): they need only the
+     * integer work signal and the per-slot results.  Longer blocks take the flat kernels, which keep
+     * two double-precision planes and per-level tables in HBM. */
     {
-        const size_t S = (size_t)chunk_blocks * slots_per_block, BC = (size_t)chunk_blocks * C;
-        const size_t ws = batch.cfg.work_stride;
-        const size_t chunks = (ws + 63u) / 64u;
-        if (lnb_buf_reserve_host(&enc->h_blocks, chunk_blocks * sizeof(LnbBlockDesc))
-            || lnb_buf_reserve_host(&enc->h_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
-            || lnb_buf_reserve_host(&enc->h_total, 64)
-            || lnb_buf_reserve_device(enc->dev, &enc->d_blocks, chunk_blocks * sizeof(LnbBlockDesc))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_params, BC * sizeof(LnbChanParams))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_est, BC * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_work, BC * ws * sizeof(int32_t))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_sig_a, S * ws * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_sig_b, S * ws * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_acorr, S * LNB_MAX_LEVELS * ws * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_cand, S * LNB_MAX_LEVELS * LNB_MAX_PARAMS * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_unit_loss, S * LNB_MAX_LEVELS * chunks * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_chosen_w, S * LNB_MAX_LAYERS * LNB_MAX_PARAMS * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_chosen_u, S * LNB_MAX_LAYERS)
-            || lnb_buf_reserve_device(enc->dev, &enc->d_final_sum, S * chunks * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_plans, BC * sizeof(LnbCoderPlan))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_plan_mean, BC * 2u * LNB_MAX_PARTITIONS * sizeof(double))
-            || lnb_buf_reserve_device(enc->dev, &enc->d_total, 64)
-            || (enc->enable_learning && !forced
-                && lnb_buf_reserve_device(enc->dev, &enc->d_train, BC * (2u * LNB_MAX_LAYERS + 1u) * ws * sizeof(double))))
-            return LINNE_APIRESULT_NG;
+        const int need_flat = NB > lnb_shim_fast_max_na();
+        const size_t ws = batch.cfg.work_stride, chunks = (ws + 63u) / 64u;
+        per_block = (size_t)slots_per_block * (LNB_MAX_LAYERS * LNB_MAX_PARAMS * sizeof(double) + chunks * sizeof(double) + 64u)
+                  + (size_t)C * (ws * sizeof(int32_t) + sizeof(LnbChanParams) + sizeof(LnbCoderPlan)
+                                 + 2u * LNB_MAX_PARTITIONS * sizeof(double) + 64u)
+                  + (enc->enable_learning ? (size_t)C * (2u * LNB_MAX_LAYERS + 1u) * ws * sizeof(double) : 0u);
+        if (need_flat)
+            per_block += (size_t)slots_per_block * (ws * sizeof(double) * 2u
+                                                    + LNB_MAX_LEVELS * (256u + LNB_MAX_PARAMS + chunks) * sizeof(double));
+        chunk_blocks = (uint32_t)(enc->scratch_budget / per_block);
+        if (chunk_blocks < 1u) chunk_blocks = 1u;
+        if (chunk_blocks > total_blocks) chunk_blocks = total_blocks;
+        while ((uint64_t)chunk_blocks * slots_per_block * ws >= 0x7FFFFFFFull && chunk_blocks > 1u) chunk_blocks /= 2u;
+        {
+            const size_t S = (size_t)chunk_blocks * slots_per_block, BC = (size_t)chunk_blocks * C;
+            if (lnb_buf_reserve_host(&enc->h_blocks, chunk_blocks * sizeof(LnbBlockDesc))
+                || lnb_buf_reserve_host(&enc->h_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
+                || lnb_buf_reserve_host(&enc->h_total, 64)
+                || lnb_buf_reserve_device(enc->dev, &enc->d_blocks, chunk_blocks * sizeof(LnbBlockDesc))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_params, BC * sizeof(LnbChanParams))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_est, BC * sizeof(double))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_work, BC * ws * sizeof(int32_t))
+                || (need_flat
+                    && (lnb_buf_reserve_device(enc->dev, &enc->d_sig_a, S * ws * sizeof(double))
+                        || lnb_buf_reserve_device(enc->dev, &enc->d_sig_b, S * ws * sizeof(double))
+                        || lnb_buf_reserve_device(enc->dev, &enc->d_acorr, S * LNB_MAX_LEVELS * 256u * sizeof(double))
+                        || lnb_buf_reserve_device(enc->dev, &enc->d_cand, S * LNB_MAX_LEVELS * LNB_MAX_PARAMS * sizeof(double))
+                        || lnb_buf_reserve_device(enc->dev, &enc->d_unit_loss, S * LNB_MAX_LEVELS * chunks * sizeof(double))))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_chosen_w, S * LNB_MAX_LAYERS * LNB_MAX_PARAMS * sizeof(double))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_chosen_u, S * LNB_MAX_LAYERS)
+                || lnb_buf_reserve_device(enc->dev, &enc->d_final_sum, S * chunks * sizeof(double))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_plans, BC * sizeof(LnbCoderPlan))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_plan_mean, BC * 2u * LNB_MAX_PARTITIONS * sizeof(double))
+                || lnb_buf_reserve_device(enc->dev, &enc->d_total, 64)
+                || (enc->enable_learning && !forced
+                    && lnb_buf_reserve_device(enc->dev, &enc->d_train, BC * (2u * LNB_MAX_LAYERS + 1u) * ws * sizeof(double))))
+                return LINNE_APIRESULT_NG;
+        }
     }
     batch.blocks = (LnbBlockDesc *)enc->d_blocks.ptr;
     batch.params = (LnbChanParams *)enc->d_params.ptr;
