@@ -32,6 +32,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+# Sixteen handles (8 encoders + 8 decoders) run on their own CUDA streams; with the default of 8 hardware
+# work queues several streams share one queue and a kernel waiting for SMs blocks unrelated work behind it.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 CLIP_SECONDS, RATE, BITS, CHANNELS, BLOCK = 10.0, 44100, 16, 2, 10240
 PRESETS = list(range(8))
 # algorithmic MACs per input sample of the default analysis, per preset

@@ -81,6 +81,12 @@ void LINNEB200_DecoderResetStageStats(struct LINNEDecoder *decoder);
 int  LINNEB200_EncoderGetStageStats(struct LINNEEncoder *encoder, struct LINNEB200StageStat *out, int max_stages);
 int  LINNEB200_DecoderGetStageStats(struct LINNEDecoder *decoder, struct LINNEB200StageStat *out, int max_stages);
 
+/* Launch timeline of a profiled handle: kernel begin/end in ms since a process-wide origin (recorded when
+ * profiling is first switched on), so handles running side by side on their own streams can be merged. */
+struct LINNEB200TimelineEntry { char name[24]; float begin_ms, end_ms; };
+int  LINNEB200_EncoderGetTimeline(struct LINNEEncoder *encoder, struct LINNEB200TimelineEntry *out, int max_entries);
+int  LINNEB200_DecoderGetTimeline(struct LINNEDecoder *decoder, struct LINNEB200TimelineEntry *out, int max_entries);
+
 /* Sustained FP64 FMA throughput (TFLOP/s) of the current device: roofline denominator of the
  * encoder's analysis kernels.  Returns 0 without a device. */
 double LINNEB200_MeasureFp64Tflops(void);

@@ -253,6 +253,10 @@ class StageStat(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("launches", C.c_uint64), ("total_ms", C.c_double)]
 
 
+class TimelineEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("begin_ms", C.c_float), ("end_ms", C.c_float)]
+
+
 class ChannelParams(C.Structure):
     """struct LINNEB200ChannelParams (include/linne_b200.h)"""
     _fields_ = [("log2_units", C.c_uint8 * 3), ("rshift", C.c_uint8 * 3), ("coef", (C.c_int8 * 128) * 3)]
@@ -278,6 +282,15 @@ class _Session:
         buf = (StageStat * 32)()
         n = getattr(self.lib, f"LINNEB200_{self._side}GetStageStats")(self.h, buf, 32)
         return {buf[i].name.decode(): (int(buf[i].launches), float(buf[i].total_ms)) for i in range(n)}
+
+    def timeline(self):
+        """[(kernel, begin_ms, end_ms)] since the process-wide origin, for the launches profiled since the last reset."""
+        buf = (TimelineEntry * 2048)()
+        f = getattr(self.lib, f"LINNEB200_{self._side}GetTimeline")
+        f.argtypes = [C.c_void_p, C.POINTER(TimelineEntry), C.c_int]
+        f.restype = C.c_int
+        n = f(self.h, buf, 2048)
+        return [(buf[i].name.decode(), float(buf[i].begin_ms), float(buf[i].end_ms)) for i in range(n)]
 
     def launch_count(self):
         return int(getattr(self.lib, f"LINNEB200_{self._side}LaunchCount")(self.h))

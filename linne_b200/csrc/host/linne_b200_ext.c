@@ -53,3 +53,12 @@ void LINNEB200_IpcClose(void *d_peer_ptr) { lnb_shim_ipc_close(d_peer_ptr); }
 int LINNEB200_DeviceCopy(void *d_dst, const void *d_src, size_t bytes) { return lnb_shim_copy(d_dst, d_src, bytes, 0); }
 int LINNEB200_CopyToDevice(void *d_dst, const void *h_src, size_t bytes) { return lnb_shim_copy(d_dst, h_src, bytes, 1); }
 int LINNEB200_CopyToHost(void *h_dst, const void *d_src, size_t bytes) { return lnb_shim_copy(h_dst, d_src, bytes, 2); }
+
+int LINNEB200_EncoderGetTimeline(struct LINNEEncoder *e, struct LINNEB200TimelineEntry *out, int n)
+{
+    return e ? lnb_shim_profile_timeline(lnb_encoder_device(e), (LnbTimelineEntry *)out, n) : 0;
+}
+int LINNEB200_DecoderGetTimeline(struct LINNEDecoder *d, struct LINNEB200TimelineEntry *out, int n)
+{
+    return d ? lnb_shim_profile_timeline(lnb_decoder_device(d), (LnbTimelineEntry *)out, n) : 0;
+}

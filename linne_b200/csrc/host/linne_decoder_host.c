@@ -111,6 +111,7 @@ LINNEApiResult LINNEDecoder_SetHeader(struct LINNEDecoder *dec, const struct LIN
     if (header->num_channels > LINNE_MAX_NUM_CHANNELS) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     dec->header = *header;
     dec->flags |= DEC_FLAG_HEADER_SET;
+    lnb_shim_set_cost_rank(dec->dev, (int)header->preset);     /* longer predictors first (scheduling hint) */
     return LINNE_APIRESULT_OK;
 }
 

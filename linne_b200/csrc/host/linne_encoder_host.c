@@ -5,12 +5,19 @@
  * analysis scratch fits, and copying the packed chunk back.  All signal processing, analysis,
  * coding and bit packing of every block x channel runs on the GPU.
  */
+#define _POSIX_C_SOURCE 199309L
 #include "linne_encoder.h"
 #include "lnb_host_util.h"
 
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+
+/* LINNE_B200_TRACE=1: host-side time stamps of the encode call's phases on stderr (debugging aid) */
+static int trace_on(void) { static int on = -1; if (on < 0) { const char *e = getenv("LINNE_B200_TRACE"); on = (e && *e == '1') ? 1 : 0; } return on; }
+static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+#define TRACE(enc, what) do { if (trace_on()) fprintf(stderr, "[trace] m%u %-14s %.3f\n", (unsigned)(enc)->header.preset, what, now_ms()); } while (0)
 
 struct LINNEEncoder {
     struct LINNEHeader header;
@@ -135,6 +142,8 @@ LINNEApiResult LINNEEncoder_SetEncodeParameter(struct LINNEEncoder *enc, const s
     enc->enable_learning = prm->enable_learning;
     enc->num_afmethod_iterations = prm->num_afmethod_iterations;
     enc->set_parameter = 1;
+    /* scheduling hint: analysis cost grows with layers x regularisers, i.e. with the preset number */
+    lnb_shim_set_cost_rank(enc->dev, (int)prm->preset);
     return LINNE_APIRESULT_OK;
 }
 
@@ -184,6 +193,8 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
                   + (size_t)C * (ws * sizeof(int32_t) + sizeof(LnbChanParams) + sizeof(LnbCoderPlan)
                                  + 2u * LNB_MAX_PARTITIONS * sizeof(double) + 64u)
                   + (enc->enable_learning ? (size_t)C * (2u * LNB_MAX_LAYERS + 1u) * ws * sizeof(double) : 0u);
+        const int need_sig_a = need_flat || (enc->num_afmethod_iterations && !forced);    /* IRLS scratch: one plane per slot */
+        if (need_sig_a && !need_flat) per_block += (size_t)slots_per_block * ws * sizeof(double);
         if (need_flat)
             per_block += (size_t)slots_per_block * (ws * sizeof(double) * 2u
                                                     + LNB_MAX_LEVELS * (256u + LNB_MAX_PARAMS + chunks) * sizeof(double));
@@ -200,9 +211,9 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
                 || lnb_buf_reserve_device(enc->dev, &enc->d_params, BC * sizeof(LnbChanParams))
                 || lnb_buf_reserve_device(enc->dev, &enc->d_est, BC * sizeof(double))
                 || lnb_buf_reserve_device(enc->dev, &enc->d_work, BC * ws * sizeof(int32_t))
+                || (need_sig_a && lnb_buf_reserve_device(enc->dev, &enc->d_sig_a, S * ws * sizeof(double)))
                 || (need_flat
-                    && (lnb_buf_reserve_device(enc->dev, &enc->d_sig_a, S * ws * sizeof(double))
-                        || lnb_buf_reserve_device(enc->dev, &enc->d_sig_b, S * ws * sizeof(double))
+                    && (lnb_buf_reserve_device(enc->dev, &enc->d_sig_b, S * ws * sizeof(double))
                         || lnb_buf_reserve_device(enc->dev, &enc->d_acorr, S * LNB_MAX_LEVELS * 256u * sizeof(double))
                         || lnb_buf_reserve_device(enc->dev, &enc->d_cand, S * LNB_MAX_LEVELS * LNB_MAX_PARAMS * sizeof(double))
                         || lnb_buf_reserve_device(enc->dev, &enc->d_unit_loss, S * LNB_MAX_LEVELS * chunks * sizeof(double))))
@@ -268,9 +279,12 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
         if (forced) lnb_shim_h2d(enc->dev, enc->d_params.ptr, forced + (size_t)first * C, (size_t)nb * C * sizeof(LnbChanParams));
         lnb_shim_h2d(enc->dev, enc->d_blocks.ptr, hb, nb * sizeof(LnbBlockDesc));
         lnb_shim_h2d(enc->dev, enc->d_welch.ptr, hw, (size_t)nb * LNB_MAX_LEVELS * sizeof(double));
+        TRACE(enc, "enqueue");
         if (lnb_shim_encode_analyze(enc->dev, &batch)) return LINNE_APIRESULT_NG;
         lnb_shim_d2h(enc->dev, enc->h_total.ptr, enc->d_total.ptr, sizeof(uint32_t));
+        TRACE(enc, "enqueued");
         if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
+        TRACE(enc, "sizes known");
         chunk_bytes = *(uint32_t *)enc->h_total.ptr;
         if ((uint64_t)out_off + chunk_bytes > data_size) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
         if (data_on_device) {
@@ -283,7 +297,9 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
             if (lnb_shim_encode_pack(enc->dev, &batch, chunk_bytes)) return LINNE_APIRESULT_NG;
             lnb_shim_d2h(enc->dev, data + out_off, enc->d_out.ptr, chunk_bytes);
         }
+        TRACE(enc, "pack enqueued");
         if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
+        TRACE(enc, "chunk done");
         out_off += chunk_bytes;
     }
     *written = out_off;

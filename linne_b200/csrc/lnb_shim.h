@@ -24,6 +24,11 @@ void lnb_shim_close(LnbDevice *dev);
 const LnbDevTables *lnb_shim_tables(const LnbDevice *dev);
 /* Launch on an externally owned stream (cudaStream_t as void*) instead of the context's own. */
 void lnb_shim_use_stream(LnbDevice *dev, void *cuda_stream);
+/* Scheduling hint: `cost_rank` 0 = cheapest work .. 7 = most expensive.  Handles that run side by side on one
+ * GPU (a server encoding several streams) finish soonest when the longest job's kernels are placed first, so
+ * the context's own stream is re-created with a CUDA stream priority that grows with the rank.  No effect on
+ * an externally supplied stream. */
+void lnb_shim_set_cost_rank(LnbDevice *dev, int cost_rank);
 const char *lnb_shim_backend(void);      /* "cuda-sm_100a" for the product */
 /* Largest analysis length the cooperative (shared-memory) encoder kernels take; 0 = none. */
 uint32_t lnb_shim_fast_max_na(void);
@@ -55,6 +60,10 @@ typedef struct LnbStageStat { char name[24]; uint64_t launches; double total_ms;
 void lnb_shim_profile_enable(LnbDevice *dev, int on);
 void lnb_shim_profile_reset(LnbDevice *dev);
 int  lnb_shim_profile_get(LnbDevice *dev, LnbStageStat *out, int max_stages);
+/* Launch timeline of the profiled kernels: begin/end in ms since a process-wide reference event, so that
+ * the timelines of handles running side by side on their own streams can be merged. */
+typedef struct LnbTimelineEntry { char name[24]; float begin_ms, end_ms; } LnbTimelineEntry;
+int  lnb_shim_profile_timeline(LnbDevice *dev, LnbTimelineEntry *out, int max_entries);
 
 /* Sustained FP64 FMA throughput of the device in TFLOP/s (2 flops per DFMA), measured with a
  * register-resident microbenchmark: the roofline denominator of the analysis kernels. */

@@ -22,10 +22,12 @@
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
+#define LNB_MAX_TIMELINE 2048
 
 struct LnbDevice {
     cudaStream_t stream;
     int owns_stream;
+    int cost_rank;
     int ordinal;
     LnbDevTables tables;
     void *table_mem;
@@ -39,7 +41,12 @@ struct LnbDevice {
     cudaEvent_t ev_begin[LNB_MAX_PENDING], ev_end[LNB_MAX_PENDING];
     int pending_stage[LNB_MAX_PENDING];
     int events_created;
+    int num_timeline;
+    LnbTimelineEntry timeline[LNB_MAX_TIMELINE];
 };
+
+static cudaEvent_t g_ref_event;              /* process-wide time origin of the launch timelines */
+static int g_ref_recorded = 0;
 
 /* The CUDA "current device" is per host thread: a handle created on one thread (and device) may be
  * driven from another, so every entry point re-binds the calling thread to the handle's device. */
@@ -66,6 +73,13 @@ static void drain_profile(LnbDevice *dev)
         if (cudaEventElapsedTime(&ms, dev->ev_begin[i], dev->ev_end[i]) == cudaSuccess) {
             dev->stages[dev->pending_stage[i]].total_ms += ms;
             dev->stages[dev->pending_stage[i]].launches += 1;
+            float t0 = 0.f;
+            if (g_ref_recorded && dev->num_timeline < LNB_MAX_TIMELINE
+                && cudaEventElapsedTime(&t0, g_ref_event, dev->ev_begin[i]) == cudaSuccess) {
+                LnbTimelineEntry *e = &dev->timeline[dev->num_timeline++];
+                memcpy(e->name, dev->stages[dev->pending_stage[i]].name, sizeof(e->name));
+                e->begin_ms = t0; e->end_ms = t0 + ms;
+            }
         }
     }
     dev->num_pending = 0;
@@ -256,6 +270,7 @@ int lnb_shim_open(LnbDevice **out, int device_ordinal)
     cudaGetDevice(&dev->ordinal);
     if (cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking) != cudaSuccess) { free(dev); return 4; }
     dev->owns_stream = 1;
+    dev->cost_rank = -1;
 
     const LnbHostTables *ht = lnb_tables_get();
     const size_t sz_lut = sizeof(ht->huff_lut), sz_code = sizeof(ht->huff_code), sz_len = 256,
@@ -295,6 +310,26 @@ void lnb_shim_use_stream(LnbDevice *dev, void *cuda_stream)
     bind_device(dev);
     if (dev->owns_stream) { cudaStreamSynchronize(dev->stream); cudaStreamDestroy(dev->stream); dev->owns_stream = 0; }
     dev->stream = (cudaStream_t)cuda_stream;
+}
+
+void lnb_shim_set_cost_rank(LnbDevice *dev, int cost_rank)
+{
+    bind_device(dev);
+    if (!dev->owns_stream || dev->cost_rank == cost_rank) return;
+    { const char *e = getenv("LINNE_B200_STREAM_PRIORITY"); if (e && *e == '0') return; }
+    int least = 0, greatest = 0;                              /* numerically: greatest priority <= least priority */
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return; }
+    int span = least - greatest;
+    if (span <= 0) return;
+    if (cost_rank < 0) cost_rank = 0;
+    if (cost_rank > 7) cost_rank = 7;
+    const int prio = least - (cost_rank * span + 3) / 7;
+    cudaStream_t s;
+    if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamSynchronize(dev->stream);
+    cudaStreamDestroy(dev->stream);
+    dev->stream = s;
+    dev->cost_rank = cost_rank;
 }
 
 void *lnb_shim_alloc(LnbDevice *dev, size_t bytes)
@@ -376,6 +411,12 @@ uint64_t lnb_shim_launch_count(const LnbDevice *dev) { return dev->launches; }
 void lnb_shim_profile_enable(LnbDevice *dev, int on)
 {
     bind_device(dev);
+    if (on && !g_ref_recorded) {
+        cudaEventCreate(&g_ref_event);
+        cudaEventRecord(g_ref_event, 0);
+        cudaEventSynchronize(g_ref_event);
+        g_ref_recorded = 1;
+    }
     if (on && !dev->events_created) {
         for (int i = 0; i < LNB_MAX_PENDING; i++) { cudaEventCreate(&dev->ev_begin[i]); cudaEventCreate(&dev->ev_end[i]); }
         dev->events_created = 1;
@@ -390,6 +431,16 @@ void lnb_shim_profile_reset(LnbDevice *dev)
     cudaStreamSynchronize(dev->stream);
     drain_profile(dev);
     for (int i = 0; i < dev->num_stages; i++) { dev->stages[i].launches = 0; dev->stages[i].total_ms = 0.0; }
+    dev->num_timeline = 0;
+}
+int lnb_shim_profile_timeline(LnbDevice *dev, LnbTimelineEntry *out, int max_entries)
+{
+    bind_device(dev);
+    cudaStreamSynchronize(dev->stream);
+    drain_profile(dev);
+    int n = dev->num_timeline < max_entries ? dev->num_timeline : max_entries;
+    for (int i = 0; i < n; i++) out[i] = dev->timeline[i];
+    return n;
 }
 int lnb_shim_profile_get(LnbDevice *dev, LnbStageStat *out, int max_stages)
 {

@@ -50,6 +50,7 @@ int lnb_shim_open(LnbDevice **out, int)
 void lnb_shim_close(LnbDevice *dev) { free(dev); }
 const LnbDevTables *lnb_shim_tables(const LnbDevice *dev) { return &dev->tables; }
 void lnb_shim_use_stream(LnbDevice *, void *) {}
+void lnb_shim_set_cost_rank(LnbDevice *, int) {}
 void *lnb_shim_alloc(LnbDevice *, size_t bytes) { return calloc(1, bytes ? bytes : 16); }
 void lnb_shim_free(LnbDevice *, void *p) { free(p); }
 void *lnb_shim_alloc_pinned(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
@@ -65,6 +66,7 @@ uint64_t lnb_shim_launch_count(const LnbDevice *dev) { return dev->launches; }
 void lnb_shim_profile_enable(LnbDevice *, int) {}
 void lnb_shim_profile_reset(LnbDevice *) {}
 int lnb_shim_profile_get(LnbDevice *, LnbStageStat *, int) { return 0; }
+int lnb_shim_profile_timeline(LnbDevice *, LnbTimelineEntry *, int) { return 0; }
 double lnb_shim_measure_fp64_tflops(LnbDevice *) { return 0.0; }
 void *lnb_shim_device_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
 void lnb_shim_device_free(void *p) { free(p); }
