@@ -36,6 +36,8 @@
 #define LNB_A3_FRONT    160          /* zeroed doubles in front of sample 0 (>= 9 * 128 / 8 + window) */
 #define LNB_A3_BACK     176          /* zeroed doubles behind the last sample (>= 9 * (128 + 24) / 8) */
 #define LNB_A3_PART     24           /* doubles per work-item partial (>= 17 lags) */
+#define LNB_A3_ITEMS    64           /* work items whose partials are kept when a task's samples are split */
+#define LNB_A3_MIRROR   (LNB_MAX_PARAMS + 8)   /* doubles per Levinson mirror buffer; a warp task uses two */
 
 __host__ __device__ inline uint32_t lnb_a3_array_doubles(uint32_t na_max)
 {
@@ -47,21 +49,33 @@ __host__ __device__ inline size_t lnb_a3_smem_doubles(uint32_t na_max)
     return (size_t)2 * lnb_a3_array_doubles(na_max)
          + (size_t)LNB_MAX_LEVELS * LNB_MAX_PARAMS        /* candidate coefficients per level */
          + (size_t)LNB_MAX_LEVELS * 256                   /* autocorrelations per level: U*(p+1) = P+U <= 256 */
-         + (size_t)LNB_A3_WARPS * LNB_A3_PART             /* work-item partials */
+         + (size_t)LNB_A3_ITEMS * LNB_A3_PART             /* work-item partials */
+         + (size_t)2 * LNB_A3_MIRROR                      /* mirrors of the level-0 Levinson recursion (runs beside the rest) */
          + 64;                                            /* level losses, block-sum scratch */
 }
 
 struct LnbA3Ctx {
     double *A, *B;               /* point at sample 0 (front pad lies below) */
-    double *cand, *acorr, *part, *misc;
+    double *cand, *acorr, *part, *lev0, *misc;
     uint32_t na, ng;             /* samples, groups of 8 */
 };
 
+/* A team = the warps that run a phase together: the whole CTA (barrier 0 = __syncthreads) or warps 0..6
+ * (named barrier 1) while warp 7 runs the long level-0 Levinson recursion beside them. */
+struct LnbA3Team {
+    uint32_t tid, nthr, warp, nwarps, bar;
+    __device__ __forceinline__ void sync() const
+    {
+        if (bar == 0u) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" :: "r"(bar), "r"(nthr) : "memory");
+    }
+};
+
 /* ---- Welch-windowed copy A -> B for unit length m (lpc.c:196-205), one group of 8 at a time ---- */
-__device__ __forceinline__ void lnb_a3_window(const LnbA3Ctx &cx, uint32_t m, double scale)
+__device__ __forceinline__ void lnb_a3_window(const LnbA3Ctx &cx, const LnbA3Team &tm, uint32_t m, double scale)
 {
     const uint32_t mg = m >> 3;
-    for (uint32_t G = threadIdx.x; G < cx.ng; G += LNB_A3_THREADS) {
+    for (uint32_t G = tm.tid; G < cx.ng; G += tm.nthr) {
         const uint32_t pos0 = (G % mg) * 8u;
         const double *src = cx.A + G * 9u;
         double *dst = cx.B + G * 9u;
@@ -135,17 +149,20 @@ __device__ __forceinline__ void lnb_a3_autocorr_item(const LnbA3Ctx &cx, uint32_
     }
 }
 
-/* ---- autocorrelation of every unit of one level: r[u][0..p] into acorr_lvl[u*(p+1) + lag] ---- */
-__device__ void lnb_a3_autocorr(const LnbA3Ctx &cx, uint32_t U, uint32_t p, double *acorr_lvl)
+/* ---- autocorrelation of every unit of one level: r[u][0..p] into acorr_lvl[u*(p+1) + lag] ----
+ * Tasks (unit, lag group) are dealt to the team's warps; when they do not deal out evenly a task's samples
+ * are split S ways and the partials summed afterwards in a fixed order. */
+__device__ void lnb_a3_autocorr(const LnbA3Ctx &cx, const LnbA3Team &tm, uint32_t U, uint32_t p, double *acorr_lvl)
 {
-    const uint32_t warp = threadIdx.x >> 5;
     const uint32_t m = cx.na / U, mg = m >> 3;
     const uint32_t nq = (p >= 16u) ? p / 16u : 1u;                   /* lag groups per unit */
     const uint32_t tasks = U * nq;
-    const uint32_t S = (tasks >= LNB_A3_WARPS) ? 1u : LNB_A3_WARPS / tasks;   /* sample splits per task */
+    uint32_t S = 1u;                                                 /* sample splits per task */
+    if ((tasks % tm.nwarps) != 0u && tasks < 4u * tm.nwarps) S = (3u * tm.nwarps + tasks - 1u) / tasks;
+    if (tasks * S > LNB_A3_ITEMS) S = LNB_A3_ITEMS / tasks;
     const uint32_t items = tasks * S;
     const uint32_t per = (mg + S - 1u) / S;
-    for (uint32_t wi = warp; wi < items; wi += LNB_A3_WARPS) {
+    for (uint32_t wi = tm.warp; wi < items; wi += tm.nwarps) {
         const uint32_t task = wi / S, split = wi % S;
         const uint32_t u = task / nq, q = task % nq;
         const uint32_t g_lo = split * per, g_hi = (g_lo + per < mg) ? g_lo + per : mg;
@@ -160,15 +177,15 @@ __device__ void lnb_a3_autocorr(const LnbA3Ctx &cx, uint32_t U, uint32_t p, doub
         else                 lnb_a3_autocorr_item<2>(cx, u, q, m, last_unit, g_lo, g_hi, out);
     }
     if (S > 1u) {                                                    /* sum the sample splits in a fixed order */
-        __syncthreads();
+        tm.sync();
         const uint32_t L_last = (p >= 16u) ? 17u : p + 1u;
-        for (uint32_t i = threadIdx.x; i < tasks * 17u; i += LNB_A3_THREADS) {
+        for (uint32_t i = tm.tid; i < tasks * 17u; i += tm.nthr) {
             const uint32_t task = i / 17u, k = i % 17u;
             const uint32_t u = task / nq, q = task % nq;
             const uint32_t Lq = (q + 1u == nq) ? L_last : 16u;
             if (k >= Lq) continue;
             double v = 0.0;
-            for (uint32_t s = 0; s < S; s++) v += cx.part[(task * S + s) * LNB_A3_PART + k];
+            for (uint32_t sp = 0; sp < S; sp++) v += cx.part[(task * S + sp) * LNB_A3_PART + k];
             acorr_lvl[u * (p + 1u) + 16u * q + k] = v;
         }
     }
@@ -186,8 +203,6 @@ __device__ __forceinline__ double lnb_a3_rcp(double x)
     y = fma(y, fma(-x, y, 1.0), y);
     return y;
 }
-
-#define LNB_A3_MIRROR (LNB_MAX_PARAMS + 8)        /* doubles per mirror buffer; a warp task uses two */
 
 /* ---- Levinson-Durbin by one warp (orders 32..128); reversed coefficients into out_w[0..p) ----
  * Lane l keeps a[l], a[l+32], ..., a[l+128] in registers; a double-buffered shared-memory mirror serves
@@ -259,12 +274,12 @@ __device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lamb
  * MODE 1: forward (y = x[t] + sum, written to Y, all samples counted)   linne_network.c:183-208
  * PS = 0: p is a multiple of 8; PS = 1, 2, 4: p = PS. */
 template <int MODE, int PS>
-__device__ __forceinline__ double lnb_a3_fir(const LnbA3Ctx &cx, const double *X, double *Y, uint32_t p, uint32_t m,
-                                             const double *cand_lvl)
+__device__ __forceinline__ double lnb_a3_fir(const LnbA3Ctx &cx, const LnbA3Team &tm, const double *X, double *Y, uint32_t p,
+                                             uint32_t m, const double *cand_lvl)
 {
     const uint32_t mg = m >> 3;
     double loss = 0.0;
-    for (uint32_t G = threadIdx.x; G < cx.ng; G += LNB_A3_THREADS) {
+    for (uint32_t G = tm.tid; G < cx.ng; G += tm.nthr) {
         const uint32_t u = G / mg;
         const double *w = cand_lvl + u * p;
         const double *Xg = X + G * 9u;
@@ -317,26 +332,72 @@ __device__ __forceinline__ double lnb_a3_fir(const LnbA3Ctx &cx, const double *X
 }
 
 template <int MODE>
-__device__ double lnb_a3_fir_any(const LnbA3Ctx &cx, const double *X, double *Y, uint32_t p, uint32_t m, const double *cand_lvl)
+__device__ double lnb_a3_fir_any(const LnbA3Ctx &cx, const LnbA3Team &tm, const double *X, double *Y, uint32_t p, uint32_t m,
+                                 const double *cand_lvl)
 {
-    if (p >= 8u) return lnb_a3_fir<MODE, 0>(cx, X, Y, p, m, cand_lvl);
-    if (p == 4u) return lnb_a3_fir<MODE, 4>(cx, X, Y, p, m, cand_lvl);
-    if (p == 2u) return lnb_a3_fir<MODE, 2>(cx, X, Y, p, m, cand_lvl);
-    return lnb_a3_fir<MODE, 1>(cx, X, Y, p, m, cand_lvl);
+    if (p >= 8u) return lnb_a3_fir<MODE, 0>(cx, tm, X, Y, p, m, cand_lvl);
+    if (p == 4u) return lnb_a3_fir<MODE, 4>(cx, tm, X, Y, p, m, cand_lvl);
+    if (p == 2u) return lnb_a3_fir<MODE, 2>(cx, tm, X, Y, p, m, cand_lvl);
+    return lnb_a3_fir<MODE, 1>(cx, tm, X, Y, p, m, cand_lvl);
 }
 
-/* block-wide sum in a fixed order; result valid in every thread */
-__device__ double lnb_a3_block_sum(double v, double *scratch /* >= 9 doubles */)
+/* team-wide sum in a fixed order; result valid in every thread of the team */
+__device__ double lnb_a3_team_sum(const LnbA3Team &tm, double v, double *scratch /* >= 8 doubles */)
 {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    __syncthreads();
-    if ((threadIdx.x & 31u) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
+    tm.sync();
+    if ((tm.tid & 31u) == 0) scratch[tm.warp] = v;
+    tm.sync();
     double s = 0.0;
-    for (int w = 0; w < LNB_A3_WARPS; w++) s += scratch[w];
-    __syncthreads();
+    for (uint32_t w = 0; w < tm.nwarps; w++) s += scratch[w];
+    tm.sync();
     return s;
+}
+__device__ double lnb_a3_block_sum(double v, double *scratch)
+{
+    const LnbA3Team all = { threadIdx.x, LNB_A3_THREADS, threadIdx.x >> 5, LNB_A3_WARPS, 0u };
+    return lnb_a3_team_sum(all, v, scratch);
+}
+
+/* Levinson-Durbin of the levels [lv_first, nlev) by a team: threads take the orders <= 16 (reference operation
+ * order), warps the orders 32..128.  `scratch` = LNB_A3_WARPS x 2 mirrors (only used by the warp tasks). */
+__device__ void lnb_a3_solve_levels(const LnbA3Ctx &cx, const LnbA3Team &tm, uint32_t P, uint32_t lv_first, uint32_t nlev,
+                                    double lambda, double *scratch)
+{
+    uint32_t thread_tasks = 0, warp_tasks = 0;
+    for (uint32_t lv = lv_first; lv < nlev; lv++) { if ((P >> lv) <= 16u) thread_tasks += 1u << lv; else warp_tasks += 1u << lv; }
+    for (uint32_t t = tm.tid; t < thread_tasks; t += tm.nthr) {
+        uint32_t rest = t;
+        for (uint32_t lv = lv_first; lv < nlev; lv++) {
+            const uint32_t U = 1u << lv, p = P / U;
+            if (p > 16u) continue;
+            if (rest < U) {
+                double r[17], a[18], coef[16];
+                const double *src = cx.acorr + lv * 256 + rest * (p + 1u);
+                for (uint32_t k = 0; k <= p; k++) r[k] = src[k];
+                r[0] = __dmul_rn(r[0], __dadd_rn(1.0, lambda));
+                lnb_levinson(r, p, a, coef, (double *)0);
+                double *dst = cx.cand + lv * LNB_MAX_PARAMS + rest * p;
+                for (uint32_t j = 0; j < p; j++) dst[j] = coef[p - 1u - j];
+                break;
+            }
+            rest -= U;
+        }
+    }
+    for (uint32_t t = tm.warp; t < warp_tasks; t += tm.nwarps) {
+        uint32_t rest = t;
+        for (uint32_t lv = lv_first; lv < nlev; lv++) {
+            const uint32_t U = 1u << lv, p = P / U;
+            if (p <= 16u) continue;
+            if (rest < U) {
+                lnb_a3_levinson_warp(cx.acorr + lv * 256 + rest * (p + 1u), p, lambda,
+                                     scratch + tm.warp * 2 * LNB_A3_MIRROR, cx.cand + lv * LNB_MAX_PARAMS + rest * p);
+                break;
+            }
+            rest -= U;
+        }
+    }
 }
 
 /* ---- any other shape up to LNB_A3_MAX_NA samples (a file's tail block): same cascade, plain layout ----
@@ -349,7 +410,7 @@ __device__ void lnb_a3_generic(const LnbEncodeBatch &b, uint32_t s, uint32_t bc,
     const uint32_t arr = lnb_a3_array_doubles(na_max);
     double *A = smem, *B = smem + arr;
     double *cand = smem + 2u * arr, *acorr = cand + LNB_MAX_LEVELS * LNB_MAX_PARAMS;
-    double *misc = acorr + LNB_MAX_LEVELS * 256 + LNB_A3_WARPS * LNB_A3_PART;
+    double *misc = acorr + LNB_MAX_LEVELS * 256 + LNB_A3_ITEMS * LNB_A3_PART + 2 * LNB_A3_MIRROR;
     {
         const int32_t *src = b.work + (size_t)bc * b.cfg.work_stride;
         const double norm = ldexp(1.0, -(int)(b.cfg.bits_per_sample - 1u));
@@ -451,7 +512,8 @@ __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEn
     cx.cand = lnb_a3_smem + 2u * arr;
     cx.acorr = cx.cand + LNB_MAX_LEVELS * LNB_MAX_PARAMS;
     cx.part = cx.acorr + LNB_MAX_LEVELS * 256;
-    cx.misc = cx.part + LNB_A3_WARPS * LNB_A3_PART;
+    cx.lev0 = cx.part + LNB_A3_ITEMS * LNB_A3_PART;
+    cx.misc = cx.lev0 + 2 * LNB_A3_MIRROR;
     const uint32_t na = cx.na;
     const double lambda = b.cfg.lambdas[lam];
 
@@ -480,58 +542,65 @@ __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEn
         uint32_t nlev = 0;
         while (nlev < LNB_MAX_LEVELS && (1u << nlev) <= P) nlev++;        /* U = 1 .. min(128, P) */
 
-        /* ---- autocorrelation of every unit of every level ---- */
-        for (uint32_t lv = 0; lv < nlev; lv++) {
-            const uint32_t U = 1u << lv, p = P / U, m = na / U;
-            lnb_a3_window(cx, m, b.welch[(size_t)blk_i * LNB_MAX_LEVELS + lv]);
-            __syncthreads();
-            lnb_a3_autocorr(cx, U, p, cx.acorr + lv * 256);
-            __syncthreads();
-        }
+        const LnbA3Team all = { c, LNB_A3_THREADS, c >> 5, LNB_A3_WARPS, 0u };
+        /* The order-P recursion of level 0 (one unit) is 127 dependent steps on ONE warp when P = 128.  It runs on
+         * warp 7 while warps 0..6 do everything else of the search that does not depend on it. */
+        const bool split = (P >= 32u) && nlev >= 2u;
+        const double *welch = b.welch + (size_t)blk_i * LNB_MAX_LEVELS;
 
-        /* ---- Levinson-Durbin: thread-serial for p <= 16, warp-cooperative above (B is free: scratch) ---- */
-        {
-            uint32_t task = c;
-            for (uint32_t lv = 0; lv < nlev; lv++) {
-                const uint32_t U = 1u << lv, p = P / U;
-                if (p > 16u) continue;
-                if (task < U) {
-                    double r[17], a[18], coef[16];
-                    const double *src = cx.acorr + lv * 256 + task * (p + 1u);
-                    for (uint32_t k = 0; k <= p; k++) r[k] = src[k];
-                    r[0] = __dmul_rn(r[0], __dadd_rn(1.0, lambda));
-                    lnb_levinson(r, p, a, coef, (double *)0);
-                    double *dst = cx.cand + lv * LNB_MAX_PARAMS + task * p;
-                    for (uint32_t j = 0; j < p; j++) dst[j] = coef[p - 1u - j];
-                    task = 0xFFFFFFFFu;
-                } else if (task != 0xFFFFFFFFu) {
-                    task -= U;
+        if (split) {
+            lnb_a3_window(cx, all, na, welch[0]);
+            __syncthreads();
+            lnb_a3_autocorr(cx, all, 1u, P, cx.acorr);
+            __syncthreads();
+            if ((c >> 5) == LNB_A3_WARPS - 1u) {
+                lnb_a3_levinson_warp(cx.acorr, P, lambda, cx.lev0, cx.cand);
+            } else {
+                const LnbA3Team rest = { c, LNB_A3_THREADS - 32u, c >> 5, LNB_A3_WARPS - 1u, 1u };
+                for (uint32_t lv = 1; lv < nlev; lv++) {
+                    const uint32_t U = 1u << lv, p = P / U, m = na / U;
+                    lnb_a3_window(cx, rest, m, welch[lv]);
+                    rest.sync();
+                    lnb_a3_autocorr(cx, rest, U, p, cx.acorr + lv * 256);
+                    rest.sync();
+                }
+                lnb_a3_solve_levels(cx, rest, P, 1u, nlev, lambda, cx.B);       /* B is free again: mirror scratch */
+                rest.sync();
+                for (uint32_t lv = 1; lv < nlev; lv++) {
+                    const uint32_t U = 1u << lv, p = P / U;
+                    const double part = lnb_a3_fir_any<0>(cx, rest, cx.A, (double *)0, p, na / U, cx.cand + lv * LNB_MAX_PARAMS);
+                    const double tot = lnb_a3_team_sum(rest, part, cx.misc + 16);
+                    if (c == 0) cx.misc[lv] = tot / (double)na;
                 }
             }
-            const uint32_t warp = c >> 5;
-            uint32_t wt = warp;
+            __syncthreads();
+            {
+                const double part = lnb_a3_fir_any<0>(cx, all, cx.A, (double *)0, P, na, cx.cand);
+                const double tot = lnb_a3_block_sum(part, cx.misc + 16);
+                if (c == 0) cx.misc[0] = tot / (double)na;
+            }
+        } else {
+            /* ---- autocorrelation of every unit of every level ---- */
+            for (uint32_t lv = 0; lv < nlev; lv++) {
+                const uint32_t U = 1u << lv, p = P / U, m = na / U;
+                lnb_a3_window(cx, all, m, welch[lv]);
+                __syncthreads();
+                lnb_a3_autocorr(cx, all, U, p, cx.acorr + lv * 256);
+                __syncthreads();
+            }
+            /* ---- Levinson-Durbin (B is free: mirror scratch) ---- */
+            lnb_a3_solve_levels(cx, all, P, 0u, nlev, lambda, cx.B);
+            __syncthreads();
+            /* ---- L1 loss of every level (linne_network.c:318-335) ---- */
             for (uint32_t lv = 0; lv < nlev; lv++) {
                 const uint32_t U = 1u << lv, p = P / U;
-                if (p <= 16u) continue;
-                if (wt < U) {
-                    lnb_a3_levinson_warp(cx.acorr + lv * 256 + wt * (p + 1u), p, lambda,
-                                         cx.B + warp * 2 * LNB_A3_MIRROR, cx.cand + lv * LNB_MAX_PARAMS + wt * p);
-                    wt = 0xFFFFFFFFu;
-                } else if (wt != 0xFFFFFFFFu) {
-                    wt -= U;
-                }
+                const double part = lnb_a3_fir_any<0>(cx, all, cx.A, (double *)0, p, na / U, cx.cand + lv * LNB_MAX_PARAMS);
+                const double tot = lnb_a3_block_sum(part, cx.misc + 16);
+                if (c == 0) cx.misc[lv] = tot / (double)na;
             }
         }
         __syncthreads();
-
-        /* ---- L1 loss of every level, first minimum wins (linne_network.c:337-341) ---- */
-        for (uint32_t lv = 0; lv < nlev; lv++) {
-            const uint32_t U = 1u << lv, p = P / U;
-            const double part = lnb_a3_fir_any<0>(cx, cx.A, (double *)0, p, na / U, cx.cand + lv * LNB_MAX_PARAMS);
-            const double tot = lnb_a3_block_sum(part, cx.misc + 16);
-            if (c == 0) cx.misc[lv] = tot / (double)na;
-        }
-        __syncthreads();
+        /* first minimum wins (linne_network.c:337-341) */
         uint32_t best = 0;
         {
             double best_loss = (double)FLT_MAX;
@@ -548,7 +617,7 @@ __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEn
         /* ---- forward: this layer's residual becomes the next layer's input ---- */
         {
             const uint32_t U = 1u << best, p = P / U;
-            const double part = lnb_a3_fir_any<1>(cx, cx.A, cx.B, p, na / U, cx.cand + best * LNB_MAX_PARAMS);
+            const double part = lnb_a3_fir_any<1>(cx, all, cx.A, cx.B, p, na / U, cx.cand + best * LNB_MAX_PARAMS);
             final_loss = lnb_a3_block_sum(part, cx.misc + 16);
         }
         __syncthreads();
