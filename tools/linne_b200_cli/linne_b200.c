@@ -1,0 +1,249 @@
+/* linne_b200 -- batch command-line driver on top of the LINNE C API as served by liblinne_b200.so.
+ *
+ * a `linne`-compatible tool (reference tools/linne_codec/linne_codec.c: same
+ * -e / -d / -m / -l / -a / -c options, same WAV <-> .lnn mapping, same encoder settings: block 10240,
+ * mid/side for >= 2 channels) that
+ *   - calls LINNEEncoder_EncodeWhole / LINNEDecoder_DecodeWhole once per FILE, so every block x channel
+ *     of a file goes to the GPU as one batch (the reference tool encodes block by block), and
+ *   - takes any number of input/output pairs, or a list file, and reuses one handle for all of them.
+ * WAV sample conventions follow reference libs/wav/src/wav.c:388-414 and :665-700 (8-bit is unsigned with
+ * a bias of 128; 16/24/32-bit little-endian signed); samples are handed to the codec right-justified
+ * (linne_codec.c:100-105) and written back the same way (:262-268).
+ *
+ *   linne_b200 -e [-m 0..7] [-l] [-a N] in.wav out.lnn [in2.wav out2.lnn ...]
+ *   linne_b200 -d [-c]                  in.lnn out.wav [in2.lnn out2.wav ...]
+ *   linne_b200 -e|-d ... -L pairs.txt   (one "input output" pair per line)
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <linne_encoder.h>
+#include <linne_decoder.h>
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define CLI_BLOCK 10240u                       /* linne_codec.c:75 */
+#define CLI_MAX_BLOCK (16u * 1024u)            /* linne_codec.c:54 */
+
+struct Wav {
+    uint32_t channels, rate, bits, frames;
+    int32_t *pcm[LINNE_MAX_NUM_CHANNELS];      /* right-justified samples, one plane per channel */
+};
+
+static uint32_t rd_le(const uint8_t *p, int n) { uint32_t v = 0; int i; for (i = n - 1; i >= 0; i--) v = (v << 8) | p[i]; return v; }
+static void wr_le(uint8_t *p, uint32_t v, int n) { int i; for (i = 0; i < n; i++) p[i] = (uint8_t)(v >> (8 * i)); }
+
+static void wav_free(struct Wav *w) { uint32_t c; for (c = 0; c < LINNE_MAX_NUM_CHANNELS; c++) { free(w->pcm[c]); w->pcm[c] = NULL; } }
+
+static uint8_t *read_file(const char *path, size_t *size)
+{
+    FILE *fp = fopen(path, "rb");
+    uint8_t *buf;
+    long n;
+    if (!fp) return NULL;
+    if (fseek(fp, 0, SEEK_END) != 0 || (n = ftell(fp)) < 0 || fseek(fp, 0, SEEK_SET) != 0) { fclose(fp); return NULL; }
+    buf = (uint8_t *)malloc((size_t)n + 16u);
+    if (buf && fread(buf, 1, (size_t)n, fp) != (size_t)n) { free(buf); buf = NULL; }
+    fclose(fp);
+    *size = (size_t)n;
+    return buf;
+}
+
+/* RIFF/WAVE, PCM (format tag 1, or WAVE_FORMAT_EXTENSIBLE carrying PCM), 8/16/24/32 bits */
+static int wav_read(const char *path, struct Wav *w)
+{
+    size_t size = 0, off = 12, data_off = 0, data_len = 0;
+    uint8_t *f = read_file(path, &size);
+    uint32_t c, i, bytes, have_fmt = 0;
+    memset(w, 0, sizeof(*w));
+    if (!f || size < 12 || memcmp(f, "RIFF", 4) != 0 || memcmp(f + 8, "WAVE", 4) != 0) { free(f); return 1; }
+    while (off + 8 <= size) {
+        const uint32_t len = rd_le(f + off + 4, 4);
+        const uint8_t *body = f + off + 8;
+        if (memcmp(f + off, "fmt ", 4) == 0 && len >= 16 && off + 8 + len <= size) {
+            uint32_t tag = rd_le(body, 2);
+            if (tag == 0xFFFEu && len >= 26) tag = rd_le(body + 24, 2);
+            if (tag != 1u) { free(f); return 2; }
+            w->channels = rd_le(body + 2, 2); w->rate = rd_le(body + 4, 4); w->bits = rd_le(body + 14, 2);
+            have_fmt = 1;
+        } else if (memcmp(f + off, "data", 4) == 0) {
+            data_off = off + 8;
+            data_len = (off + 8 + len <= size) ? len : size - (off + 8);
+            break;
+        }
+        off += 8 + (size_t)len + (len & 1u);
+    }
+    bytes = w->bits / 8u;
+    if (!have_fmt || !data_off || w->channels == 0 || w->channels > LINNE_MAX_NUM_CHANNELS
+        || (w->bits != 8 && w->bits != 16 && w->bits != 24 && w->bits != 32)) { free(f); return 3; }
+    w->frames = (uint32_t)(data_len / ((size_t)bytes * w->channels));
+    for (c = 0; c < w->channels; c++)
+        if (!(w->pcm[c] = (int32_t *)malloc(sizeof(int32_t) * (w->frames ? w->frames : 1u)))) { wav_free(w); free(f); return 4; }
+    for (i = 0; i < w->frames; i++)
+        for (c = 0; c < w->channels; c++) {
+            const uint8_t *p = f + data_off + ((size_t)i * w->channels + c) * bytes;
+            int32_t v;
+            if (w->bits == 8) v = (int32_t)p[0] - 128;
+            else if (w->bits == 16) v = (int16_t)rd_le(p, 2);
+            else if (w->bits == 24) v = (int32_t)(rd_le(p, 3) << 8) >> 8;
+            else v = (int32_t)rd_le(p, 4);
+            w->pcm[c][i] = v;
+        }
+    free(f);
+    return 0;
+}
+
+static int wav_write(const char *path, const struct Wav *w)
+{
+    const uint32_t bytes = w->bits / 8u;
+    const size_t data_len = (size_t)w->frames * w->channels * bytes;
+    uint8_t *f = (uint8_t *)malloc(44u + data_len);
+    uint32_t c, i;
+    FILE *fp;
+    int rc = 0;
+    if (!f) return 1;
+    memcpy(f, "RIFF", 4); wr_le(f + 4, (uint32_t)(36u + data_len), 4); memcpy(f + 8, "WAVEfmt ", 8);
+    wr_le(f + 16, 16, 4); wr_le(f + 20, 1, 2); wr_le(f + 22, w->channels, 2); wr_le(f + 24, w->rate, 4);
+    wr_le(f + 28, w->rate * w->channels * bytes, 4); wr_le(f + 32, w->channels * bytes, 2); wr_le(f + 34, w->bits, 2);
+    memcpy(f + 36, "data", 4); wr_le(f + 40, (uint32_t)data_len, 4);
+    for (i = 0; i < w->frames; i++)
+        for (c = 0; c < w->channels; c++) {
+            uint8_t *p = f + 44u + ((size_t)i * w->channels + c) * bytes;
+            const int32_t v = w->pcm[c][i];
+            if (w->bits == 8) p[0] = (uint8_t)((v + 128) & 0xFF);
+            else wr_le(p, (uint32_t)v, (int)bytes);
+        }
+    if (!(fp = fopen(path, "wb"))) { free(f); return 2; }
+    if (fwrite(f, 1, 44u + data_len, fp) != 44u + data_len) rc = 3;
+    fclose(fp);
+    free(f);
+    return rc;
+}
+
+struct Options { int encode, decode, preset, learning, af, no_crc; const char *list; };
+
+static int encode_one(struct LINNEEncoder *enc, const struct Options *o, const char *in, const char *out)
+{
+    struct Wav w;
+    struct LINNEEncodeParameter prm;
+    uint8_t *buf;
+    uint32_t cap, size = 0;
+    LINNEApiResult ret;
+    FILE *fp;
+    int rc;
+    if ((rc = wav_read(in, &w)) != 0) { fprintf(stderr, "linne_b200: cannot read %s (%d)\n", in, rc); return 1; }
+    prm.num_channels = (uint16_t)w.channels;
+    prm.bits_per_sample = (uint16_t)w.bits;
+    prm.sampling_rate = w.rate;
+    prm.num_samples_per_block = (uint16_t)CLI_BLOCK;
+    prm.preset = (uint8_t)o->preset;
+    prm.ch_process_method = (w.channels >= 2) ? LINNE_CH_PROCESS_METHOD_MS : LINNE_CH_PROCESS_METHOD_NONE;
+    prm.enable_learning = (uint8_t)o->learning;
+    prm.num_afmethod_iterations = (uint8_t)o->af;
+    if ((ret = LINNEEncoder_SetEncodeParameter(enc, &prm)) != LINNE_APIRESULT_OK) {
+        fprintf(stderr, "linne_b200: %s: cannot set the encode parameters (%d)\n", in, (int)ret);
+        wav_free(&w); return 1;
+    }
+    /* worst case: every block stored raw, plus block and stream headers */
+    cap = LINNE_HEADER_SIZE + w.frames * w.channels * (w.bits / 8u) + 11u * (w.frames / CLI_BLOCK + 2u) + 4096u;
+    if (!(buf = (uint8_t *)malloc(cap))) { wav_free(&w); return 1; }
+    ret = LINNEEncoder_EncodeWhole(enc, (const int32_t *const *)w.pcm, w.frames, buf, cap, &size);
+    if (ret != LINNE_APIRESULT_OK) { fprintf(stderr, "linne_b200: %s: encode failed (%d)\n", in, (int)ret); free(buf); wav_free(&w); return 1; }
+    if (!(fp = fopen(out, "wb")) || fwrite(buf, 1, size, fp) != size) { fprintf(stderr, "linne_b200: cannot write %s\n", out); if (fp) fclose(fp); free(buf); wav_free(&w); return 1; }
+    fclose(fp);
+    printf("%s -> %s: %u samples x %u ch, %u bytes\n", in, out, w.frames, w.channels, size);
+    free(buf);
+    wav_free(&w);
+    return 0;
+}
+
+static int decode_one(struct LINNEDecoder *dec, const char *in, const char *out)
+{
+    size_t size = 0;
+    uint8_t *buf = read_file(in, &size);
+    struct LINNEHeader h;
+    struct Wav w;
+    LINNEApiResult ret;
+    uint32_t c;
+    if (!buf) { fprintf(stderr, "linne_b200: cannot read %s\n", in); return 1; }
+    if ((ret = LINNEDecoder_DecodeHeader(buf, (uint32_t)size, &h)) != LINNE_APIRESULT_OK) {
+        fprintf(stderr, "linne_b200: %s: not a LINNE stream (%d)\n", in, (int)ret); free(buf); return 1;
+    }
+    memset(&w, 0, sizeof(w));
+    w.channels = h.num_channels; w.rate = h.sampling_rate; w.bits = h.bits_per_sample; w.frames = h.num_samples;
+    if (w.channels == 0 || w.channels > LINNE_MAX_NUM_CHANNELS) { free(buf); return 1; }
+    for (c = 0; c < w.channels; c++)
+        if (!(w.pcm[c] = (int32_t *)calloc(w.frames ? w.frames : 1u, sizeof(int32_t)))) { wav_free(&w); free(buf); return 1; }
+    ret = LINNEDecoder_DecodeWhole(dec, buf, (uint32_t)size, w.pcm, w.channels, w.frames);
+    free(buf);
+    if (ret != LINNE_APIRESULT_OK) { fprintf(stderr, "linne_b200: %s: decode failed (%d)\n", in, (int)ret); wav_free(&w); return 1; }
+    if (wav_write(out, &w) != 0) { fprintf(stderr, "linne_b200: cannot write %s\n", out); wav_free(&w); return 1; }
+    printf("%s -> %s: %u samples x %u ch\n", in, out, w.frames, w.channels);
+    wav_free(&w);
+    return 0;
+}
+
+static void usage(const char *argv0)
+{
+    fprintf(stderr,
+        "usage: %s -e [-m 0..7] [-l] [-a N] in.wav out.lnn [in2.wav out2.lnn ...]\n"
+        "       %s -d [-c] in.lnn out.wav [in2.lnn out2.wav ...]\n"
+        "       -L FILE reads \"input output\" pairs from FILE (one per line)\n"
+        "  -e encode  -d decode  -m compress mode (default 0)  -l learning  -a auxiliary-function iterations\n"
+        "  -c do NOT check CRC16 when decoding\n", argv0, argv0);
+}
+
+int main(int argc, char **argv)
+{
+    struct Options o;
+    const char *files[4096];
+    char *owned[4096];
+    int nfiles = 0, nowned = 0, i, failures = 0;
+    struct LINNEEncoder *enc = NULL;
+    struct LINNEDecoder *dec = NULL;
+    memset(&o, 0, sizeof(o));
+    for (i = 1; i < argc; i++) {
+        const char *a = argv[i];
+        if (!strcmp(a, "-e") || !strcmp(a, "--encode")) o.encode = 1;
+        else if (!strcmp(a, "-d") || !strcmp(a, "--decode")) o.decode = 1;
+        else if (!strcmp(a, "-l") || !strcmp(a, "--enable-learning")) o.learning = 1;
+        else if (!strcmp(a, "-c") || !strcmp(a, "--no-crc-check")) o.no_crc = 1;
+        else if ((!strcmp(a, "-m") || !strcmp(a, "--mode")) && i + 1 < argc) o.preset = atoi(argv[++i]);
+        else if ((!strcmp(a, "-a") || !strcmp(a, "--auxiliary-function-iteration")) && i + 1 < argc) o.af = atoi(argv[++i]);
+        else if (!strcmp(a, "-L") && i + 1 < argc) o.list = argv[++i];
+        else if (!strcmp(a, "-h") || !strcmp(a, "--help")) { usage(argv[0]); return 0; }
+        else if (a[0] == '-' && a[1] != '\0') { fprintf(stderr, "%s: unknown option %s\n", argv[0], a); usage(argv[0]); return 1; }
+        else if (nfiles < 4096) files[nfiles++] = a;
+    }
+    if (o.list) {
+        FILE *fp = fopen(o.list, "r");
+        char a[2048], b[2048];
+        if (!fp) { fprintf(stderr, "%s: cannot open %s\n", argv[0], o.list); return 1; }
+        while (fscanf(fp, "%2047s %2047s", a, b) == 2 && nfiles + 2 <= 4096 && nowned + 2 <= 4096) {
+            files[nfiles++] = owned[nowned++] = strdup(a);
+            files[nfiles++] = owned[nowned++] = strdup(b);
+        }
+        fclose(fp);
+    }
+    if (o.encode == o.decode) { fprintf(stderr, "%s: exactly one of -e and -d must be given\n", argv[0]); usage(argv[0]); return 1; }
+    if (nfiles < 2 || (nfiles & 1)) { fprintf(stderr, "%s: input and output files must come in pairs\n", argv[0]); return 1; }
+    if (o.preset < 0 || o.preset >= LINNE_NUM_PARAMETER_PRESETS || o.af < 0 || o.af >= 255) { fprintf(stderr, "%s: option out of range\n", argv[0]); return 1; }
+
+    if (o.encode) {
+        struct LINNEEncoderConfig cfg;
+        cfg.max_num_channels = LINNE_MAX_NUM_CHANNELS; cfg.max_num_samples_per_block = CLI_MAX_BLOCK;
+        cfg.max_num_layers = 5; cfg.max_num_parameters_per_layer = 128;          /* linne_codec.c:53-56 */
+        if (!(enc = LINNEEncoder_Create(&cfg, NULL, 0))) { fprintf(stderr, "%s: cannot create the encoder\n", argv[0]); return 1; }
+        for (i = 0; i < nfiles; i += 2) failures += encode_one(enc, &o, files[i], files[i + 1]);
+        LINNEEncoder_Destroy(enc);
+    } else {
+        struct LINNEDecoderConfig cfg;
+        cfg.max_num_channels = LINNE_MAX_NUM_CHANNELS; cfg.max_num_layers = 5;
+        cfg.max_num_parameters_per_layer = 128; cfg.check_crc = (uint8_t)(o.no_crc ? 0 : 1);   /* linne_codec.c:205-208 */
+        if (!(dec = LINNEDecoder_Create(&cfg, NULL, 0))) { fprintf(stderr, "%s: cannot create the decoder\n", argv[0]); return 1; }
+        for (i = 0; i < nfiles; i += 2) failures += decode_one(dec, files[i], files[i + 1]);
+        LINNEDecoder_Destroy(dec);
+    }
+    for (i = 0; i < nowned; i++) free(owned[i]);
+    return failures ? 1 : 0;
+}
