@@ -44,6 +44,17 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *decoder,
         const uint8_t *data, const uint8_t *d_data, uint32_t data_size,
         int32_t *d_pcm, uint32_t pcm_stride, uint32_t buffer_num_channels, uint32_t buffer_num_samples);
 
+/* ---- packed PCM entry points ------------------------------------------------------------
+ * `pcm` = interleaved little-endian samples exactly as in a WAV data chunk (8-bit unsigned with a bias of 128,
+ * 16/24/32-bit signed; bits per sample = the encoder's parameter / the stream header).  The conversion to and
+ * from the int32 planes runs on the device, so the PCIe bytes per sample are bits/8 instead of 4.
+ * `num_samples` and `pcm_capacity_frames` count frames (samples per channel).  Same result codes as
+ * EncodeWhole / DecodeWhole; `*num_frames` = frames written (all of them on success). */
+LINNEApiResult LINNEB200_EncodeWholePacked(struct LINNEEncoder *encoder, const uint8_t *pcm, uint32_t num_samples,
+        uint8_t *data, uint32_t data_size, uint32_t *output_size);
+LINNEApiResult LINNEB200_DecodeWholePacked(struct LINNEDecoder *decoder, const uint8_t *data, uint32_t data_size,
+        uint8_t *pcm, uint32_t pcm_capacity_frames, uint32_t *num_frames);
+
 /* ---- encode with externally supplied analysis results ------------------------------------------
  * One record per (block, channel), block-major.  Used to show that identical quantised
  * coefficients yield byte-identical residuals and coded bits (north star, parity leg 3). */

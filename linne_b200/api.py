@@ -224,6 +224,10 @@ def bind_ext_api(lib):
     lib.LINNEB200_IpcOpen.argtypes = [u8p]
     lib.LINNEB200_IpcOpen.restype = C.c_void_p
     lib.LINNEB200_IpcClose.argtypes = [C.c_void_p]
+    lib.LINNEB200_EncodeWholePacked.argtypes = [C.c_void_p, u8p, C.c_uint32, u8p, C.c_uint32, u32p]
+    lib.LINNEB200_EncodeWholePacked.restype = C.c_int
+    lib.LINNEB200_DecodeWholePacked.argtypes = [C.c_void_p, u8p, C.c_uint32, u8p, C.c_uint32, u32p]
+    lib.LINNEB200_DecodeWholePacked.restype = C.c_int
     for name in ("DeviceCopy", "CopyToDevice", "CopyToHost"):
         f = getattr(lib, f"LINNEB200_{name}")
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -446,6 +450,58 @@ class Product(LinneApi):
 
     def measure_fp64_tflops(self) -> float:
         return float(self.lib.LINNEB200_MeasureFp64Tflops())
+
+    def encode_packed(self, packed: bytes, channels, bits=16, rate=44100, block=10240, preset=0, ms=None, return_code=False):
+        """`packed`: interleaved little-endian PCM as in a WAV data chunk (LINNEB200_EncodeWholePacked)."""
+        u8p = C.POINTER(C.c_uint8)
+        nbytes = bits // 8
+        n = len(packed) // (channels * nbytes)
+        if ms is None:
+            ms = 1 if channels >= 2 else 0
+        enc = self.make_encoder(channels, block)
+        try:
+            prm = LINNEEncodeParameter(channels, bits, rate, block, preset, ms, 0, 0)
+            rc = self.lib.LINNEEncoder_SetEncodeParameter(enc, C.byref(prm))
+            if rc != OK:
+                raise RuntimeError(f"SetEncodeParameter rc={rc}")
+            cap = 30 + 2 * channels * n * 4 + 4096
+            out = np.zeros(cap, dtype=np.uint8)
+            src = np.frombuffer(packed, dtype=np.uint8)
+            size = C.c_uint32(0)
+            rc = self.lib.LINNEB200_EncodeWholePacked(enc, src.ctypes.data_as(u8p), n, out.ctypes.data_as(u8p), cap, C.byref(size))
+            if return_code:
+                return rc, out[:size.value].tobytes() if rc == OK else b""
+            if rc != OK:
+                raise RuntimeError(f"EncodeWholePacked rc={rc}")
+            return out[:size.value].tobytes()
+        finally:
+            self.lib.LINNEEncoder_Destroy(enc)
+
+    def decode_packed(self, data: bytes, check_crc=1, return_code=False):
+        """-> interleaved little-endian PCM bytes (LINNEB200_DecodeWholePacked)."""
+        u8p = C.POINTER(C.c_uint8)
+        rc, hdr = self.decode_header(data)
+        if rc != OK:
+            raise RuntimeError(f"DecodeHeader rc={rc}")
+        cfg = LINNEDecoderConfig(8, 3, 128, check_crc)
+        dec = self.lib.LINNEDecoder_Create(C.byref(cfg), None, 0)
+        if not dec:
+            raise RuntimeError("LINNEDecoder_Create failed")
+        try:
+            nbytes = hdr.bits_per_sample // 8
+            out = np.zeros(max(1, hdr.num_samples * hdr.num_channels * nbytes), dtype=np.uint8)
+            buf = np.frombuffer(data, dtype=np.uint8)
+            frames = C.c_uint32(0)
+            rc = self.lib.LINNEB200_DecodeWholePacked(dec, buf.ctypes.data_as(u8p), len(data), out.ctypes.data_as(u8p),
+                                                      hdr.num_samples, C.byref(frames))
+            res = out[:frames.value * hdr.num_channels * nbytes].tobytes()
+            if return_code:
+                return rc, res
+            if rc != OK:
+                raise RuntimeError(f"DecodeWholePacked rc={rc}")
+            return res
+        finally:
+            self.lib.LINNEDecoder_Destroy(dec)
 
     def encode_with_params(self, pcm, params, bits=16, rate=44100, block=10240, preset=0, ms=None):
         """params: ctypes array of ChannelParams, one per (block, channel), block-major."""

@@ -22,7 +22,7 @@ struct LINNEDecoder {
     uint32_t flags;
     void *work;
     LnbDevice *dev;
-    LnbBuf d_stream, d_blocks, d_params, d_pcm;
+    LnbBuf d_stream, d_blocks, d_params, d_pcm, d_packed;
     LnbBuf h_blocks;                       /* pinned LnbBlockDesc[] */
     LnbBuf h_stream;                       /* pinned copy of a device-resident stream (block hop) */
 };
@@ -88,6 +88,7 @@ void LINNEDecoder_Destroy(struct LINNEDecoder *dec)
         lnb_buf_release_device(dec->dev, &dec->d_blocks);
         lnb_buf_release_device(dec->dev, &dec->d_params);
         lnb_buf_release_device(dec->dev, &dec->d_pcm);
+        lnb_buf_release_device(dec->dev, &dec->d_packed);
         lnb_buf_release_host(&dec->h_blocks);
         lnb_buf_release_host(&dec->h_stream);
         lnb_shim_close(dec->dev);
@@ -350,4 +351,36 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uin
         || pcm_stride < buffer_num_samples) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, NULL, buffer_num_samples,
                         header.num_samples, 0, NULL, NULL, d_data, d_pcm, pcm_stride);
+}
+
+/* Packed interleaved PCM out (the bytes of a WAV data chunk), converted from the planes on the device.
+ * `pcm` holds `pcm_capacity_frames` frames; `num_frames` receives the frames written.  SURVEY 8f.2. */
+LINNEApiResult LINNEB200_DecodeWholePacked(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
+        uint8_t *pcm, uint32_t pcm_capacity_frames, uint32_t *num_frames)
+{
+    struct LINNEHeader header;
+    LINNEApiResult ret;
+    uint32_t decoded = 0, bytes;
+    size_t stride;
+    if (dec == NULL || data == NULL || pcm == NULL || num_frames == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    *num_frames = 0;
+    if ((ret = LINNEDecoder_DecodeHeader(data, data_size, &header)) != LINNE_APIRESULT_OK) return ret;
+    if ((ret = LINNEDecoder_SetHeader(dec, &header)) != LINNE_APIRESULT_OK) return ret;
+    if (pcm_capacity_frames < header.num_samples) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    bytes = header.bits_per_sample / 8u;
+    if (bytes == 0 || bytes > 4u || (header.bits_per_sample % 8u) != 0u) return LINNE_APIRESULT_INVALID_FORMAT;
+    stride = LNB_ROUNDUP((size_t)header.num_samples + (size_t)header.num_samples_per_block + 4u, 4u);   /* room for a parked terminal block */
+    if (lnb_buf_reserve_device(dec->dev, &dec->d_pcm, stride * header.num_channels * sizeof(int32_t))
+        || lnb_buf_reserve_device(dec->dev, &dec->d_packed, (size_t)header.num_samples * header.num_channels * bytes + 16u))
+        return LINNE_APIRESULT_NG;
+    ret = decode_range(dec, data, data_size, LINNE_HEADER_SIZE, NULL, header.num_samples, header.num_samples, 0,
+                       NULL, &decoded, NULL, (int32_t *)dec->d_pcm.ptr, (uint32_t)stride);
+    if (decoded) {          /* every sample the reference would have produced before stopping */
+        if (lnb_shim_pack_pcm(dec->dev, (const int32_t *)dec->d_pcm.ptr, (uint8_t *)dec->d_packed.ptr, (uint32_t)stride,
+                              decoded, header.num_channels, bytes)) return LINNE_APIRESULT_NG;
+        lnb_shim_d2h(dec->dev, pcm, dec->d_packed.ptr, (size_t)decoded * header.num_channels * bytes);
+        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+    }
+    *num_frames = decoded;
+    return ret;
 }

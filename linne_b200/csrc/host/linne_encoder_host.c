@@ -27,7 +27,7 @@ struct LINNEEncoder {
     LnbDevice *dev;
     size_t scratch_budget;                 /* bytes of analysis scratch per chunk */
     LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_acorr, d_cand, d_unit_loss,
-           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train;
+           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train, d_packed;
     LnbBuf h_blocks, h_welch, h_total;
     const int32_t *cur_pcm;                /* device PCM planes of the call in flight */
     uint32_t cur_pcm_stride;
@@ -98,7 +98,7 @@ void LINNEEncoder_Destroy(struct LINNEEncoder *enc)
         LnbBuf *dbufs[] = { &enc->d_pcm, &enc->d_blocks, &enc->d_params, &enc->d_est, &enc->d_work, &enc->d_sig_a,
                             &enc->d_sig_b, &enc->d_acorr, &enc->d_cand, &enc->d_unit_loss, &enc->d_chosen_w,
                             &enc->d_chosen_u, &enc->d_final_sum, &enc->d_welch, &enc->d_plans, &enc->d_plan_mean,
-                            &enc->d_out, &enc->d_total, &enc->d_train };
+                            &enc->d_out, &enc->d_total, &enc->d_train, &enc->d_packed };
         size_t i;
         for (i = 0; i < sizeof(dbufs) / sizeof(dbufs[0]); i++) lnb_buf_release_device(enc->dev, dbufs[i]);
         lnb_buf_release_host(&enc->h_blocks);
@@ -413,6 +413,37 @@ LINNEApiResult LINNEB200_EncodeWholeResident(struct LINNEEncoder *enc, const int
     enc->cur_pcm = d_pcm;
     enc->cur_pcm_stride = pcm_stride;
     ret = encode_blocks(enc, num_samples, d_data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, 1, NULL, &written);
+    if (ret != LINNE_APIRESULT_OK) return ret;
+    *output_size = LINNE_HEADER_SIZE + written;
+    return LINNE_APIRESULT_OK;
+}
+
+/* Packed interleaved PCM in (the bytes of a WAV data chunk), converted to planes on the device: half (16-bit) or
+ * three quarters (24-bit) of the PCIe bytes of the int32-planar call.  SURVEY 8f.2. */
+LINNEApiResult LINNEB200_EncodeWholePacked(struct LINNEEncoder *enc, const uint8_t *pcm, uint32_t num_samples,
+        uint8_t *data, uint32_t data_size, uint32_t *output_size)
+{
+    LINNEApiResult ret;
+    uint32_t written = 0, C, bytes;
+    size_t stride, packed_bytes;
+    if (enc == NULL || pcm == NULL || data == NULL || output_size == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
+    if (unsupported_analysis(enc)) return LINNE_APIRESULT_NG;
+    C = enc->header.num_channels;
+    bytes = enc->header.bits_per_sample / 8u;
+    if (bytes == 0 || bytes > 4u || (enc->header.bits_per_sample % 8u) != 0u) return LINNE_APIRESULT_INVALID_FORMAT;
+    enc->header.num_samples = num_samples;
+    if ((ret = LINNEEncoder_EncodeHeader(&enc->header, data, data_size)) != LINNE_APIRESULT_OK) return ret;
+    stride = LNB_ROUNDUP((size_t)num_samples + 4u, 4u);
+    packed_bytes = (size_t)num_samples * C * bytes;
+    if (lnb_buf_reserve_device(enc->dev, &enc->d_pcm, stride * C * sizeof(int32_t))
+        || lnb_buf_reserve_device(enc->dev, &enc->d_packed, packed_bytes + 16u)) return LINNE_APIRESULT_NG;
+    lnb_shim_h2d(enc->dev, enc->d_packed.ptr, pcm, packed_bytes);
+    if (lnb_shim_unpack_pcm(enc->dev, (const uint8_t *)enc->d_packed.ptr, (int32_t *)enc->d_pcm.ptr, (uint32_t)stride,
+                            num_samples, C, bytes)) return LINNE_APIRESULT_NG;
+    enc->cur_pcm = (const int32_t *)enc->d_pcm.ptr;
+    enc->cur_pcm_stride = (uint32_t)stride;
+    ret = encode_blocks(enc, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, 0, NULL, &written);
     if (ret != LINNE_APIRESULT_OK) return ret;
     *output_size = LINNE_HEADER_SIZE + written;
     return LINNE_APIRESULT_OK;

@@ -113,6 +113,49 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
 }
 
 /* =============================================================================================
+ * Packed PCM <-> int32 planes: interleaved little-endian samples as in a WAV data chunk
+ * (8-bit unsigned with a bias of 128, 16/24/32-bit signed; reference libs/wav/src/wav.c:388-414, :665-700),
+ * right-justified in the planes like tools/linne_codec/linne_codec.c:100-105.  Item = one frame.
+ * ============================================================================================= */
+struct LnbItemUnpackPcm {
+    const uint8_t *packed; int32_t *pcm; uint32_t stride, channels, bytes;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        const uint8_t *p = packed + (size_t)i * channels * bytes;
+        for (uint32_t c = 0; c < channels; c++, p += bytes) {
+            int32_t v;
+            if (bytes == 1u) v = (int32_t)p[0] - 128;
+            else if (bytes == 2u) v = (int16_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8));
+            else if (bytes == 3u) v = (int32_t)(((uint32_t)p[0] << 8) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 24)) >> 8;
+            else v = (int32_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24));
+            pcm[(size_t)c * stride + i] = v;
+        }
+    }
+};
+struct LnbItemPackPcm {
+    const int32_t *pcm; uint8_t *packed; uint32_t stride, channels, bytes;
+    LNB_HDM void operator()(uint32_t i) const
+    {
+        uint8_t *p = packed + (size_t)i * channels * bytes;
+        for (uint32_t c = 0; c < channels; c++, p += bytes) {
+            const int32_t v = pcm[(size_t)c * stride + i];
+            if (bytes == 1u) p[0] = (uint8_t)((v + 128) & 0xFF);
+            else for (uint32_t k = 0; k < bytes; k++) p[k] = (uint8_t)((uint32_t)v >> (8u * k));
+        }
+    }
+};
+template <class Exec>
+void lnb_unpack_pcm_pipeline(Exec &ex, const uint8_t *packed, int32_t *pcm, uint32_t stride, uint32_t frames, uint32_t channels, uint32_t bytes)
+{
+    ex.run("unpack_pcm", frames, LnbItemUnpackPcm{packed, pcm, stride, channels, bytes});
+}
+template <class Exec>
+void lnb_pack_pcm_pipeline(Exec &ex, const int32_t *pcm, uint8_t *packed, uint32_t stride, uint32_t frames, uint32_t channels, uint32_t bytes)
+{
+    ex.run("pack_pcm", frames, LnbItemPackPcm{pcm, packed, stride, channels, bytes});
+}
+
+/* =============================================================================================
  * Encode
  * ============================================================================================= */
 

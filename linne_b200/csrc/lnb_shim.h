@@ -51,6 +51,12 @@ int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *batch);
 int lnb_shim_encode_analyze(LnbDevice *dev, const LnbEncodeBatch *batch);
 int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *batch, uint32_t out_capacity);
 
+/* packed interleaved PCM (WAV data-chunk layout, `bytes` per sample) <-> int32 planes, on the device (enqueue only) */
+int lnb_shim_unpack_pcm(LnbDevice *dev, const uint8_t *d_packed, int32_t *d_pcm, uint32_t pcm_stride,
+                        uint32_t frames, uint32_t channels, uint32_t bytes);
+int lnb_shim_pack_pcm(LnbDevice *dev, const int32_t *d_pcm, uint8_t *d_packed, uint32_t pcm_stride,
+                      uint32_t frames, uint32_t channels, uint32_t bytes);
+
 /* number of kernels launched through this context since it was opened (bench.py's gpu_launches) */
 uint64_t lnb_shim_launch_count(const LnbDevice *dev);
 

@@ -406,6 +406,23 @@ int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *batch, uint32_t o
     return dev->last_error == cudaSuccess ? 0 : 1;
 }
 
+int lnb_shim_unpack_pcm(LnbDevice *dev, const uint8_t *d_packed, int32_t *d_pcm, uint32_t pcm_stride,
+                        uint32_t frames, uint32_t channels, uint32_t bytes)
+{
+    bind_device(dev);
+    CudaExec ex{dev};
+    lnb_unpack_pcm_pipeline(ex, d_packed, d_pcm, pcm_stride, frames, channels, bytes);
+    return dev->last_error == cudaSuccess ? 0 : 1;
+}
+int lnb_shim_pack_pcm(LnbDevice *dev, const int32_t *d_pcm, uint8_t *d_packed, uint32_t pcm_stride,
+                      uint32_t frames, uint32_t channels, uint32_t bytes)
+{
+    bind_device(dev);
+    CudaExec ex{dev};
+    lnb_pack_pcm_pipeline(ex, d_pcm, d_packed, pcm_stride, frames, channels, bytes);
+    return dev->last_error == cudaSuccess ? 0 : 1;
+}
+
 uint64_t lnb_shim_launch_count(const LnbDevice *dev) { return dev->launches; }
 
 void lnb_shim_profile_enable(LnbDevice *dev, int on)

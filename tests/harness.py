@@ -318,6 +318,18 @@ class HostSim(LinneApi):
         super().__init__(bind_ext_api(C.CDLL(HOSTSIM_SO, mode=getattr(os, "RTLD_LOCAL", 0))))
         assert self.lib.LINNEB200_Backend() == b"hostsim"
         self.encode_with_params = Product.encode_with_params.__get__(self)
+        self.encode_packed = Product.encode_packed.__get__(self)
+        self.decode_packed = Product.decode_packed.__get__(self)
+
+
+def pack_pcm(pcm, bits):
+    """int32 [C][n] right-justified -> interleaved little-endian bytes as in a WAV data chunk."""
+    inter = np.ascontiguousarray(pcm.T).reshape(-1).astype(np.int64)
+    if bits == 8:
+        return ((inter + 128) & 0xFF).astype(np.uint8).tobytes()
+    nbytes = bits // 8
+    raw = (inter & ((1 << bits) - 1)).astype("<u8").view(np.uint8).reshape(-1, 8)[:, :nbytes]
+    return np.ascontiguousarray(raw).tobytes()
 
 
 def params_from_golden(g):

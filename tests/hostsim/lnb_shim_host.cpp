@@ -62,6 +62,10 @@ int lnb_shim_sync(LnbDevice *) { return 0; }
 int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *b) { LoopExec ex{dev}; lnb_decode_pipeline(ex, *b); return 0; }
 int lnb_shim_encode_analyze(LnbDevice *dev, const LnbEncodeBatch *b) { LoopExec ex{dev}; lnb_encode_analyze_pipeline(ex, *b); return 0; }
 int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *b, uint32_t cap) { LoopExec ex{dev}; lnb_encode_pack_pipeline(ex, *b, cap); return 0; }
+int lnb_shim_unpack_pcm(LnbDevice *dev, const uint8_t *pk, int32_t *pcm, uint32_t stride, uint32_t frames, uint32_t ch, uint32_t bytes)
+{ LoopExec ex{dev}; lnb_unpack_pcm_pipeline(ex, pk, pcm, stride, frames, ch, bytes); return 0; }
+int lnb_shim_pack_pcm(LnbDevice *dev, const int32_t *pcm, uint8_t *pk, uint32_t stride, uint32_t frames, uint32_t ch, uint32_t bytes)
+{ LoopExec ex{dev}; lnb_pack_pcm_pipeline(ex, pcm, pk, stride, frames, ch, bytes); return 0; }
 uint64_t lnb_shim_launch_count(const LnbDevice *dev) { return dev->launches; }
 void lnb_shim_profile_enable(LnbDevice *, int) {}
 void lnb_shim_profile_reset(LnbDevice *) {}

@@ -3,8 +3,9 @@
  * a `linne`-compatible tool (reference tools/linne_codec/linne_codec.c: same
  * -e / -d / -m / -l / -a / -c options, same WAV <-> .lnn mapping, same encoder settings: block 10240,
  * mid/side for >= 2 channels) that
- *   - calls LINNEEncoder_EncodeWhole / LINNEDecoder_DecodeWhole once per FILE, so every block x channel
- *     of a file goes to the GPU as one batch (the reference tool encodes block by block), and
+ *   - encodes / decodes a whole FILE per call (LINNEB200_EncodeWholePacked / DecodeWholePacked: the WAV data
+ *     chunk goes to the device as it is and is converted there), so every block x channel of a file is one
+ *     GPU batch (the reference tool encodes block by block through int32 planes), and
  *   - takes any number of input/output pairs, or a list file, and reuses one handle for all of them.
  * WAV sample conventions follow reference libs/wav/src/wav.c:388-414 and :665-700 (8-bit is unsigned with
  * a bias of 128; 16/24/32-bit little-endian signed); samples are handed to the codec right-justified
@@ -17,6 +18,7 @@
 #define _POSIX_C_SOURCE 200809L
 #include <linne_encoder.h>
 #include <linne_decoder.h>
+#include <linne_b200.h>
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,13 +29,12 @@
 
 struct Wav {
     uint32_t channels, rate, bits, frames;
-    int32_t *pcm[LINNE_MAX_NUM_CHANNELS];      /* right-justified samples, one plane per channel */
+    uint8_t *file;                             /* whole file image (owned) */
+    const uint8_t *data;                       /* interleaved little-endian samples inside `file` */
 };
 
 static uint32_t rd_le(const uint8_t *p, int n) { uint32_t v = 0; int i; for (i = n - 1; i >= 0; i--) v = (v << 8) | p[i]; return v; }
 static void wr_le(uint8_t *p, uint32_t v, int n) { int i; for (i = 0; i < n; i++) p[i] = (uint8_t)(v >> (8 * i)); }
-
-static void wav_free(struct Wav *w) { uint32_t c; for (c = 0; c < LINNE_MAX_NUM_CHANNELS; c++) { free(w->pcm[c]); w->pcm[c] = NULL; } }
 
 static uint8_t *read_file(const char *path, size_t *size)
 {
@@ -54,7 +55,7 @@ static int wav_read(const char *path, struct Wav *w)
 {
     size_t size = 0, off = 12, data_off = 0, data_len = 0;
     uint8_t *f = read_file(path, &size);
-    uint32_t c, i, bytes, have_fmt = 0;
+    uint32_t bytes, have_fmt = 0;
     memset(w, 0, sizeof(*w));
     if (!f || size < 12 || memcmp(f, "RIFF", 4) != 0 || memcmp(f + 8, "WAVE", 4) != 0) { free(f); return 1; }
     while (off + 8 <= size) {
@@ -77,46 +78,25 @@ static int wav_read(const char *path, struct Wav *w)
     if (!have_fmt || !data_off || w->channels == 0 || w->channels > LINNE_MAX_NUM_CHANNELS
         || (w->bits != 8 && w->bits != 16 && w->bits != 24 && w->bits != 32)) { free(f); return 3; }
     w->frames = (uint32_t)(data_len / ((size_t)bytes * w->channels));
-    for (c = 0; c < w->channels; c++)
-        if (!(w->pcm[c] = (int32_t *)malloc(sizeof(int32_t) * (w->frames ? w->frames : 1u)))) { wav_free(w); free(f); return 4; }
-    for (i = 0; i < w->frames; i++)
-        for (c = 0; c < w->channels; c++) {
-            const uint8_t *p = f + data_off + ((size_t)i * w->channels + c) * bytes;
-            int32_t v;
-            if (w->bits == 8) v = (int32_t)p[0] - 128;
-            else if (w->bits == 16) v = (int16_t)rd_le(p, 2);
-            else if (w->bits == 24) v = (int32_t)(rd_le(p, 3) << 8) >> 8;
-            else v = (int32_t)rd_le(p, 4);
-            w->pcm[c][i] = v;
-        }
-    free(f);
+    w->file = f;
+    w->data = f + data_off;
     return 0;
 }
 
-static int wav_write(const char *path, const struct Wav *w)
+/* canonical 44-byte header + data chunk; `buf` = 44 bytes of room followed by the samples */
+static int wav_write(const char *path, uint8_t *buf, const struct Wav *w)
 {
     const uint32_t bytes = w->bits / 8u;
     const size_t data_len = (size_t)w->frames * w->channels * bytes;
-    uint8_t *f = (uint8_t *)malloc(44u + data_len);
-    uint32_t c, i;
     FILE *fp;
     int rc = 0;
-    if (!f) return 1;
-    memcpy(f, "RIFF", 4); wr_le(f + 4, (uint32_t)(36u + data_len), 4); memcpy(f + 8, "WAVEfmt ", 8);
-    wr_le(f + 16, 16, 4); wr_le(f + 20, 1, 2); wr_le(f + 22, w->channels, 2); wr_le(f + 24, w->rate, 4);
-    wr_le(f + 28, w->rate * w->channels * bytes, 4); wr_le(f + 32, w->channels * bytes, 2); wr_le(f + 34, w->bits, 2);
-    memcpy(f + 36, "data", 4); wr_le(f + 40, (uint32_t)data_len, 4);
-    for (i = 0; i < w->frames; i++)
-        for (c = 0; c < w->channels; c++) {
-            uint8_t *p = f + 44u + ((size_t)i * w->channels + c) * bytes;
-            const int32_t v = w->pcm[c][i];
-            if (w->bits == 8) p[0] = (uint8_t)((v + 128) & 0xFF);
-            else wr_le(p, (uint32_t)v, (int)bytes);
-        }
-    if (!(fp = fopen(path, "wb"))) { free(f); return 2; }
-    if (fwrite(f, 1, 44u + data_len, fp) != 44u + data_len) rc = 3;
+    memcpy(buf, "RIFF", 4); wr_le(buf + 4, (uint32_t)(36u + data_len), 4); memcpy(buf + 8, "WAVEfmt ", 8);
+    wr_le(buf + 16, 16, 4); wr_le(buf + 20, 1, 2); wr_le(buf + 22, w->channels, 2); wr_le(buf + 24, w->rate, 4);
+    wr_le(buf + 28, w->rate * w->channels * bytes, 4); wr_le(buf + 32, w->channels * bytes, 2); wr_le(buf + 34, w->bits, 2);
+    memcpy(buf + 36, "data", 4); wr_le(buf + 40, (uint32_t)data_len, 4);
+    if (!(fp = fopen(path, "wb"))) return 2;
+    if (fwrite(buf, 1, 44u + data_len, fp) != 44u + data_len) rc = 3;
     fclose(fp);
-    free(f);
     return rc;
 }
 
@@ -142,44 +122,43 @@ static int encode_one(struct LINNEEncoder *enc, const struct Options *o, const c
     prm.num_afmethod_iterations = (uint8_t)o->af;
     if ((ret = LINNEEncoder_SetEncodeParameter(enc, &prm)) != LINNE_APIRESULT_OK) {
         fprintf(stderr, "linne_b200: %s: cannot set the encode parameters (%d)\n", in, (int)ret);
-        wav_free(&w); return 1;
+        free(w.file); return 1;
     }
     /* worst case: every block stored raw, plus block and stream headers */
     cap = LINNE_HEADER_SIZE + w.frames * w.channels * (w.bits / 8u) + 11u * (w.frames / CLI_BLOCK + 2u) + 4096u;
-    if (!(buf = (uint8_t *)malloc(cap))) { wav_free(&w); return 1; }
-    ret = LINNEEncoder_EncodeWhole(enc, (const int32_t *const *)w.pcm, w.frames, buf, cap, &size);
-    if (ret != LINNE_APIRESULT_OK) { fprintf(stderr, "linne_b200: %s: encode failed (%d)\n", in, (int)ret); free(buf); wav_free(&w); return 1; }
-    if (!(fp = fopen(out, "wb")) || fwrite(buf, 1, size, fp) != size) { fprintf(stderr, "linne_b200: cannot write %s\n", out); if (fp) fclose(fp); free(buf); wav_free(&w); return 1; }
+    if (!(buf = (uint8_t *)malloc(cap))) { free(w.file); return 1; }
+    ret = LINNEB200_EncodeWholePacked(enc, w.data, w.frames, buf, cap, &size);
+    if (ret != LINNE_APIRESULT_OK) { fprintf(stderr, "linne_b200: %s: encode failed (%d)\n", in, (int)ret); free(buf); free(w.file); return 1; }
+    if (!(fp = fopen(out, "wb")) || fwrite(buf, 1, size, fp) != size) { fprintf(stderr, "linne_b200: cannot write %s\n", out); if (fp) fclose(fp); free(buf); free(w.file); return 1; }
     fclose(fp);
     printf("%s -> %s: %u samples x %u ch, %u bytes\n", in, out, w.frames, w.channels, size);
     free(buf);
-    wav_free(&w);
+    free(w.file);
     return 0;
 }
 
 static int decode_one(struct LINNEDecoder *dec, const char *in, const char *out)
 {
     size_t size = 0;
-    uint8_t *buf = read_file(in, &size);
+    uint8_t *buf = read_file(in, &size), *wav;
     struct LINNEHeader h;
     struct Wav w;
     LINNEApiResult ret;
-    uint32_t c;
+    uint32_t frames = 0;
     if (!buf) { fprintf(stderr, "linne_b200: cannot read %s\n", in); return 1; }
     if ((ret = LINNEDecoder_DecodeHeader(buf, (uint32_t)size, &h)) != LINNE_APIRESULT_OK) {
         fprintf(stderr, "linne_b200: %s: not a LINNE stream (%d)\n", in, (int)ret); free(buf); return 1;
     }
     memset(&w, 0, sizeof(w));
     w.channels = h.num_channels; w.rate = h.sampling_rate; w.bits = h.bits_per_sample; w.frames = h.num_samples;
-    if (w.channels == 0 || w.channels > LINNE_MAX_NUM_CHANNELS) { free(buf); return 1; }
-    for (c = 0; c < w.channels; c++)
-        if (!(w.pcm[c] = (int32_t *)calloc(w.frames ? w.frames : 1u, sizeof(int32_t)))) { wav_free(&w); free(buf); return 1; }
-    ret = LINNEDecoder_DecodeWhole(dec, buf, (uint32_t)size, w.pcm, w.channels, w.frames);
+    if (w.channels == 0 || w.channels > LINNE_MAX_NUM_CHANNELS || (w.bits != 8 && w.bits != 16 && w.bits != 24 && w.bits != 32)) { free(buf); return 1; }
+    if (!(wav = (uint8_t *)calloc(44u + (size_t)w.frames * w.channels * (w.bits / 8u) + 16u, 1))) { free(buf); return 1; }
+    ret = LINNEB200_DecodeWholePacked(dec, buf, (uint32_t)size, wav + 44, w.frames, &frames);
     free(buf);
-    if (ret != LINNE_APIRESULT_OK) { fprintf(stderr, "linne_b200: %s: decode failed (%d)\n", in, (int)ret); wav_free(&w); return 1; }
-    if (wav_write(out, &w) != 0) { fprintf(stderr, "linne_b200: cannot write %s\n", out); wav_free(&w); return 1; }
+    if (ret != LINNE_APIRESULT_OK) { fprintf(stderr, "linne_b200: %s: decode failed (%d)\n", in, (int)ret); free(wav); return 1; }
+    if (wav_write(out, wav, &w) != 0) { fprintf(stderr, "linne_b200: cannot write %s\n", out); free(wav); return 1; }
     printf("%s -> %s: %u samples x %u ch\n", in, out, w.frames, w.channels);
-    wav_free(&w);
+    free(wav);
     return 0;
 }
 
