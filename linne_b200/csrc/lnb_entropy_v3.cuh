@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(LNB_E3_THREADS) lnb_entropy_v3_kernel(LnbDecod
             const uint32_t my_rel = lane * step;                  /* guessed start of this lane's code word, relative to pos */
             const uint32_t my_end = my_rel + k2 + 1u;             /* + max(lz, 1) = end of the code word */
             uint32_t rem = len;
+            const uint32_t k2mask = (1u << k2) - 1u;
             while (rem) {
                 if (pos > win.limit) lnb_e3_fill(win, pos >> 5, lane);
                 const uint32_t cnt = rem < 32u ? rem : 32u;
@@ -205,13 +206,14 @@ __global__ void __launch_bounds__(LNB_E3_THREADS) lnb_entropy_v3_kernel(LnbDecod
                 const uint32_t r = __reduce_min_sync(0xffffffffu, key);
                 const uint32_t first = r >> 16;
                 uint32_t n_ok = first + ((r >> 15) & 1u);
-                if (lane < n_ok) {
-                    const uint32_t t = (hi << ml) << 1;                /* the k2 bits after the unary part */
-                    const uint32_t low = (t >> 1) >> (31u - k2);
+                {
+                    /* the k2 bits after the unary part sit (ml + 1) bits below the top of the peek */
+                    const uint32_t low = (hi >> ((31u - k2) - ml)) & k2mask;
                     const uint32_t mult = lz ? lz + 1u : ((hi >> 30) & 1u);
-                    out[done + lane] = lnb_zz_dec((mult << k2) + low);
+                    const int32_t v = lnb_zz_dec((mult << k2) + low);
+                    if (lane < n_ok) out[done + lane] = v;
                 }
-                if (r & 0x8000u) {
+                if (__builtin_expect((r & 0x8000u) != 0u, 1)) {
                     pos += r & 0x7FFFu;
                 } else {
                     /* code word longer than 32 bits: its lane finishes it on the serial reader */
