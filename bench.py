@@ -487,12 +487,17 @@ def run_b200(args, rank, world, local_rank):
     dec_kernels = {"crc_v2", "entropy_v3", "synth_v2", "crc", "entropy", "synth", "deemph", "ms_inverse"}
     dom = max(stage_serial.items(), key=lambda kv: kv[1][1]) if stage_serial else ("none", [1, 1.0])
     dom_name, (dom_cnt, dom_ms) = dom[0], dom[1]
+    try:        # DRAM bytes per launch of that kernel from the committed ncu capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(dom_name)
+    except Exception:
+        traffic = None
     samples_done = len(PRESETS) * n_samples * serial_steps
     if dom_name in analysis_kernels:
         flops = 2.0 * sum(MAC_PER_SAMPLE[m] for m in PRESETS) * n_samples * serial_steps
         achieved = flops / (dom_ms / 1e3) / 1e12
         roofline = {"bound": "fp64", "kernel": dom_name, "achieved": round(achieved, 4), "peak": round(fp64_peak, 3),
-                    "unit": "TFLOP/s", "frac": round(achieved / fp64_peak, 5) if fp64_peak else None, "traffic": None,
+                    "unit": "TFLOP/s", "frac": round(achieved / fp64_peak, 5) if fp64_peak else None, "traffic": traffic,
                     "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
                     "note": "encoder analysis is FP64-pipe bound (SURVEY 8d): algorithmic FLOPs = 2 x MAC/sample table "
                             "(un-deduplicated) over this kernel's summed launch time; peak = DFMA microbenchmark on this GPU"}
@@ -500,7 +505,9 @@ def run_b200(args, rank, world, local_rank):
         by = hbm_bytes_per_sample * samples_done
         achieved = by / (dom_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 3), "peak": hbm_peak,
-                    "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
+                    "traffic_note": "ncu dram bytes per launch at -m 7 (profiles/ncu_traffic.json); algorithmic bytes per launch = "
+                                    + str(int(hbm_bytes_per_sample * n_samples)),
                     "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
                     "bytes_per_sample": round(hbm_bytes_per_sample, 3),
                     "note": "latency-bound at this batch size (44 blocks per launch): one warp per block / block-channel"}
