@@ -420,14 +420,22 @@ __device__ void lnb_a3_generic(const LnbEncodeBatch &b, uint32_t s, uint32_t bc,
     double final_loss = 0.0;
     for (uint32_t l = 0; l < b.cfg.num_layers; l++) {
         const uint32_t P = b.cfg.layer_params[l];
-        for (uint32_t lv = 0; lv < LNB_MAX_LEVELS; lv++) {           /* lpc.c:196-249, window applied on the fly */
+        for (uint32_t lv = 0; lv < LNB_MAX_LEVELS; lv++) {           /* lpc.c:196-249 */
             if (!lnb_level_valid(lv, P, na)) continue;
             const uint32_t U = 1u << lv, p = P / U, m = na / U;
             const double scale = b.welch[(size_t)blk_i * LNB_MAX_LEVELS + lv];
-            for (uint32_t cell = c; cell < U * (p + 1u); cell += LNB_A3_THREADS)
-                acorr[lv * 256u + cell] = lnb_acorr_lag(A + (size_t)(cell / (p + 1u)) * m, m, cell % (p + 1u), scale);
+            for (uint32_t i = c; i < na; i += LNB_A3_THREADS)        /* windowed copy (same products as lnb_acorr_lag) */
+                B[i] = lnb_mul_rn(A[i], lnb_welch_weight(scale, i % m, m));
+            __syncthreads();
+            for (uint32_t cell = c; cell < U * (p + 1u); cell += LNB_A3_THREADS) {
+                const uint32_t lag = cell % (p + 1u);
+                const double *xs = B + (size_t)(cell / (p + 1u)) * m;
+                double sum = 0.0;
+                for (uint32_t i = 0; i + lag < m; i++) sum = lnb_mac(xs[i], xs[i + lag], sum);
+                acorr[lv * 256u + cell] = sum;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         {   /* regularised solve: threads take the short orders, warps the long ones (B is free: mirror scratch) */
             uint32_t task = c, wt = warp;
             for (uint32_t lv = 0; lv < LNB_MAX_LEVELS; lv++) {
