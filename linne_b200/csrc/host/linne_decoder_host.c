@@ -241,6 +241,14 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
 
     /* a terminal block with a post-CRC error takes part in the CRC pass only */
     for (i = scan.num_decodable; i < scan.num_blocks; i++) blocks[i].type = 0xFFu;
+    {   /* compressed blocks go to the fused streaming kernel; count what is left for the split kernels */
+        const char *split = getenv("LINNE_B200_SPLIT_DECODE");
+        batch.fused_max_n = (split && *split == '1') ? 0u : lnb_shim_fused_max_n();
+        batch.num_plain_blocks = 0;
+        for (i = 0; i < scan.num_blocks; i++)
+            if (blocks[i].type != LNB_BLOCK_COMPRESSED || blocks[i].nsmp == 0u || blocks[i].nsmp > batch.fused_max_n)
+                batch.num_plain_blocks++;
+    }
 
     batch.tab = *lnb_shim_tables(dec->dev);
     batch.stream = d_stream_ext ? d_stream_ext : (const uint8_t *)dec->d_stream.ptr;

@@ -72,57 +72,33 @@ __device__ __forceinline__ uint32_t lnb_e3_get(const LnbE3Win &w, uint32_t &pos,
     return v;
 }
 
-__global__ void __launch_bounds__(LNB_E3_THREADS) lnb_entropy_v3_kernel(LnbDecodeBatch b)
+/* Where the residuals of a compressed block go.  The stand-alone kernel writes them to the PCM planes; the
+ * fused decoder (lnb_stream_v1.cuh) writes them to shared memory and publishes its progress to the synthesis
+ * warps.  `params` receives the side information of the block's channels. */
+struct LnbE3PlaneSink {
+    static constexpr bool kPublish = false;
+    LnbChanParams *params;
+    int32_t *pcm; uint32_t stride, smp_off;
+    __device__ __forceinline__ int32_t *channel(uint32_t c) const { return pcm + (size_t)c * stride + smp_off; }
+    __device__ __forceinline__ void begin_channel(uint32_t, uint32_t, uint32_t) const {}
+    __device__ __forceinline__ void publish(uint32_t, uint32_t, uint32_t, uint32_t) const {}
+    __device__ __forceinline__ void abort(uint32_t) const {}
+};
+
+/* payload of one COMPRESSED block, decoded by one warp */
+template <class Sink>
+__device__ void lnb_e3_compressed_block(const LnbDecodeBatch &b, LnbBlockDesc &gblk, const LnbBlockDesc &blk, LnbE3Win &win,
+                                        const uint16_t *huff1, Sink &sink, uint32_t lane)
 {
-    __shared__ uint32_t s_win[LNB_E3_WARPS][LNB_E3_WIN + 2];
-    __shared__ uint16_t s_huff1[1u << LNB_E3_HUFF1_BITS];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t blk_i = blockIdx.x * LNB_E3_WARPS + warp;
-
-    /* first-level coefficient table: code words of at most LNB_E3_HUFF1_BITS bits resolve in shared memory */
-    for (uint32_t i = threadIdx.x; i < (1u << LNB_E3_HUFF1_BITS); i += LNB_E3_THREADS) {
-        const uint16_t e = b.tab.huff_lut[i << (LNB_HUFF_LUT_BITS - LNB_E3_HUFF1_BITS)];
-        s_huff1[i] = ((e & 15u) <= LNB_E3_HUFF1_BITS) ? e : (uint16_t)0;
-    }
-    __syncthreads();
-    if (blk_i >= b.num_blocks) return;
-
-    LnbBlockDesc &gblk = b.blocks[blk_i];
-    const LnbBlockDesc blk = gblk;
     const LnbStreamCfg &cfg = b.cfg;
     const uint32_t C = cfg.num_channels, n = blk.nsmp;
     const uint32_t payload_off = blk.byte_off + LNB_BLOCK_HEADER_SIZE;
     uint32_t end_byte = blk.byte_off + blk.byte_size;
     if (end_byte > b.stream_size) end_byte = b.stream_size;
-
-    if (blk.type == LNB_BLOCK_SILENT) {                          /* linne_decoder.c:554-557 */
-        for (uint32_t c = 0; c < C; c++) {
-            int32_t *dst = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;
-            for (uint32_t i = lane; i < n; i += 32u) dst[i] = 0;
-        }
-        if (lane == 0) gblk.na = 0;
-        return;
-    }
-    if (blk.type == LNB_BLOCK_RAW) {                             /* linne_decoder.c:387-421 */
-        const uint32_t bytes = cfg.bits_per_sample >> 3;
-        if ((uint64_t)payload_off + (uint64_t)bytes * n * C > end_byte) { if (lane == 0) gblk.status = blk.status | LNB_ST_OVERRUN; return; }
-        const uint8_t *p = b.stream + payload_off;
-        for (uint32_t c = 0; c < C; c++) {
-            int32_t *dst = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;
-            for (uint32_t i = lane; i < n; i += 32u)
-                dst[i] = lnb_zz_dec(lnb_get_be(p + ((size_t)i * C + c) * bytes, (int)bytes));
-        }
-        if (lane == 0) gblk.na = bytes * n * C;
-        return;
-    }
-    if (blk.type != LNB_BLOCK_COMPRESSED) { if (lane == 0) gblk.status = blk.status | LNB_ST_BAD_TYPE; return; }
-
     /* bit positions are relative to the aligned word that holds the block's first byte, so 32-bit
      * positions never overflow however large the stream is */
     const uint32_t word0 = blk.byte_off >> 2;
-    LnbE3Win win;
-    win.buf = s_win[warp];
-    win.words = (const uint32_t *)b.stream + word0;
+        win.words = (const uint32_t *)b.stream + word0;
     const uint32_t rel_payload = payload_off - word0 * 4u, rel_end = end_byte - word0 * 4u;
     win.end_word = (rel_end + 3u) >> 2;
     uint32_t pos = rel_payload * 8u;
@@ -131,7 +107,7 @@ __global__ void __launch_bounds__(LNB_E3_THREADS) lnb_entropy_v3_kernel(LnbDecod
 
     /* ---- side information (linne_decoder.c:457-486): every lane reads the same fields ---- */
     {
-        LnbChanParams *params = b.params + (size_t)blk_i * C;
+        LnbChanParams *params = sink.params;
         for (uint32_t c = 0; c < C; c++)
             for (int f = 0; f < LNB_NUM_PREEM; f++) {
                 lnb_e3_ensure(win, pos, 64u, lane);
@@ -152,7 +128,7 @@ __global__ void __launch_bounds__(LNB_E3_THREADS) lnb_entropy_v3_kernel(LnbDecod
                     const uint32_t lim = (P - i0 < 32u) ? P - i0 : 32u;
                     for (uint32_t i = 0; i < lim; i++) {
                         const uint32_t top = lnb_e3_peek(win, pos);
-                        uint32_t e = s_huff1[top >> (32 - LNB_E3_HUFF1_BITS)];
+                        uint32_t e = huff1[top >> (32 - LNB_E3_HUFF1_BITS)];
                         if (e == 0u) e = b.tab.huff_lut[top >> (32 - LNB_HUFF_LUT_BITS)];
                         pos += e & 15u;
                         if (i == lane) mine = lnb_zz_dec(e >> 4);
@@ -164,11 +140,14 @@ __global__ void __launch_bounds__(LNB_E3_THREADS) lnb_entropy_v3_kernel(LnbDecod
 
     /* ---- residuals, channel after channel (linne_coder.c:306-327) ---- */
     for (uint32_t c = 0; c < C; c++) {
-        int32_t *out = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;
         if (overrun) {                                           /* broken stream: the remaining channels read as silence */
-            for (uint32_t i = lane; i < n; i += 32u) out[i] = 0;
+            int32_t *gout = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;
+            for (uint32_t i = lane; i < n; i += 32u) gout[i] = 0;
             continue;
         }
+        sink.begin_channel(c, n, lane);
+        int32_t *out = sink.channel(c);
+        uint32_t published = 0;
         lnb_e3_ensure(win, pos, 64u, lane);
         uint32_t porder = lnb_e3_get(win, pos, 10);
         if (porder > LNB_MAX_PORDER) { overrun = 1; porder = 0; }
@@ -234,15 +213,74 @@ __global__ void __launch_bounds__(LNB_E3_THREADS) lnb_entropy_v3_kernel(LnbDecod
                 }
                 done += n_ok;
                 rem -= n_ok;
+                if (Sink::kPublish && done - published >= 128u) { sink.publish(c, n, done, lane); published = done; }
             }
+            if (Sink::kPublish) { sink.publish(c, n, done, lane); published = done; }
         }
         /* samples a broken stream leaves uncovered */
         if (overrun || parts * len < n)
             for (uint32_t i = done + lane; i < n; i += 32u) if (overrun || i >= parts * len) out[i] = 0;
+        if (overrun) sink.abort(lane);
+        else if (Sink::kPublish) sink.publish(c, n, n, lane);
     }
+    if (overrun) sink.abort(lane);
     if (lane == 0) {
         const uint32_t used = (pos - rel_payload * 8u + 7u) >> 3;
         gblk.na = used;                                          /* payload bytes consumed (reference Flush + Tell) */
         if (overrun || rel_payload + used > rel_end) gblk.status = blk.status | LNB_ST_OVERRUN;
     }
+}
+
+__global__ void __launch_bounds__(LNB_E3_THREADS) lnb_entropy_v3_kernel(LnbDecodeBatch b)
+{
+    __shared__ uint32_t s_win[LNB_E3_WARPS][LNB_E3_WIN + 2];
+    __shared__ uint16_t s_huff1[1u << LNB_E3_HUFF1_BITS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t blk_i = blockIdx.x * LNB_E3_WARPS + warp;
+
+    /* first-level coefficient table: code words of at most LNB_E3_HUFF1_BITS bits resolve in shared memory */
+    for (uint32_t i = threadIdx.x; i < (1u << LNB_E3_HUFF1_BITS); i += LNB_E3_THREADS) {
+        const uint16_t e = b.tab.huff_lut[i << (LNB_HUFF_LUT_BITS - LNB_E3_HUFF1_BITS)];
+        s_huff1[i] = ((e & 15u) <= LNB_E3_HUFF1_BITS) ? e : (uint16_t)0;
+    }
+    __syncthreads();
+    if (blk_i >= b.num_blocks) return;
+
+    LnbBlockDesc &gblk = b.blocks[blk_i];
+    const LnbBlockDesc blk = gblk;
+    const LnbStreamCfg &cfg = b.cfg;
+    const uint32_t C = cfg.num_channels, n = blk.nsmp;
+    const uint32_t payload_off = blk.byte_off + LNB_BLOCK_HEADER_SIZE;
+    uint32_t end_byte = blk.byte_off + blk.byte_size;
+    if (end_byte > b.stream_size) end_byte = b.stream_size;
+
+    if (blk.type == LNB_BLOCK_SILENT) {                          /* linne_decoder.c:554-557 */
+        for (uint32_t c = 0; c < C; c++) {
+            int32_t *dst = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;
+            for (uint32_t i = lane; i < n; i += 32u) dst[i] = 0;
+        }
+        if (lane == 0) gblk.na = 0;
+        return;
+    }
+    if (blk.type == LNB_BLOCK_RAW) {                             /* linne_decoder.c:387-421 */
+        const uint32_t bytes = cfg.bits_per_sample >> 3;
+        if ((uint64_t)payload_off + (uint64_t)bytes * n * C > end_byte) { if (lane == 0) gblk.status = blk.status | LNB_ST_OVERRUN; return; }
+        const uint8_t *p = b.stream + payload_off;
+        for (uint32_t c = 0; c < C; c++) {
+            int32_t *dst = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;
+            for (uint32_t i = lane; i < n; i += 32u)
+                dst[i] = lnb_zz_dec(lnb_get_be(p + ((size_t)i * C + c) * bytes, (int)bytes));
+        }
+        if (lane == 0) gblk.na = bytes * n * C;
+        return;
+    }
+    if (blk.type != LNB_BLOCK_COMPRESSED) { if (lane == 0) gblk.status = blk.status | LNB_ST_BAD_TYPE; return; }
+    if (b.fused_max_n && n <= b.fused_max_n && n > 0u) return;   /* taken (or, after a failed CRC, dropped) by the fused kernel */
+
+    LnbE3Win win;
+    win.buf = s_win[warp];
+    LnbE3PlaneSink sink;
+    sink.params = b.params + (size_t)blk_i * C;
+    sink.pcm = b.pcm; sink.stride = cfg.pcm_stride; sink.smp_off = blk.smp_off;
+    lnb_e3_compressed_block(b, gblk, blk, win, s_huff1, sink, lane);
 }

@@ -83,6 +83,7 @@ struct LnbItemMsInverse {
         const uint32_t blk_i = i / b.cfg.block_size, s = i % b.cfg.block_size;
         const LnbBlockDesc &blk = b.blocks[blk_i];
         if (blk.type != LNB_BLOCK_COMPRESSED || blk.status || s >= blk.nsmp) return;
+        if (b.fused_max_n && blk.nsmp <= b.fused_max_n) return;       /* done inside the fused streaming kernel */
         int32_t *l = b.pcm + blk.smp_off + s;
         lnb_ms_to_lr(l[0], l[b.cfg.pcm_stride]);
     }
@@ -95,12 +96,15 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
     if (B == 0) return;
     if (Exec::cooperative) {
         ex.crc_cooperative(b);                            /* one CTA per block, chunk CRCs combined in GF(2) */
-        ex.entropy_cooperative(b);                        /* one warp per block: 32 speculative code-word starts per round */
-        ex.synth_cooperative(b);                          /* one warp per (block, channel): systolic synthesis + de-emphasis */
-        if (b.cfg.block_size > ex.synth_max_n()) {        /* longer block-channels: flat kernels (they skip the short ones) */
-            for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)
-                ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l, ex.synth_max_n()});
-            ex.run("deemph", B * C, LnbItemDeemph{b, ex.synth_max_n()});
+        if (b.fused_max_n) ex.stream_cooperative(b);      /* one CTA per block: entropy decode feeding synthesis, de-emphasis, M/S */
+        if (!b.fused_max_n || b.num_plain_blocks) {       /* raw / silent / long blocks (or the fused kernel switched off) */
+            ex.entropy_cooperative(b);                    /* one warp per block: 32 speculative code-word starts per round */
+            ex.synth_cooperative(b);                      /* one warp per (block, channel): systolic synthesis + de-emphasis */
+            if (b.cfg.block_size > ex.synth_max_n()) {    /* longer block-channels: flat kernels (they skip the short ones) */
+                for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)
+                    ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l, ex.synth_max_n()});
+                ex.run("deemph", B * C, LnbItemDeemph{b, ex.synth_max_n()});
+            }
         }
     } else {
         ex.run("crc", B, LnbItemCrc{b});
@@ -109,7 +113,8 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
             ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l, 0u});
         ex.run("deemph", B * C, LnbItemDeemph{b, 0u});
     }
-    if (b.cfg.ms && C >= 2u) ex.run("ms_inverse", B * b.cfg.block_size, LnbItemMsInverse{b});
+    if (b.cfg.ms && C >= 2u && (!b.fused_max_n || b.num_plain_blocks))
+        ex.run("ms_inverse", B * b.cfg.block_size, LnbItemMsInverse{b});
 }
 
 /* =============================================================================================

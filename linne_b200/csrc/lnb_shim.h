@@ -34,6 +34,8 @@ const char *lnb_shim_backend(void);      /* "cuda-sm_100a" for the product */
 uint32_t lnb_shim_fast_max_na(void);
 /* Longest block (samples per channel) the cooperative prepare / predict+plan kernels take; 0 = none. */
 uint32_t lnb_shim_coop_max_n(void);
+/* Longest block the fused streaming decoder (entropy decode -> synthesis -> de-emphasis in one kernel) takes; 0 = none. */
+uint32_t lnb_shim_fused_max_n(void);
 /* Longest analysis length the IRLS / SGD refinement kernel takes; 0 = those paths are unavailable. */
 uint32_t lnb_shim_refine_max_na(void);
 

@@ -19,6 +19,7 @@
 #include "lnb_entropy_v3.cuh"
 #include "lnb_refine_v2.cuh"
 #include "lnb_scan_v2.cuh"
+#include "lnb_stream_v1.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -115,6 +116,20 @@ struct CudaExec {
     {
         const int slot = begin_stage("entropy_v3");
         lnb_entropy_v3_kernel<<<(b.num_blocks + LNB_E3_WARPS - 1) / LNB_E3_WARPS, LNB_E3_THREADS, 0, dev->stream>>>(b);
+        end_stage(slot);
+    }
+    void stream_cooperative(const LnbDecodeBatch &b)
+    {
+        uint32_t n_max = b.cfg.block_size < LNB_DS_MAX_N ? b.cfg.block_size : LNB_DS_MAX_N;
+        n_max = (n_max + 3u) & ~3u;
+        const size_t smem = (size_t)n_max * sizeof(int32_t);
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(lnb_stream_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        const int slot = begin_stage("stream_v1");
+        lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, dev->stream>>>(b, n_max);
         end_stage(slot);
     }
     void crc_cooperative(const LnbDecodeBatch &b)
@@ -257,6 +272,7 @@ const char *lnb_shim_backend(void) { return "cuda-sm_100a"; }
 uint32_t lnb_shim_fast_max_na(void) { return LNB_A3_MAX_NA; }
 uint32_t lnb_shim_coop_max_n(void) { return LNB_FR_MAX_N; }
 uint32_t lnb_shim_refine_max_na(void) { return LNB_RF_MAX_NA; }
+uint32_t lnb_shim_fused_max_n(void) { return LNB_DS_MAX_N; }
 
 int lnb_shim_open(LnbDevice **out, int device_ordinal)
 {

@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(LNB_SY_THREADS) lnb_synth_v2_kernel(LnbDecodeB
     if (blk.type != LNB_BLOCK_COMPRESSED || blk.status) return;
     const uint32_t n = blk.nsmp;
     if (n > n_max) return;
+    if (b.fused_max_n && n <= b.fused_max_n) return;         /* done inside the fused streaming kernel */
     const LnbChanParams &prm = b.params[bc];
     int32_t *gx = b.pcm + (size_t)ch * b.cfg.pcm_stride + blk.smp_off;
     int32_t *x = lnb_sy_smem + (size_t)warp * n_max;

@@ -84,6 +84,8 @@ typedef struct LnbDecodeBatch {
     uint32_t num_blocks;
     LnbChanParams *params;          /* [num_blocks * C] */
     int32_t *pcm;                   /* [C][pcm_stride] */
+    uint32_t fused_max_n;           /* > 0: compressed blocks of at most this many samples take the fused streaming kernel */
+    uint32_t num_plain_blocks;      /* blocks left to the split kernels (raw, silent, longer than fused_max_n) */
 } LnbDecodeBatch;
 
 /* ---- one encode batch (all pointers are device pointers) ---- */

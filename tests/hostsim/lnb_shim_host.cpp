@@ -18,6 +18,7 @@ struct LoopExec {
     void crc_cooperative(const LnbDecodeBatch &) {}
     void entropy_cooperative(const LnbDecodeBatch &) {}
     void synth_cooperative(const LnbDecodeBatch &) {}
+    void stream_cooperative(const LnbDecodeBatch &) {}
     uint32_t synth_max_n() const { return 0; }
     template <class F> void run_per_warp(const char *n, uint32_t c, const F &f) { run(n, c, f); }
     template <class F> void run(const char *, uint32_t n, const F &f)
@@ -38,6 +39,7 @@ const char *lnb_shim_backend(void) { return "hostsim"; }
 uint32_t lnb_shim_fast_max_na(void) { return 0; }
 uint32_t lnb_shim_coop_max_n(void) { return 0; }
 uint32_t lnb_shim_refine_max_na(void) { return 0; }
+uint32_t lnb_shim_fused_max_n(void) { return 0; }
 int lnb_shim_open(LnbDevice **out, int)
 {
     LnbDevice *dev = (LnbDevice *)calloc(1, sizeof(LnbDevice));
