@@ -30,7 +30,7 @@
 
 #define LNB_DS_MAX_N    10240u
 #define LNB_DS_WARPS    (2u + LNB_MAX_LAYERS)          /* entropy + layers + de-emphasis */
-#define LNB_DS_THREADS  (32u * LNB_DS_WARPS)
+#define LNB_DS_THREADS  (32u * (LNB_DS_WARPS + 1u))    /* warp 4 stays empty: it would share a scheduler with the entropy warp */
 #define LNB_DS_BATCH    32u                            /* steps between progress updates */
 #define LNB_DS_ABORT    0xFFFFFFFFu
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ bool lnb_ds_wait(LnbDsShared &sm, uint32_t stage, uin
 {
     while (sm.prog[stage] < need) {
         if (sm.abort) return false;
-        __nanosleep(64);
+        __nanosleep(256);                                      /* a batch of 32 samples takes the entropy warp ~1.5 us */
     }
     __threadfence_block();
     return sm.abort == 0u;
@@ -157,11 +157,21 @@ __device__ bool lnb_ds_unit_lane(LnbDsShared &sm, uint32_t up, uint32_t self, ui
         const uint32_t B = left < LNB_DS_BATCH ? ((left + 3u) & ~3u) : LNB_DS_BATCH;      /* multiple of 4, hence of TT */
         const uint32_t need = g0 + j + B + 3u;
         if (!lnb_ds_wait(sm, up, need < g_end ? need : g_end)) return false;
-        for (uint32_t t = 0; t < B; t += TT) {
-            lnb_sy_lane_step<TT, 0, true>(xu, j + t, m, p, rs, half, active, c, acc, y, d1, d2);
-            if (TT > 1) lnb_sy_lane_step<TT, 1 % TT, true>(xu, j + t + 1u, m, p, rs, half, active, c, acc, y, d1, d2);
-            if (TT > 2) lnb_sy_lane_step<TT, 2 % TT, true>(xu, j + t + 2u, m, p, rs, half, active, c, acc, y, d1, d2);
-            if (TT > 2) lnb_sy_lane_step<TT, 3 % TT, true>(xu, j + t + 3u, m, p, rs, half, active, c, acc, y, d1, d2);
+        if (j + B + 3u < m) {
+#pragma unroll 2
+            for (uint32_t t = 0; t < B; t += TT) {
+                lnb_sy_lane_step<TT, 0, false>(xu, j + t, m, p, rs, half, active, c, acc, y, d1, d2);
+                if (TT > 1) lnb_sy_lane_step<TT, 1 % TT, false>(xu, j + t + 1u, m, p, rs, half, active, c, acc, y, d1, d2);
+                if (TT > 2) lnb_sy_lane_step<TT, 2 % TT, false>(xu, j + t + 2u, m, p, rs, half, active, c, acc, y, d1, d2);
+                if (TT > 2) lnb_sy_lane_step<TT, 3 % TT, false>(xu, j + t + 3u, m, p, rs, half, active, c, acc, y, d1, d2);
+            }
+        } else {
+            for (uint32_t t = 0; t < B; t += TT) {
+                lnb_sy_lane_step<TT, 0, true>(xu, j + t, m, p, rs, half, active, c, acc, y, d1, d2);
+                if (TT > 1) lnb_sy_lane_step<TT, 1 % TT, true>(xu, j + t + 1u, m, p, rs, half, active, c, acc, y, d1, d2);
+                if (TT > 2) lnb_sy_lane_step<TT, 2 % TT, true>(xu, j + t + 2u, m, p, rs, half, active, c, acc, y, d1, d2);
+                if (TT > 2) lnb_sy_lane_step<TT, 3 % TT, true>(xu, j + t + 3u, m, p, rs, half, active, c, acc, y, d1, d2);
+            }
         }
         j += B;
         const uint32_t fin = (j + 1u < m) ? j + 1u : m;
@@ -243,7 +253,10 @@ __global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v1_kernel(LnbDecode
 {
     extern __shared__ __align__(16) int32_t lnb_ds_line[];
     __shared__ LnbDsShared sm;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    /* Warps map to the SM's four schedulers by index mod 4.  The entropy warp (role 0) is the pipeline's pace maker:
+     * it gets scheduler 0 to itself (hardware warp 4 exits), the stages take warps 1, 2, 3 and 5. */
+    const uint32_t hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t warp = (hw_warp < 4u) ? hw_warp : (hw_warp == 4u ? 0xFFu : 4u);        /* role: 0 entropy, 1.. stages */
     const uint32_t blk_i = blockIdx.x;
     LnbBlockDesc &gblk = b.blocks[blk_i];
     const LnbBlockDesc blk = gblk;
@@ -261,6 +274,7 @@ __global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v1_kernel(LnbDecode
     __syncthreads();
 
     const uint32_t last = L + 1u;                              /* stage index of the de-emphasis warp */
+    if (warp == 0xFFu) return;
     if (warp == 0u) {
         LnbE3Win win;
         win.buf = sm.win;
