@@ -50,9 +50,14 @@ __device__ __forceinline__ void lnb_ds_publish(LnbDsShared &sm, uint32_t stage, 
 /* wait until stage `stage` has finished at least `need` samples; false when the block was aborted */
 __device__ __forceinline__ bool lnb_ds_wait(LnbDsShared &sm, uint32_t stage, uint32_t need)
 {
-    while (sm.prog[stage] < need) {
+    for (;;) {
+        const uint32_t have = sm.prog[stage];
+        if (have >= need) break;
         if (sm.abort) return false;
-        __nanosleep(256);                                      /* a batch of 32 samples takes the entropy warp ~1.5 us */
+        /* the pace maker (entropy warp) needs ~50 ns per sample: sleep roughly until the missing samples can exist,
+         * so waiting stages leave the issue slots to the warps that have work */
+        const uint32_t ns = (need - have) * 32u;
+        __nanosleep(ns < 64u ? 64u : (ns > 4000u ? 4000u : ns));
     }
     __threadfence_block();
     return sm.abort == 0u;
