@@ -279,27 +279,52 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
         if (forced) lnb_shim_h2d(enc->dev, enc->d_params.ptr, forced + (size_t)first * C, (size_t)nb * C * sizeof(LnbChanParams));
         lnb_shim_h2d(enc->dev, enc->d_blocks.ptr, hb, nb * sizeof(LnbBlockDesc));
         lnb_shim_h2d(enc->dev, enc->d_welch.ptr, hw, (size_t)nb * LNB_MAX_LEVELS * sizeof(double));
-        TRACE(enc, "enqueue");
-        if (lnb_shim_encode_analyze(enc->dev, &batch)) return LINNE_APIRESULT_NG;
-        lnb_shim_d2h(enc->dev, enc->h_total.ptr, enc->d_total.ptr, sizeof(uint32_t));
-        TRACE(enc, "enqueued");
-        if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
-        TRACE(enc, "sizes known");
-        chunk_bytes = *(uint32_t *)enc->h_total.ptr;
-        if ((uint64_t)out_off + chunk_bytes > data_size) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
-        if (data_on_device) {
-            /* block offsets from the scan are relative to the chunk: pack straight into the caller's device buffer */
-            batch.out = data + out_off;
-            if (lnb_shim_encode_pack(enc->dev, &batch, chunk_bytes)) return LINNE_APIRESULT_NG;
-        } else {
-            if (lnb_buf_reserve_device(enc->dev, &enc->d_out, (size_t)chunk_bytes + 64u)) return LINNE_APIRESULT_NG;
-            batch.out = (uint8_t *)enc->d_out.ptr;
-            if (lnb_shim_encode_pack(enc->dev, &batch, chunk_bytes)) return LINNE_APIRESULT_NG;
-            lnb_shim_d2h(enc->dev, data + out_off, enc->d_out.ptr, chunk_bytes);
+        {
+            /* Pack speculatively right behind the size scan -- no host round trip in between.  The staging buffer is
+             * sized for twice the raw bound of the chunk; should a chunk ever exceed that (or the caller's device
+             * buffer be too small) the packer skips the blocks that do not fit and the second attempt below packs
+             * again once the exact size is known. */
+            const size_t raw_bound = (size_t)nb * (LNB_BLOCK_HEADER_SIZE + (size_t)NB * C * ((h->bits_per_sample + 7u) / 8u));
+            size_t spec_cap;
+            int attempt;
+            for (attempt = 0; attempt < 2; attempt++) {
+                TRACE(enc, "enqueue");
+                if (attempt == 1) {   /* rare: start the chunk over (the packed flags live in the block table) */
+                    lnb_shim_h2d(enc->dev, enc->d_blocks.ptr, hb, nb * sizeof(LnbBlockDesc));
+                }
+                if (lnb_shim_encode_analyze(enc->dev, &batch)) return LINNE_APIRESULT_NG;
+                if (attempt == 0) {
+                    if (data_on_device) {
+                        spec_cap = (size_t)data_size - out_off;
+                        batch.out = data + out_off;       /* block offsets from the scan are relative to the chunk */
+                    } else {
+                        spec_cap = 2u * raw_bound + 4096u;
+                        if (spec_cap > 0xFFFFFF00u) spec_cap = 0xFFFFFF00u;
+                        if (lnb_buf_reserve_device(enc->dev, &enc->d_out, spec_cap + 64u)) return LINNE_APIRESULT_NG;
+                        batch.out = (uint8_t *)enc->d_out.ptr;
+                    }
+                    if (lnb_shim_encode_pack(enc->dev, &batch, (uint32_t)spec_cap)) return LINNE_APIRESULT_NG;
+                }
+                lnb_shim_d2h(enc->dev, enc->h_total.ptr, enc->d_total.ptr, sizeof(uint32_t));
+                TRACE(enc, "enqueued");
+                if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
+                TRACE(enc, "sizes known");
+                chunk_bytes = *(uint32_t *)enc->h_total.ptr;
+                if ((uint64_t)out_off + chunk_bytes > data_size) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+                if (attempt == 0 && chunk_bytes <= spec_cap) break;          /* everything fitted: the chunk is packed */
+                if (attempt == 1) {
+                    if (!data_on_device) {
+                        if (lnb_buf_reserve_device(enc->dev, &enc->d_out, (size_t)chunk_bytes + 64u)) return LINNE_APIRESULT_NG;
+                        batch.out = (uint8_t *)enc->d_out.ptr;
+                    }
+                    if (lnb_shim_encode_pack(enc->dev, &batch, chunk_bytes)) return LINNE_APIRESULT_NG;
+                }
+            }
+            if (!data_on_device) lnb_shim_d2h(enc->dev, data + out_off, enc->d_out.ptr, chunk_bytes);
+            TRACE(enc, "pack enqueued");
+            if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
+            TRACE(enc, "chunk done");
         }
-        TRACE(enc, "pack enqueued");
-        if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
-        TRACE(enc, "chunk done");
         out_off += chunk_bytes;
     }
     *written = out_off;
