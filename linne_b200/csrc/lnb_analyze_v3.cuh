@@ -41,7 +41,7 @@
 
 __host__ __device__ inline uint32_t lnb_a3_array_doubles(uint32_t na_max)
 {
-    if (na_max < 2048u) na_max = 2048u;            /* the sample area doubles as Levinson scratch: 8 warps x 2 mirrors */
+    if (na_max < 4096u) na_max = 4096u;            /* the sample area doubles as solver scratch: 8 warps x 3 x 136 doubles */
     return LNB_A3_FRONT + na_max / 8u * 9u + LNB_A3_BACK;
 }
 __host__ __device__ inline size_t lnb_a3_smem_doubles(uint32_t na_max)
@@ -50,7 +50,7 @@ __host__ __device__ inline size_t lnb_a3_smem_doubles(uint32_t na_max)
          + (size_t)LNB_MAX_LEVELS * LNB_MAX_PARAMS        /* candidate coefficients per level */
          + (size_t)LNB_MAX_LEVELS * 256                   /* autocorrelations per level: U*(p+1) = P+U <= 256 */
          + (size_t)LNB_A3_ITEMS * LNB_A3_PART             /* work-item partials */
-         + (size_t)2 * LNB_A3_MIRROR                      /* mirrors of the level-0 Levinson recursion (runs beside the rest) */
+         + (size_t)3 * LNB_A3_MIRROR                      /* scratch of the level-0 Toeplitz solve (runs beside the rest) */
          + 64;                                            /* level losses, block-sum scratch */
 }
 
@@ -71,7 +71,10 @@ struct LnbA3Team {
     }
 };
 
-/* ---- Welch-windowed copy A -> B for unit length m (lpc.c:196-205), one group of 8 at a time ---- */
+/* ---- Welch-windowed copy A -> B for unit length m (lpc.c:196-205), one group of 8 at a time ----
+ * w = (scale * q) * (m-1-q) with q = min(pos, m-1-pos): positions are exact in double, so they are stepped by
+ * additions from one conversion per group, and min / max are resolved once per group (a group crosses the
+ * window's centre at most once). */
 __device__ __forceinline__ void lnb_a3_window(const LnbA3Ctx &cx, const LnbA3Team &tm, uint32_t m, double scale)
 {
     const uint32_t mg = m >> 3;
@@ -79,12 +82,23 @@ __device__ __forceinline__ void lnb_a3_window(const LnbA3Ctx &cx, const LnbA3Tea
         const uint32_t pos0 = (G % mg) * 8u;
         const double *src = cx.A + G * 9u;
         double *dst = cx.B + G * 9u;
+        const uint32_t back0 = m - 1u - pos0;                        /* m-1-pos of the group's first sample */
+        const double a0 = (double)pos0, b0 = (double)back0;
+        if (pos0 + 7u <= back0 - 7u || pos0 >= back0) {              /* whole group on one side of the centre */
+            const bool rising = pos0 < back0;
 #pragma unroll
-        for (uint32_t e = 0; e < 8u; e++) {
-            const uint32_t pos = pos0 + e;
-            const uint32_t q = (pos < m - 1u - pos) ? pos : (m - 1u - pos);
-            const double w = __dmul_rn(__dmul_rn(scale, (double)q), (double)(m - 1u - q));
-            dst[e] = __dmul_rn(src[e], w);
+            for (uint32_t e = 0; e < 8u; e++) {
+                const double a = a0 + (double)e, b = b0 - (double)e;
+                const double w = rising ? __dmul_rn(__dmul_rn(scale, a), b) : __dmul_rn(__dmul_rn(scale, b), a);
+                dst[e] = __dmul_rn(src[e], w);
+            }
+        } else {
+#pragma unroll
+            for (uint32_t e = 0; e < 8u; e++) {
+                const double a = a0 + (double)e, b = b0 - (double)e;
+                const double q = (a < b) ? a : b, r = (a < b) ? b : a;
+                dst[e] = __dmul_rn(src[e], __dmul_rn(__dmul_rn(scale, q), r));
+            }
         }
     }
 }
@@ -140,12 +154,39 @@ __device__ __forceinline__ void lnb_a3_autocorr_item(const LnbA3Ctx &cx, uint32_
             lnb_a3_tile<L, false>(Bu + gg * 9u, qoff, 0, acc);
         }
     }
+    /* lane partials -> sums, fixed order.  The first N = 2^n lags are reduced by a transposing butterfly: at each
+     * of the first n steps a lane hands half of its values to its partner and keeps the other half, so 2N-ish
+     * exchanges replace 5N; lane l ends up with lag (l >> (5-n)).  A seventeenth / ninth / .. lag takes the plain
+     * butterfly. */
+    constexpr int N = (L >= 16) ? 16 : (L >= 8) ? 8 : (L >= 4) ? 4 : 2;
+    constexpr int LOGN = (N == 16) ? 4 : (N == 8) ? 3 : (N == 4) ? 2 : 1;
+    {
+        int cnt = N;
 #pragma unroll
-    for (int k = 0; k < L; k++) {
-        double v = acc[k];
+        for (int off = 16; off > 0; off >>= 1) {
+            if (cnt > 1) {
+                const bool upper = (lane & (uint32_t)off) != 0u;
+                const int half = cnt / 2;
+#pragma unroll
+                for (int k = 0; k < N / 2; k++) {
+                    if (k < half) {
+                        const double send = upper ? acc[k] : acc[k + half];
+                        const double keep = upper ? acc[k + half] : acc[k];
+                        acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                cnt = half;
+            } else {
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], off);
+            }
+        }
+        if ((lane & ((1u << (5 - LOGN)) - 1u)) == 0u) out[lane >> (5 - LOGN)] = acc[0];
+    }
+    if (L > N) {
+        double v = acc[L - 1];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) out[k] = v;
+        if (lane == 0) out[L - 1] = v;
     }
 }
 
@@ -204,12 +245,18 @@ __device__ __forceinline__ double lnb_a3_rcp(double x)
     return y;
 }
 
-/* ---- Levinson-Durbin by one warp (orders 32..128); reversed coefficients into out_w[0..p) ----
- * Lane l keeps a[l], a[l+32], ..., a[l+128] in registers; a double-buffered shared-memory mirror serves
- * the reversed reads a[k+1-i] (one warp barrier per step).  The body updates a (step k) and accumulates
- * the dot product of step k+1 in one pass; the reciprocal of the next error is computed while the update
- * is in flight.  Control flow is warp-uniform (slot count), per-lane cases are selects. */
-__device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lambda, double *mirror /* 2 * LNB_A3_MIRROR */, double *out_w)
+/* ---- regularised Toeplitz solve by one warp (orders 32..128); reversed coefficients into out_w[0..p) ----
+ * Same system as the Levinson-Durbin recursion of lpc.c:252-324, computed in two dot-product-free passes so that
+ * a step costs a handful of instructions instead of a 32-lane reduction:
+ *   1. Schur (Le Roux-Gueguen) recursion for the reflection coefficients.  With F_m[i] = e^f_m[i+m] and
+ *      B_m[i] = e^b_m[i+m]:  k_m = -F_{m-1}[1] / B_{m-1}[0],  B_m[i] = B_{m-1}[i] + k_m F_{m-1}[i+1],
+ *      F_m[i] = F_{m-1}[i+1] + k_m B_{m-1}[i]  (B_m[0] is the prediction error).  B stays in registers (lane l
+ *      holds i = l, l+32, ..), F is double-buffered in shared memory for the shifted read; the work shrinks by
+ *      one element per step.
+ *   2. step-up: a_m[i] = a_{m-1}[i] + k_m a_{m-1}[m-i], a_m[m] = k_m, the reversed read again from a
+ *      double-buffered mirror.
+ * `scr` = 3 * LNB_A3_MIRROR doubles (two buffers + the reflection coefficients). */
+__device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lambda, double *scr, double *out_w)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const double r0 = __dmul_rn(r_in[0], __dadd_rn(1.0, lambda));
@@ -217,49 +264,64 @@ __device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lamb
         for (uint32_t i = lane; i < p; i += 32u) out_w[i] = 0.0;
         return;
     }
-    double a[5];                                                     /* a[s] = coefficient lane + 32 s (0 .. p <= 128) */
+    double *cur = scr, *nxt = scr + LNB_A3_MIRROR, *gam = scr + 2 * LNB_A3_MIRROR;
+    double B[5];
 #pragma unroll
-    for (int s = 0; s < 5; s++) a[s] = 0.0;
-    const double a1 = -r_in[1] / r0;
-    if (lane == 0) a[0] = 1.0;
-    if (lane == 1) a[0] = a1;
-    double err = __dadd_rn(r0, __dmul_rn(r_in[1], a1));
-    double *cur = mirror, *nxt = mirror + LNB_A3_MIRROR;
-    for (uint32_t i = lane; i < LNB_A3_MIRROR; i += 32u) { cur[i] = (i == 0u) ? 1.0 : (i == 1u) ? a1 : 0.0; nxt[i] = 0.0; }
+    for (int s = 0; s < 5; s++) {
+        const uint32_t i = lane + 32u * (uint32_t)s;
+        const double ri = (i <= p) ? r_in[i] : 0.0;
+        B[s] = (i == 0u) ? r0 : ri;
+        if (i < LNB_A3_MIRROR) { cur[i] = ri; nxt[i] = 0.0; }
+    }
     __syncwarp();
-    /* dot product for k = 1: sum_{i=0..1} a[i] r[2-i] */
-    double part = 0.0;
-    if (lane < 2u) part = a[0] * ((lane == 0u) ? r_in[2] : r_in[1]);
-    double rinv = lnb_a3_rcp(-err);
-    for (uint32_t k = 1; k < p; k++) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-        const double gamma = part * rinv;
-        err = __dmul_rn(err, __dadd_rn(1.0, -__dmul_rn(gamma, gamma)));
-        const double rinv_next = lnb_a3_rcp(-err);
-        /* a_new[i] = a[i] + gamma * a[k+1-i] (i = 1..k), a_new[k+1] = gamma; then the next dot product */
-        const uint32_t ns = ((k + 1u) >> 5) + 1u;                    /* slots holding an index <= k+1 */
-        double np = 0.0;
+    double rinv = lnb_a3_rcp(r0);
+    for (uint32_t m = 1; m <= p; m++) {
+        const double gamma = -cur[1] * rinv;
+        if (lane == 0) gam[m] = gamma;
+        const uint32_t cnt = p - m;                                  /* B_m[0..cnt], F_m[1..cnt] are what later steps read */
+        const uint32_t ns = (cnt >> 5) + 1u;
 #pragma unroll
         for (int s = 0; s < 5; s++) {
             if ((uint32_t)s < ns) {
                 const uint32_t i = lane + 32u * (uint32_t)s;
-                const bool inside = i <= k + 1u;
-                const double rev = cur[inside ? k + 1u - i : 0u];
-                double v = a[s];
-                if (i >= 1u && i <= k) v = fma(gamma, rev, v);
-                if (i == k + 1u) v = gamma;
-                a[s] = v;
-                if (i < LNB_A3_MIRROR) nxt[i] = v;
-                const uint32_t ri = k + 2u - i;                      /* next step pairs a_new[i] with r[k+2-i] */
-                const double rr = (inside && ri <= p) ? r_in[ri] : 0.0;
-                np = fma(v, rr, np);
+                if (i <= cnt) {
+                    const double fs = cur[i + 1u];
+                    const double b = B[s];
+                    B[s] = fma(gamma, fs, b);
+                    nxt[i] = fma(gamma, b, fs);
+                }
+            }
+        }
+        const double err = __shfl_sync(0xffffffffu, B[0], 0);        /* B_m[0] */
+        rinv = lnb_a3_rcp(err);
+        __syncwarp();
+        double *t = cur; cur = nxt; nxt = t;
+    }
+    /* step-up on the same buffers (now mirrors of a) */
+    double a[5];
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const uint32_t i = lane + 32u * (uint32_t)s;
+        a[s] = (i == 0u) ? 1.0 : 0.0;
+        if (i < LNB_A3_MIRROR) { cur[i] = a[s]; nxt[i] = a[s]; }
+    }
+    __syncwarp();
+    for (uint32_t m = 1; m <= p; m++) {
+        const double g = gam[m];
+        const uint32_t ns = (m >> 5) + 1u;
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            if ((uint32_t)s < ns) {
+                const uint32_t i = lane + 32u * (uint32_t)s;
+                if (i >= 1u && i <= m) {
+                    const double v = (i == m) ? g : fma(g, cur[m - i], a[s]);
+                    a[s] = v;
+                    nxt[i] = v;
+                }
             }
         }
         __syncwarp();
         double *t = cur; cur = nxt; nxt = t;
-        part = np;
-        rinv = rinv_next;
     }
 #pragma unroll
     for (int s = 0; s < 5; s++) {
@@ -267,6 +329,23 @@ __device__ void lnb_a3_levinson_warp(const double *r_in, uint32_t p, double lamb
         if (i >= 1u && i <= p) out_w[p - i] = a[s];
     }
     __syncwarp();
+}
+
+/* eight taps of the sliding FIR tile: window = prev[1..7] ++ next[0..7] (next = the group at base + 7 .. + 15) */
+__device__ __forceinline__ void lnb_a3_fir8(const double *base, const double *w, const double (&prev)[8], double (&next)[8],
+                                            double (&acc)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) next[k] = base[7 + k + ((7 + k) >> 3)];      /* window samples 7..14 (the pad slot is skipped) */
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+        const double wj = w[jj];
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            const int t = jj + o;
+            acc[o] = fma(wj, (t < 7) ? prev[t + 1] : next[t - 7], acc[o]);
+        }
+    }
 }
 
 /* ---- FIR over whole groups: res[t] = init + sum_j w[j] * x[t-p+j]  (x[<0] = 0) ----
@@ -288,22 +367,19 @@ __device__ __forceinline__ double lnb_a3_fir(const LnbA3Ctx &cx, const LnbA3Team
         for (int o = 0; o < 8; o++) acc[o] = (MODE == 0) ? Xg[o] : 0.0;
         if (PS == 0) {
             const double *base = Xg - (p >> 3) * 9u;                 /* sample 8G - p */
-            double xw[15];
+            /* sliding window of 15 samples = the last 7 of the previous group + the 8 of the next one, kept in two
+             * register sets that swap roles every 8 taps (no register moves) */
+            double P[8], Q[8];
 #pragma unroll
-            for (int k = 0; k < 7; k++) xw[k] = base[k];
-            for (uint32_t j0 = 0; j0 < p; j0 += 8u) {
-#pragma unroll
-                for (int k = 7; k < 15; k++) xw[k] = base[k + (k >> 3)];   /* window samples 7..14 (the pad slot is skipped) */
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) {
-                    const double wj = w[j0 + jj];
-#pragma unroll
-                    for (int o = 0; o < 8; o++) acc[o] = fma(wj, xw[jj + o], acc[o]);
-                }
-#pragma unroll
-                for (int k = 0; k < 7; k++) xw[k] = xw[k + 8];
+            for (int k = 0; k < 7; k++) P[k + 1] = base[k];
+            uint32_t j0 = 0;
+            for (; j0 + 16u <= p; j0 += 16u) {
+                lnb_a3_fir8(base, w + j0, P, Q, acc);
+                base += 9;
+                lnb_a3_fir8(base, w + j0 + 8u, Q, P, acc);
                 base += 9;
             }
+            if (j0 < p) lnb_a3_fir8(base, w + j0, P, Q, acc);
         } else {
             double xw[PS + 7];
 #pragma unroll
@@ -361,7 +437,7 @@ __device__ double lnb_a3_block_sum(double v, double *scratch)
 }
 
 /* Levinson-Durbin of the levels [lv_first, nlev) by a team: threads take the orders <= 16 (reference operation
- * order), warps the orders 32..128.  `scratch` = LNB_A3_WARPS x 2 mirrors (only used by the warp tasks). */
+ * order), warps the orders 32..128.  `scratch` = LNB_A3_WARPS x 3 x LNB_A3_MIRROR doubles (only used by the warp tasks). */
 __device__ void lnb_a3_solve_levels(const LnbA3Ctx &cx, const LnbA3Team &tm, uint32_t P, uint32_t lv_first, uint32_t nlev,
                                     double lambda, double *scratch)
 {
@@ -392,7 +468,7 @@ __device__ void lnb_a3_solve_levels(const LnbA3Ctx &cx, const LnbA3Team &tm, uin
             if (p <= 16u) continue;
             if (rest < U) {
                 lnb_a3_levinson_warp(cx.acorr + lv * 256 + rest * (p + 1u), p, lambda,
-                                     scratch + tm.warp * 2 * LNB_A3_MIRROR, cx.cand + lv * LNB_MAX_PARAMS + rest * p);
+                                     scratch + tm.warp * 3 * LNB_A3_MIRROR, cx.cand + lv * LNB_MAX_PARAMS + rest * p);
                 break;
             }
             rest -= U;
@@ -410,7 +486,7 @@ __device__ void lnb_a3_generic(const LnbEncodeBatch &b, uint32_t s, uint32_t bc,
     const uint32_t arr = lnb_a3_array_doubles(na_max);
     double *A = smem, *B = smem + arr;
     double *cand = smem + 2u * arr, *acorr = cand + LNB_MAX_LEVELS * LNB_MAX_PARAMS;
-    double *misc = acorr + LNB_MAX_LEVELS * 256 + LNB_A3_ITEMS * LNB_A3_PART + 2 * LNB_A3_MIRROR;
+    double *misc = acorr + LNB_MAX_LEVELS * 256 + LNB_A3_ITEMS * LNB_A3_PART + 3 * LNB_A3_MIRROR;
     {
         const int32_t *src = b.work + (size_t)bc * b.cfg.work_stride;
         const double norm = ldexp(1.0, -(int)(b.cfg.bits_per_sample - 1u));
@@ -457,7 +533,7 @@ __device__ void lnb_a3_generic(const LnbEncodeBatch &b, uint32_t s, uint32_t bc,
                     if (wt < U) {
                         double *dst = cand + lv * LNB_MAX_PARAMS + wt * p;
                         if (m < p) { for (uint32_t j = c & 31u; j < p; j += 32u) dst[j] = 0.0; }
-                        else lnb_a3_levinson_warp(acorr + lv * 256u + wt * (p + 1u), p, lambda, B + warp * 2 * LNB_A3_MIRROR, dst);
+                        else lnb_a3_levinson_warp(acorr + lv * 256u + wt * (p + 1u), p, lambda, B + warp * 3 * LNB_A3_MIRROR, dst);
                         wt = 0xFFFFFFFFu;
                     } else if (wt != 0xFFFFFFFFu) wt -= U;
                 }
@@ -521,7 +597,7 @@ __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEn
     cx.acorr = cx.cand + LNB_MAX_LEVELS * LNB_MAX_PARAMS;
     cx.part = cx.acorr + LNB_MAX_LEVELS * 256;
     cx.lev0 = cx.part + LNB_A3_ITEMS * LNB_A3_PART;
-    cx.misc = cx.lev0 + 2 * LNB_A3_MIRROR;
+    cx.misc = cx.lev0 + 3 * LNB_A3_MIRROR;
     const uint32_t na = cx.na;
     const double lambda = b.cfg.lambdas[lam];
 
