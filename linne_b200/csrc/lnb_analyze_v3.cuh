@@ -51,7 +51,7 @@ __host__ __device__ inline size_t lnb_a3_smem_doubles(uint32_t na_max)
          + (size_t)LNB_MAX_LEVELS * 256                   /* autocorrelations per level: U*(p+1) = P+U <= 256 */
          + (size_t)LNB_A3_ITEMS * LNB_A3_PART             /* work-item partials */
          + (size_t)3 * LNB_A3_MIRROR                      /* scratch of the level-0 Toeplitz solve (runs beside the rest) */
-         + 64;                                            /* level losses, block-sum scratch */
+         + 128;                                           /* level losses, block-sum scratch, per-warp level partials */
 }
 
 struct LnbA3Ctx {
@@ -436,6 +436,27 @@ __device__ double lnb_a3_block_sum(double v, double *scratch)
     return lnb_a3_team_sum(all, v, scratch);
 }
 
+/* L1 loss of the levels [lv_first, nlev) (linne_network.c:318-335) by a team, mean losses into cx.misc[lv].
+ * Every warp leaves its partial of every level in shared memory and ONE team barrier precedes the final sums
+ * (same summation order as a per-level reduction, a fraction of the barriers).  The caller synchronises after. */
+__device__ void lnb_a3_level_losses(const LnbA3Ctx &cx, const LnbA3Team &tm, uint32_t P, uint32_t lv_first, uint32_t nlev)
+{
+    double *parts = cx.misc + 32;                                    /* [warp][LNB_MAX_LEVELS] */
+    for (uint32_t lv = lv_first; lv < nlev; lv++) {
+        const uint32_t U = 1u << lv, p = P / U;
+        double v = lnb_a3_fir_any<0>(cx, tm, cx.A, (double *)0, p, cx.na / U, cx.cand + lv * LNB_MAX_PARAMS);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((tm.tid & 31u) == 0u) parts[tm.warp * LNB_MAX_LEVELS + lv] = v;
+    }
+    tm.sync();
+    if (tm.tid >= lv_first && tm.tid < nlev) {
+        double sum = 0.0;
+        for (uint32_t w = 0; w < tm.nwarps; w++) sum += parts[w * LNB_MAX_LEVELS + tm.tid];
+        cx.misc[tm.tid] = sum / (double)cx.na;
+    }
+}
+
 /* Levinson-Durbin of the levels [lv_first, nlev) by a team: threads take the orders <= 16 (reference operation
  * order), warps the orders 32..128.  `scratch` = LNB_A3_WARPS x 3 x LNB_A3_MIRROR doubles (only used by the warp tasks). */
 __device__ void lnb_a3_solve_levels(const LnbA3Ctx &cx, const LnbA3Team &tm, uint32_t P, uint32_t lv_first, uint32_t nlev,
@@ -650,19 +671,10 @@ __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEn
                 }
                 lnb_a3_solve_levels(cx, rest, P, 1u, nlev, lambda, cx.B);       /* B is free again: mirror scratch */
                 rest.sync();
-                for (uint32_t lv = 1; lv < nlev; lv++) {
-                    const uint32_t U = 1u << lv, p = P / U;
-                    const double part = lnb_a3_fir_any<0>(cx, rest, cx.A, (double *)0, p, na / U, cx.cand + lv * LNB_MAX_PARAMS);
-                    const double tot = lnb_a3_team_sum(rest, part, cx.misc + 16);
-                    if (c == 0) cx.misc[lv] = tot / (double)na;
-                }
+                lnb_a3_level_losses(cx, rest, P, 1u, nlev);
             }
             __syncthreads();
-            {
-                const double part = lnb_a3_fir_any<0>(cx, all, cx.A, (double *)0, P, na, cx.cand);
-                const double tot = lnb_a3_block_sum(part, cx.misc + 16);
-                if (c == 0) cx.misc[0] = tot / (double)na;
-            }
+            lnb_a3_level_losses(cx, all, P, 0u, 1u);
         } else {
             /* ---- autocorrelation of every unit of every level ---- */
             for (uint32_t lv = 0; lv < nlev; lv++) {
@@ -676,12 +688,7 @@ __global__ void __launch_bounds__(LNB_A3_THREADS, 1) lnb_analyze_v3_kernel(LnbEn
             lnb_a3_solve_levels(cx, all, P, 0u, nlev, lambda, cx.B);
             __syncthreads();
             /* ---- L1 loss of every level (linne_network.c:318-335) ---- */
-            for (uint32_t lv = 0; lv < nlev; lv++) {
-                const uint32_t U = 1u << lv, p = P / U;
-                const double part = lnb_a3_fir_any<0>(cx, all, cx.A, (double *)0, p, na / U, cx.cand + lv * LNB_MAX_PARAMS);
-                const double tot = lnb_a3_block_sum(part, cx.misc + 16);
-                if (c == 0) cx.misc[lv] = tot / (double)na;
-            }
+            lnb_a3_level_losses(cx, all, P, 0u, nlev);
         }
         __syncthreads();
         /* first minimum wins (linne_network.c:337-341) */
