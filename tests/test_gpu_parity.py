@@ -176,3 +176,22 @@ def test_sgd_training_path(gpu, oracle):
     # 2000 chaotic gradient steps amplify last-bit differences of the summation order: allow 0.5 % here
     assert abs(len(got) - len(want)) <= 0.005 * len(want), (len(got), len(want))
     assert got != gpu.encode(pcm, preset=0, block=2048)
+
+
+# ---- robustness: corrupted payloads with the CRC check off must come back (any result code), never hang ----
+@pytest.mark.timeout(120)
+def test_corrupted_payloads_do_not_hang(gpu, oracle):
+    rng = np.random.default_rng(1234)
+    pcm = harness.synth_pcm(n=4096 * 3 + 700, channels=2, bits=16, seed=55)
+    for preset in (0, 5):
+        good = oracle.encode(pcm, preset=preset, block=4096)
+        for trial in range(24):
+            bad = bytearray(good)
+            # leave the 30-byte stream header and the block framing (sync, size) alone: hit type / payload bytes
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(41, len(bad)))
+                bad[pos] = int(rng.integers(0, 256))
+            rc, out = gpu.decode(bytes(bad), check_crc=0, return_code=True)
+            assert rc in range(8)
+    # and the undamaged stream still decodes afterwards (no state left behind)
+    assert np.array_equal(gpu.decode(good), pcm)
