@@ -371,6 +371,11 @@ def run_b200(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- linne_b200 has no CPU fallback")
+    # Eight host threads per rank wait on their streams; when the ranks of a box outnumber its cores, spinning waits
+    # starve each other, so the library's waits are switched to sleeping ones (LINNE_B200_SYNC=block).
+    oversubscribed = world * len(PRESETS) > 0.75 * (os.cpu_count() or 1)
+    if oversubscribed:
+        os.environ.setdefault("LINNE_B200_SYNC", "block")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -605,7 +610,8 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": "C2: 10 s 44.1 kHz 16-bit stereo synthetic clip, -m 0..7 sweep, encode+decode",
                    "block": BLOCK, "ms": 1, "presets": PRESETS, "l2": "256 MiB flush write between timed iterations",
                    "per_rank": "each rank runs the whole sweep on its own clip",
-                   "concurrency": "serial" if args.serial else "8 presets on 8 host threads / CUDA streams"},
+                   "concurrency": "serial" if args.serial else "8 presets on 8 host threads / CUDA streams",
+                   "host_wait": os.environ.get("LINNE_B200_SYNC", "spin"), "host_cores": os.cpu_count()},
         "e2e": {"value": round(e2e_value, 3), "unit": "MSamples/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),

@@ -44,6 +44,8 @@ struct LnbDevice {
     int events_created;
     int num_timeline;
     LnbTimelineEntry timeline[LNB_MAX_TIMELINE];
+    cudaEvent_t sync_event;              /* LINNE_B200_SYNC=block: host threads sleep in the driver instead of spinning */
+    int blocking_sync;
 };
 
 static cudaEvent_t g_ref_event;              /* process-wide time origin of the launch timelines */
@@ -287,6 +289,12 @@ int lnb_shim_open(LnbDevice **out, int device_ordinal)
     if (cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking) != cudaSuccess) { free(dev); return 4; }
     dev->owns_stream = 1;
     dev->cost_rank = -1;
+    {   /* many handles driven from many host threads (several ranks per box) oversubscribe the cores when every
+         * waiting thread spins; LINNE_B200_SYNC=block makes the waits sleep (a little more wake-up latency) */
+        const char *mode = getenv("LINNE_B200_SYNC");
+        if (mode && mode[0] == 'b' && cudaEventCreateWithFlags(&dev->sync_event, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess)
+            dev->blocking_sync = 1;
+    }
 
     const LnbHostTables *ht = lnb_tables_get();
     const size_t sz_lut = sizeof(ht->huff_lut), sz_code = sizeof(ht->huff_code), sz_len = 256,
@@ -315,6 +323,7 @@ void lnb_shim_close(LnbDevice *dev)
     if (dev->events_created)
         for (int i = 0; i < LNB_MAX_PENDING; i++) { cudaEventDestroy(dev->ev_begin[i]); cudaEventDestroy(dev->ev_end[i]); }
     cudaFree(dev->table_mem);
+    if (dev->blocking_sync) cudaEventDestroy(dev->sync_event);
     if (dev->owns_stream) cudaStreamDestroy(dev->stream);
     free(dev);
 }
@@ -388,7 +397,13 @@ int lnb_shim_memset(LnbDevice *dev, void *dst, int value, size_t bytes)
 int lnb_shim_sync(LnbDevice *dev)
 {
     bind_device(dev);
-    cudaError_t e = cudaStreamSynchronize(dev->stream);
+    cudaError_t e;
+    if (dev->blocking_sync) {
+        e = cudaEventRecord(dev->sync_event, dev->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(dev->sync_event);
+    } else {
+        e = cudaStreamSynchronize(dev->stream);
+    }
     if (e == cudaSuccess && dev->profiling) drain_profile(dev);
     if (e == cudaSuccess) e = dev->last_error;
     if (e != cudaSuccess) {
