@@ -55,6 +55,20 @@ LINNEApiResult LINNEB200_EncodeWholePacked(struct LINNEEncoder *encoder, const u
 LINNEApiResult LINNEB200_DecodeWholePacked(struct LINNEDecoder *decoder, const uint8_t *data, uint32_t data_size,
         uint8_t *pcm, uint32_t pcm_capacity_frames, uint32_t *num_frames);
 
+/* ---- streaming: block-at-a-time callers ------------------------------------------------
+ * LINNEDecoder_DecodeBlock decodes `blocks` blocks per GPU batch when the caller's buffer holds that many
+ * (a player passes everything that is left of its stream, tools/linne_player/linne_player.c:110-121) and
+ * serves the following calls from pinned host memory.  A cached block is handed out only if the bytes the
+ * caller passes equal the bytes that were decoded, so results and error codes are those of the batch of one.
+ * 0 or 1 switches it off (the default; the environment variable LINNE_B200_READAHEAD sets the default). */
+void LINNEB200_DecoderSetReadahead(struct LINNEDecoder *decoder, uint32_t blocks);
+
+/* Page-locked host memory for the buffers handed to EncodeWhole / DecodeWhole and their packed variants
+ * (SURVEY 8f.3): copies from and to such memory are DMA transfers that overlap with kernels of other
+ * handles.  NULL when no device is usable. */
+void *LINNEB200_HostAlloc(size_t bytes);
+void  LINNEB200_HostFree(void *h_ptr);
+
 /* ---- encode with externally supplied analysis results ------------------------------------------
  * One record per (block, channel), block-major.  Used to show that identical quantised
  * coefficients yield byte-identical residuals and coded bits (north star, parity leg 3). */

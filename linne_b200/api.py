@@ -228,6 +228,10 @@ def bind_ext_api(lib):
     lib.LINNEB200_EncodeWholePacked.restype = C.c_int
     lib.LINNEB200_DecodeWholePacked.argtypes = [C.c_void_p, u8p, C.c_uint32, u8p, C.c_uint32, u32p]
     lib.LINNEB200_DecodeWholePacked.restype = C.c_int
+    lib.LINNEB200_DecoderSetReadahead.argtypes = [C.c_void_p, C.c_uint32]
+    lib.LINNEB200_HostAlloc.argtypes = [C.c_size_t]
+    lib.LINNEB200_HostAlloc.restype = C.c_void_p
+    lib.LINNEB200_HostFree.argtypes = [C.c_void_p]
     for name in ("DeviceCopy", "CopyToDevice", "CopyToHost"):
         f = getattr(lib, f"LINNEB200_{name}")
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]

@@ -6,6 +6,7 @@
  * defined next to the struct definitions */
 LnbDevice *lnb_encoder_device(const struct LINNEEncoder *enc);
 LnbDevice *lnb_decoder_device(const struct LINNEDecoder *dec);
+void lnb_decoder_set_readahead(struct LINNEDecoder *dec, uint32_t blocks);
 
 const char *LINNEB200_Backend(void) { return lnb_shim_backend(); }
 
@@ -21,6 +22,10 @@ uint64_t LINNEB200_EncoderLaunchCount(const struct LINNEEncoder *e) { return e ?
 uint64_t LINNEB200_DecoderLaunchCount(const struct LINNEDecoder *d) { return d ? lnb_shim_launch_count(lnb_decoder_device(d)) : 0; }
 void LINNEB200_EncoderUseStream(struct LINNEEncoder *e, void *s) { if (e) lnb_shim_use_stream(lnb_encoder_device(e), s); }
 void LINNEB200_DecoderUseStream(struct LINNEDecoder *d, void *s) { if (d) lnb_shim_use_stream(lnb_decoder_device(d), s); }
+
+void LINNEB200_DecoderSetReadahead(struct LINNEDecoder *d, uint32_t blocks) { if (d) lnb_decoder_set_readahead(d, blocks); }
+void *LINNEB200_HostAlloc(size_t bytes) { return lnb_shim_alloc_pinned(bytes); }
+void LINNEB200_HostFree(void *h_ptr) { if (h_ptr) lnb_shim_free_pinned(h_ptr); }
 
 void LINNEB200_EncoderSetProfiling(struct LINNEEncoder *e, int on) { if (e) lnb_shim_profile_enable(lnb_encoder_device(e), on); }
 void LINNEB200_DecoderSetProfiling(struct LINNEDecoder *d, int on) { if (d) lnb_shim_profile_enable(lnb_decoder_device(d), on); }

@@ -25,7 +25,17 @@ struct LINNEDecoder {
     LnbBuf d_stream, d_blocks, d_params, d_pcm, d_packed;
     LnbBuf h_blocks;                       /* pinned LnbBlockDesc[] */
     LnbBuf h_stream;                       /* pinned copy of a device-resident stream (block hop) */
+    LnbBuf h_pcm;                          /* pinned int32 [C][stage_stride]: PCM staging of DecodeBlock / read-ahead cache */
+    /* DecodeBlock read-ahead: blocks decoded ahead of the caller in one batch and served from here */
+    uint32_t readahead;                    /* blocks decoded per batch by DecodeBlock (<= 1: batch of one) */
+    uint32_t stage_stride;                 /* samples per plane of h_pcm in the last staged call */
+    uint32_t ra_count, ra_next;            /* cached blocks / next one to serve */
+    uint8_t *ra_image;                     /* the cached blocks' bytes (validated against the caller's on every hit) */
+    size_t ra_image_cap;
+    struct LnbCachedBlock { uint32_t byte_off, byte_size, smp_off, nsmp; } *ra_blocks;
+    uint32_t ra_blocks_cap;
 };
+#define LNB_MAX_READAHEAD 4096u
 
 /* reference linne_decoder.c:60-131 */
 LINNEApiResult LINNEDecoder_DecodeHeader(const uint8_t *data, uint32_t data_size, struct LINNEHeader *header)
@@ -71,6 +81,11 @@ struct LINNEDecoder *LINNEDecoder_Create(const struct LINNEDecoderConfig *config
     dec->max_num_parameters_per_layer = config->max_num_parameters_per_layer;
     if (own) dec->flags |= DEC_FLAG_OWN_WORK;
     if (config->check_crc == 1) dec->flags |= DEC_FLAG_CHECK_CRC;
+    {   /* LINNE_B200_READAHEAD=K: DecodeBlock decodes K blocks per batch (same results, see decode_block_cached) */
+        const char *e = getenv("LINNE_B200_READAHEAD");
+        const long k = e ? strtol(e, NULL, 10) : 0;
+        dec->readahead = (k > 1) ? (uint32_t)(k > (long)LNB_MAX_READAHEAD ? (long)LNB_MAX_READAHEAD : k) : 0u;
+    }
     if (lnb_shim_open(&dec->dev, -1) != 0) {
         fprintf(stderr, "linne_b200: no usable CUDA device -- the decoder has no CPU fallback\n");
         if (own) free(work);
@@ -91,6 +106,10 @@ void LINNEDecoder_Destroy(struct LINNEDecoder *dec)
         lnb_buf_release_device(dec->dev, &dec->d_packed);
         lnb_buf_release_host(&dec->h_blocks);
         lnb_buf_release_host(&dec->h_stream);
+        lnb_buf_release_host(&dec->h_pcm);
+        free(dec->ra_image); dec->ra_image = NULL; dec->ra_image_cap = 0;
+        free(dec->ra_blocks); dec->ra_blocks = NULL; dec->ra_blocks_cap = 0;
+        dec->ra_count = dec->ra_next = 0;
         lnb_shim_close(dec->dev);
         dec->dev = NULL;
     }
@@ -112,6 +131,7 @@ LINNEApiResult LINNEDecoder_SetHeader(struct LINNEDecoder *dec, const struct LIN
     if (header->num_channels > LINNE_MAX_NUM_CHANNELS) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     dec->header = *header;
     dec->flags |= DEC_FLAG_HEADER_SET;
+    dec->ra_count = dec->ra_next = 0;                          /* cached blocks belong to the previous header */
     lnb_shim_set_cost_rank(dec->dev, (int)header->preset);     /* longer predictors first (scheduling hint) */
     return LINNE_APIRESULT_OK;
 }
@@ -135,7 +155,7 @@ typedef struct {
 } BlockScan;
 
 static int scan_blocks(const struct LINNEHeader *h, const uint8_t *data, uint32_t data_size,
-                       uint32_t start_offset, uint32_t max_samples, uint32_t sample_limit, int single,
+                       uint32_t start_offset, uint32_t max_samples, uint32_t sample_limit, uint32_t block_limit,
                        LnbBlockDesc *table, uint32_t table_cap, BlockScan *out)
 {
     uint32_t off = start_offset, progress = 0, nb = 0;
@@ -176,7 +196,7 @@ static int scan_blocks(const struct LINNEHeader *h, const uint8_t *data, uint32_
         out->num_decodable = nb;
         progress += ns;
         off += consumed;
-        if (single) break;
+        if (block_limit && nb >= block_limit) break;
     }
     out->num_blocks = nb;
     out->total_samples = progress;
@@ -184,47 +204,61 @@ static int scan_blocks(const struct LINNEHeader *h, const uint8_t *data, uint32_
     return 0;
 }
 
-/* shared by DecodeBlock (single = 1) and DecodeWhole */
+/* shared by DecodeBlock (block_limit >= 1, staged) and DecodeWhole (block_limit = 0) */
 /* Resident mode (d_stream_ext / d_pcm_ext non-NULL): the stream image and/or the PCM planes already
  * live on the device, so the corresponding bulk copy is skipped; `data` (host) is still needed for
- * the block hop. */
+ * the block hop.
+ * Staged mode (`staged`): the PCM comes back into the handle's pinned planes (dec->h_pcm, stride
+ * dec->stage_stride) together with the block table, behind ONE synchronisation; the caller hands samples on
+ * from there.  `scan_out` (optional) receives the hop's result; the block table stays in dec->h_blocks. */
 static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
                                    uint32_t start_offset, int32_t **buffer, uint32_t buffer_num_samples,
-                                   uint32_t sample_limit, int single,
+                                   uint32_t sample_limit, uint32_t block_limit, int staged,
                                    uint32_t *consumed_bytes, uint32_t *decoded_samples,
-                                   const uint8_t *d_stream_ext, int32_t *d_pcm_ext, uint32_t pcm_stride_ext)
+                                   const uint8_t *d_stream_ext, int32_t *d_pcm_ext, uint32_t pcm_stride_ext,
+                                   BlockScan *scan_out, uint32_t *first_bad_out)
 {
     const struct LINNEHeader *h = &dec->header;
     const uint32_t C = h->num_channels;
     LnbDecodeBatch batch;
     BlockScan scan;
     LnbBlockDesc *blocks;
-    uint32_t guess, first_bad, ok_samples, c, i;
+    uint32_t guess, first_bad, ok_samples, c, i, used;
     size_t padded;
     LINNEApiResult result;
 
     /* block table in pinned host memory; grow until the hop fits */
-    guess = single ? 1u : (uint32_t)((uint64_t)(data_size - start_offset) / 64u + 16u);
-    if (!single && h->num_samples_per_block) {
+    guess = block_limit ? block_limit : (uint32_t)((uint64_t)(data_size - start_offset) / 64u + 16u);
+    if (!block_limit && h->num_samples_per_block) {
         const uint32_t by_samples = sample_limit / h->num_samples_per_block + 16u;
         if (by_samples < guess) guess = by_samples * 2u;
     }
     for (;;) {
         if (lnb_buf_reserve_host(&dec->h_blocks, (size_t)guess * sizeof(LnbBlockDesc))) return LINNE_APIRESULT_NG;
         blocks = (LnbBlockDesc *)dec->h_blocks.ptr;
-        if (scan_blocks(h, data, data_size, start_offset, buffer_num_samples, sample_limit, single,
+        if (scan_blocks(h, data, data_size, start_offset, buffer_num_samples, sample_limit, block_limit,
                         blocks, guess, &scan) == 0) break;
         guess *= 2u;
     }
+    if (scan_out) *scan_out = scan;
+    if (first_bad_out) *first_bad_out = 0;
 
     if (consumed_bytes) *consumed_bytes = 0;
     if (decoded_samples) *decoded_samples = 0;
     if (scan.num_blocks == 0) return scan.framing_error;      /* OK when there was simply nothing to do */
 
+    /* bytes of the image the blocks of this call span: a streaming caller passes everything that is left of its
+     * stream with every DecodeBlock (tools/linne_player/linne_player.c:110-121) -- only this much is uploaded */
+    used = scan.end_offset;
+    for (i = 0; i < scan.num_blocks; i++) {
+        const uint64_t end = (uint64_t)blocks[i].byte_off + blocks[i].byte_size;
+        if (end > used) used = (end > data_size) ? data_size : (uint32_t)end;
+    }
+    if (!block_limit || d_stream_ext) used = data_size;
+
     /* device buffers */
-    padded = LNB_ROUNDUP((size_t)data_size + 16u, 16u);
+    padded = LNB_ROUNDUP((size_t)used + 16u, 16u);
     lnb_fill_stream_cfg(&batch.cfg, h);
-    batch.cfg.pcm_stride = (uint32_t)LNB_ROUNDUP((size_t)scan.total_samples + 4u, 4u);
     {   /* the terminal block (post-CRC error) may not fit the PCM planes: park it inside the stride */
         uint32_t worst = scan.total_samples;
         if (scan.num_blocks > scan.num_decodable) worst += blocks[scan.num_blocks - 1].nsmp;
@@ -236,7 +270,8 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
     if ((!d_stream_ext && lnb_buf_reserve_device(dec->dev, &dec->d_stream, padded))
         || lnb_buf_reserve_device(dec->dev, &dec->d_blocks, (size_t)scan.num_blocks * sizeof(LnbBlockDesc))
         || lnb_buf_reserve_device(dec->dev, &dec->d_params, (size_t)scan.num_blocks * C * sizeof(LnbChanParams))
-        || (!d_pcm_ext && lnb_buf_reserve_device(dec->dev, &dec->d_pcm, (size_t)batch.cfg.pcm_stride * C * sizeof(int32_t))))
+        || (!d_pcm_ext && lnb_buf_reserve_device(dec->dev, &dec->d_pcm, (size_t)batch.cfg.pcm_stride * C * sizeof(int32_t)))
+        || (staged && lnb_buf_reserve_host(&dec->h_pcm, (size_t)batch.cfg.pcm_stride * C * sizeof(int32_t))))
         return LINNE_APIRESULT_NG;
 
     /* a terminal block with a post-CRC error takes part in the CRC pass only */
@@ -252,7 +287,7 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
 
     batch.tab = *lnb_shim_tables(dec->dev);
     batch.stream = d_stream_ext ? d_stream_ext : (const uint8_t *)dec->d_stream.ptr;
-    batch.stream_size = data_size;
+    batch.stream_size = used;
     batch.blocks = (LnbBlockDesc *)dec->d_blocks.ptr;
     batch.num_blocks = scan.num_blocks;
     batch.params = (LnbChanParams *)dec->d_params.ptr;
@@ -260,11 +295,19 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
 
     if (!d_stream_ext) {
         lnb_shim_memset(dec->dev, (uint8_t *)dec->d_stream.ptr + (padded - 16u), 0, 16u);
-        lnb_shim_h2d(dec->dev, dec->d_stream.ptr, data, data_size);
+        lnb_shim_h2d(dec->dev, dec->d_stream.ptr, data, used);
     }
     lnb_shim_h2d(dec->dev, dec->d_blocks.ptr, blocks, (size_t)scan.num_blocks * sizeof(LnbBlockDesc));
     if (lnb_shim_decode(dec->dev, &batch)) return LINNE_APIRESULT_NG;
     lnb_shim_d2h(dec->dev, blocks, dec->d_blocks.ptr, (size_t)scan.num_blocks * sizeof(LnbBlockDesc));
+    if (staged && scan.total_samples) {
+        /* pinned planes: the samples travel with the block table, the verdict below decides what is handed on */
+        dec->stage_stride = batch.cfg.pcm_stride;
+        for (c = 0; c < C; c++)
+            lnb_shim_d2h(dec->dev, (int32_t *)dec->h_pcm.ptr + (size_t)c * batch.cfg.pcm_stride,
+                         (int32_t *)dec->d_pcm.ptr + (size_t)c * batch.cfg.pcm_stride,
+                         (size_t)scan.total_samples * sizeof(int32_t));
+    }
     if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
 
     /* first block (stream order) whose CRC failed outranks everything after it */
@@ -283,23 +326,84 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
         result = scan.framing_error;
         ok_samples = scan.total_samples;
     }
+    if (first_bad_out) *first_bad_out = first_bad;
 
     /* hand back every sample the reference would have produced before stopping */
-    if (!d_pcm_ext) {
+    if (!d_pcm_ext && !staged) {
         for (c = 0; c < C; c++)
             lnb_shim_d2h(dec->dev, buffer[c], (int32_t *)dec->d_pcm.ptr + (size_t)c * batch.cfg.pcm_stride,
                          (size_t)ok_samples * sizeof(int32_t));
         if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
     }
 
-    if (single && result == LINNE_APIRESULT_OK) {
-        if (consumed_bytes) *consumed_bytes = LNB_BLOCK_HEADER_SIZE + blocks[0].na;
-        if (decoded_samples) *decoded_samples = blocks[0].nsmp;
-    } else {
-        if (consumed_bytes) *consumed_bytes = scan.end_offset - start_offset;
-        if (decoded_samples) *decoded_samples = ok_samples;
-    }
+    if (consumed_bytes) *consumed_bytes = scan.end_offset - start_offset;
+    if (decoded_samples) *decoded_samples = ok_samples;
     return result;
+}
+
+/* ---- DecodeBlock: batch of one, or read-ahead ---------------------------------------------
+ * A streaming caller (tools/linne_player/linne_player.c:110-121) asks for one block per call and passes all
+ * that is left of its stream.  With read-ahead K the first call decodes the next K blocks in ONE batch
+ * (K CTAs instead of one: the kernel is latency-bound per block, so K blocks take about as long as one) and
+ * keeps their PCM in pinned host memory; the following calls are served from there.  A hit requires the
+ * caller's bytes to equal the bytes that were decoded (memcmp of the whole block), so the result is the
+ * function of (header, block bytes) it is in the reference, whatever the caller did in between; only
+ * blocks that decoded cleanly are kept, every error takes the ordinary batch-of-one path. */
+static int serve_cached_block(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
+                              int32_t **buffer, uint32_t buffer_num_samples, uint32_t *decode_size, uint32_t *num_decode_samples)
+{
+    const struct LnbCachedBlock *b;
+    uint32_t c;
+    if (dec->ra_next >= dec->ra_count) return 0;
+    b = &dec->ra_blocks[dec->ra_next];
+    if (data_size < b->byte_size || b->nsmp > buffer_num_samples
+        || memcmp(data, dec->ra_image + b->byte_off, b->byte_size) != 0) {
+        dec->ra_count = dec->ra_next = 0;
+        return 0;
+    }
+    for (c = 0; c < dec->header.num_channels; c++)
+        memcpy(buffer[c], (const int32_t *)dec->h_pcm.ptr + (size_t)c * dec->stage_stride + b->smp_off, (size_t)b->nsmp * sizeof(int32_t));
+    *decode_size = b->byte_size;
+    *num_decode_samples = b->nsmp;
+    dec->ra_next++;
+    return 1;
+}
+
+static void fill_block_cache(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size)
+{
+    const LnbBlockDesc *blocks;
+    BlockScan scan;
+    uint32_t first_bad = 0, i, n, span;
+    dec->ra_count = dec->ra_next = 0;
+    (void)decode_range(dec, data, data_size, 0, NULL, 0xFFFFFFFFu, 0xFFFFFFFFu, dec->readahead, 1,
+                       NULL, NULL, NULL, NULL, 0, &scan, &first_bad);
+    blocks = (const LnbBlockDesc *)dec->h_blocks.ptr;
+    n = (first_bad < scan.num_decodable) ? first_bad : scan.num_decodable;
+    /* a block whose payload does not end where its size field says is left to the ordinary path */
+    for (i = 0; i < n; i++) {
+        uint32_t walked = LNB_BLOCK_HEADER_SIZE;
+        if (blocks[i].type == LNB_BLOCK_COMPRESSED) walked += blocks[i].na;
+        else if (blocks[i].type == LNB_BLOCK_RAW) walked += (dec->header.bits_per_sample / 8u) * blocks[i].nsmp * dec->header.num_channels;
+        if (walked != blocks[i].byte_size) { n = i; break; }
+    }
+    if (n < 2) return;                                         /* nothing gained over a batch of one */
+    span = blocks[n - 1].byte_off + blocks[n - 1].byte_size;
+    if (span > dec->ra_image_cap) {
+        uint8_t *p = (uint8_t *)realloc(dec->ra_image, span);
+        if (!p) return;
+        dec->ra_image = p; dec->ra_image_cap = span;
+    }
+    if (n > dec->ra_blocks_cap) {
+        struct LnbCachedBlock *p = (struct LnbCachedBlock *)realloc(dec->ra_blocks, (size_t)n * sizeof(*p));
+        if (!p) return;
+        dec->ra_blocks = p; dec->ra_blocks_cap = n;
+    }
+    memcpy(dec->ra_image, data, span);
+    for (i = 0; i < n; i++) {
+        dec->ra_blocks[i].byte_off = blocks[i].byte_off; dec->ra_blocks[i].byte_size = blocks[i].byte_size;
+        dec->ra_blocks[i].smp_off = blocks[i].smp_off; dec->ra_blocks[i].nsmp = blocks[i].nsmp;
+    }
+    dec->ra_count = n;
 }
 
 /* reference linne_decoder.c:564-668 */
@@ -307,15 +411,35 @@ LINNEApiResult LINNEDecoder_DecodeBlock(struct LINNEDecoder *dec, const uint8_t 
         int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples,
         uint32_t *decode_size, uint32_t *num_decode_samples)
 {
-    uint32_t c;
+    LINNEApiResult ret;
+    uint32_t c, ok_samples = 0, consumed = 0;
     if (dec == NULL || data == NULL || buffer == NULL || decode_size == NULL || num_decode_samples == NULL)
         return LINNE_APIRESULT_INVALID_ARGUMENT;
     if (!(dec->flags & DEC_FLAG_HEADER_SET)) return LINNE_APIRESULT_PARAMETER_NOT_SET;
     if (buffer_num_channels < dec->header.num_channels) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     for (c = 0; c < dec->header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     if (data_size == 0) return LINNE_APIRESULT_INSUFFICIENT_DATA;
-    return decode_range(dec, data, data_size, 0, buffer, buffer_num_samples, 0xFFFFFFFFu, 1,
-                        decode_size, num_decode_samples, NULL, NULL, 0);
+
+    if (dec->readahead > 1u) {
+        if (serve_cached_block(dec, data, data_size, buffer, buffer_num_samples, decode_size, num_decode_samples))
+            return LINNE_APIRESULT_OK;
+        fill_block_cache(dec, data, data_size);
+        if (serve_cached_block(dec, data, data_size, buffer, buffer_num_samples, decode_size, num_decode_samples))
+            return LINNE_APIRESULT_OK;
+        dec->ra_count = dec->ra_next = 0;
+    }
+    ret = decode_range(dec, data, data_size, 0, NULL, buffer_num_samples, 0xFFFFFFFFu, 1, 1,
+                       &consumed, &ok_samples, NULL, NULL, 0, NULL, NULL);
+    for (c = 0; ok_samples && c < dec->header.num_channels; c++)
+        memcpy(buffer[c], (const int32_t *)dec->h_pcm.ptr + (size_t)c * dec->stage_stride, (size_t)ok_samples * sizeof(int32_t));
+    if (ret == LINNE_APIRESULT_OK) {
+        /* the bytes the payload reader walked over (linne_decoder.c:655-661) */
+        const LnbBlockDesc *blk = (const LnbBlockDesc *)dec->h_blocks.ptr;
+        consumed = LNB_BLOCK_HEADER_SIZE + blk[0].na;
+    }
+    *decode_size = consumed;
+    *num_decode_samples = ok_samples;
+    return ret;
 }
 
 /* reference linne_decoder.c:671-730 */
@@ -332,10 +456,16 @@ LINNEApiResult LINNEDecoder_DecodeWhole(struct LINNEDecoder *dec, const uint8_t 
         return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     for (c = 0; c < header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, buffer, buffer_num_samples,
-                        header.num_samples, 0, NULL, NULL, NULL, NULL, 0);
+                        header.num_samples, 0, 0, NULL, NULL, NULL, NULL, 0, NULL, NULL);
 }
 
 LnbDevice *lnb_decoder_device(const struct LINNEDecoder *dec) { return dec->dev; }
+
+void lnb_decoder_set_readahead(struct LINNEDecoder *dec, uint32_t blocks)
+{
+    dec->readahead = (blocks > LNB_MAX_READAHEAD) ? LNB_MAX_READAHEAD : blocks;
+    dec->ra_count = dec->ra_next = 0;
+}
 
 /* ---- extension entry point (include/linne_b200.h) ---- */
 #include "linne_b200.h"
@@ -358,7 +488,7 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uin
     if (buffer_num_channels < header.num_channels || buffer_num_samples < header.num_samples
         || pcm_stride < buffer_num_samples) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, NULL, buffer_num_samples,
-                        header.num_samples, 0, NULL, NULL, d_data, d_pcm, pcm_stride);
+                        header.num_samples, 0, 0, NULL, NULL, d_data, d_pcm, pcm_stride, NULL, NULL);
 }
 
 /* Packed interleaved PCM out (the bytes of a WAV data chunk), converted from the planes on the device.
@@ -381,8 +511,8 @@ LINNEApiResult LINNEB200_DecodeWholePacked(struct LINNEDecoder *dec, const uint8
     if (lnb_buf_reserve_device(dec->dev, &dec->d_pcm, stride * header.num_channels * sizeof(int32_t))
         || lnb_buf_reserve_device(dec->dev, &dec->d_packed, (size_t)header.num_samples * header.num_channels * bytes + 16u))
         return LINNE_APIRESULT_NG;
-    ret = decode_range(dec, data, data_size, LINNE_HEADER_SIZE, NULL, header.num_samples, header.num_samples, 0,
-                       NULL, &decoded, NULL, (int32_t *)dec->d_pcm.ptr, (uint32_t)stride);
+    ret = decode_range(dec, data, data_size, LINNE_HEADER_SIZE, NULL, header.num_samples, header.num_samples, 0, 0,
+                       NULL, &decoded, NULL, (int32_t *)dec->d_pcm.ptr, (uint32_t)stride, NULL, NULL);
     if (decoded) {          /* every sample the reference would have produced before stopping */
         if (lnb_shim_pack_pcm(dec->dev, (const int32_t *)dec->d_pcm.ptr, (uint8_t *)dec->d_packed.ptr, (uint32_t)stride,
                               decoded, header.num_channels, bytes)) return LINNE_APIRESULT_NG;

@@ -273,6 +273,76 @@ def test_decode_block_streaming(codec, oracle):
         L.LINNEDecoder_Destroy(dec)
 
 
+def _block_loop(L, dec, buf, size, channels, cap, start=30):
+    """DecodeBlock until the stream ends or a call fails: [(rc, used, samples)], PCM [C][total]."""
+    out = np.full((channels, cap), -7, np.int32)
+    used, got = C.c_uint32(0), C.c_uint32(0)
+    off, calls, pcm = start, [], []
+    while off < size:
+        rc = L.LINNEDecoder_DecodeBlock(dec, C.cast(buf.ctypes.data + off, C.POINTER(C.c_uint8)), size - off,
+                                        harness._chan_ptrs(out), channels, cap, C.byref(used), C.byref(got))
+        calls.append((rc, used.value, got.value))
+        if rc != OK:
+            break
+        pcm.append(out[:, :got.value].copy())
+        off += used.value
+    return calls, (np.concatenate(pcm, axis=1) if pcm else np.zeros((channels, 0), np.int32))
+
+
+@pytest.mark.parametrize("readahead", [2, 3, 16])
+def test_decode_block_readahead_equals_batch_of_one(codec, oracle, readahead):
+    """DecodeBlock with K blocks decoded per batch returns what the batch of one returns, call by
+    call -- clean streams, mixed block types, a corrupted block in the middle, bytes changed between calls."""
+    skip_on_reference(codec, "has no read-ahead")
+    L = codec.lib
+    cases = [(harness.synth_pcm(n=1024 * 7 + 300, channels=2, bits=16, seed=21), 16, 2, 1024),
+             (harness.mixed_types_pcm(), 16, 5, 10240)]         # raw, silent and compressed blocks
+    for pcm, bits, preset, block in cases:
+        stream = oracle.encode(pcm, bits=bits, preset=preset, block=block)
+        rc, hdr = codec.decode_header(stream)
+        sizes, off = [], 30
+        while off < len(stream):
+            sizes.append(int.from_bytes(stream[off + 2:off + 6], "big") + 6); off += sizes[-1]
+        variants = [bytearray(stream)]
+        bad = bytearray(stream); bad[30 + sum(sizes[:3]) + 25] ^= 0x10; variants.append(bad)        # block 3 corrupted
+        bad = bytearray(stream); bad[30 + sum(sizes[:2])] = 0x00; variants.append(bad)              # block 2 loses its sync code
+        for image in variants:
+            buf = np.zeros(len(image) + 16, np.uint8); buf[:len(image)] = np.frombuffer(bytes(image), np.uint8)
+            results = []
+            for k in (0, readahead):
+                dec = L.LINNEDecoder_Create(C.byref(LINNEDecoderConfig(pcm.shape[0], 3, 128, 1)), None, 0)
+                try:
+                    assert L.LINNEDecoder_SetHeader(dec, C.byref(hdr)) == OK
+                    L.LINNEB200_DecoderSetReadahead(dec, k)
+                    results.append(_block_loop(L, dec, buf, len(image), pcm.shape[0], block))
+                finally:
+                    L.LINNEDecoder_Destroy(dec)
+            assert results[0][0] == results[1][0]
+            assert np.array_equal(results[0][1], results[1][1])
+        # the caller's bytes change after the batch was decoded: the cached copy must not be served
+        buf = np.zeros(len(stream) + 16, np.uint8); buf[:len(stream)] = np.frombuffer(stream, np.uint8)
+        dec = L.LINNEDecoder_Create(C.byref(LINNEDecoderConfig(pcm.shape[0], 3, 128, 1)), None, 0)
+        try:
+            assert L.LINNEDecoder_SetHeader(dec, C.byref(hdr)) == OK
+            L.LINNEB200_DecoderSetReadahead(dec, readahead)
+            out = np.zeros((pcm.shape[0], block), np.int32)
+            used, got = C.c_uint32(0), C.c_uint32(0)
+            assert L.LINNEDecoder_DecodeBlock(dec, C.cast(buf.ctypes.data + 30, C.POINTER(C.c_uint8)), len(stream) - 30,
+                                              harness._chan_ptrs(out), pcm.shape[0], block, C.byref(used), C.byref(got)) == OK
+            assert used.value == sizes[0] and np.array_equal(out[:, :got.value], pcm[:, :got.value])
+            buf[30 + sizes[0] + 30] ^= 0x04
+            assert L.LINNEDecoder_DecodeBlock(dec, C.cast(buf.ctypes.data + 30 + sizes[0], C.POINTER(C.c_uint8)),
+                                              len(stream) - 30 - sizes[0], harness._chan_ptrs(out), pcm.shape[0], block,
+                                              C.byref(used), C.byref(got)) == DATA_CORRUPTION
+            # too small a buffer for a cached block: the ordinary path answers
+            buf[30 + sizes[0] + 30] ^= 0x04
+            assert L.LINNEDecoder_DecodeBlock(dec, C.cast(buf.ctypes.data + 30 + sizes[0], C.POINTER(C.c_uint8)),
+                                              len(stream) - 30 - sizes[0], harness._chan_ptrs(out), pcm.shape[0], block - 1,
+                                              C.byref(used), C.byref(got)) == INSUFFICIENT_BUFFER
+        finally:
+            L.LINNEDecoder_Destroy(dec)
+
+
 def test_encode_block_loop_equals_encode_whole(codec):
     # the CLI encodes with EncodeHeader + EncodeBlock per block (tools/linne_codec/linne_codec.c:123-161)
     pcm = harness.synth_pcm(n=2500, channels=2, bits=16, seed=10)

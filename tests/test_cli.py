@@ -81,6 +81,47 @@ def test_cli_hostsim_matches_reference_tool(tmp_path):
     roundtrip(HOSTSIM_CLI, tmp_path, "sim")
 
 
+def pipeline(cli, tmp_path, tag):
+    """many files through `-j N` workers give the files the one-worker run gives."""
+    import json
+    pairs_e, pairs_d, files = [], [], []
+    for i in range(7):
+        ch, bits, n = [(2, 16, 10240 + 512 * i), (1, 24, 4096 + 100 * i), (2, 8, 3000 + i)][i % 3]
+        pcm = harness.synth_pcm(n=n, channels=ch, bits=bits, seed=40 + i)
+        wav = tmp_path / f"p_{tag}_{i}.wav"
+        write_wav(str(wav), pcm, bits)
+        files.append((wav, tmp_path / f"p_{tag}_{i}.j1.lnn", tmp_path / f"p_{tag}_{i}.j3.lnn", tmp_path / f"p_{tag}_{i}.back.wav"))
+    for col, jobs in ((1, "1"), (2, "3")):
+        lst = tmp_path / f"enc_{tag}_{jobs}.txt"
+        lst.write_text("".join(f"{f[0]} {f[col]}\n" for f in files))
+        res = run(cli, "-e", "-m", "2", "-j", jobs, "-s", "-L", str(lst))
+        stats = json.loads(res.stderr.strip().splitlines()[-1])
+        assert stats["files"] == len(files) and stats["workers"] == int(jobs) and stats["samples"] > 0
+    lst = tmp_path / f"dec_{tag}.txt"
+    lst.write_text("".join(f"{f[2]} {f[3]}\n" for f in files))
+    run(cli, "-d", "-j", "3", "-L", str(lst))
+    for wav, one, three, back in files:
+        assert one.read_bytes() == three.read_bytes()
+        assert wav_data(str(back)) == wav_data(str(wav))
+    # a missing file fails that pair only; the others are still written
+    lst = tmp_path / f"bad_{tag}.txt"
+    good = tmp_path / f"good_{tag}.lnn"
+    lst.write_text(f"{tmp_path / 'nope.wav'} {tmp_path / 'nope.lnn'}\n{files[0][0]} {good}\n")
+    res = subprocess.run([cli, "-e", "-m", "2", "-j", "2", "-L", str(lst)], capture_output=True, text=True, timeout=600)
+    assert res.returncode != 0 and good.read_bytes() == files[0][1].read_bytes()
+
+
+@pytest.mark.skipif(not os.path.exists(HOSTSIM_CLI), reason="CLI binary not built")
+def test_cli_hostsim_file_pipeline(tmp_path):
+    pipeline(HOSTSIM_CLI, tmp_path, "sim")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(B200_CLI), reason="CLI binary not built")
+def test_cli_b200_file_pipeline(tmp_path):
+    pipeline(B200_CLI, tmp_path, "gpu")
+
+
 @pytest.mark.skipif(not os.path.exists(HOSTSIM_CLI), reason="CLI binary not built")
 def test_cli_usage_errors(tmp_path):
     for args in (["-e"], ["-e", "-d", "a", "b"], ["-e", "-m", "9", "a", "b"], ["-x", "a", "b"], ["-e", "only_one"]):
