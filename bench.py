@@ -288,6 +288,312 @@ def run_c3(args, dev, hbm_peak, fp64_peak):
     return out
 
 
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if xs else None
+
+
+def run_streaming(args, pcm):
+    """the block-at-a-time callers (tools/linne_codec encodes with EncodeBlock per block,
+    tools/linne_player decodes with DecodeBlock per block).  Host wall clock around every synchronous call, host buffers;
+    DecodeBlock with and without read-ahead; the unmodified reference through the same calls beside it."""
+    import torch
+    import harness
+    from harness import LINNEEncodeParameter, LINNEEncoderConfig, LINNEDecoderConfig
+    from linne_b200 import Product
+    nch, n = pcm.shape
+    u8p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    impls = [("b200", Product())]
+    if harness.have_ref():
+        impls.append(("reference", harness.Ref()))
+    out = {"workload": f"C2 clip block by block ({(n + BLOCK - 1) // BLOCK} blocks of {BLOCK} frames x {nch} ch), host buffers, "
+                       "wall clock per synchronous call", "unit": "us per call (median)"}
+    h_pcm = torch.from_numpy(pcm.copy()).pin_memory()
+    cap = 2 * nch * BLOCK * 4 + 4096
+    h_blk = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    h_back = torch.zeros((nch, BLOCK), dtype=torch.int32).pin_memory()
+    back_ptrs = (i32p * nch)(*[C.cast(h_back[c].data_ptr(), i32p) for c in range(nch)])
+    for m in (0, 7):
+        res = {}
+        stream = None
+        for name, impl in impls:
+            L = impl.lib
+            enc = L.LINNEEncoder_Create(C.byref(LINNEEncoderConfig(nch, BLOCK, 3, 128)), None, 0)
+            L.LINNEEncoder_SetEncodeParameter(enc, C.byref(LINNEEncodeParameter(nch, BITS, RATE, BLOCK, m, 1, 0, 0)))
+            size = C.c_uint32(0)
+            for attempt in range(2 if name == "b200" else 1):                    # first pass warms the handle up
+                lat, parts = [], []
+                for lo in range(0, n, BLOCK):
+                    k = min(BLOCK, n - lo)
+                    ptrs = (i32p * nch)(*[C.cast(h_pcm[c].data_ptr() + 4 * lo, i32p) for c in range(nch)])
+                    t0 = time.perf_counter()
+                    rc = L.LINNEEncoder_EncodeBlock(enc, ptrs, k, C.cast(h_blk.data_ptr(), u8p), cap, C.byref(size))
+                    lat.append(time.perf_counter() - t0)
+                    if rc != 0:
+                        raise RuntimeError(f"EncodeBlock rc={rc}")
+                    parts.append(h_blk[:size.value].numpy().tobytes())
+            L.LINNEEncoder_Destroy(enc)
+            body = b"".join(parts)
+            res[name + "_encode_block"] = round(1e6 * _median(lat), 1)
+            res[name + "_encode_msamples_s"] = round(nch * n / sum(lat) / 1e6, 3)
+            if name == "b200":
+                stream = body
+            h_img = torch.zeros(len(stream) + 16, dtype=torch.uint8).pin_memory()
+            h_img[:len(stream)] = torch.frombuffer(bytearray(stream), dtype=torch.uint8)
+            hdr = harness.LINNEHeader(1, 2, nch, n, RATE, BITS, BLOCK, m, 1)
+            for k_ahead in ((0, 16) if name == "b200" else (0,)):
+                dec = L.LINNEDecoder_Create(C.byref(LINNEDecoderConfig(nch, 3, 128, 1)), None, 0)
+                L.LINNEDecoder_SetHeader(dec, C.byref(hdr))
+                if name == "b200":
+                    L.LINNEB200_DecoderSetReadahead(dec, k_ahead)
+                used, got = C.c_uint32(0), C.c_uint32(0)
+                for attempt in range(2 if name == "b200" else 1):
+                    lat, off, done, ok = [], 0, 0, True
+                    while off < len(stream):
+                        t0 = time.perf_counter()
+                        rc = L.LINNEDecoder_DecodeBlock(dec, C.cast(h_img.data_ptr() + off, u8p), len(stream) - off, back_ptrs, nch, BLOCK,
+                                                        C.byref(used), C.byref(got))
+                        lat.append(time.perf_counter() - t0)
+                        if rc != 0:
+                            raise RuntimeError(f"DecodeBlock rc={rc}")
+                        ok = ok and bool(np.array_equal(h_back.numpy()[:, :got.value], pcm[:, done:done + got.value]))
+                        off += used.value; done += got.value
+                L.LINNEDecoder_Destroy(dec)
+                tag = name + "_decode_block" + (f"_readahead{k_ahead}" if k_ahead else "")
+                res[tag] = round(1e6 * _median(lat), 1)
+                res[tag + "_mean"] = round(1e6 * sum(lat) / len(lat), 1)
+                res[tag.replace("_block", "") + "_msamples_s"] = round(nch * n / sum(lat) / 1e6, 3)
+                res[tag + "_lossless"] = ok and done == n
+        out[f"m{m}"] = res
+    return out
+
+
+def run_c4(args, dev, fp64_peak):
+    """C4 (BASELINE.json configs[3]): 24-bit 96 kHz 8-channel synthetic audio, encode at -m 7."""
+    import torch
+    import harness
+    from linne_b200 import EncoderSession, DecoderSession, Product
+    bits, rate, nch = 24, 96000, 8
+    base = harness.synth_pcm(seconds=5.0, sr=rate, channels=nch, bits=bits, seed=4)
+    reps = max(1, int(round(args.c4_seconds / 5.0)))
+    pcm = np.ascontiguousarray(np.tile(base, (1, reps)))
+    n = pcm.shape[1]
+    stride = (n + 4 + 3) // 4 * 4
+    samples = nch * n
+    h_pcm = torch.from_numpy(pcm).pin_memory()
+    d_pcm = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+    d_pcm[:, :n].copy_(h_pcm)
+    cap = 30 + nch * n * 3 + 11 * (n // BLOCK + 2) + 65536
+    d_stream = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
+    h_stream = torch.zeros(cap + 64, dtype=torch.uint8).pin_memory()
+    enc = EncoderSession(nch, bits=bits, rate=rate, block=BLOCK, preset=7)
+    dec = DecoderSession(channels=nch)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_once(fn):
+        torch.cuda.synchronize()
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    size = [0]
+    chan_in = (C.POINTER(C.c_int32) * nch)(*[C.cast(h_pcm[c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
+    def enc_resident():
+        size[0] = enc.encode_whole_resident(d_pcm.data_ptr(), stride, n, d_stream.data_ptr(), cap)
+    def enc_e2e():
+        size[0] = enc.encode_whole(chan_in, n, h_stream.data_ptr(), cap)
+    enc_resident(); enc_e2e()
+    enc.set_profiling(True); enc.reset_stage_stats()
+    ms_res = min(timed_once(enc_resident) for _ in range(2))
+    stages = {k: round(v[1] / 2.0, 3) for k, v in sorted(enc.stage_stats().items(), key=lambda kv: -kv[1][1])}
+    enc.set_profiling(False)
+    ms_e2e = min(timed_once(enc_e2e) for _ in range(2))
+    sz = size[0]
+    # packed 24-bit interleaved in (3 B per sample over PCIe instead of 4)
+    packed = np.ascontiguousarray(pcm.T).astype("<i4").view(np.uint8).reshape(n, nch, 4)[:, :, :3]
+    h_packed = torch.from_numpy(np.ascontiguousarray(packed).reshape(-1)).pin_memory()
+    u8p = C.POINTER(C.c_uint8)
+    osz = C.c_uint32(0)
+    def enc_packed():
+        rc = enc.lib.LINNEB200_EncodeWholePacked(enc.h, C.cast(h_packed.data_ptr(), u8p), n, C.cast(h_stream.data_ptr(), u8p), cap, C.byref(osz))
+        if rc != 0:
+            raise RuntimeError(f"EncodeWholePacked rc={rc}")
+    enc_packed()
+    ms_packed = min(timed_once(enc_packed) for _ in range(2))
+    same_packed = osz.value == sz
+    d_back = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+    def dec_resident():
+        dec.decode_whole_resident(None, d_stream.data_ptr(), sz, d_back.data_ptr(), stride, nch, n)
+    enc_resident(); dec_resident()
+    ms_dec = min(timed_once(dec_resident) for _ in range(2))
+    ok = bool(torch.equal(d_back[:, :n], d_pcm[:, :n]))
+    out = {
+        "workload": f"C4: {n / rate:.0f} s 96 kHz 24-bit 8-channel synthetic, -m 7, {(n + BLOCK - 1) // BLOCK} blocks, encode",
+        "value": round(samples / (ms_res / 1e3) / 1e6, 1), "unit": "MSamples/s", "ms": round(ms_res, 3),
+        "e2e": {"value": round(samples / (ms_e2e / 1e3) / 1e6, 1), "ms": round(ms_e2e, 3), "h2d_bytes": int(4 * samples), "d2h_bytes": int(sz)},
+        "e2e_packed": {"value": round(samples / (ms_packed / 1e3) / 1e6, 1), "ms": round(ms_packed, 3), "h2d_bytes": int(3 * samples),
+                       "d2h_bytes": int(sz), "same_bytes": bool(same_packed)},
+        "stream_bytes": int(sz), "ratio": round(sz / (3.0 * samples), 4), "lossless": ok, "stages_ms": stages,
+        "fp64_frac": round(2.0 * MAC_PER_SAMPLE[7] * samples / (stages.get("analyze_v3", ms_res) / 1e3) / 1e12 / fp64_peak, 4) if fp64_peak else None,
+        "decode": {"value": round(samples / (ms_dec / 1e3) / 1e6, 1), "ms": round(ms_dec, 3)},
+    }
+    try:
+        if harness.have_ref():
+            sub = np.ascontiguousarray(pcm[:, :2 * BLOCK])
+            ref = harness.Ref()
+            t0 = time.perf_counter(); rs = ref.encode(sub, bits=bits, rate=rate, preset=7); dt = time.perf_counter() - t0
+            ours = Product().encode(sub, bits=bits, rate=rate, preset=7)
+            out["cpu_baseline"] = {"value": round(sub.size / dt / 1e6, 4), "unit": "MSamples/s", "cores": 1, "kind": "reference",
+                                   "sample": f"reference encoder -m 7 on the first 2 blocks x 8 ch ({sub.size} samples), {dt:.1f} s",
+                                   "reference_bytes": len(rs), "b200_bytes": len(ours), "identical": bool(rs == ours)}
+    except Exception as e:  # pragma: no cover
+        out["cpu_baseline"] = {"value": None, "kind": "unavailable", "sample": repr(e)}
+    enc.close(); dec.close()
+    del d_pcm, d_stream, d_back, h_pcm, h_stream, h_packed
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_c5(args, dev, rank, world):
+    """C5 (BASELINE.json configs[4]): a corpus of --c5-files stereo 16-bit 44.1 kHz files of 6 minutes each (1000 files =
+    100 hours), sharded over the ranks by contiguous file (= block) ranges, encode AND decode of every file.
+    No exchange between ranks.  The PCM of a few distinct files stays resident in HBM and is cycled (127 GB of int32
+    PCM is not materialised); every file is a full EncodeWhole + DecodeWhole.  Time = max over ranks (CUDA events)."""
+    import torch
+    import torch.distributed as dist
+    from linne_b200 import EncoderSession, DecoderSession
+    clip = make_clip()
+    nch = clip.shape[0]
+    n = int(round(args.c5_file_seconds * RATE))
+    reps = (n + clip.shape[1] - 1) // clip.shape[1]
+    stride = (n + 4 + 3) // 4 * 4
+    variants = []
+    for v in range(3):
+        x = np.ascontiguousarray(np.tile(np.roll(clip, 7919 * v, axis=1), (1, reps))[:, :n])
+        d = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+        d[:, :n].copy_(torch.from_numpy(x))
+        variants.append(d)
+    samples_per_file = nch * n
+    cap = 30 + nch * n * 2 + 11 * (n // BLOCK + 2) + 65536
+    lo, hi = rank * args.c5_files // world, (rank + 1) * args.c5_files // world
+    J = max(1, args.c5_workers)
+    out = {"workload": f"C5: {args.c5_files} files x {args.c5_file_seconds:.0f} s stereo 16-bit 44.1 kHz "
+                       f"({args.c5_files * args.c5_file_seconds / 3600.0:.1f} h), {(n + BLOCK - 1) // BLOCK} blocks per file, "
+                       "encode + decode of every file, files sharded by contiguous range over the ranks",
+           "unit": "MSamples/s", "scaling": "strong", "workers_per_rank": J, "files_per_rank": hi - lo,
+           "note": "samples counted once per file (a file that went through encode and decode counts once)"}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    for m, frac in ((0, 1.0), (7, args.c5_m7_fraction)):
+        nfiles = max(J, int(round((hi - lo) * frac))) if frac > 0 else 0
+        if nfiles == 0:
+            continue
+        total_files = nfiles * world if frac < 1.0 else args.c5_files
+        encs = [EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=m) for _ in range(J)]
+        decs = [DecoderSession(channels=nch) for _ in range(J)]
+        d_streams = [torch.zeros(cap + 64, dtype=torch.uint8, device=dev) for _ in range(J)]
+        d_backs = [torch.zeros((nch, stride), dtype=torch.int32, device=dev) for _ in range(J)]
+        last = [None] * J
+        sizes = [0] * J
+        errs = []
+
+        def work(j, count):
+            try:
+                for f in range(j, count, J):
+                    v = (lo + f) % len(variants)
+                    sz = encs[j].encode_whole_resident(variants[v].data_ptr(), stride, n, d_streams[j].data_ptr(), cap)
+                    decs[j].decode_whole_resident(None, d_streams[j].data_ptr(), sz, d_backs[j].data_ptr(), stride, nch, n)
+                    last[j], sizes[j] = v, sz
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+
+        def run(count):
+            ts = [threading.Thread(target=work, args=(j, count)) for j in range(J)]
+            for t in ts: t.start()
+            for t in ts: t.join()
+            if errs:
+                raise errs[0]
+        run(J)                                                      # warm-up: allocations
+        barrier()
+        e0.record(); run(nfiles); e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        ok = all(last[j] is not None and bool(torch.equal(d_backs[j][:, :n], variants[last[j]][:, :n])) for j in range(J))
+        launches = sum(s.launch_count() for s in encs + decs)
+        if m == 0:
+            size_m0 = int(sizes[0])
+        out[f"m{m}"] = {"files": total_files, "hours_of_audio": round(total_files * args.c5_file_seconds / 3600.0, 2),
+                        "value": round(total_files * samples_per_file / (ms / 1e3) / 1e6, 1), "seconds": round(ms / 1e3, 3),
+                        "ms_per_file_per_rank": round(ms / nfiles, 3), "lossless": ok, "bytes_last_file": int(sizes[0]),
+                        "ratio": round(sizes[0] / (2.0 * samples_per_file), 4), "gpu_launches_rank0": int(launches)}
+        for s in encs + decs:
+            s.close()
+        del d_streams, d_backs
+
+    # ---- the file pipeline end to end (SURVEY 8f.3): packed PCM in host memory -> .lnn -> packed PCM in host memory ----
+    # what linne_b200_cli does per file between its disk read and its disk write, with 1 and with 3 workers per rank
+    if args.c5_e2e_files > 0:
+        u8p = C.POINTER(C.c_uint8)
+        host_pcm = torch.from_numpy(np.ascontiguousarray(variants[0][:, :n].cpu().numpy().T).astype("<i2").view(np.uint8).reshape(-1)).pin_memory()
+        e2e = {}
+        for J2 in (1, 3):
+            encs = [EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=0) for _ in range(J2)]
+            decs = [DecoderSession(channels=nch) for _ in range(J2)]
+            h_lnn = [torch.zeros(cap, dtype=torch.uint8).pin_memory() for _ in range(J2)]
+            h_out = [torch.zeros(host_pcm.numel(), dtype=torch.uint8).pin_memory() for _ in range(J2)]
+            errs = []
+
+            def work2(j, count):
+                try:
+                    sz, fr = C.c_uint32(0), C.c_uint32(0)
+                    for f in range(j, count, J2):
+                        rc = encs[j].lib.LINNEB200_EncodeWholePacked(encs[j].h, C.cast(host_pcm.data_ptr(), u8p), n,
+                                                                     C.cast(h_lnn[j].data_ptr(), u8p), cap, C.byref(sz))
+                        rc = rc or decs[j].lib.LINNEB200_DecodeWholePacked(decs[j].h, C.cast(h_lnn[j].data_ptr(), u8p), sz.value,
+                                                                           C.cast(h_out[j].data_ptr(), u8p), n, C.byref(fr))
+                        if rc != 0:
+                            raise RuntimeError(f"packed call rc={rc}")
+                except Exception as e:  # pragma: no cover
+                    errs.append(e)
+
+            def run2(count):
+                ts = [threading.Thread(target=work2, args=(j, count)) for j in range(J2)]
+                for t in ts: t.start()
+                for t in ts: t.join()
+                if errs:
+                    raise errs[0]
+            run2(J2)
+            barrier()
+            e0.record(); run2(args.c5_e2e_files); e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            ok = all(bool(torch.equal(h, host_pcm)) for h in h_out)
+            e2e[f"workers{J2}"] = {"value": round(world * args.c5_e2e_files * samples_per_file / (ms / 1e3) / 1e6, 1),
+                                   "ms_per_file_per_rank": round(ms / args.c5_e2e_files, 3), "lossless": ok}
+            for s in encs + decs:
+                s.close()
+            del h_lnn, h_out
+        e2e["files_per_rank"] = args.c5_e2e_files
+        e2e["preset"] = 0
+        e2e["h2d_bytes_per_file"] = int(host_pcm.numel()) + size_m0
+        e2e["d2h_bytes_per_file"] = int(host_pcm.numel()) + size_m0
+        e2e["call"] = "LINNEB200_EncodeWholePacked + LINNEB200_DecodeWholePacked on page-locked host buffers (what linne_b200_cli -j N runs per file)"
+        out["e2e_pipeline_m0"] = e2e
+    del variants
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_sharded(args, dev, rank, world):
     """One long stream sharded by contiguous block ranges over the ranks, PCM ranges resident in HBM:
     every rank encodes its range at -m 7; shard byte counts are all-gathered and scanned; every rank writes its shard
@@ -524,7 +830,7 @@ def run_b200(args, rank, world, local_rank):
     total_comp = sum(comp_bytes.values())
     hbm_bytes_per_sample = 4.0 + total_comp / (len(PRESETS) * n_samples)      # int32 PCM + compressed bytes
     analysis_kernels = {"analyze_v3", "to_double", "acorr", "solve", "loss", "select", "forward", "refine_v2"}
-    dec_kernels = {"crc_v2", "stream_v1", "entropy_v3", "synth_v2", "crc", "entropy", "synth", "deemph", "ms_inverse"}
+    dec_kernels = {"crc_v2", "stream_v1", "tp_entropy", "tp_synth", "entropy_v3", "synth_v2", "crc", "entropy", "synth", "deemph", "ms_inverse"}
     dom = max(stage_serial.items(), key=lambda kv: kv[1][1]) if stage_serial else ("none", [1, 1.0])
     dom_name, (dom_cnt, dom_ms) = dom[0], dom[1]
     try:        # DRAM bytes per launch of that kernel from the committed ncu capture (profiles/)
@@ -575,10 +881,27 @@ def run_b200(args, rank, world, local_rank):
             sharded = run_sharded(args, dev, rank, world)
         except Exception as e:      # pragma: no cover
             sharded = {"error": repr(e)}
+    c5 = None
+    if args.c5_files > 0:
+        try:
+            c5 = run_c5(args, dev, rank, world)
+        except Exception as e:      # pragma: no cover
+            c5 = {"error": repr(e)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    c4 = streaming = None
+    if world == 1 and args.c4_seconds > 0:
+        try:
+            c4 = run_c4(args, dev, fp64_peak)
+        except Exception as e:      # pragma: no cover
+            c4 = {"error": repr(e)}
+    if world == 1 and not args.no_streaming:
+        try:
+            streaming = run_streaming(args, pcm)
+        except Exception as e:      # pragma: no cover
+            streaming = {"error": repr(e)}
     c3 = None
     if world == 1 and args.c3_seconds > 0:
         try:
@@ -628,6 +951,12 @@ def run_b200(args, rank, world, local_rank):
         line["c3_decode"] = c3
     if sharded is not None:
         line["sharded_stream"] = sharded
+    if c4 is not None:
+        line["c4_encode"] = c4
+    if c5 is not None:
+        line["c5_corpus"] = c5
+    if streaming is not None:
+        line["streaming"] = streaming
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -644,6 +973,15 @@ def main():
                     help="N=1: length of the C3 decode-only stream (BASELINE.json configs[2]); 0 = skip")
     ap.add_argument("--shard-seconds", type=float, default=600.0,
                     help="N>1: length of the stream sharded by block range over the ranks; 0 = skip")
+    ap.add_argument("--c4-seconds", type=float, default=60.0,
+                    help="N=1: length of the C4 clip (24-bit 96 kHz 8 ch, -m 7 encode; BASELINE.json configs[3]); 0 = skip")
+    ap.add_argument("--c5-files", type=int, default=1000,
+                    help="files of the C5 corpus (BASELINE.json configs[4]), sharded over the ranks; 0 = skip")
+    ap.add_argument("--c5-file-seconds", type=float, default=360.0)
+    ap.add_argument("--c5-m7-fraction", type=float, default=0.1, help="share of each rank's files also run at -m 7 (bounded)")
+    ap.add_argument("--c5-workers", type=int, default=2, help="handle pairs (host threads / CUDA streams) per rank in the C5 leg")
+    ap.add_argument("--c5-e2e-files", type=int, default=24, help="files per rank of the host-buffer pipeline leg; 0 = skip")
+    ap.add_argument("--no-streaming", action="store_true", help="skip the EncodeBlock / DecodeBlock latency leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -36,6 +36,7 @@ struct LINNEDecoder {
     uint32_t ra_blocks_cap;
 };
 #define LNB_MAX_READAHEAD 4096u
+#define LNB_TPUT_MIN_BLOCKS 4096ul
 
 /* reference linne_decoder.c:60-131 */
 LINNEApiResult LINNEDecoder_DecodeHeader(const uint8_t *data, uint32_t data_size, struct LINNEHeader *header)
@@ -283,6 +284,16 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
         for (i = 0; i < scan.num_blocks; i++)
             if (blocks[i].type != LNB_BLOCK_COMPRESSED || blocks[i].nsmp == 0u || blocks[i].nsmp > batch.fused_max_n)
                 batch.num_plain_blocks++;
+    }
+
+    {   /* Large batches: one lane per block / per (block, channel) instead of one CTA per block (lnb_tput_v1.cuh).
+         * LINNE_B200_TPUT_MIN_BLOCKS moves the switch-over point (0 = never). */
+        const char *e = getenv("LINNE_B200_TPUT_MIN_BLOCKS");
+        const unsigned long min_blocks = e ? strtoul(e, NULL, 10) : LNB_TPUT_MIN_BLOCKS;
+        const int32_t *pcm_base = d_pcm_ext ? d_pcm_ext : (const int32_t *)dec->d_pcm.ptr;
+        batch.tput = (min_blocks && scan.num_blocks >= min_blocks && batch.fused_max_n
+                      && ((uintptr_t)pcm_base & 15u) == 0u && (batch.cfg.pcm_stride & 3u) == 0u
+                      && lnb_shim_tput_supported(&batch.cfg)) ? 1u : 0u;
     }
 
     batch.tab = *lnb_shim_tables(dec->dev);

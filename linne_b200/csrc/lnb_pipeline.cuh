@@ -96,6 +96,7 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
     if (B == 0) return;
     if (Exec::cooperative) {
         ex.crc_cooperative(b);                            /* one CTA per block, chunk CRCs combined in GF(2) */
+        if (b.fused_max_n && b.tput) ex.tput_cooperative(b);   /* large batches: one lane per block / per (block, channel) */
         if (b.fused_max_n) ex.stream_cooperative(b);      /* one CTA per block: entropy decode feeding synthesis, de-emphasis, M/S */
         if (!b.fused_max_n || b.num_plain_blocks) {       /* raw / silent / long blocks (or the fused kernel switched off) */
             ex.entropy_cooperative(b);                    /* one warp per block: 32 speculative code-word starts per round */

@@ -36,6 +36,9 @@ uint32_t lnb_shim_fast_max_na(void);
 uint32_t lnb_shim_coop_max_n(void);
 /* Longest block the fused streaming decoder (entropy decode -> synthesis -> de-emphasis in one kernel) takes; 0 = none. */
 uint32_t lnb_shim_fused_max_n(void);
+/* 1 when the throughput decoder (one lane per block / per block-channel, for large batches) takes streams of this
+ * configuration; 0 = never (the host then leaves LnbDecodeBatch.tput clear). */
+int lnb_shim_tput_supported(const LnbStreamCfg *cfg);
 /* Longest analysis length the IRLS / SGD refinement kernel takes; 0 = those paths are unavailable. */
 uint32_t lnb_shim_refine_max_na(void);
 

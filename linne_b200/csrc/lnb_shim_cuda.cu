@@ -104,6 +104,16 @@ __global__ void __launch_bounds__(128) lnb_items_per_warp_kernel(uint32_t n, F f
     if (i < n && (threadIdx.x & 31u) == 0u) f(i);
 }
 
+/* layer shapes the throughput decoder is instantiated for (the presets of linne_internal.c:16-41) */
+static int lnb_tput_shape(const LnbStreamCfg *cfg)
+{
+    const uint32_t *P = cfg->layer_params;
+    if (cfg->num_layers == 2u && P[0] == 2u && P[1] == 32u) return 1;
+    if (cfg->num_layers == 3u && P[0] == 4u && P[1] == 64u && P[2] == 8u) return 2;
+    if (cfg->num_layers == 3u && P[0] == 4u && P[1] == 128u && P[2] == 16u) return 3;
+    return 0;
+}
+
 struct CudaExec {
     static constexpr bool cooperative = true;
     LnbDevice *dev;
@@ -133,6 +143,30 @@ struct CudaExec {
         const int slot = begin_stage("stream_v1");
         lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, dev->stream>>>(b, n_max);
         end_stage(slot);
+    }
+    template <int Q0, int Q1, int Q2> void tput_synth(const LnbDecodeBatch &b)
+    {
+        const size_t smem = LnbTpLayer<Q0>::smem_bytes + LnbTpLayer<Q1>::smem_bytes + LnbTpLayer<Q2>::smem_bytes + 16u;
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(lnb_tp_synth_kernel<Q0, Q1, Q2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = smem;
+        }
+        const uint32_t seqs = b.num_blocks * b.cfg.num_channels;
+        const int slot = begin_stage("tp_synth");
+        lnb_tp_synth_kernel<Q0, Q1, Q2><<<(seqs + 31u) / 32u, 32, smem, dev->stream>>>(b);
+        end_stage(slot);
+    }
+    void tput_cooperative(const LnbDecodeBatch &b)
+    {
+        const int shape = lnb_tput_shape(&b.cfg);
+        if (!shape) return;                                /* the host asks lnb_shim_tput_min_blocks(cfg) first */
+        const int slot = begin_stage("tp_entropy");
+        lnb_tp_entropy_kernel<<<(b.num_blocks + 31u) / 32u, 32, 0, dev->stream>>>(b);
+        end_stage(slot);
+        if (shape == 1) tput_synth<32, 2, 0>(b);
+        else if (shape == 2) tput_synth<8, 64, 4>(b);
+        else tput_synth<16, 128, 4>(b);
     }
     void crc_cooperative(const LnbDecodeBatch &b)
     {
@@ -275,6 +309,11 @@ uint32_t lnb_shim_fast_max_na(void) { return LNB_A3_MAX_NA; }
 uint32_t lnb_shim_coop_max_n(void) { return LNB_FR_MAX_N; }
 uint32_t lnb_shim_refine_max_na(void) { return LNB_RF_MAX_NA; }
 uint32_t lnb_shim_fused_max_n(void) { return LNB_DS_MAX_N; }
+int lnb_shim_tput_supported(const LnbStreamCfg *cfg)
+{
+    return lnb_tput_shape(cfg) != 0 && cfg->block_size <= LNB_DS_MAX_N && (cfg->block_size & 1023u) == 0u
+        && cfg->bits_per_sample <= 31u && !(cfg->ms && (cfg->num_channels & 1u));
+}
 
 int lnb_shim_open(LnbDevice **out, int device_ordinal)
 {

@@ -27,6 +27,7 @@
 #include "lnb_decode_core.cuh"
 #include "lnb_entropy_v3.cuh"
 #include "lnb_synth_v2.cuh"
+#include "lnb_tput_v1.cuh"
 
 #define LNB_DS_MAX_N    10240u
 #define LNB_DS_WARPS    (2u + LNB_MAX_LAYERS)          /* entropy + layers + de-emphasis */
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v1_kernel(LnbDecode
     const LnbStreamCfg &cfg = b.cfg;
     const uint32_t C = cfg.num_channels, n = blk.nsmp, L = cfg.num_layers;
     /* blocks this kernel does not take are left to the split kernels (same rule on both sides) */
-    if (blk.type != LNB_BLOCK_COMPRESSED || blk.status || n > n_max || n == 0u) return;
+    if (blk.type != LNB_BLOCK_COMPRESSED || blk.status || n > n_max || n == 0u || lnb_tp_takes(b, blk)) return;
 
     for (uint32_t i = threadIdx.x; i < (1u << LNB_E3_HUFF1_BITS); i += LNB_DS_THREADS) {
         const uint16_t e = b.tab.huff_lut[i << (LNB_HUFF_LUT_BITS - LNB_E3_HUFF1_BITS)];

@@ -86,6 +86,7 @@ typedef struct LnbDecodeBatch {
     int32_t *pcm;                   /* [C][pcm_stride] */
     uint32_t fused_max_n;           /* > 0: compressed blocks of at most this many samples take the fused streaming kernel */
     uint32_t num_plain_blocks;      /* blocks left to the split kernels (raw, silent, longer than fused_max_n) */
+    uint32_t tput;                  /* 1: full compressed blocks take the throughput kernels (lnb_tput_v1.cuh); needs fused_max_n */
 } LnbDecodeBatch;
 
 /* ---- one encode batch (all pointers are device pointers) ---- */

@@ -16,6 +16,7 @@ struct LoopExec {
     static constexpr bool cooperative = false;
     LnbDevice *dev;
     void crc_cooperative(const LnbDecodeBatch &) {}
+    void tput_cooperative(const LnbDecodeBatch &) {}
     void entropy_cooperative(const LnbDecodeBatch &) {}
     void synth_cooperative(const LnbDecodeBatch &) {}
     void stream_cooperative(const LnbDecodeBatch &) {}
@@ -40,6 +41,7 @@ uint32_t lnb_shim_fast_max_na(void) { return 0; }
 uint32_t lnb_shim_coop_max_n(void) { return 0; }
 uint32_t lnb_shim_refine_max_na(void) { return 0; }
 uint32_t lnb_shim_fused_max_n(void) { return 0; }
+int lnb_shim_tput_supported(const LnbStreamCfg *) { return 0; }
 int lnb_shim_open(LnbDevice **out, int)
 {
     LnbDevice *dev = (LnbDevice *)calloc(1, sizeof(LnbDevice));
