@@ -150,12 +150,6 @@ LNB_HD void lnb_fr_refill(LnbFastReader &r)                     /* call when nbi
     r.next++;
     r.pre = lnb_fr_word(r, r.next);
     if (r.next > r.end_word + 2u) r.overrun = 1;
-#if defined(__CUDA_ARCH__)
-    /* a lane that walks its payload alone (lnb_tput_v1.cuh) would stall on every new 128-byte line: ask for the
-     * line two ahead whenever a 64-byte boundary is crossed */
-    if ((r.next & 15u) == 0u && r.next + 64u < r.end_word)
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(r.words + r.next + 64u));
-#endif
 }
 LNB_HD void lnb_fr_open(LnbFastReader &r, const uint32_t *words, uint64_t bit_position, uint32_t end_word)
 {

@@ -96,8 +96,9 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
     if (B == 0) return;
     if (Exec::cooperative) {
         ex.crc_cooperative(b);                            /* one CTA per block, chunk CRCs combined in GF(2) */
-        if (b.fused_max_n && b.tput) ex.tput_cooperative(b);   /* large batches: one lane per block / per (block, channel) */
-        if (b.fused_max_n) ex.stream_cooperative(b);      /* one CTA per block: entropy decode feeding synthesis, de-emphasis, M/S */
+        /* one CTA per block: entropy decode feeding synthesis, de-emphasis, M/S; with b.tput the full blocks of a large
+         * batch take one lane per block / per (block, channel) instead and this kernel keeps the rest, side by side */
+        if (b.fused_max_n) ex.stream_cooperative(b);
         if (!b.fused_max_n || b.num_plain_blocks) {       /* raw / silent / long blocks (or the fused kernel switched off) */
             ex.entropy_cooperative(b);                    /* one warp per block: 32 speculative code-word starts per round */
             ex.synth_cooperative(b);                      /* one warp per (block, channel): systolic synthesis + de-emphasis */

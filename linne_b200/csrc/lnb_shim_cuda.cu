@@ -46,6 +46,11 @@ struct LnbDevice {
     LnbTimelineEntry timeline[LNB_MAX_TIMELINE];
     cudaEvent_t sync_event;              /* LINNE_B200_SYNC=block: host threads sleep in the driver instead of spinning */
     int blocking_sync;
+    /* side stream of the throughput decoder: the per-block pipeline kernel for the few blocks the lane-per-block
+     * kernels leave (tail blocks) runs beside them instead of behind them */
+    cudaStream_t aux_stream;
+    cudaEvent_t ev_fork, ev_join;
+    int aux_created;
 };
 
 static cudaEvent_t g_ref_event;              /* process-wide time origin of the launch timelines */
@@ -140,6 +145,23 @@ struct CudaExec {
             cudaFuncSetAttribute(lnb_stream_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
+        if (b.tput) {
+            /* fork: what the throughput kernels leave (tail blocks) is decoded beside them on the side stream */
+            if (!dev->aux_created) {
+                cudaStreamCreateWithFlags(&dev->aux_stream, cudaStreamNonBlocking);
+                cudaEventCreateWithFlags(&dev->ev_fork, cudaEventDisableTiming);
+                cudaEventCreateWithFlags(&dev->ev_join, cudaEventDisableTiming);
+                dev->aux_created = 1;
+            }
+            cudaEventRecord(dev->ev_fork, dev->stream);
+            cudaStreamWaitEvent(dev->aux_stream, dev->ev_fork, 0);
+            lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, dev->aux_stream>>>(b, n_max);
+            cudaEventRecord(dev->ev_join, dev->aux_stream);
+            dev->launches++;
+            tput_cooperative(b);
+            cudaStreamWaitEvent(dev->stream, dev->ev_join, 0);
+            return;
+        }
         const int slot = begin_stage("stream_v1");
         lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, dev->stream>>>(b, n_max);
         end_stage(slot);
@@ -162,7 +184,7 @@ struct CudaExec {
         const int shape = lnb_tput_shape(&b.cfg);
         if (!shape) return;                                /* the host asks lnb_shim_tput_min_blocks(cfg) first */
         const int slot = begin_stage("tp_entropy");
-        lnb_tp_entropy_kernel<<<(b.num_blocks + 31u) / 32u, 32, 0, dev->stream>>>(b);
+        lnb_tp_entropy_kernel<<<(b.num_blocks + LNB_TG_PER_WARP - 1u) / LNB_TG_PER_WARP, 32, 0, dev->stream>>>(b);
         end_stage(slot);
         if (shape == 1) tput_synth<32, 2, 0>(b);
         else if (shape == 2) tput_synth<8, 64, 4>(b);
@@ -363,6 +385,7 @@ void lnb_shim_close(LnbDevice *dev)
         for (int i = 0; i < LNB_MAX_PENDING; i++) { cudaEventDestroy(dev->ev_begin[i]); cudaEventDestroy(dev->ev_end[i]); }
     cudaFree(dev->table_mem);
     if (dev->blocking_sync) cudaEventDestroy(dev->sync_event);
+    if (dev->aux_created) { cudaStreamDestroy(dev->aux_stream); cudaEventDestroy(dev->ev_fork); cudaEventDestroy(dev->ev_join); }
     if (dev->owns_stream) cudaStreamDestroy(dev->stream);
     free(dev);
 }

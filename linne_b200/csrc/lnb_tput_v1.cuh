@@ -36,7 +36,6 @@
 #include "lnb_common.cuh"
 #include "lnb_decode_core.cuh"
 
-#define LNB_TP_TILE_STRIDE 33u
 
 /* same rule on every side: the host only sets `tput`, the kernels decide per block */
 LNB_HD bool lnb_tp_takes(const LnbDecodeBatch &b, const LnbBlockDesc &blk)
@@ -48,105 +47,200 @@ LNB_HD bool lnb_tp_takes(const LnbDecodeBatch &b, const LnbBlockDesc &blk)
 #if defined(__CUDACC__)
 
 /* ------------------------------------------------------------------------------------------------------
- * entropy: lane = block
+ * entropy: LNB_TG lanes per block, 32 / LNB_TG blocks per warp.
+ *
+ * One lane per block leaves the machine empty (a 1-hour stream has 15 504 blocks = 485 warps) and a lane's
+ * symbol chain of ~90 dependent instructions runs at one instruction per ~7 cycles when nothing else shares
+ * its scheduler; a whole warp per block (lnb_entropy_v3.cuh) retires ~3 code words per round on 32 lanes.  Eight
+ * lanes per block sit between: with k1 = k2 + 1 the code words of residuals below 3 * 2^k2 -- the large
+ * majority -- are all k2 + 2 bits long, so lane j of a group reads the field at  pos + j * (k2 + 2);  the first
+ * lane that sees a longer code word ('00' prefix) ends the round, every lane before it holds a valid residual
+ * (~4 per round), and the group's eight stores form one 32-byte sector.  Groups of a warp run the same flat
+ * loop (one round per pass, headers and window refills as short predicated detours), so the warp does not
+ * serialise them, and 3 876 warps keep every scheduler busy.
+ * The payload of a group is staged in a shared-memory window of LNB_TG_WIN words filled by the group itself.
  * ------------------------------------------------------------------------------------------------------ */
+#define LNB_TG            8u
+#define LNB_TG_PER_WARP   (32u / LNB_TG)
+#define LNB_TG_WIN        128u
+#define LNB_TG_ROUND_BITS (LNB_TG * 33u + 64u)       /* furthest bit a round can look at, relative to its start */
+
+struct LnbTgWin {
+    uint32_t *buf;              /* [LNB_TG_WIN + 2] */
+    const uint32_t *words;      /* global, word 0 = aligned word holding the block's first byte */
+    uint32_t wb;                /* index of the word held in buf[0] */
+    uint32_t end_word;          /* words at or past this index read as zero */
+    uint32_t limit;             /* a round may start at bit positions up to this one without a refill */
+};
+__device__ __forceinline__ void lnb_tg_fill(LnbTgWin &w, uint32_t word_idx, uint32_t lg, uint32_t gmask)
+{
+    __syncwarp(gmask);
+    w.wb = word_idx;
+    w.limit = (word_idx + LNB_TG_WIN) * 32u - LNB_TG_ROUND_BITS;
+#pragma unroll 4
+    for (uint32_t i = lg; i < LNB_TG_WIN + 2u; i += LNB_TG) {
+        const uint32_t idx = word_idx + i;
+        w.buf[i] = (idx < w.end_word) ? lnb_bswap32(w.words[idx]) : 0u;
+    }
+    __syncwarp(gmask);
+}
+__device__ __forceinline__ void lnb_tg_ensure(LnbTgWin &w, uint32_t pos, uint32_t span, uint32_t lg, uint32_t gmask)
+{
+    if (((pos + span) >> 5) + 2u > w.wb + LNB_TG_WIN + 2u || (pos >> 5) < w.wb) lnb_tg_fill(w, pos >> 5, lg, gmask);
+}
+__device__ __forceinline__ uint32_t lnb_tg_peek(const LnbTgWin &w, uint32_t pos)
+{
+    const uint32_t i = (pos >> 5) - w.wb;
+    return __funnelshift_l(w.buf[i + 1u], w.buf[i], pos & 31u);
+}
+__device__ __forceinline__ uint32_t lnb_tg_get(const LnbTgWin &w, uint32_t &pos, uint32_t n)   /* 1 <= n <= 32 */
+{
+    const uint32_t v = lnb_tg_peek(w, pos) >> (32u - n);
+    pos += n;
+    return v;
+}
+
 __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
 {
-    __shared__ int32_t tile[32u * LNB_TP_TILE_STRIDE];
-    const uint32_t lane = threadIdx.x;
-    const uint32_t blk_i = blockIdx.x * 32u + lane;
+    __shared__ uint32_t s_win[LNB_TG_PER_WARP][LNB_TG_WIN + 2u];
+    const uint32_t lane = threadIdx.x, g = lane / LNB_TG, lg = lane % LNB_TG;
+    const uint32_t gmask = ((1u << LNB_TG) - 1u) << (g * LNB_TG);
+    const uint32_t blk_i = blockIdx.x * LNB_TG_PER_WARP + g;
     const LnbStreamCfg &cfg = b.cfg;
     const uint32_t C = cfg.num_channels, n = cfg.block_size;
-    const bool have = blk_i < b.num_blocks;
     LnbBlockDesc blk;
-    if (have) blk = b.blocks[blk_i];
-    const bool mine = have && lnb_tp_takes(b, blk);
-    if (__ballot_sync(0xffffffffu, mine) == 0u) return;
+    bool active = blk_i < b.num_blocks;
+    if (active) { blk = b.blocks[blk_i]; active = lnb_tp_takes(b, blk); }
+    if (__ballot_sync(0xffffffffu, active) == 0u) return;
 
-    LnbFastReader fr;
-    uint32_t payload_bit = 0, rel_end_byte = 0, overrun = mine ? 0u : 1u;
-    if (mine) {
+    LnbTgWin win;
+    win.buf = s_win[g];
+    win.words = (const uint32_t *)b.stream; win.wb = 0; win.end_word = 0; win.limit = 0;
+    uint32_t pos = 0, rel_payload = 0, rel_end = 0, overrun = 0;
+
+    /* ---- side information (linne_decoder.c:457-486): every lane of the group reads the same fields ---- */
+    if (active) {
         const uint32_t payload_off = blk.byte_off + LNB_BLOCK_HEADER_SIZE;
         uint32_t end_byte = blk.byte_off + blk.byte_size;
         if (end_byte > b.stream_size) end_byte = b.stream_size;
-        /* positions relative to the aligned word holding the block's first byte (32-bit bit positions) */
-        const uint32_t word0 = blk.byte_off >> 2;
-        payload_bit = (payload_off - word0 * 4u) * 8u;
-        rel_end_byte = end_byte - word0 * 4u;
-        lnb_fr_open(fr, (const uint32_t *)b.stream + word0, payload_bit, (rel_end_byte + 3u) >> 2);
-    } else {
-        fr.words = (const uint32_t *)b.stream; fr.end_word = 0; fr.overrun = 0;
-        fr.hi = fr.lo = fr.pre = 0; fr.nbits = 64u; fr.next = 2u;
-    }
-
-    /* ---- side information (linne_decoder.c:457-486) ---- */
-    if (mine) {
+        const uint32_t word0 = blk.byte_off >> 2;               /* bit positions relative to this word never overflow */
+        win.words = (const uint32_t *)b.stream + word0;
+        rel_payload = payload_off - word0 * 4u; rel_end = end_byte - word0 * 4u;
+        win.end_word = (rel_end + 3u) >> 2;
+        pos = rel_payload * 8u;
+        lnb_tg_fill(win, pos >> 5, lg, gmask);
         LnbChanParams *params = b.params + (size_t)blk_i * C;
         for (uint32_t c = 0; c < C; c++)
             for (int f = 0; f < LNB_NUM_PREEM; f++) {
-                params[c].preem_prev[f] = lnb_zz_dec(lnb_fr_get(fr, cfg.bits_per_sample + 1u));
-                params[c].preem_coef[f] = (uint8_t)lnb_fr_get(fr, LNB_PREEM_SHIFT - 1);
+                lnb_tg_ensure(win, pos, 64u, lg, gmask);
+                const int32_t prev = lnb_zz_dec(lnb_tg_get(win, pos, cfg.bits_per_sample + 1u));
+                const uint32_t coef = lnb_tg_get(win, pos, LNB_PREEM_SHIFT - 1);
+                if (lg == 0u) { params[c].preem_prev[f] = prev; params[c].preem_coef[f] = (uint8_t)coef; }
             }
         for (uint32_t c = 0; c < C; c++)
             for (uint32_t l = 0; l < cfg.num_layers; l++) {
-                params[c].log2_units[l] = (uint8_t)lnb_fr_get(fr, 3);
-                params[c].rshift[l] = (uint8_t)lnb_fr_get(fr, 4);
-                int8_t *q = params[c].coef + l * LNB_MAX_PARAMS;
                 const uint32_t P = cfg.layer_params[l];
-                for (uint32_t i = 0; i < P; i += 4u) {               /* P is a multiple of 4 or equals 2 */
-                    uint32_t packed = 0;
-                    const uint32_t lim = (P - i < 4u) ? P - i : 4u;
-                    for (uint32_t t = 0; t < lim; t++) {
-                        const uint32_t e = b.tab.huff_lut[fr.hi >> (32 - LNB_HUFF_LUT_BITS)];
-                        lnb_fr_skip(fr, e & 15u);
-                        packed |= ((uint32_t)lnb_zz_dec(e >> 4) & 0xFFu) << (8u * t);
+                lnb_tg_ensure(win, pos, 7u + P * 14u + 32u, lg, gmask);
+                const uint32_t lu = lnb_tg_get(win, pos, 3), rs = lnb_tg_get(win, pos, 4);
+                if (lg == 0u) { params[c].log2_units[l] = (uint8_t)lu; params[c].rshift[l] = (uint8_t)rs; }
+                int8_t *q = params[c].coef + l * LNB_MAX_PARAMS;
+                for (uint32_t i0 = 0; i0 < P; i0 += LNB_TG) {    /* lane j keeps coefficients j, j + 8, ... */
+                    int32_t keep = 0;
+                    const uint32_t lim = (P - i0 < LNB_TG) ? P - i0 : LNB_TG;
+                    for (uint32_t i = 0; i < lim; i++) {
+                        const uint32_t e = b.tab.huff_lut[lnb_tg_peek(win, pos) >> (32 - LNB_HUFF_LUT_BITS)];
+                        pos += e & 15u;
+                        if (i == lg) keep = lnb_zz_dec(e >> 4);
                     }
-                    if (lim == 4u) *(uint32_t *)(q + i) = packed;
-                    else for (uint32_t t = 0; t < lim; t++) q[i + t] = (int8_t)(packed >> (8u * t));
+                    if (lg < lim) q[i0 + lg] = (int8_t)keep;
                 }
             }
     }
 
-    /* ---- residuals, channel after channel; all lanes walk the same sample index ---- */
-    for (uint32_t c = 0; c < C; c++) {
-        int32_t *dst = b.pcm + (size_t)c * cfg.pcm_stride + (mine ? blk.smp_off : 0u);
-        uint32_t porder = overrun ? 0u : lnb_fr_get(fr, 10);
-        if (porder > LNB_MAX_PORDER) { overrun = 1u; porder = 0u; }
-        const uint32_t len = n >> porder;
-        uint32_t k2 = 0, left = 0, first = 1u;
-        for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
-#pragma unroll 2
-            for (uint32_t r = 0; r < 32u; r++) {
-                uint32_t u = 0;
-                if (!overrun) {
-                    if (left == 0u) {                              /* partition header (linne_coder.c:311-318) */
-                        if (first) { k2 = lnb_fr_get(fr, 5); first = 0u; }
-                        else k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(lnb_get_gamma(fr)));
-                        if (k2 > 30u) { overrun = 1u; k2 = 30u; }
-                        left = len;
-                    }
-                    u = lnb_get_rice(fr, k2 + 1u, k2);
-                    left--;
-                    overrun |= fr.overrun;
-                }
-                tile[r * LNB_TP_TILE_STRIDE + lane] = overrun ? 0 : lnb_zz_dec(u);
+    /* ---- residuals: one flat loop, one round per group and pass ---- */
+    uint32_t chan = 0, done = n, left = 0, parts_left = 0, len = 0, k2 = 0, first_part = 0;
+    bool running = active;
+    int32_t *out = b.pcm;
+    while (__any_sync(0xffffffffu, running)) {
+        if (running && done == n && left == 0u && parts_left == 0u) {           /* next channel, or the end of the block */
+            if (chan == C || overrun) {
+                running = false;
+            } else {
+                lnb_tg_ensure(win, pos, 64u, lg, gmask);
+                uint32_t porder = lnb_tg_get(win, pos, 10);
+                if (porder > LNB_MAX_PORDER) { overrun = 1u; porder = 0u; }
+                len = n >> porder; parts_left = 1u << porder; first_part = 1u; done = 0u;
+                out = b.pcm + (size_t)chan * cfg.pcm_stride + blk.smp_off;
+                chan++;
             }
-            __syncwarp();
-            /* row l of the transposed tile = 32 consecutive samples of lane l's sequence: one 128-byte store each */
-#pragma unroll 4
-            for (uint32_t l = 0; l < 32u; l++) {
-                const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)dst, (int)l);
-                const bool on = (__shfl_sync(0xffffffffu, mine ? 1u : 0u, (int)l)) != 0u;
-                if (on) ((int32_t *)(uintptr_t)p)[i0 + lane] = tile[lane * LNB_TP_TILE_STRIDE + l];
-            }
-            __syncwarp();
         }
-        overrun |= fr.overrun;
+        if (running && left == 0u && parts_left != 0u && !overrun) {             /* partition header (linne_coder.c:311-318) */
+            lnb_tg_ensure(win, pos, 96u, lg, gmask);
+            if (first_part) {
+                k2 = lnb_tg_get(win, pos, 5); first_part = 0u;
+            } else {                                                             /* gamma code of zigzag(k2 - previous k2) */
+                const uint32_t h = lnb_tg_peek(win, pos);
+                const uint32_t lz = lnb_clz32(h);
+                if (lz > 15u) overrun = 1u;
+                else {
+                    const uint32_t v = ((h << lz) >> (31u - lz)) - 1u;
+                    pos += 2u * lz + 1u;
+                    k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(v));
+                }
+            }
+            if (k2 > 30u) { overrun = 1u; k2 = 30u; }
+            left = len; parts_left--;
+        }
+        if (running && overrun) {                                                /* broken payload: flagged below, the block reads as silence */
+            left = 0u; parts_left = 0u; done = n; chan = C;
+        }
+        const bool go = running && left != 0u;
+        if (go && pos > win.limit) lnb_tg_fill(win, pos >> 5, lg, gmask);
+        /* the round: lane j guesses that code word j starts at pos + j * (k2 + 2) */
+        const uint32_t step = k2 + 2u;
+        const uint32_t my_rel = lg * step, my_end = my_rel + k2 + 1u;
+        const uint32_t cnt = left < LNB_TG ? left : LNB_TG;
+        const uint32_t hi = go ? lnb_tg_peek(win, pos + my_rel) : 0xFFFFFFFFu;
+        const uint32_t lz = lnb_clz32(hi);
+        const uint32_t ml = (lz > 1u) ? lz : 1u;
+        const bool resolves = go && (hi < 0x40000000u || lg + 1u == cnt) && lg < cnt;
+        const uint32_t is_short = (lz + k2 <= 31u) ? 0x8000u : 0u;               /* whole code word inside the 32-bit peek */
+        uint32_t r = resolves ? ((lg << 16) | is_short | (my_end + ml)) : 0xFFFFFFFFu;
+        r = min(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = min(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = min(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        if (go) {
+            const uint32_t first = r >> 16;
+            uint32_t n_ok = first + ((r >> 15) & 1u);
+            {
+                const uint32_t low = (hi >> ((31u - k2) - ml)) & ((1u << k2) - 1u);
+                const uint32_t mult = lz ? lz + 1u : ((hi >> 30) & 1u);
+                if (lg < n_ok) out[done + lg] = lnb_zz_dec((mult << k2) + low);
+            }
+            if (__builtin_expect((r & 0x8000u) != 0u, 1)) {
+                pos += r & 0x7FFFu;
+            } else {                                                             /* code word longer than 32 bits: its lane finishes it serially */
+                uint32_t endl = 0, bad = 0;
+                if (lg == first) {
+                    LnbFastReader fr;
+                    lnb_fr_open(fr, win.words, pos + my_rel, win.end_word);
+                    const uint32_t q = lnb_fr_zero_run(fr);
+                    const uint32_t u = (q == 0u) ? lnb_fr_get(fr, k2 + 1u) : lnb_fr_get(fr, k2) + (2u << k2) + ((q - 1u) << k2);
+                    out[done + lg] = lnb_zz_dec(u);
+                    endl = (uint32_t)lnb_fr_position(fr);
+                    bad = fr.overrun;
+                }
+                pos = __shfl_sync(gmask, endl, (int)(g * LNB_TG + first));
+                n_ok = first + 1u;
+                if (__shfl_sync(gmask, bad, (int)(g * LNB_TG + first))) overrun = 1u;
+            }
+            done += n_ok; left -= n_ok;
+        }
     }
-    if (mine) {
-        const uint32_t used = (uint32_t)((lnb_fr_position(fr) - payload_bit + 7u) >> 3);
-        b.blocks[blk_i].na = used;                                  /* payload bytes consumed (reference Flush + Tell) */
-        if (overrun || (payload_bit >> 3) + used > rel_end_byte) b.blocks[blk_i].status = blk.status | LNB_ST_OVERRUN;
+    if (active && lg == 0u) {
+        const uint32_t used = (pos - rel_payload * 8u + 7u) >> 3;
+        b.blocks[blk_i].na = used;                                               /* payload bytes consumed (reference Flush + Tell) */
+        if (overrun || rel_payload + used > rel_end) b.blocks[blk_i].status = blk.status | LNB_ST_OVERRUN;
     }
 }
 
