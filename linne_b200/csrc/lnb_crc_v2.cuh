@@ -40,6 +40,6 @@ __global__ void __launch_bounds__(LNB_CRC_THREADS) lnb_crc_v2_kernel(LnbDecodeBa
     if (tid == 0) {
         const uint32_t got = part[0];
         gblk.crc = got;
-        if (b.cfg.check_crc && got != lnb_get_be(base + 6, 2)) gblk.status = blk.status | LNB_ST_CRC_MISMATCH;
+        if (b.cfg.check_crc && got != lnb_get_be(base + 6, 2)) atomicOr(&gblk.status, (uint32_t)LNB_ST_CRC_MISMATCH);   /* the throughput entropy stage may flag the block at the same time */
     }
 }

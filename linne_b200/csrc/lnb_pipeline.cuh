@@ -95,10 +95,14 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
     const uint32_t B = b.num_blocks, C = b.cfg.num_channels;
     if (B == 0) return;
     if (Exec::cooperative) {
-        ex.crc_cooperative(b);                            /* one CTA per block, chunk CRCs combined in GF(2) */
-        /* one CTA per block: entropy decode feeding synthesis, de-emphasis, M/S; with b.tput the full blocks of a large
-         * batch take one lane per block / per (block, channel) instead and this kernel keeps the rest, side by side */
-        if (b.fused_max_n) ex.stream_cooperative(b);
+        if (b.fused_max_n && b.tput) {
+            /* large batches: the full blocks take the lane-per-block kernels; CRC pass and the per-block pipeline kernel
+             * for the rest run beside them */
+            ex.tput_decode(b);
+        } else {
+            ex.crc_cooperative(b);                        /* one CTA per block, chunk CRCs combined in GF(2) */
+            if (b.fused_max_n) ex.stream_cooperative(b);  /* one CTA per block: entropy decode feeding synthesis, de-emphasis, M/S */
+        }
         if (!b.fused_max_n || b.num_plain_blocks) {       /* raw / silent / long blocks (or the fused kernel switched off) */
             ex.entropy_cooperative(b);                    /* one warp per block: 32 speculative code-word starts per round */
             ex.synth_cooperative(b);                      /* one warp per (block, channel): systolic synthesis + de-emphasis */

@@ -145,23 +145,6 @@ struct CudaExec {
             cudaFuncSetAttribute(lnb_stream_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = smem;
         }
-        if (b.tput) {
-            /* fork: what the throughput kernels leave (tail blocks) is decoded beside them on the side stream */
-            if (!dev->aux_created) {
-                cudaStreamCreateWithFlags(&dev->aux_stream, cudaStreamNonBlocking);
-                cudaEventCreateWithFlags(&dev->ev_fork, cudaEventDisableTiming);
-                cudaEventCreateWithFlags(&dev->ev_join, cudaEventDisableTiming);
-                dev->aux_created = 1;
-            }
-            cudaEventRecord(dev->ev_fork, dev->stream);
-            cudaStreamWaitEvent(dev->aux_stream, dev->ev_fork, 0);
-            lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, dev->aux_stream>>>(b, n_max);
-            cudaEventRecord(dev->ev_join, dev->aux_stream);
-            dev->launches++;
-            tput_cooperative(b);
-            cudaStreamWaitEvent(dev->stream, dev->ev_join, 0);
-            return;
-        }
         const int slot = begin_stage("stream_v1");
         lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, dev->stream>>>(b, n_max);
         end_stage(slot);
@@ -179,13 +162,36 @@ struct CudaExec {
         lnb_tp_synth_kernel<Q0, Q1, Q2><<<(seqs + 31u) / 32u, 32, smem, dev->stream>>>(b);
         end_stage(slot);
     }
-    void tput_cooperative(const LnbDecodeBatch &b)
+    /* Large batches (b.tput, lnb_tput_v1.cuh).  The entropy stage needs nothing from the CRC pass -- it decodes every
+     * full block and the synthesis stage drops those whose CRC failed -- so the CRC pass and the per-block pipeline
+     * kernel for what the lane-per-block kernels leave (tail blocks) run beside it on a side stream:
+     *     side:  crc_v2 -> stream_v1            main:  tp_entropy -> (join) -> tp_synth                          */
+    void tput_decode(const LnbDecodeBatch &b)
     {
-        const int shape = lnb_tput_shape(&b.cfg);
-        if (!shape) return;                                /* the host asks lnb_shim_tput_min_blocks(cfg) first */
+        const int shape = lnb_tput_shape(&b.cfg);           /* non-zero: the host asked lnb_shim_tput_supported(cfg) */
+        if (!dev->aux_created) {
+            cudaStreamCreateWithFlags(&dev->aux_stream, cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&dev->ev_fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&dev->ev_join, cudaEventDisableTiming);
+            dev->aux_created = 1;
+        }
+        cudaEventRecord(dev->ev_fork, dev->stream);
+        cudaStreamWaitEvent(dev->aux_stream, dev->ev_fork, 0);
+        {
+            int slot = begin_stage("crc_v2", dev->aux_stream);
+            lnb_crc_v2_kernel<<<b.num_blocks, LNB_CRC_THREADS, 0, dev->aux_stream>>>(b);
+            end_stage(slot, dev->aux_stream);
+            uint32_t n_max = b.cfg.block_size < LNB_DS_MAX_N ? b.cfg.block_size : LNB_DS_MAX_N;
+            n_max = (n_max + 3u) & ~3u;
+            slot = begin_stage("stream_v1", dev->aux_stream);
+            lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, (size_t)n_max * sizeof(int32_t), dev->aux_stream>>>(b, n_max);
+            end_stage(slot, dev->aux_stream);
+        }
+        cudaEventRecord(dev->ev_join, dev->aux_stream);
         const int slot = begin_stage("tp_entropy");
         lnb_tp_entropy_kernel<<<(b.num_blocks + LNB_TG_PER_WARP - 1u) / LNB_TG_PER_WARP, 32, 0, dev->stream>>>(b);
         end_stage(slot);
+        cudaStreamWaitEvent(dev->stream, dev->ev_join, 0);
         if (shape == 1) tput_synth<32, 2, 0>(b);
         else if (shape == 2) tput_synth<8, 64, 4>(b);
         else tput_synth<16, 128, 4>(b);
@@ -212,18 +218,22 @@ struct CudaExec {
         lnb_synth_v2_kernel<<<(items + LNB_SY_WARPS - 1) / LNB_SY_WARPS, LNB_SY_THREADS, smem, dev->stream>>>(b, n_max);
         end_stage(slot);
     }
-    int begin_stage(const char *name)
+    int begin_stage(const char *name, cudaStream_t on = nullptr)
     {
         if (!dev->profiling) return -1;
-        if (dev->num_pending >= LNB_MAX_PENDING) { cudaStreamSynchronize(dev->stream); drain_profile(dev); }
+        if (dev->num_pending >= LNB_MAX_PENDING) {
+            cudaStreamSynchronize(dev->stream);
+            if (dev->aux_created) cudaStreamSynchronize(dev->aux_stream);
+            drain_profile(dev);
+        }
         const int slot = dev->num_pending++;
         dev->pending_stage[slot] = stage_index(dev, name);
-        cudaEventRecord(dev->ev_begin[slot], dev->stream);
+        cudaEventRecord(dev->ev_begin[slot], on ? on : dev->stream);
         return slot;
     }
-    void end_stage(int slot)
+    void end_stage(int slot, cudaStream_t on = nullptr)
     {
-        if (slot >= 0) cudaEventRecord(dev->ev_end[slot], dev->stream);
+        if (slot >= 0) cudaEventRecord(dev->ev_end[slot], on ? on : dev->stream);
         dev->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess && dev->last_error == cudaSuccess) dev->last_error = e;

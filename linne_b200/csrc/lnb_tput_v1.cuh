@@ -38,10 +38,15 @@
 
 
 /* same rule on every side: the host only sets `tput`, the kernels decide per block */
+LNB_HD bool lnb_tp_shape_ok(const LnbDecodeBatch &b, const LnbBlockDesc &blk)
+{
+    return b.tput && blk.type == LNB_BLOCK_COMPRESSED
+        && blk.nsmp == b.cfg.block_size && blk.nsmp != 0u && (blk.nsmp & 1023u) == 0u && (blk.smp_off & 3u) == 0u;
+}
+/* ... and the block's CRC check did not fail (the entropy stage runs beside the CRC pass and does not look) */
 LNB_HD bool lnb_tp_takes(const LnbDecodeBatch &b, const LnbBlockDesc &blk)
 {
-    return b.tput && blk.type == LNB_BLOCK_COMPRESSED && !(blk.status & (LNB_ST_CRC_MISMATCH | LNB_ST_BAD_TYPE))
-        && blk.nsmp == b.cfg.block_size && blk.nsmp != 0u && (blk.nsmp & 1023u) == 0u && (blk.smp_off & 3u) == 0u;
+    return lnb_tp_shape_ok(b, blk) && !(blk.status & (LNB_ST_CRC_MISMATCH | LNB_ST_BAD_TYPE));
 }
 
 #if defined(__CUDACC__)
@@ -63,7 +68,7 @@ LNB_HD bool lnb_tp_takes(const LnbDecodeBatch &b, const LnbBlockDesc &blk)
 #define LNB_TG            8u
 #define LNB_TG_PER_WARP   (32u / LNB_TG)
 #define LNB_TG_WIN        128u
-#define LNB_TG_ROUND_BITS (LNB_TG * 33u + 64u)       /* furthest bit a round can look at, relative to its start */
+#define LNB_TG_ROUND_BITS (LNB_TG * 33u + 64u + 32u) /* furthest bit a partition header plus a round can look at, relative to their start */
 
 struct LnbTgWin {
     uint32_t *buf;              /* [LNB_TG_WIN + 2] */
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
     const uint32_t C = cfg.num_channels, n = cfg.block_size;
     LnbBlockDesc blk;
     bool active = blk_i < b.num_blocks;
-    if (active) { blk = b.blocks[blk_i]; active = lnb_tp_takes(b, blk); }
+    if (active) { blk = b.blocks[blk_i]; active = lnb_tp_shape_ok(b, blk); }
     if (__ballot_sync(0xffffffffu, active) == 0u) return;
 
     LnbTgWin win;
@@ -157,90 +162,89 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
             }
     }
 
-    /* ---- residuals: one flat loop, one round per group and pass ---- */
-    uint32_t chan = 0, done = n, left = 0, parts_left = 0, len = 0, k2 = 0, first_part = 0;
+    /* ---- residuals.  Outer pass: channel starts and the end of the block (twice per channel).  Inner loop: one
+     *      round per group and pass, with the window refill and the partition header (a gamma-coded delta of k2) of
+     *      the groups that need one as short predicated detours in front of it. ---- */
+    uint32_t chan = 0, left = 0, parts_left = 0, len = 0, k2 = 0;
+    uint32_t my_rel = 0, my_end = 0, k2mask = 0, sh = 31u;       /* per-partition constants of this lane */
     bool running = active;
-    int32_t *out = b.pcm;
+    int32_t *wp = b.pcm;                                         /* where this lane's residual of the next round goes */
     while (__any_sync(0xffffffffu, running)) {
-        if (running && done == n && left == 0u && parts_left == 0u) {           /* next channel, or the end of the block */
+        if (running && left == 0u && parts_left == 0u) {                         /* next channel, or the end of the block */
             if (chan == C || overrun) {
                 running = false;
             } else {
                 lnb_tg_ensure(win, pos, 64u, lg, gmask);
                 uint32_t porder = lnb_tg_get(win, pos, 10);
                 if (porder > LNB_MAX_PORDER) { overrun = 1u; porder = 0u; }
-                len = n >> porder; parts_left = 1u << porder; first_part = 1u; done = 0u;
-                out = b.pcm + (size_t)chan * cfg.pcm_stride + blk.smp_off;
+                len = n >> porder; parts_left = (1u << porder) - 1u;
+                k2 = lnb_tg_get(win, pos, 5);                                    /* first partition: k2 itself (linne_coder.c:313) */
+                if (k2 > 30u) { overrun = 1u; k2 = 30u; }
+                left = overrun ? 0u : len;
+                if (overrun) parts_left = 0u;
+                my_rel = lg * (k2 + 2u); my_end = my_rel + k2 + 1u; k2mask = (1u << k2) - 1u; sh = 31u - k2;
+                wp = b.pcm + (size_t)chan * cfg.pcm_stride + blk.smp_off + lg;
                 chan++;
             }
         }
-        if (running && left == 0u && parts_left != 0u && !overrun) {             /* partition header (linne_coder.c:311-318) */
-            lnb_tg_ensure(win, pos, 96u, lg, gmask);
-            if (first_part) {
-                k2 = lnb_tg_get(win, pos, 5); first_part = 0u;
-            } else {                                                             /* gamma code of zigzag(k2 - previous k2) */
+        while (__all_sync(0xffffffffu, !running || left != 0u || parts_left != 0u)) {
+            if (!__any_sync(0xffffffffu, running)) break;
+            if (running && pos > win.limit) lnb_tg_fill(win, pos >> 5, lg, gmask);
+            if (running && left == 0u) {                                         /* partition header: gamma code of zigzag(k2 - previous k2) */
                 const uint32_t h = lnb_tg_peek(win, pos);
                 const uint32_t lz = lnb_clz32(h);
-                if (lz > 15u) overrun = 1u;
-                else {
-                    const uint32_t v = ((h << lz) >> (31u - lz)) - 1u;
-                    pos += 2u * lz + 1u;
-                    k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(v));
+                const uint32_t v = ((h << (lz & 15u)) >> (31u - (lz & 15u))) - 1u;
+                pos += 2u * lz + 1u;
+                k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(v));
+                left = len; parts_left--;
+                if (lz > 15u || k2 > 30u) { overrun = 1u; k2 = 30u; left = 0u; parts_left = 0u; }
+                my_rel = lg * (k2 + 2u); my_end = my_rel + k2 + 1u; k2mask = (1u << k2) - 1u; sh = 31u - k2;
+            }
+            /* the round: lane j guesses that code word j starts at pos + j * (k2 + 2) */
+            const bool go = running && left != 0u;
+            const uint32_t last = (left < LNB_TG ? left : LNB_TG) - 1u;
+            const uint32_t hi = go ? lnb_tg_peek(win, pos + my_rel) : 0xFFFFFFFFu;
+            const uint32_t lz = lnb_clz32(hi);
+            const uint32_t ml = (lz > 1u) ? lz : 1u;
+            const bool resolves = go && (hi < 0x40000000u || lg == last) && lg <= last;
+            const uint32_t is_short = (lz <= sh) ? 0x8000u : 0u;                 /* whole code word inside the 32-bit peek */
+            uint32_t r = resolves ? ((lg << 16) | is_short | (my_end + ml)) : 0xFFFFFFFFu;
+            r = min(r, __shfl_xor_sync(0xffffffffu, r, 1));
+            r = min(r, __shfl_xor_sync(0xffffffffu, r, 2));
+            r = min(r, __shfl_xor_sync(0xffffffffu, r, 4));
+            if (go) {
+                const uint32_t first = r >> 16;
+                uint32_t n_ok = first + ((r >> 15) & 1u);
+                {
+                    const uint32_t low = (hi >> (sh - ml)) & k2mask;
+                    const uint32_t mult = lz ? lz + 1u : ((hi >> 30) & 1u);
+                    if (lg < n_ok) *wp = lnb_zz_dec((mult << k2) + low);
                 }
-            }
-            if (k2 > 30u) { overrun = 1u; k2 = 30u; }
-            left = len; parts_left--;
-        }
-        if (running && overrun) {                                                /* broken payload: flagged below, the block reads as silence */
-            left = 0u; parts_left = 0u; done = n; chan = C;
-        }
-        const bool go = running && left != 0u;
-        if (go && pos > win.limit) lnb_tg_fill(win, pos >> 5, lg, gmask);
-        /* the round: lane j guesses that code word j starts at pos + j * (k2 + 2) */
-        const uint32_t step = k2 + 2u;
-        const uint32_t my_rel = lg * step, my_end = my_rel + k2 + 1u;
-        const uint32_t cnt = left < LNB_TG ? left : LNB_TG;
-        const uint32_t hi = go ? lnb_tg_peek(win, pos + my_rel) : 0xFFFFFFFFu;
-        const uint32_t lz = lnb_clz32(hi);
-        const uint32_t ml = (lz > 1u) ? lz : 1u;
-        const bool resolves = go && (hi < 0x40000000u || lg + 1u == cnt) && lg < cnt;
-        const uint32_t is_short = (lz + k2 <= 31u) ? 0x8000u : 0u;               /* whole code word inside the 32-bit peek */
-        uint32_t r = resolves ? ((lg << 16) | is_short | (my_end + ml)) : 0xFFFFFFFFu;
-        r = min(r, __shfl_xor_sync(0xffffffffu, r, 1));
-        r = min(r, __shfl_xor_sync(0xffffffffu, r, 2));
-        r = min(r, __shfl_xor_sync(0xffffffffu, r, 4));
-        if (go) {
-            const uint32_t first = r >> 16;
-            uint32_t n_ok = first + ((r >> 15) & 1u);
-            {
-                const uint32_t low = (hi >> ((31u - k2) - ml)) & ((1u << k2) - 1u);
-                const uint32_t mult = lz ? lz + 1u : ((hi >> 30) & 1u);
-                if (lg < n_ok) out[done + lg] = lnb_zz_dec((mult << k2) + low);
-            }
-            if (__builtin_expect((r & 0x8000u) != 0u, 1)) {
-                pos += r & 0x7FFFu;
-            } else {                                                             /* code word longer than 32 bits: its lane finishes it serially */
-                uint32_t endl = 0, bad = 0;
-                if (lg == first) {
-                    LnbFastReader fr;
-                    lnb_fr_open(fr, win.words, pos + my_rel, win.end_word);
-                    const uint32_t q = lnb_fr_zero_run(fr);
-                    const uint32_t u = (q == 0u) ? lnb_fr_get(fr, k2 + 1u) : lnb_fr_get(fr, k2) + (2u << k2) + ((q - 1u) << k2);
-                    out[done + lg] = lnb_zz_dec(u);
-                    endl = (uint32_t)lnb_fr_position(fr);
-                    bad = fr.overrun;
+                if (__builtin_expect((r & 0x8000u) != 0u, 1)) {
+                    pos += r & 0x7FFFu;
+                } else {                                                         /* code word longer than 32 bits: its lane finishes it serially */
+                    uint32_t endl = 0, bad = 0;
+                    if (lg == first) {
+                        LnbFastReader fr;
+                        lnb_fr_open(fr, win.words, pos + my_rel, win.end_word);
+                        const uint32_t q = lnb_fr_zero_run(fr);
+                        const uint32_t u = (q == 0u) ? lnb_fr_get(fr, k2 + 1u) : lnb_fr_get(fr, k2) + (2u << k2) + ((q - 1u) << k2);
+                        *wp = lnb_zz_dec(u);
+                        endl = (uint32_t)lnb_fr_position(fr);
+                        bad = fr.overrun;
+                    }
+                    pos = __shfl_sync(gmask, endl, (int)(g * LNB_TG + first));
+                    n_ok = first + 1u;
+                    if (__shfl_sync(gmask, bad, (int)(g * LNB_TG + first))) { overrun = 1u; left = n_ok; parts_left = 0u; }
                 }
-                pos = __shfl_sync(gmask, endl, (int)(g * LNB_TG + first));
-                n_ok = first + 1u;
-                if (__shfl_sync(gmask, bad, (int)(g * LNB_TG + first))) overrun = 1u;
+                left -= n_ok; wp += n_ok;
             }
-            done += n_ok; left -= n_ok;
         }
     }
     if (active && lg == 0u) {
         const uint32_t used = (pos - rel_payload * 8u + 7u) >> 3;
         b.blocks[blk_i].na = used;                                               /* payload bytes consumed (reference Flush + Tell) */
-        if (overrun || rel_payload + used > rel_end) b.blocks[blk_i].status = blk.status | LNB_ST_OVERRUN;
+        if (overrun || rel_payload + used > rel_end) atomicOr(&b.blocks[blk_i].status, (uint32_t)LNB_ST_OVERRUN);
     }
 }
 

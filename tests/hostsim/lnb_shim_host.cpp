@@ -16,7 +16,7 @@ struct LoopExec {
     static constexpr bool cooperative = false;
     LnbDevice *dev;
     void crc_cooperative(const LnbDecodeBatch &) {}
-    void tput_cooperative(const LnbDecodeBatch &) {}
+    void tput_decode(const LnbDecodeBatch &) {}
     void entropy_cooperative(const LnbDecodeBatch &) {}
     void synth_cooperative(const LnbDecodeBatch &) {}
     void stream_cooperative(const LnbDecodeBatch &) {}
