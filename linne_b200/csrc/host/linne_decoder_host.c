@@ -36,7 +36,7 @@ struct LINNEDecoder {
     uint32_t ra_blocks_cap;
 };
 #define LNB_MAX_READAHEAD 4096u
-#define LNB_TPUT_MIN_BLOCKS 3072ul
+#define LNB_TPUT_MIN_BLOCKS 2560ul
 
 /* reference linne_decoder.c:60-131 */
 LINNEApiResult LINNEDecoder_DecodeHeader(const uint8_t *data, uint32_t data_size, struct LINNEHeader *header)

@@ -100,7 +100,7 @@ def test_tput_many_blocks_unit_counts_and_types(gpu, oracle, tput):
 
 
 def test_tput_long_stream_default_threshold(gpu, oracle):
-    """above the default switch-over point without any override: 4200 blocks of 1024 samples"""
+    """above the default switch-over point (2560 blocks) without any override: 4200 blocks of 1024 samples"""
     pcm = harness.synth_pcm(n=1024 * 20, channels=2, bits=16, seed=31)
     base = oracle.encode(pcm, preset=6, block=1024)
     times = 210
