@@ -680,6 +680,7 @@ def run_b200(args, rank, world, local_rank):
     # Eight host threads per rank wait on their streams; when the ranks of a box outnumber its cores, spinning waits
     # starve each other, so the library's waits are switched to sleeping ones (LINNE_B200_SYNC=block).
     oversubscribed = world * len(PRESETS) > 0.75 * (os.cpu_count() or 1)
+    sync_mode_forced = oversubscribed and "LINNE_B200_SYNC" not in os.environ
     if oversubscribed:
         os.environ.setdefault("LINNE_B200_SYNC", "block")
     torch.cuda.set_device(local_rank)
@@ -871,8 +872,11 @@ def run_b200(args, rank, world, local_rank):
                        "peak_source": peak_src, "bytes_per_sample": round(hbm_bytes_per_sample, 3)}
 
     # ---- at-scale legs: free the sweep's buffers first ----
+    host_wait_sweep = os.environ.get("LINNE_B200_SYNC", "spin")
     for sess in list(encs.values()) + list(decs.values()):
         sess.close()
+    if sync_mode_forced:
+        del os.environ["LINNE_B200_SYNC"]                # the legs below drive one or two handles per rank: spinning waits again
     del d_out, d_backs, h_outs, h_backs, l2_flush
     torch.cuda.empty_cache()
     sharded = None
@@ -934,7 +938,7 @@ def run_b200(args, rank, world, local_rank):
                    "block": BLOCK, "ms": 1, "presets": PRESETS, "l2": "256 MiB flush write between timed iterations",
                    "per_rank": "each rank runs the whole sweep on its own clip",
                    "concurrency": "serial" if args.serial else "8 presets on 8 host threads / CUDA streams",
-                   "host_wait": os.environ.get("LINNE_B200_SYNC", "spin"), "host_cores": os.cpu_count()},
+                   "host_wait": host_wait_sweep, "host_cores": os.cpu_count()},
         "e2e": {"value": round(e2e_value, 3), "unit": "MSamples/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
