@@ -52,7 +52,9 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons while the timed region runs.  NVML in-process (one cheap call per sample); the
+    nvidia-smi command line is only the fall-back: a new nvidia-smi process per rank every 200 ms initialises NVML for
+    every GPU of the box and disturbed the timed region at 8 ranks."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -60,18 +62,43 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda name: "Active" if r & getattr(n, name, 0) else "Not Active"
+        return [str(sm), str(mx), flag("nvmlClocksThrottleReasonHwSlowdown"), flag("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                flag("nvmlClocksThrottleReasonSwThermalSlowdown"), flag("nvmlClocksThrottleReasonSwPowerCap")]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self.nvml is not None:
+                    self.samples.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    parts = [x.strip() for x in out.strip().split(",")]
+                    if len(parts) >= 6:
+                        self.samples.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05 if self.nvml is not None else 0.2)
 
     def summary(self):
         if not self.samples:
@@ -81,7 +108,7 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(s[2 + i] == "Active" for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_clip():
@@ -253,6 +280,11 @@ def run_c3(args, dev, hbm_peak, fp64_peak):
     bytes_per_sample = 4.0 + sz / samples
     dec_stage_ms = {k: round(v[1] / 3.0, 3) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][1])}
     dom = max(dec_stage_ms.items(), key=lambda kv: kv[1])
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            c3_traffic = json.load(f)
+    except Exception:
+        c3_traffic = {}
     out = {
         "workload": f"C3: {args.c3_seconds:.0f} s 44.1 kHz 16-bit stereo, -m 7, {n // BLOCK + 1} blocks, decode-only",
         "value": round(samples / (ms_res / 1e3) / 1e6, 1), "unit": "MSamples/s", "ms": round(ms_res, 3),
@@ -265,7 +297,9 @@ def run_c3(args, dev, hbm_peak, fp64_peak):
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": round(bytes_per_sample * samples / (dom[1] / 1e3) / 1e9, 1),
                      "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(bytes_per_sample * samples / (dom[1] / 1e3) / 1e9 / hbm_peak, 4),
-                     "bytes_per_sample": round(bytes_per_sample, 3), "traffic": None},
+                     "bytes_per_sample": round(bytes_per_sample, 3), "traffic": c3_traffic.get(dom[0]),
+                     "traffic_note": "ncu dram bytes per launch on a stream of this size (profiles/ncu_traffic.json, r1_tput_ncu_full.md): "
+                                     "the residuals make one pass through HBM between the two throughput kernels"},
         "encode_m7": {"value": round(samples / (ms_enc / 1e3) / 1e6, 1), "unit": "MSamples/s", "ms": round(ms_enc, 2),
                       "stages_ms": enc_stages,
                       "fp64_frac": round(2.0 * MAC_PER_SAMPLE[7] * samples / (enc_stages.get("analyze_v3", ms_enc) / 1e3) / 1e12
