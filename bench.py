@@ -513,6 +513,7 @@ def run_c5(args, dev, rank, world):
                        f"({args.c5_files * args.c5_file_seconds / 3600.0:.1f} h), {(n + BLOCK - 1) // BLOCK} blocks per file, "
                        "encode + decode of every file, files sharded by contiguous range over the ranks",
            "unit": "MSamples/s", "scaling": "strong", "workers_per_rank": J, "files_per_rank": hi - lo,
+           "decoder_throughput_blocks": args.c5_tput_blocks,
            "note": "samples counted once per file (a file that went through encode and decode counts once)"}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -535,6 +536,8 @@ def run_c5(args, dev, rank, world):
         total_files = nfiles * world if frac < 1.0 else args.c5_files
         encs = [EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=m) for _ in range(J)]
         decs = [DecoderSession(channels=nch) for _ in range(J)]
+        for s_ in decs:                                             # several handles in flight: see include/linne_b200.h
+            s_.lib.LINNEB200_DecoderSetThroughputBlocks(s_.h, args.c5_tput_blocks)
         d_streams = [torch.zeros(cap + 64, dtype=torch.uint8, device=dev) for _ in range(J)]
         d_backs = [torch.zeros((nch, stride), dtype=torch.int32, device=dev) for _ in range(J)]
         last = [None] * J
@@ -583,6 +586,8 @@ def run_c5(args, dev, rank, world):
         for J2 in (1, 3):
             encs = [EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=0) for _ in range(J2)]
             decs = [DecoderSession(channels=nch) for _ in range(J2)]
+            for s_ in decs:
+                s_.lib.LINNEB200_DecoderSetThroughputBlocks(s_.h, args.c5_tput_blocks if J2 > 1 else 2560)
             h_lnn = [torch.zeros(cap, dtype=torch.uint8).pin_memory() for _ in range(J2)]
             h_out = [torch.zeros(host_pcm.numel(), dtype=torch.uint8).pin_memory() for _ in range(J2)]
             errs = []
@@ -1017,7 +1022,9 @@ def main():
                     help="files of the C5 corpus (BASELINE.json configs[4]), sharded over the ranks; 0 = skip")
     ap.add_argument("--c5-file-seconds", type=float, default=360.0)
     ap.add_argument("--c5-m7-fraction", type=float, default=0.1, help="share of each rank's files also run at -m 7 (bounded)")
-    ap.add_argument("--c5-workers", type=int, default=2, help="handle pairs (host threads / CUDA streams) per rank in the C5 leg")
+    ap.add_argument("--c5-workers", type=int, default=4, help="handle pairs (host threads / CUDA streams) per rank in the C5 leg")
+    ap.add_argument("--c5-tput-blocks", type=int, default=1024,
+                    help="C5 leg: LINNEB200_DecoderSetThroughputBlocks of its decoders (several handles in flight)")
     ap.add_argument("--c5-e2e-files", type=int, default=24, help="files per rank of the host-buffer pipeline leg; 0 = skip")
     ap.add_argument("--no-streaming", action="store_true", help="skip the EncodeBlock / DecodeBlock latency leg")
     args = ap.parse_args()

@@ -63,6 +63,16 @@ LINNEApiResult LINNEB200_DecodeWholePacked(struct LINNEDecoder *decoder, const u
  * 0 or 1 switches it off (the default; the environment variable LINNE_B200_READAHEAD sets the default). */
 void LINNEB200_DecoderSetReadahead(struct LINNEDecoder *decoder, uint32_t blocks);
 
+/* ---- decoding many streams at once ------------------------------------------------------------------
+ * DecodeWhole has two data paths.  The per-block pipeline (one CTA per block) has the shortest latency for one
+ * call but fills the GPU's issue slots from ~600 blocks on, so concurrent calls queue behind each other.  The
+ * throughput kernels (eight lanes per block, one lane per block-channel) need ~10x fewer instructions per sample
+ * but ~5 ms per call whatever its size; calls of several handles overlap almost freely.  A call takes them when it
+ * holds at least `min_blocks` full blocks: default 2560 (where they win for a single call); a corpus tool that
+ * keeps several handles busy lowers it to ~1024 (what linne_b200_cli -j N and bench.py's corpus leg do);
+ * 0 = never.  Results are identical either way.  Environment default: LINNE_B200_TPUT_MIN_BLOCKS. */
+void LINNEB200_DecoderSetThroughputBlocks(struct LINNEDecoder *decoder, uint32_t min_blocks);
+
 /* Page-locked host memory for the buffers handed to EncodeWhole / DecodeWhole and their packed variants
  * (SURVEY 8f.3): copies from and to such memory are DMA transfers that overlap with kernels of other
  * handles.  NULL when no device is usable. */

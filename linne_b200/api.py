@@ -229,6 +229,7 @@ def bind_ext_api(lib):
     lib.LINNEB200_DecodeWholePacked.argtypes = [C.c_void_p, u8p, C.c_uint32, u8p, C.c_uint32, u32p]
     lib.LINNEB200_DecodeWholePacked.restype = C.c_int
     lib.LINNEB200_DecoderSetReadahead.argtypes = [C.c_void_p, C.c_uint32]
+    lib.LINNEB200_DecoderSetThroughputBlocks.argtypes = [C.c_void_p, C.c_uint32]
     lib.LINNEB200_HostAlloc.argtypes = [C.c_size_t]
     lib.LINNEB200_HostAlloc.restype = C.c_void_p
     lib.LINNEB200_HostFree.argtypes = [C.c_void_p]

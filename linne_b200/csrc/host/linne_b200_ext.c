@@ -7,6 +7,7 @@
 LnbDevice *lnb_encoder_device(const struct LINNEEncoder *enc);
 LnbDevice *lnb_decoder_device(const struct LINNEDecoder *dec);
 void lnb_decoder_set_readahead(struct LINNEDecoder *dec, uint32_t blocks);
+void lnb_decoder_set_tput_min_blocks(struct LINNEDecoder *dec, uint32_t blocks);
 
 const char *LINNEB200_Backend(void) { return lnb_shim_backend(); }
 
@@ -24,6 +25,7 @@ void LINNEB200_EncoderUseStream(struct LINNEEncoder *e, void *s) { if (e) lnb_sh
 void LINNEB200_DecoderUseStream(struct LINNEDecoder *d, void *s) { if (d) lnb_shim_use_stream(lnb_decoder_device(d), s); }
 
 void LINNEB200_DecoderSetReadahead(struct LINNEDecoder *d, uint32_t blocks) { if (d) lnb_decoder_set_readahead(d, blocks); }
+void LINNEB200_DecoderSetThroughputBlocks(struct LINNEDecoder *d, uint32_t min_blocks) { if (d) lnb_decoder_set_tput_min_blocks(d, min_blocks); }
 void *LINNEB200_HostAlloc(size_t bytes) { return lnb_shim_alloc_pinned(bytes); }
 void LINNEB200_HostFree(void *h_ptr) { if (h_ptr) lnb_shim_free_pinned(h_ptr); }
 

@@ -28,6 +28,7 @@ struct LINNEDecoder {
     LnbBuf h_pcm;                          /* pinned int32 [C][stage_stride]: PCM staging of DecodeBlock / read-ahead cache */
     /* DecodeBlock read-ahead: blocks decoded ahead of the caller in one batch and served from here */
     uint32_t readahead;                    /* blocks decoded per batch by DecodeBlock (<= 1: batch of one) */
+    uint32_t tput_min_blocks;              /* batches of at least this many blocks take the throughput kernels (0 = never) */
     uint32_t stage_stride;                 /* samples per plane of h_pcm in the last staged call */
     uint32_t ra_count, ra_next;            /* cached blocks / next one to serve */
     uint8_t *ra_image;                     /* the cached blocks' bytes (validated against the caller's on every hit) */
@@ -86,6 +87,10 @@ struct LINNEDecoder *LINNEDecoder_Create(const struct LINNEDecoderConfig *config
         const char *e = getenv("LINNE_B200_READAHEAD");
         const long k = e ? strtol(e, NULL, 10) : 0;
         dec->readahead = (k > 1) ? (uint32_t)(k > (long)LNB_MAX_READAHEAD ? (long)LNB_MAX_READAHEAD : k) : 0u;
+    }
+    {   /* LINNE_B200_TPUT_MIN_BLOCKS=N moves the switch-over point to the throughput decoder (0 = never) */
+        const char *e = getenv("LINNE_B200_TPUT_MIN_BLOCKS");
+        dec->tput_min_blocks = e ? (uint32_t)strtoul(e, NULL, 10) : (uint32_t)LNB_TPUT_MIN_BLOCKS;
     }
     if (lnb_shim_open(&dec->dev, -1) != 0) {
         fprintf(stderr, "linne_b200: no usable CUDA device -- the decoder has no CPU fallback\n");
@@ -286,10 +291,8 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
                 batch.num_plain_blocks++;
     }
 
-    {   /* Large batches: one lane per block / per (block, channel) instead of one CTA per block (lnb_tput_v1.cuh).
-         * LINNE_B200_TPUT_MIN_BLOCKS moves the switch-over point (0 = never). */
-        const char *e = getenv("LINNE_B200_TPUT_MIN_BLOCKS");
-        const unsigned long min_blocks = e ? strtoul(e, NULL, 10) : LNB_TPUT_MIN_BLOCKS;
+    {   /* Large batches: eight lanes per block / one per (block, channel) instead of one CTA per block (lnb_tput_v1.cuh) */
+        const uint32_t min_blocks = dec->tput_min_blocks;
         const int32_t *pcm_base = d_pcm_ext ? d_pcm_ext : (const int32_t *)dec->d_pcm.ptr;
         batch.tput = (min_blocks && scan.num_blocks >= min_blocks && batch.fused_max_n
                       && ((uintptr_t)pcm_base & 15u) == 0u && (batch.cfg.pcm_stride & 3u) == 0u
@@ -471,6 +474,8 @@ LINNEApiResult LINNEDecoder_DecodeWhole(struct LINNEDecoder *dec, const uint8_t 
 }
 
 LnbDevice *lnb_decoder_device(const struct LINNEDecoder *dec) { return dec->dev; }
+
+void lnb_decoder_set_tput_min_blocks(struct LINNEDecoder *dec, uint32_t blocks) { dec->tput_min_blocks = blocks; }
 
 void lnb_decoder_set_readahead(struct LINNEDecoder *dec, uint32_t blocks)
 {

@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
                 chan++;
             }
         }
+        if (!__any_sync(0xffffffffu, running)) break;
+        /* `running` does not change inside the round loop and a running group runs out of code words eventually */
         while (__all_sync(0xffffffffu, !running || left != 0u || parts_left != 0u)) {
-            if (!__any_sync(0xffffffffu, running)) break;
             if (running && pos > win.limit) lnb_tg_fill(win, pos >> 5, lg, gmask);
             if (running && left == 0u) {                                         /* partition header: gamma code of zigzag(k2 - previous k2) */
                 const uint32_t h = lnb_tg_peek(win, pos);

@@ -291,6 +291,8 @@ int main(int argc, char **argv)
             cfg.max_num_channels = LINNE_MAX_NUM_CHANNELS; cfg.max_num_layers = 5;
             cfg.max_num_parameters_per_layer = 128; cfg.check_crc = (uint8_t)(o.no_crc ? 0 : 1);   /* linne_codec.c:205-208 */
             workers[i].wk.dec = LINNEDecoder_Create(&cfg, NULL, 0);
+            /* several decoders at work: long files take the throughput kernels, whose calls overlap (linne_b200.h) */
+            if (workers[i].wk.dec && jobs > 1) LINNEB200_DecoderSetThroughputBlocks(workers[i].wk.dec, 1024u);
         }
         if (!workers[i].wk.enc && !workers[i].wk.dec) {
             fprintf(stderr, "%s: cannot create the %s\n", argv[0], o.encode ? "encoder" : "decoder");
