@@ -915,21 +915,36 @@ def run_b200(args, rank, world, local_rank):
     for sess in list(encs.values()) + list(decs.values()):
         sess.close()
     if sync_mode_forced:
-        del os.environ["LINNE_B200_SYNC"]                # the legs below drive one or two handles per rank: spinning waits again
+        del os.environ["LINNE_B200_SYNC"]                # the legs below choose for their own thread counts
+    user_sync_mode = "LINNE_B200_SYNC" in os.environ
+
+    def choose_host_wait(threads_per_rank):
+        """sleeping waits when the waiting host threads of the box would outnumber three quarters of its cores"""
+        if user_sync_mode:
+            return os.environ["LINNE_B200_SYNC"]
+        if world * threads_per_rank > 0.75 * (os.cpu_count() or 1):
+            os.environ["LINNE_B200_SYNC"] = "block"
+            return "block"
+        os.environ.pop("LINNE_B200_SYNC", None)
+        return "spin"
     del d_out, d_backs, h_outs, h_backs, l2_flush
     torch.cuda.empty_cache()
     sharded = None
     if world > 1 and args.shard_seconds > 0:
         try:
+            choose_host_wait(1)
             sharded = run_sharded(args, dev, rank, world)
         except Exception as e:      # pragma: no cover
             sharded = {"error": repr(e)}
     c5 = None
     if args.c5_files > 0:
         try:
+            wait_mode = choose_host_wait(max(1, args.c5_workers))      # read by the handles when they are created
             c5 = run_c5(args, dev, rank, world)
+            c5["host_wait"] = wait_mode
         except Exception as e:      # pragma: no cover
             c5 = {"error": repr(e)}
+        choose_host_wait(1)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -210,9 +210,7 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
             const bool resolves = go && (hi < 0x40000000u || lg == last) && lg <= last;
             const uint32_t is_short = (lz <= sh) ? 0x8000u : 0u;                 /* whole code word inside the 32-bit peek */
             uint32_t r = resolves ? ((lg << 16) | is_short | (my_end + ml)) : 0xFFFFFFFFu;
-            r = min(r, __shfl_xor_sync(0xffffffffu, r, 1));
-            r = min(r, __shfl_xor_sync(0xffffffffu, r, 2));
-            r = min(r, __shfl_xor_sync(0xffffffffu, r, 4));
+            r = __reduce_min_sync(gmask, r);                                     /* one redux per group (tiled-partition style mask) */
             if (go) {
                 const uint32_t first = r >> 16;
                 uint32_t n_ok = first + ((r >> 15) & 1u);
