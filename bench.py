@@ -919,10 +919,11 @@ def run_b200(args, rank, world, local_rank):
     user_sync_mode = "LINNE_B200_SYNC" in os.environ
 
     def choose_host_wait(threads_per_rank):
-        """sleeping waits when the waiting host threads of the box would outnumber three quarters of its cores"""
+        """sleeping waits only when the waiting host threads of the box outnumber its cores: a sleeping wait costs a
+        wake-up per synchronisation, which the short per-file call chains of these legs feel"""
         if user_sync_mode:
             return os.environ["LINNE_B200_SYNC"]
-        if world * threads_per_rank > 0.75 * (os.cpu_count() or 1):
+        if world * threads_per_rank > (os.cpu_count() or 1):
             os.environ["LINNE_B200_SYNC"] = "block"
             return "block"
         os.environ.pop("LINNE_B200_SYNC", None)

@@ -27,8 +27,9 @@ struct LINNEEncoder {
     LnbDevice *dev;
     size_t scratch_budget;                 /* bytes of analysis scratch per chunk */
     LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_acorr, d_cand, d_unit_loss,
-           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train, d_packed;
+           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train, d_packed, d_sinwin;
     LnbBuf h_blocks, h_welch, h_total;
+    uint32_t sinwin_n;                     /* block length d_sinwin was tabulated for (0 = none) */
     const int32_t *cur_pcm;                /* device PCM planes of the call in flight */
     uint32_t cur_pcm_stride;
 };
@@ -98,7 +99,7 @@ void LINNEEncoder_Destroy(struct LINNEEncoder *enc)
         LnbBuf *dbufs[] = { &enc->d_pcm, &enc->d_blocks, &enc->d_params, &enc->d_est, &enc->d_work, &enc->d_sig_a,
                             &enc->d_sig_b, &enc->d_acorr, &enc->d_cand, &enc->d_unit_loss, &enc->d_chosen_w,
                             &enc->d_chosen_u, &enc->d_final_sum, &enc->d_welch, &enc->d_plans, &enc->d_plan_mean,
-                            &enc->d_out, &enc->d_total, &enc->d_train, &enc->d_packed };
+                            &enc->d_out, &enc->d_total, &enc->d_train, &enc->d_packed, &enc->d_sinwin };
         size_t i;
         for (i = 0; i < sizeof(dbufs) / sizeof(dbufs[0]); i++) lnb_buf_release_device(enc->dev, dbufs[i]);
         lnb_buf_release_host(&enc->h_blocks);
@@ -242,6 +243,14 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     batch.chosen_log2u = (uint8_t *)enc->d_chosen_u.ptr;
     batch.final_sum = (double *)enc->d_final_sum.ptr;
     batch.welch = (const double *)enc->d_welch.ptr;
+    /* sine window of the block-type estimate, tabulated once per block length for the cooperative prepare kernel */
+    if (NB >= 2u && NB <= lnb_shim_coop_max_n() && enc->sinwin_n != NB) {
+        enc->sinwin_n = 0;
+        if (!lnb_buf_reserve_device(enc->dev, &enc->d_sinwin, (size_t)NB * sizeof(double))
+            && lnb_shim_fill_sine_window(enc->dev, (double *)enc->d_sinwin.ptr, NB) == 0) enc->sinwin_n = NB;
+    }
+    batch.sinwin = (enc->sinwin_n == NB) ? (const double *)enc->d_sinwin.ptr : NULL;
+    batch.sinwin_n = enc->sinwin_n;
     batch.plans = (LnbCoderPlan *)enc->d_plans.ptr;
     batch.plan_mean = (double *)enc->d_plan_mean.ptr;
     batch.total_size = (uint32_t *)enc->d_total.ptr;

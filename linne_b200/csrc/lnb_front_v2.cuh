@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(LNB_FR_THREADS) lnb_prepare_v2_kernel(LnbEncod
                 if ((uint32_t)e < cnt + p0 && j < n && cnt) {
                     const int32_t xi = x[j];
                     if ((uint32_t)e < cnt && xi != 0) nonzero = true;
-                    v = ((double)xi * norm) * sin((pi * (double)j) / (double)(n - 1u));
+                    /* the window of full blocks is tabulated (same expression, lnb_sine_window_kernel): FP64 sin per
+                     * sample was four fifths of this kernel */
+                    const double sw = (b.sinwin && n == b.sinwin_n) ? __ldg(b.sinwin + j) : sin((pi * (double)j) / (double)(n - 1u));
+                    v = ((double)xi * norm) * sw;
                 }
                 w[e] = v;
             }

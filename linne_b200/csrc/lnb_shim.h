@@ -62,6 +62,11 @@ int lnb_shim_unpack_pcm(LnbDevice *dev, const uint8_t *d_packed, int32_t *d_pcm,
 int lnb_shim_pack_pcm(LnbDevice *dev, const int32_t *d_pcm, uint8_t *d_packed, uint32_t pcm_stride,
                       uint32_t frames, uint32_t channels, uint32_t bytes);
 
+/* dst[j] = sin(pi * j / (n - 1)), j < n: the sine window of the block-type estimate (reference lpc.c:176-212 via
+ * :810-865), tabulated once per handle and block length with the very function the prepare kernel would call per
+ * sample.  Enqueue only; non-zero when the back end has no use for the table (the host then passes none). */
+int lnb_shim_fill_sine_window(LnbDevice *dev, double *dst, uint32_t n);
+
 /* number of kernels launched through this context since it was opened (bench.py's gpu_launches) */
 uint64_t lnb_shim_launch_count(const LnbDevice *dev);
 

@@ -585,6 +585,22 @@ __global__ void __launch_bounds__(256) lnb_fp64_peak_kernel(double *sink, double
     if (s == 12345.678) sink[0] = s;
 }
 
+__global__ void __launch_bounds__(256) lnb_sine_window_kernel(double *dst, uint32_t n)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const double pi = 3.1415926535897932384626433832795029;
+    if (j < n) dst[j] = sin((pi * (double)j) / (double)(n - 1u));       /* the expression of lnb_prepare_v2_kernel */
+}
+
+int lnb_shim_fill_sine_window(LnbDevice *dev, double *dst, uint32_t n)
+{
+    bind_device(dev);
+    if (n < 2u) return 1;
+    lnb_sine_window_kernel<<<(n + 255u) / 256u, 256, 0, dev->stream>>>(dst, n);
+    dev->launches++;
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 double lnb_shim_measure_fp64_tflops(LnbDevice *dev)
 {
     bind_device(dev);

@@ -108,6 +108,8 @@ typedef struct LnbEncodeBatch {
     uint8_t *chosen_log2u;          /* [S][LNB_MAX_LAYERS] */
     double *final_sum;              /* [S][chunks] partial |residual| sums of the last layer */
     const double *welch;            /* [B][LNB_MAX_LEVELS] window scale per unit-count level */
+    const double *sinwin;           /* [sinwin_n] sine window of the block-type estimate for blocks of sinwin_n samples, or NULL */
+    uint32_t sinwin_n;
     LnbCoderPlan *plans;            /* [B*C] */
     double *plan_mean;              /* [B*C][2*LNB_MAX_PARTITIONS] */
     uint8_t *out;                   /* device image of the output stream */

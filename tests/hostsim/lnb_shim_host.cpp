@@ -76,6 +76,7 @@ void lnb_shim_profile_reset(LnbDevice *) {}
 int lnb_shim_profile_get(LnbDevice *, LnbStageStat *, int) { return 0; }
 int lnb_shim_profile_timeline(LnbDevice *, LnbTimelineEntry *, int) { return 0; }
 double lnb_shim_measure_fp64_tflops(LnbDevice *) { return 0.0; }
+int lnb_shim_fill_sine_window(LnbDevice *, double *, uint32_t) { return 1; }
 void *lnb_shim_device_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 16); }
 void lnb_shim_device_free(void *p) { free(p); }
 int lnb_shim_ipc_export(const void *, unsigned char *) { return 1; }          /* no peers on the CPU */
