@@ -1,3 +1,4 @@
+"""tools/c5_stages.py -- per-kernel device times of one six-minute stereo file (a C5 corpus file): encode + decode at -m 0 and -m 7."""
 import sys, os
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np, ctypes as C, torch
