@@ -36,7 +36,8 @@ struct LINNEDecoder {
     struct LnbCachedBlock { uint32_t byte_off, byte_size, smp_off, nsmp; } *ra_blocks;
     uint32_t ra_blocks_cap;
 };
-#define LNB_MAX_READAHEAD 4096u
+#define LNB_MAX_READAHEAD 1024u
+#define LNB_READAHEAD_MAX_SAMPLES (1u << 21)  /* per channel and batch: bounds the pinned PCM cache (8 ch: 64 MiB) */
 #define LNB_TPUT_MIN_BLOCKS 2560ul
 
 /* reference linne_decoder.c:60-131 */
@@ -389,7 +390,7 @@ static void fill_block_cache(struct LINNEDecoder *dec, const uint8_t *data, uint
     BlockScan scan;
     uint32_t first_bad = 0, i, n, span;
     dec->ra_count = dec->ra_next = 0;
-    (void)decode_range(dec, data, data_size, 0, NULL, 0xFFFFFFFFu, 0xFFFFFFFFu, dec->readahead, 1,
+    (void)decode_range(dec, data, data_size, 0, NULL, 0xFFFFFFFFu, LNB_READAHEAD_MAX_SAMPLES, dec->readahead, 1,
                        NULL, NULL, NULL, NULL, 0, &scan, &first_bad);
     blocks = (const LnbBlockDesc *)dec->h_blocks.ptr;
     n = (first_bad < scan.num_decodable) ? first_bad : scan.num_decodable;
