@@ -44,6 +44,25 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *decoder,
         const uint8_t *data, const uint8_t *d_data, uint32_t data_size,
         int32_t *d_pcm, uint32_t pcm_stride, uint32_t buffer_num_channels, uint32_t buffer_num_samples);
 
+/* ---- corpus batches: several files per call -------------------------------------------------
+ * Blocks are independent, across files too, so a corpus tool can hand the kernels the blocks of many files at once:
+ * fewer, larger launches (the per-file chain of a dozen launches and several synchronisations is what limits many
+ * handles on many GPUs) and full waves for every kernel.  All files of a call share the handle's stream parameters.
+ * The PCM of the files sits in one set of device planes [C][pcm_stride], file i at samples [first_sample,
+ * first_sample + num_samples); the streams sit one after the other in `d_data` (out_offset / out_size: written by
+ * the encoder, read by the decoder; the image must be followed by >= 16 readable bytes).  Every stream is
+ * byte-identical with what EncodeWhole writes for that file; the decoder returns the first file's error, if any,
+ * and leaves every file's own result in `status`. */
+struct LINNEB200FileDesc {
+    uint32_t first_sample, num_samples;     /* where the file's PCM is (encode: in, decode: in) */
+    uint32_t out_offset, out_size;          /* where the file's stream is in d_data (encode: out, decode: in) */
+    int32_t  status;                        /* decode: LINNEApiResult of this file */
+};
+LINNEApiResult LINNEB200_EncodeFilesResident(struct LINNEEncoder *encoder, const int32_t *d_pcm, uint32_t pcm_stride,
+        struct LINNEB200FileDesc *files, uint32_t num_files, uint8_t *d_data, uint32_t data_size, uint32_t *output_size);
+LINNEApiResult LINNEB200_DecodeFilesResident(struct LINNEDecoder *decoder, const uint8_t *d_data, uint32_t data_size,
+        struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride);
+
 /* ---- packed PCM entry points ------------------------------------------------------------
  * `pcm` = interleaved little-endian samples exactly as in a WAV data chunk (8-bit unsigned with a bias of 128,
  * 16/24/32-bit signed; bits per sample = the encoder's parameter / the stream header).  The conversion to and

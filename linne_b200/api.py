@@ -228,6 +228,12 @@ def bind_ext_api(lib):
     lib.LINNEB200_EncodeWholePacked.restype = C.c_int
     lib.LINNEB200_DecodeWholePacked.argtypes = [C.c_void_p, u8p, C.c_uint32, u8p, C.c_uint32, u32p]
     lib.LINNEB200_DecodeWholePacked.restype = C.c_int
+    lib.LINNEB200_EncodeFilesResident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(FileDesc), C.c_uint32,
+                                                  C.c_void_p, C.c_uint32, u32p]
+    lib.LINNEB200_EncodeFilesResident.restype = C.c_int
+    lib.LINNEB200_DecodeFilesResident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(FileDesc), C.c_uint32,
+                                                  C.c_void_p, C.c_uint32]
+    lib.LINNEB200_DecodeFilesResident.restype = C.c_int
     lib.LINNEB200_DecoderSetReadahead.argtypes = [C.c_void_p, C.c_uint32]
     lib.LINNEB200_DecoderSetThroughputBlocks.argtypes = [C.c_void_p, C.c_uint32]
     lib.LINNEB200_HostAlloc.argtypes = [C.c_size_t]
@@ -264,6 +270,12 @@ class StageStat(C.Structure):
 
 class TimelineEntry(C.Structure):
     _fields_ = [("name", C.c_char * 24), ("begin_ms", C.c_float), ("end_ms", C.c_float)]
+
+
+class FileDesc(C.Structure):
+    """struct LINNEB200FileDesc (include/linne_b200.h)"""
+    _fields_ = [("first_sample", C.c_uint32), ("num_samples", C.c_uint32), ("out_offset", C.c_uint32),
+                ("out_size", C.c_uint32), ("status", C.c_int32)]
 
 
 class ChannelParams(C.Structure):

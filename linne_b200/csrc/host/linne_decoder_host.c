@@ -508,6 +508,104 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uin
                         header.num_samples, 0, 0, NULL, NULL, d_data, d_pcm, pcm_stride, NULL, NULL);
 }
 
+/* Several streams per call (corpus batches): the streams sit one after the other in the device image
+ * `d_data` (files[i].out_offset / out_size), all with the same stream parameters; the blocks of all of them go
+ * through the kernels as ONE batch and every file's PCM lands at files[i].first_sample of the planes. */
+LINNEApiResult LINNEB200_DecodeFilesResident(struct LINNEDecoder *dec, const uint8_t *d_data, uint32_t data_size,
+        struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride)
+{
+    struct LINNEHeader h0, h1;
+    LnbDecodeBatch batch;
+    LnbBlockDesc *blocks;
+    const uint8_t *img;
+    LINNEApiResult ret, overall = LINNE_APIRESULT_OK;
+    uint32_t i, k, nb = 0, cap, C;
+    uint32_t *first_block;
+    if (dec == NULL || d_data == NULL || files == NULL || num_files == 0 || d_pcm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    for (i = 0; i < num_files; i++) {
+        if ((uint64_t)files[i].out_offset + files[i].out_size > data_size
+            || (uint64_t)files[i].first_sample + files[i].num_samples > pcm_stride) return LINNE_APIRESULT_INVALID_ARGUMENT;
+        files[i].status = (int32_t)LINNE_APIRESULT_OK;
+    }
+    /* the image comes to the host once for the block hop (it is ~4x smaller than the PCM it decodes to) */
+    if (lnb_buf_reserve_host(&dec->h_stream, (size_t)data_size + 16u)) return LINNE_APIRESULT_NG;
+    lnb_shim_d2h(dec->dev, dec->h_stream.ptr, d_data, data_size);
+    if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+    img = (const uint8_t *)dec->h_stream.ptr;
+    if ((ret = LINNEDecoder_DecodeHeader(img + files[0].out_offset, files[0].out_size, &h0)) != LINNE_APIRESULT_OK) return ret;
+    if ((ret = LINNEDecoder_SetHeader(dec, &h0)) != LINNE_APIRESULT_OK) return ret;
+    C = h0.num_channels;
+    if (!(first_block = (uint32_t *)malloc(((size_t)num_files + 1u) * sizeof(uint32_t)))) return LINNE_APIRESULT_NG;
+
+    cap = 64u;
+    for (i = 0; i < num_files; i++) cap += files[i].out_size / 64u + 16u;
+    if (lnb_buf_reserve_host(&dec->h_blocks, (size_t)cap * sizeof(LnbBlockDesc))) { free(first_block); return LINNE_APIRESULT_NG; }
+    blocks = (LnbBlockDesc *)dec->h_blocks.ptr;
+    for (i = 0; i < num_files; i++) {
+        BlockScan scan;
+        first_block[i] = nb;
+        ret = LINNEDecoder_DecodeHeader(img + files[i].out_offset, files[i].out_size, &h1);
+        if (ret == LINNE_APIRESULT_OK
+            && (h1.num_channels != h0.num_channels || h1.bits_per_sample != h0.bits_per_sample || h1.preset != h0.preset
+                || h1.num_samples_per_block != h0.num_samples_per_block || h1.ch_process_method != h0.ch_process_method
+                || h1.format_version != h0.format_version || h1.codec_version != h0.codec_version))
+            ret = LINNE_APIRESULT_INVALID_FORMAT;                     /* one set of stream parameters per batch */
+        if (ret == LINNE_APIRESULT_OK && files[i].num_samples < h1.num_samples) ret = LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+        if (ret != LINNE_APIRESULT_OK) { files[i].status = (int32_t)ret; continue; }
+        /* offsets relative to the image; a file's hop cannot run into its neighbour */
+        if (scan_blocks(&h1, img, files[i].out_offset + files[i].out_size, files[i].out_offset + LINNE_HEADER_SIZE,
+                        files[i].num_samples, h1.num_samples, 0, blocks + nb, cap - nb, &scan)) {
+            free(first_block);
+            return LINNE_APIRESULT_NG;                                /* the table bound above covers every legal stream */
+        }
+        for (k = 0; k < scan.num_blocks; k++) blocks[nb + k].smp_off += files[i].first_sample;
+        for (k = scan.num_decodable; k < scan.num_blocks; k++) blocks[nb + k].type = 0xFFu;    /* CRC pass only */
+        if (scan.num_blocks > scan.num_decodable) files[i].status = (int32_t)scan.post_crc_error;
+        else files[i].status = (int32_t)scan.framing_error;
+        nb += scan.num_blocks;
+    }
+    first_block[num_files] = nb;
+
+    if (nb) {
+        lnb_fill_stream_cfg(&batch.cfg, &h0);
+        batch.cfg.pcm_stride = pcm_stride;
+        batch.cfg.work_stride = 0;
+        batch.cfg.check_crc = (dec->flags & DEC_FLAG_CHECK_CRC) ? 1u : 0u;
+        if (lnb_buf_reserve_device(dec->dev, &dec->d_blocks, (size_t)nb * sizeof(LnbBlockDesc))
+            || lnb_buf_reserve_device(dec->dev, &dec->d_params, (size_t)nb * C * sizeof(LnbChanParams))) { free(first_block); return LINNE_APIRESULT_NG; }
+        {
+            const char *split = getenv("LINNE_B200_SPLIT_DECODE");
+            batch.fused_max_n = (split && *split == '1') ? 0u : lnb_shim_fused_max_n();
+            batch.num_plain_blocks = 0;
+            for (k = 0; k < nb; k++)
+                if (blocks[k].type != LNB_BLOCK_COMPRESSED || blocks[k].nsmp == 0u || blocks[k].nsmp > batch.fused_max_n)
+                    batch.num_plain_blocks++;
+        }
+        batch.tput = (dec->tput_min_blocks && nb >= dec->tput_min_blocks && batch.fused_max_n
+                      && ((uintptr_t)d_pcm & 15u) == 0u && (pcm_stride & 3u) == 0u
+                      && lnb_shim_tput_supported(&batch.cfg)) ? 1u : 0u;
+        batch.tab = *lnb_shim_tables(dec->dev);
+        batch.stream = d_data;
+        batch.stream_size = data_size;
+        batch.blocks = (LnbBlockDesc *)dec->d_blocks.ptr;
+        batch.num_blocks = nb;
+        batch.params = (LnbChanParams *)dec->d_params.ptr;
+        batch.pcm = d_pcm;
+        lnb_shim_h2d(dec->dev, dec->d_blocks.ptr, blocks, (size_t)nb * sizeof(LnbBlockDesc));
+        if (lnb_shim_decode(dec->dev, &batch)) { free(first_block); return LINNE_APIRESULT_NG; }
+        lnb_shim_d2h(dec->dev, blocks, dec->d_blocks.ptr, (size_t)nb * sizeof(LnbBlockDesc));
+        if (lnb_shim_sync(dec->dev)) { free(first_block); return LINNE_APIRESULT_NG; }
+    }
+    for (i = 0; i < num_files; i++) {
+        if (dec->flags & DEC_FLAG_CHECK_CRC)
+            for (k = first_block[i]; k < first_block[i + 1u]; k++)
+                if (blocks[k].status & LNB_ST_CRC_MISMATCH) { files[i].status = (int32_t)LINNE_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+        if (overall == LINNE_APIRESULT_OK && files[i].status != (int32_t)LINNE_APIRESULT_OK) overall = (LINNEApiResult)files[i].status;
+    }
+    free(first_block);
+    return overall;
+}
+
 /* Packed interleaved PCM out (the bytes of a WAV data chunk), converted from the planes on the device.
  * `pcm` holds `pcm_capacity_frames` frames; `num_frames` receives the frames written.  SURVEY 8f.2. */
 LINNEApiResult LINNEB200_DecodeWholePacked(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,

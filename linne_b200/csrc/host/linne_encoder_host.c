@@ -7,6 +7,7 @@
  */
 #define _POSIX_C_SOURCE 199309L
 #include "linne_encoder.h"
+#include "linne_b200.h"
 #include "lnb_host_util.h"
 
 #include <stdio.h>
@@ -18,6 +19,8 @@
 static int trace_on(void) { static int on = -1; if (on < 0) { const char *e = getenv("LINNE_B200_TRACE"); on = (e && *e == '1') ? 1 : 0; } return on; }
 static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 #define TRACE(enc, what) do { if (trace_on()) fprintf(stderr, "[trace] m%u %-14s %.3f\n", (unsigned)(enc)->header.preset, what, now_ms()); } while (0)
+
+struct LnbFileRange { uint32_t first_sample, num_samples, first_block, num_blocks; };
 
 struct LINNEEncoder {
     struct LINNEHeader header;
@@ -32,6 +35,11 @@ struct LINNEEncoder {
     uint32_t sinwin_n;                     /* block length d_sinwin was tabulated for (0 = none) */
     const int32_t *cur_pcm;                /* device PCM planes of the call in flight */
     uint32_t cur_pcm_stride;
+    /* corpus batches (LINNEB200_EncodeFilesResident): the sample ranges of the files of the call in flight */
+    const struct LnbFileRange *ranges;
+    uint32_t num_ranges;
+    struct LINNEB200FileDesc *file_out;    /* per-file results of that call */
+    LnbBuf h_headers;                      /* pinned 32-byte slots for the files' stream headers */
 };
 
 /* reference linne_encoder.c:53-138 */
@@ -105,6 +113,7 @@ void LINNEEncoder_Destroy(struct LINNEEncoder *enc)
         lnb_buf_release_host(&enc->h_blocks);
         lnb_buf_release_host(&enc->h_welch);
         lnb_buf_release_host(&enc->h_total);
+        lnb_buf_release_host(&enc->h_headers);
         lnb_shim_close(enc->dev);
         enc->dev = NULL;
     }
@@ -162,16 +171,24 @@ static uint32_t analysis_length(const LnbStreamCfg *cfg, uint32_t n)
 /* Encode the blocks covering samples [first_sample, first_sample + num_samples) of the device PCM
  * planes into data[0..data_size); blocks are cut every header.num_samples_per_block samples. */
 /* `data` is a host buffer unless `data_on_device` is set; `forced` (optional, host memory,
- * [total_blocks * C]) supplies unit counts / shifts / coefficients and skips the analysis. */
+ * [total_blocks * C]) supplies unit counts / shifts / coefficients and skips the analysis.
+ * data_on_device == 2 (corpus batch, enc->ranges set): the blocks of SEVERAL files go through the kernels as one
+ * batch -- blocks are cut per file, packed back to back into the staging buffer, and every file's byte range is then
+ * moved behind its own 30-byte header in `data` (device-to-device), files laid out one after the other. */
 static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_samples,
                                     uint8_t *data, uint32_t data_size, int data_on_device,
                                     const LnbChanParams *forced, uint32_t *written)
 {
     const struct LINNEHeader *h = &enc->header;
     const uint32_t C = h->num_channels, NB = h->num_samples_per_block;
-    const uint32_t total_blocks = (uint32_t)(((uint64_t)num_samples + NB - 1u) / NB);
+    const int files_mode = (data_on_device == 2);
+    const uint32_t total_blocks = files_mode
+        ? enc->ranges[enc->num_ranges - 1u].first_block + enc->ranges[enc->num_ranges - 1u].num_blocks
+        : (uint32_t)(((uint64_t)num_samples + NB - 1u) / NB);
     LnbEncodeBatch batch;
     uint32_t lambdas, slots_per_block, chunk_blocks, first, out_off = 0, i, lvl;
+    uint32_t fcur = 0;                     /* files mode: file of the first block of the chunk being built */
+    uint32_t fdone = 0, fbytes = 0;        /* files mode: file being written out, block bytes it has received so far */
     size_t per_block;
 
     memset(&batch, 0, sizeof(batch));
@@ -205,7 +222,7 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
         while ((uint64_t)chunk_blocks * slots_per_block * ws >= 0x7FFFFFFFull && chunk_blocks > 1u) chunk_blocks /= 2u;
         {
             const size_t S = (size_t)chunk_blocks * slots_per_block, BC = (size_t)chunk_blocks * C;
-            if (lnb_buf_reserve_host(&enc->h_blocks, chunk_blocks * sizeof(LnbBlockDesc))
+            if (lnb_buf_reserve_host(&enc->h_blocks, 2u * (size_t)chunk_blocks * sizeof(LnbBlockDesc))
                 || lnb_buf_reserve_host(&enc->h_welch, (size_t)chunk_blocks * LNB_MAX_LEVELS * sizeof(double))
                 || lnb_buf_reserve_host(&enc->h_total, 64)
                 || lnb_buf_reserve_device(enc->dev, &enc->d_blocks, chunk_blocks * sizeof(LnbBlockDesc))
@@ -262,12 +279,23 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     for (first = 0; first < total_blocks; first += chunk_blocks) {
         const uint32_t nb = (total_blocks - first < chunk_blocks) ? total_blocks - first : chunk_blocks;
         LnbBlockDesc *hb = (LnbBlockDesc *)enc->h_blocks.ptr;
+        LnbBlockDesc *hres = hb + chunk_blocks;                 /* files mode: second half of h_blocks */
         double *hw = (double *)enc->h_welch.ptr;
         uint32_t chunk_bytes, num_fast = 0, num_coop = 0;
         const uint32_t fast_max_na = lnb_shim_fast_max_na(), coop_max_n = lnb_shim_coop_max_n();
         for (i = 0; i < nb; i++) {
-            const uint32_t start = (first + i) * NB;
-            const uint32_t n = (num_samples - start < NB) ? num_samples - start : NB;
+            uint32_t start, n;
+            if (files_mode) {
+                const struct LnbFileRange *fr;
+                while (first + i >= enc->ranges[fcur].first_block + enc->ranges[fcur].num_blocks) fcur++;
+                fr = &enc->ranges[fcur];
+                start = (first + i - fr->first_block) * NB;
+                n = (fr->num_samples - start < NB) ? fr->num_samples - start : NB;
+                start += fr->first_sample;
+            } else {
+                start = (first + i) * NB;
+                n = (num_samples - start < NB) ? num_samples - start : NB;
+            }
             memset(&hb[i], 0, sizeof(hb[i]));
             hb[i].smp_off = start; hb[i].nsmp = n; hb[i].na = analysis_length(&batch.cfg, n);
             if (hb[i].na <= fast_max_na) {                      /* cooperative analysis: fast layout or generic path */
@@ -303,7 +331,7 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
                 }
                 if (lnb_shim_encode_analyze(enc->dev, &batch)) return LINNE_APIRESULT_NG;
                 if (attempt == 0) {
-                    if (data_on_device) {
+                    if (data_on_device == 1) {
                         spec_cap = (size_t)data_size - out_off;
                         batch.out = data + out_off;       /* block offsets from the scan are relative to the chunk */
                     } else {
@@ -315,14 +343,15 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
                     if (lnb_shim_encode_pack(enc->dev, &batch, (uint32_t)spec_cap)) return LINNE_APIRESULT_NG;
                 }
                 lnb_shim_d2h(enc->dev, enc->h_total.ptr, enc->d_total.ptr, sizeof(uint32_t));
+                if (files_mode) lnb_shim_d2h(enc->dev, hres, enc->d_blocks.ptr, nb * sizeof(LnbBlockDesc));   /* byte offsets */
                 TRACE(enc, "enqueued");
                 if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
                 TRACE(enc, "sizes known");
                 chunk_bytes = *(uint32_t *)enc->h_total.ptr;
-                if ((uint64_t)out_off + chunk_bytes > data_size) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+                if (!files_mode && (uint64_t)out_off + chunk_bytes > data_size) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
                 if (attempt == 0 && chunk_bytes <= spec_cap) break;          /* everything fitted: the chunk is packed */
                 if (attempt == 1) {
-                    if (!data_on_device) {
+                    if (data_on_device != 1) {
                         if (lnb_buf_reserve_device(enc->dev, &enc->d_out, (size_t)chunk_bytes + 64u)) return LINNE_APIRESULT_NG;
                         batch.out = (uint8_t *)enc->d_out.ptr;
                     }
@@ -330,11 +359,39 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
                 }
             }
             if (!data_on_device) lnb_shim_d2h(enc->dev, data + out_off, enc->d_out.ptr, chunk_bytes);
+            if (files_mode) {
+                /* runs of blocks of one file are contiguous in the staging buffer: move each run behind its file's
+                 * header; a file that has all its blocks gets its header and its entry in the result table */
+                uint32_t lo = 0;
+                const LnbBlockDesc *hb = hres;                                             /* the table as the device left it */
+                while (lo < nb) {
+                    const struct LnbFileRange *fr = &enc->ranges[fdone];
+                    const uint32_t file_end = fr->first_block + fr->num_blocks;            /* global block index */
+                    const uint32_t hi = (file_end - first < nb) ? file_end - first : nb;   /* chunk-relative */
+                    const uint32_t run = hb[hi - 1u].byte_off + hb[hi - 1u].byte_size - hb[lo].byte_off;
+                    if ((uint64_t)out_off + LINNE_HEADER_SIZE + fbytes + run > data_size) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+                    lnb_shim_d2d(enc->dev, data + out_off + LINNE_HEADER_SIZE + fbytes,
+                                 (const uint8_t *)enc->d_out.ptr + hb[lo].byte_off, run);
+                    fbytes += run;
+                    lo = hi;
+                    if (first + hi == file_end) {                                          /* the file is complete */
+                        uint8_t *hdr = (uint8_t *)enc->h_headers.ptr + 32u * fdone;
+                        struct LINNEHeader h1 = *h;
+                        h1.num_samples = fr->num_samples;
+                        lnb_header_write(&h1, hdr);
+                        lnb_shim_h2d(enc->dev, data + out_off, hdr, LINNE_HEADER_SIZE);
+                        enc->file_out[fdone].out_offset = out_off;
+                        enc->file_out[fdone].out_size = LINNE_HEADER_SIZE + fbytes;
+                        out_off += LINNE_HEADER_SIZE + fbytes;
+                        fbytes = 0; fdone++;
+                    }
+                }
+            }
             TRACE(enc, "pack enqueued");
             if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
             TRACE(enc, "chunk done");
         }
-        out_off += chunk_bytes;
+        if (!files_mode) out_off += chunk_bytes;
     }
     *written = out_off;
     return LINNE_APIRESULT_OK;
@@ -449,6 +506,43 @@ LINNEApiResult LINNEB200_EncodeWholeResident(struct LINNEEncoder *enc, const int
     ret = encode_blocks(enc, num_samples, d_data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, 1, NULL, &written);
     if (ret != LINNE_APIRESULT_OK) return ret;
     *output_size = LINNE_HEADER_SIZE + written;
+    return LINNE_APIRESULT_OK;
+}
+
+/* Several files per call (corpus batches, SURVEY 8e: "concatenate files' block lists, keeping per-file boundaries").
+ * All files share the encoder's parameters; their PCM sits in one set of device planes [C][pcm_stride], file i at
+ * samples [first_sample, first_sample + num_samples).  Every block x channel of every file is one batch for the
+ * kernels; the streams are written one after the other into `d_data` (header + blocks each, byte-identical with
+ * what EncodeWhole writes for that file) and files[i].out_offset / out_size say where. */
+LINNEApiResult LINNEB200_EncodeFilesResident(struct LINNEEncoder *enc, const int32_t *d_pcm, uint32_t pcm_stride,
+        struct LINNEB200FileDesc *files, uint32_t num_files, uint8_t *d_data, uint32_t data_size, uint32_t *output_size)
+{
+    struct LnbFileRange *ranges;
+    LINNEApiResult ret;
+    uint32_t written = 0, i, blocks = 0, NB;
+    if (enc == NULL || d_pcm == NULL || files == NULL || num_files == 0 || d_data == NULL || output_size == NULL)
+        return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
+    if (unsupported_analysis(enc)) return LINNE_APIRESULT_NG;
+    NB = enc->header.num_samples_per_block;
+    if (!(ranges = (struct LnbFileRange *)malloc((size_t)num_files * sizeof(*ranges)))) return LINNE_APIRESULT_NG;
+    for (i = 0; i < num_files; i++) {
+        if (files[i].num_samples == 0 || (uint64_t)files[i].first_sample + files[i].num_samples > pcm_stride) { free(ranges); return LINNE_APIRESULT_INVALID_ARGUMENT; }
+        ranges[i].first_sample = files[i].first_sample; ranges[i].num_samples = files[i].num_samples;
+        ranges[i].first_block = blocks;
+        ranges[i].num_blocks = (uint32_t)(((uint64_t)files[i].num_samples + NB - 1u) / NB);
+        blocks += ranges[i].num_blocks;
+        files[i].out_offset = files[i].out_size = 0;
+    }
+    if (lnb_buf_reserve_host(&enc->h_headers, (size_t)num_files * 32u)) { free(ranges); return LINNE_APIRESULT_NG; }
+    enc->ranges = ranges; enc->num_ranges = num_files; enc->file_out = files;
+    enc->cur_pcm = d_pcm; enc->cur_pcm_stride = pcm_stride;
+    enc->header.num_samples = files[0].num_samples;
+    ret = encode_blocks(enc, 0, d_data, data_size, 2, NULL, &written);
+    enc->ranges = NULL; enc->num_ranges = 0; enc->file_out = NULL;
+    free(ranges);
+    if (ret != LINNE_APIRESULT_OK) return ret;
+    *output_size = written;
     return LINNE_APIRESULT_OK;
 }
 

@@ -48,6 +48,7 @@ void *lnb_shim_alloc_pinned(size_t bytes);
 void  lnb_shim_free_pinned(void *ptr);
 int   lnb_shim_h2d(LnbDevice *dev, void *dst, const void *src, size_t bytes);      /* async on the stream */
 int   lnb_shim_d2h(LnbDevice *dev, void *dst, const void *src, size_t bytes);      /* async on the stream */
+int   lnb_shim_d2d(LnbDevice *dev, void *dst, const void *src, size_t bytes);      /* async on the stream */
 int   lnb_shim_memset(LnbDevice *dev, void *dst, int value, size_t bytes);
 int   lnb_shim_sync(LnbDevice *dev);     /* 0 on success; non-zero reports a CUDA error */
 

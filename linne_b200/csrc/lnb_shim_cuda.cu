@@ -456,6 +456,11 @@ int lnb_shim_h2d(LnbDevice *dev, void *dst, const void *src, size_t bytes)
     bind_device(dev);
     return bytes ? note(dev, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, dev->stream)) : 0;
 }
+int lnb_shim_d2d(LnbDevice *dev, void *dst, const void *src, size_t bytes)
+{
+    bind_device(dev);
+    return bytes ? note(dev, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, dev->stream)) : 0;
+}
 int lnb_shim_d2h(LnbDevice *dev, void *dst, const void *src, size_t bytes)
 {
     bind_device(dev);

@@ -61,6 +61,7 @@ void *lnb_shim_alloc_pinned(size_t bytes) { return calloc(1, bytes ? bytes : 16)
 void lnb_shim_free_pinned(void *p) { free(p); }
 int lnb_shim_h2d(LnbDevice *, void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
 int lnb_shim_d2h(LnbDevice *, void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); return 0; }
+int lnb_shim_d2d(LnbDevice *, void *d, const void *s, size_t n) { if (n) memmove(d, s, n); return 0; }
 int lnb_shim_memset(LnbDevice *, void *d, int v, size_t n) { if (n) memset(d, v, n); return 0; }
 int lnb_shim_sync(LnbDevice *) { return 0; }
 int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *b) { LoopExec ex{dev}; lnb_decode_pipeline(ex, *b); return 0; }
