@@ -509,11 +509,17 @@ def run_c5(args, dev, rank, world):
     cap = 30 + nch * n * 2 + 11 * (n // BLOCK + 2) + 65536
     lo, hi = rank * args.c5_files // world, (rank + 1) * args.c5_files // world
     J = max(1, args.c5_workers)
+    K = max(1, args.c5_batch)
+    if K > 1:
+        from linne_b200 import FileDesc
+        d_corpus = torch.zeros((nch, K * stride), dtype=torch.int32, device=dev)      # K files side by side, variants cycled
+        for s_ in range(K):
+            d_corpus[:, s_ * stride:s_ * stride + stride].copy_(variants[s_ % len(variants)])
     out = {"workload": f"C5: {args.c5_files} files x {args.c5_file_seconds:.0f} s stereo 16-bit 44.1 kHz "
                        f"({args.c5_files * args.c5_file_seconds / 3600.0:.1f} h), {(n + BLOCK - 1) // BLOCK} blocks per file, "
                        "encode + decode of every file, files sharded by contiguous range over the ranks",
            "unit": "MSamples/s", "scaling": "strong", "workers_per_rank": J, "files_per_rank": hi - lo,
-           "decoder_throughput_blocks": args.c5_tput_blocks,
+           "decoder_throughput_blocks": args.c5_tput_blocks, "files_per_call": K,
            "note": "samples counted once per file (a file that went through encode and decode counts once)"}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -538,21 +544,52 @@ def run_c5(args, dev, rank, world):
         decs = [DecoderSession(channels=nch) for _ in range(J)]
         for s_ in decs:                                             # several handles in flight: see include/linne_b200.h
             s_.lib.LINNEB200_DecoderSetThroughputBlocks(s_.h, args.c5_tput_blocks)
-        d_streams = [torch.zeros(cap + 64, dtype=torch.uint8, device=dev) for _ in range(J)]
-        d_backs = [torch.zeros((nch, stride), dtype=torch.int32, device=dev) for _ in range(J)]
         last = [None] * J
         sizes = [0] * J
         errs = []
+        if K > 1:
+            # corpus batches: K files per call (LINNEB200_EncodeFilesResident / DecodeFilesResident)
+            d_streams = [torch.zeros(K * cap + 64, dtype=torch.uint8, device=dev) for _ in range(J)]
+            d_backs = [torch.zeros((nch, K * stride), dtype=torch.int32, device=dev) for _ in range(J)]
+            descs = [(FileDesc * K)() for _ in range(J)]
 
-        def work(j, count):
-            try:
-                for f in range(j, count, J):
-                    v = (lo + f) % len(variants)
-                    sz = encs[j].encode_whole_resident(variants[v].data_ptr(), stride, n, d_streams[j].data_ptr(), cap)
-                    decs[j].decode_whole_resident(None, d_streams[j].data_ptr(), sz, d_backs[j].data_ptr(), stride, nch, n)
-                    last[j], sizes[j] = v, sz
-            except Exception as e:  # pragma: no cover
-                errs.append(e)
+            def work(j, count):
+                try:
+                    total = C.c_uint32(0)
+                    lib = encs[j].lib
+                    for b0 in range(j * K, count, J * K):
+                        k = min(K, count - b0)
+                        for s_ in range(k):
+                            descs[j][s_] = FileDesc(s_ * stride, n, 0, 0, 0)
+                        rc = lib.LINNEB200_EncodeFilesResident(encs[j].h, C.c_void_p(d_corpus.data_ptr()), K * stride, descs[j], k,
+                                                               C.c_void_p(d_streams[j].data_ptr()), K * cap, C.byref(total))
+                        rc = rc or lib.LINNEB200_DecodeFilesResident(decs[j].h, C.c_void_p(d_streams[j].data_ptr()), total.value, descs[j], k,
+                                                                     C.c_void_p(d_backs[j].data_ptr()), K * stride)
+                        if rc != 0:
+                            raise RuntimeError(f"corpus batch rc={rc}")
+                        last[j], sizes[j] = k, int(descs[j][0].out_size)
+                except Exception as e:  # pragma: no cover
+                    errs.append(e)
+
+            def check(j):
+                return last[j] is not None and all(bool(torch.equal(d_backs[j][:, s_ * stride:s_ * stride + n], d_corpus[:, s_ * stride:s_ * stride + n]))
+                                                   for s_ in range(last[j]))
+        else:
+            d_streams = [torch.zeros(cap + 64, dtype=torch.uint8, device=dev) for _ in range(J)]
+            d_backs = [torch.zeros((nch, stride), dtype=torch.int32, device=dev) for _ in range(J)]
+
+            def work(j, count):
+                try:
+                    for f in range(j, count, J):
+                        v = (lo + f) % len(variants)
+                        sz = encs[j].encode_whole_resident(variants[v].data_ptr(), stride, n, d_streams[j].data_ptr(), cap)
+                        decs[j].decode_whole_resident(None, d_streams[j].data_ptr(), sz, d_backs[j].data_ptr(), stride, nch, n)
+                        last[j], sizes[j] = v, sz
+                except Exception as e:  # pragma: no cover
+                    errs.append(e)
+
+            def check(j):
+                return last[j] is not None and bool(torch.equal(d_backs[j][:, :n], variants[last[j]][:, :n]))
 
         def run(count):
             ts = [threading.Thread(target=work, args=(j, count)) for j in range(J)]
@@ -560,12 +597,12 @@ def run_c5(args, dev, rank, world):
             for t in ts: t.join()
             if errs:
                 raise errs[0]
-        run(J)                                                      # warm-up: allocations
+        run(J * K)                                                  # warm-up: allocations
         barrier()
         e0.record(); run(nfiles); e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        ok = all(last[j] is not None and bool(torch.equal(d_backs[j][:, :n], variants[last[j]][:, :n])) for j in range(J))
+        ok = all(check(j) for j in range(J))
         launches = sum(s.launch_count() for s in encs + decs)
         if m == 0:
             size_m0 = int(sizes[0])
@@ -1039,6 +1076,8 @@ def main():
     ap.add_argument("--c5-file-seconds", type=float, default=360.0)
     ap.add_argument("--c5-m7-fraction", type=float, default=0.1, help="share of each rank's files also run at -m 7 (bounded)")
     ap.add_argument("--c5-workers", type=int, default=4, help="handle pairs (host threads / CUDA streams) per rank in the C5 leg")
+    ap.add_argument("--c5-batch", type=int, default=8,
+                    help="C5 leg: files per call (LINNEB200_EncodeFilesResident / DecodeFilesResident); 1 = one call per file")
     ap.add_argument("--c5-tput-blocks", type=int, default=1024,
                     help="C5 leg: LINNEB200_DecoderSetThroughputBlocks of its decoders (several handles in flight)")
     ap.add_argument("--c5-e2e-files", type=int, default=24, help="files per rank of the host-buffer pipeline leg; 0 = skip")
