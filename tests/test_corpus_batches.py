@@ -137,22 +137,22 @@ def test_corpus_batch_takes_the_throughput_decoder(gpu, oracle):
     """a batch of many files is one large decode: above the switch-over point it runs on the throughput kernels"""
     import torch
     L = gpu.lib
-    pcm = harness.synth_pcm(n=1024 * 40, channels=2, bits=16, seed=77)
-    nfiles, n = 80, pcm.shape[1]                                  # 80 files x 40 blocks of 1024 = 3200 blocks
+    pcm = harness.synth_pcm(n=2048 * 20, channels=2, bits=16, seed=77)
+    nfiles, n = 140, pcm.shape[1]                                 # 140 files x 20 blocks of 2048 = 2800 blocks
     planes = np.ascontiguousarray(np.tile(pcm, (1, nfiles)))
     d_pcm = torch.from_numpy(planes).cuda()
     cap = nfiles * (30 + pcm.size * 4 + 4096)
     d_out = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
     desc = (FileDesc * nfiles)(*[FileDesc(i * n, n, 0, 0, 0) for i in range(nfiles)])
-    enc = L.LINNEEncoder_Create(C.byref(LINNEEncoderConfig(2, 1024, 3, 128)), None, 0)
+    enc = L.LINNEEncoder_Create(C.byref(LINNEEncoderConfig(2, 2048, 3, 128)), None, 0)
     from linne_b200 import DecoderSession
     dec = DecoderSession(channels=2)
     try:
-        assert L.LINNEEncoder_SetEncodeParameter(enc, C.byref(LINNEEncodeParameter(2, 16, 44100, 1024, 6, 1, 0, 0))) == OK
+        assert L.LINNEEncoder_SetEncodeParameter(enc, C.byref(LINNEEncodeParameter(2, 16, 44100, 2048, 6, 1, 0, 0))) == OK
         total = C.c_uint32(0)
         assert L.LINNEB200_EncodeFilesResident(enc, C.c_void_p(d_pcm.data_ptr()), planes.shape[1], desc, nfiles,
                                                C.c_void_p(d_out.data_ptr()), cap, C.byref(total)) == OK
-        one = gpu.encode(pcm, preset=6, block=1024)
+        one = gpu.encode(pcm, preset=6, block=2048)
         image = d_out[:total.value].cpu().numpy()
         assert all(image[d.out_offset:d.out_offset + d.out_size].tobytes() == one for d in desc)
         d_back = torch.zeros_like(d_pcm)
