@@ -507,7 +507,8 @@ def run_c5(args, dev, rank, world):
         variants.append(d)
     samples_per_file = nch * n
     cap = 30 + nch * n * 2 + 11 * (n // BLOCK + 2) + 65536
-    lo, hi = rank * args.c5_files // world, (rank + 1) * args.c5_files // world
+    from linne_b200 import shard
+    lo, hi = shard.file_ranges(args.c5_files, world)[rank]
     J = max(1, args.c5_workers)
     K = max(1, args.c5_batch)
     if K > 1:

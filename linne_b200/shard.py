@@ -28,6 +28,12 @@ import numpy as np
 HEADER = 30
 
 
+def file_ranges(num_files: int, world: int):
+    """Contiguous file ranges [(lo, hi)] of a corpus over `world` ranks (per-file API calls are independent,
+    so ranks take whole files; bench.py's C5 leg and the corpus tools use the same split)."""
+    return [(r * num_files // world, (r + 1) * num_files // world) for r in range(world)]
+
+
 def block_ranges(num_samples: int, block: int, world: int):
     """Contiguous block ranges, as sample ranges [(lo, hi)] per rank (may be empty for high ranks)."""
     nblocks = (num_samples + block - 1) // block

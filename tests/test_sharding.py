@@ -59,3 +59,73 @@ def test_gloo_world_size_2_encode(hostsim, oracle):
     stream = results["stream"]
     assert stream == hostsim.encode(pcm, preset=0, block=2048)
     assert np.array_equal(oracle.decode(stream), pcm)
+
+
+# ---- a corpus sharded by contiguous FILE ranges, several files per call (LINNEB200_EncodeFilesResident) ----
+def test_file_ranges_cover_the_corpus():
+    for files, world in ((1000, 8), (5, 2), (3, 4), (1, 2)):
+        r = shard.file_ranges(files, world)
+        assert r[0][0] == 0 and r[-1][1] == files and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+
+
+def _encode_files_batch(codec, files, block, preset):
+    """one LINNEB200_EncodeFilesResident call over `files` (int32 [C][n] each) on the simulator -> [stream bytes]"""
+    import ctypes as C
+    from harness import LINNEEncodeParameter, LINNEEncoderConfig, OK
+    from linne_b200.api import FileDesc
+    if not files:
+        return []
+    L = codec.lib
+    nch = files[0].shape[0]
+    starts, off = [], 0
+    for f in files:
+        starts.append(off); off += (f.shape[1] + 3) // 4 * 4
+    planes = np.zeros((nch, max(off, 4)), np.int32)
+    for f, s in zip(files, starts):
+        planes[:, s:s + f.shape[1]] = f
+    cap = sum(30 + f.size * 4 + 4096 for f in files)
+    out = np.zeros(cap + 64, np.uint8)
+    desc = (FileDesc * len(files))(*[FileDesc(s, f.shape[1], 0, 0, 0) for f, s in zip(files, starts)])
+    enc = L.LINNEEncoder_Create(C.byref(LINNEEncoderConfig(nch, block, 3, 128)), None, 0)
+    try:
+        assert L.LINNEEncoder_SetEncodeParameter(enc, C.byref(LINNEEncodeParameter(nch, 16, 44100, block, preset, 1, 0, 0))) == OK
+        total = C.c_uint32(0)
+        assert L.LINNEB200_EncodeFilesResident(enc, C.c_void_p(planes.ctypes.data), planes.shape[1], desc, len(files),
+                                               C.c_void_p(out.ctypes.data), cap, C.byref(total)) == OK
+        return [out[d.out_offset:d.out_offset + d.out_size].tobytes() for d in desc]
+    finally:
+        L.LINNEEncoder_Destroy(enc)
+
+
+def _corpus_worker(rank, world, port, corpus, results):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        codec = harness.HostSim()
+        lo, hi = shard.file_ranges(len(corpus), world)[rank]
+        mine = _encode_files_batch(codec, corpus[lo:hi], 2048, 3)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(mine, gathered, dst=0)              # control plane only: the streams stay where they were made
+        if rank == 0:
+            results["streams"] = [s for part in gathered for s in part]
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_corpus_by_file_ranges(hostsim, oracle):
+    import torch.multiprocessing as mp
+    corpus = [harness.synth_pcm(n=n, channels=2, bits=16, seed=60 + i) for i, n in enumerate((2048 * 2 + 100, 2048, 3000, 2048 * 3, 700))]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_corpus_worker, args=(2, port, corpus, results), nprocs=2, join=True)
+    streams = results["streams"]
+    assert len(streams) == len(corpus)
+    for f, st in zip(corpus, streams):
+        assert st == hostsim.encode(f, preset=3, block=2048)
+        assert np.array_equal(oracle.decode(st), f)
