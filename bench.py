@@ -511,8 +511,8 @@ def run_c5(args, dev, rank, world):
     lo, hi = shard.file_ranges(args.c5_files, world)[rank]
     J = max(1, args.c5_workers)
     K = max(1, args.c5_batch)
+    from linne_b200 import FileDesc
     if K > 1:
-        from linne_b200 import FileDesc
         d_corpus = torch.zeros((nch, K * stride), dtype=torch.int32, device=dev)      # K files side by side, variants cycled
         for s_ in range(K):
             d_corpus[:, s_ * stride:s_ * stride + stride].copy_(variants[s_ % len(variants)])
@@ -621,18 +621,37 @@ def run_c5(args, dev, rank, world):
         u8p = C.POINTER(C.c_uint8)
         host_pcm = torch.from_numpy(np.ascontiguousarray(variants[0][:, :n].cpu().numpy().T).astype("<i2").view(np.uint8).reshape(-1)).pin_memory()
         e2e = {}
-        for J2 in (1, 3):
+        K2max = max(1, min(K, 4))
+        host_pcm_k = host_pcm
+        if K2max > 1:
+            host_pcm_k = torch.zeros(K2max * host_pcm.numel(), dtype=torch.uint8).pin_memory()
+            for s_ in range(K2max):
+                host_pcm_k[s_ * host_pcm.numel():(s_ + 1) * host_pcm.numel()].copy_(host_pcm)
+        for J2, K2 in ((1, 1), (3, 1), (3, K2max)):
             encs = [EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=0) for _ in range(J2)]
             decs = [DecoderSession(channels=nch) for _ in range(J2)]
             for s_ in decs:
                 s_.lib.LINNEB200_DecoderSetThroughputBlocks(s_.h, args.c5_tput_blocks if J2 > 1 else 2560)
-            h_lnn = [torch.zeros(cap, dtype=torch.uint8).pin_memory() for _ in range(J2)]
-            h_out = [torch.zeros(host_pcm.numel(), dtype=torch.uint8).pin_memory() for _ in range(J2)]
+            h_lnn = [torch.zeros(K2 * cap, dtype=torch.uint8).pin_memory() for _ in range(J2)]
+            h_out = [torch.zeros(K2 * host_pcm.numel(), dtype=torch.uint8).pin_memory() for _ in range(J2)]
             errs = []
 
             def work2(j, count):
                 try:
                     sz, fr = C.c_uint32(0), C.c_uint32(0)
+                    if K2 > 1:                                  # K2 files per call: LINNEB200_EncodeFilesPacked / DecodeFilesPacked
+                        desc = (FileDesc * K2)()
+                        for b0 in range(j * K2, count, J2 * K2):
+                            k = min(K2, count - b0)
+                            for s_ in range(k):
+                                desc[s_] = FileDesc(0, n, 0, 0, 0)
+                            rc = encs[j].lib.LINNEB200_EncodeFilesPacked(encs[j].h, C.cast(host_pcm_k.data_ptr(), u8p), desc, k,
+                                                                         C.cast(h_lnn[j].data_ptr(), u8p), K2 * cap, C.byref(sz))
+                            rc = rc or decs[j].lib.LINNEB200_DecodeFilesPacked(decs[j].h, C.cast(h_lnn[j].data_ptr(), u8p), sz.value, desc, k,
+                                                                               C.cast(h_out[j].data_ptr(), u8p))
+                            if rc != 0:
+                                raise RuntimeError(f"packed corpus batch rc={rc}")
+                        return
                     for f in range(j, count, J2):
                         rc = encs[j].lib.LINNEB200_EncodeWholePacked(encs[j].h, C.cast(host_pcm.data_ptr(), u8p), n,
                                                                      C.cast(h_lnn[j].data_ptr(), u8p), cap, C.byref(sz))
@@ -649,14 +668,16 @@ def run_c5(args, dev, rank, world):
                 for t in ts: t.join()
                 if errs:
                     raise errs[0]
-            run2(J2)
+            nf = max(J2 * K2, (args.c5_e2e_files // (J2 * K2)) * J2 * K2)      # whole batches for every worker
+            run2(J2 * K2)
             barrier()
-            e0.record(); run2(args.c5_e2e_files); e1.record()
+            e0.record(); run2(nf); e1.record()
             barrier()
             ms = max_over_ranks(e0.elapsed_time(e1))
-            ok = all(bool(torch.equal(h, host_pcm)) for h in h_out)
-            e2e[f"workers{J2}"] = {"value": round(world * args.c5_e2e_files * samples_per_file / (ms / 1e3) / 1e6, 1),
-                                   "ms_per_file_per_rank": round(ms / args.c5_e2e_files, 3), "lossless": ok}
+            ok = all(bool(torch.equal(h[:host_pcm.numel()], host_pcm)) and bool(torch.equal(h[-host_pcm.numel():], host_pcm)) for h in h_out)
+            tag = f"workers{J2}" + (f"_files_per_call{K2}" if K2 > 1 else "")
+            e2e[tag] = {"value": round(world * nf * samples_per_file / (ms / 1e3) / 1e6, 1),
+                        "ms_per_file_per_rank": round(ms / nf, 3), "files_per_rank": nf, "lossless": ok}
             for s in encs + decs:
                 s.close()
             del h_lnn, h_out
@@ -664,7 +685,8 @@ def run_c5(args, dev, rank, world):
         e2e["preset"] = 0
         e2e["h2d_bytes_per_file"] = int(host_pcm.numel()) + size_m0
         e2e["d2h_bytes_per_file"] = int(host_pcm.numel()) + size_m0
-        e2e["call"] = "LINNEB200_EncodeWholePacked + LINNEB200_DecodeWholePacked on page-locked host buffers (what linne_b200_cli -j N runs per file)"
+        e2e["call"] = ("LINNEB200_EncodeWholePacked + LINNEB200_DecodeWholePacked on page-locked host buffers (what linne_b200_cli -j N runs "
+                       "per file); files_per_call: LINNEB200_EncodeFilesPacked + LINNEB200_DecodeFilesPacked")
         out["e2e_pipeline_m0"] = e2e
     del variants
     torch.cuda.empty_cache()

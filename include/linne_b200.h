@@ -62,6 +62,13 @@ LINNEApiResult LINNEB200_EncodeFilesResident(struct LINNEEncoder *encoder, const
         struct LINNEB200FileDesc *files, uint32_t num_files, uint8_t *d_data, uint32_t data_size, uint32_t *output_size);
 LINNEApiResult LINNEB200_DecodeFilesResident(struct LINNEDecoder *decoder, const uint8_t *d_data, uint32_t data_size,
         struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride);
+/* The same with host buffers, as a corpus tool holds them: the files' frames back to back as packed interleaved PCM
+ * (WAV data-chunk layout, files[i].num_samples frames each; first_sample is filled in) and the streams one after the
+ * other in a host image.  One transfer up, one conversion, one batch for the kernels, one transfer down. */
+LINNEApiResult LINNEB200_EncodeFilesPacked(struct LINNEEncoder *encoder, const uint8_t *pcm, struct LINNEB200FileDesc *files,
+        uint32_t num_files, uint8_t *data, uint32_t data_size, uint32_t *output_size);
+LINNEApiResult LINNEB200_DecodeFilesPacked(struct LINNEDecoder *decoder, const uint8_t *data, uint32_t data_size,
+        struct LINNEB200FileDesc *files, uint32_t num_files, uint8_t *pcm);
 
 /* ---- packed PCM entry points ------------------------------------------------------------
  * `pcm` = interleaved little-endian samples exactly as in a WAV data chunk (8-bit unsigned with a bias of 128,

@@ -234,6 +234,10 @@ def bind_ext_api(lib):
     lib.LINNEB200_DecodeFilesResident.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(FileDesc), C.c_uint32,
                                                   C.c_void_p, C.c_uint32]
     lib.LINNEB200_DecodeFilesResident.restype = C.c_int
+    lib.LINNEB200_EncodeFilesPacked.argtypes = [C.c_void_p, u8p, C.POINTER(FileDesc), C.c_uint32, u8p, C.c_uint32, u32p]
+    lib.LINNEB200_EncodeFilesPacked.restype = C.c_int
+    lib.LINNEB200_DecodeFilesPacked.argtypes = [C.c_void_p, u8p, C.c_uint32, C.POINTER(FileDesc), C.c_uint32, u8p]
+    lib.LINNEB200_DecodeFilesPacked.restype = C.c_int
     lib.LINNEB200_DecoderSetReadahead.argtypes = [C.c_void_p, C.c_uint32]
     lib.LINNEB200_DecoderSetThroughputBlocks.argtypes = [C.c_void_p, C.c_uint32]
     lib.LINNEB200_HostAlloc.argtypes = [C.c_size_t]

@@ -511,7 +511,7 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uin
 /* Several streams per call (corpus batches): the streams sit one after the other in the device image
  * `d_data` (files[i].out_offset / out_size), all with the same stream parameters; the blocks of all of them go
  * through the kernels as ONE batch and every file's PCM lands at files[i].first_sample of the planes. */
-LINNEApiResult LINNEB200_DecodeFilesResident(struct LINNEDecoder *dec, const uint8_t *d_data, uint32_t data_size,
+static LINNEApiResult decode_files(struct LINNEDecoder *dec, const uint8_t *host_image, const uint8_t *d_data, uint32_t data_size,
         struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride)
 {
     struct LINNEHeader h0, h1;
@@ -527,11 +527,15 @@ LINNEApiResult LINNEB200_DecodeFilesResident(struct LINNEDecoder *dec, const uin
             || (uint64_t)files[i].first_sample + files[i].num_samples > pcm_stride) return LINNE_APIRESULT_INVALID_ARGUMENT;
         files[i].status = (int32_t)LINNE_APIRESULT_OK;
     }
-    /* the image comes to the host once for the block hop (it is ~4x smaller than the PCM it decodes to) */
-    if (lnb_buf_reserve_host(&dec->h_stream, (size_t)data_size + 16u)) return LINNE_APIRESULT_NG;
-    lnb_shim_d2h(dec->dev, dec->h_stream.ptr, d_data, data_size);
-    if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
-    img = (const uint8_t *)dec->h_stream.ptr;
+    if (host_image) {
+        img = host_image;
+    } else {
+        /* the image comes to the host once for the block hop (it is ~4x smaller than the PCM it decodes to) */
+        if (lnb_buf_reserve_host(&dec->h_stream, (size_t)data_size + 16u)) return LINNE_APIRESULT_NG;
+        lnb_shim_d2h(dec->dev, dec->h_stream.ptr, d_data, data_size);
+        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+        img = (const uint8_t *)dec->h_stream.ptr;
+    }
     if ((ret = LINNEDecoder_DecodeHeader(img + files[0].out_offset, files[0].out_size, &h0)) != LINNE_APIRESULT_OK) return ret;
     if ((ret = LINNEDecoder_SetHeader(dec, &h0)) != LINNE_APIRESULT_OK) return ret;
     C = h0.num_channels;
@@ -604,6 +608,46 @@ LINNEApiResult LINNEB200_DecodeFilesResident(struct LINNEDecoder *dec, const uin
     }
     free(first_block);
     return overall;
+}
+
+LINNEApiResult LINNEB200_DecodeFilesResident(struct LINNEDecoder *dec, const uint8_t *d_data, uint32_t data_size,
+        struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride)
+{
+    return decode_files(dec, NULL, d_data, data_size, files, num_files, d_pcm, pcm_stride);
+}
+
+/* The same for host buffers: the streams in the host image `data` (files[i].out_offset / out_size), the PCM of the
+ * files back to back as packed interleaved samples in `pcm`, files[i].num_samples frames of room each
+ * (first_sample is filled in: the frame offset of the file in `pcm`).  One transfer up, one batch, one down. */
+LINNEApiResult LINNEB200_DecodeFilesPacked(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
+        struct LINNEB200FileDesc *files, uint32_t num_files, uint8_t *pcm)
+{
+    struct LINNEHeader h0;
+    LINNEApiResult ret;
+    uint64_t total = 0;
+    uint32_t i, bytes, C;
+    size_t stride, padded;
+    if (dec == NULL || data == NULL || files == NULL || num_files == 0 || pcm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (files[0].out_offset > data_size || files[0].out_size > data_size - files[0].out_offset) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if ((ret = LINNEDecoder_DecodeHeader(data + files[0].out_offset, files[0].out_size, &h0)) != LINNE_APIRESULT_OK) return ret;
+    bytes = h0.bits_per_sample / 8u; C = h0.num_channels;
+    if (bytes == 0 || bytes > 4u || (h0.bits_per_sample % 8u) != 0u || C == 0u) return LINNE_APIRESULT_INVALID_FORMAT;
+    for (i = 0; i < num_files; i++) { files[i].first_sample = (uint32_t)total; total += files[i].num_samples; }
+    if (total == 0 || total > 0xFFFFFFF0ull) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    stride = LNB_ROUNDUP((size_t)total + 4u, 4u);
+    padded = LNB_ROUNDUP((size_t)data_size + 16u, 16u);
+    if (lnb_buf_reserve_device(dec->dev, &dec->d_stream, padded)
+        || lnb_buf_reserve_device(dec->dev, &dec->d_pcm, stride * C * sizeof(int32_t))
+        || lnb_buf_reserve_device(dec->dev, &dec->d_packed, (size_t)total * C * bytes + 16u)) return LINNE_APIRESULT_NG;
+    lnb_shim_memset(dec->dev, (uint8_t *)dec->d_stream.ptr + (padded - 16u), 0, 16u);
+    lnb_shim_h2d(dec->dev, dec->d_stream.ptr, data, data_size);
+    ret = decode_files(dec, data, (const uint8_t *)dec->d_stream.ptr, data_size, files, num_files, (int32_t *)dec->d_pcm.ptr, (uint32_t)stride);
+    /* every file that decoded is handed back; a failed file's frames are undefined */
+    if (lnb_shim_pack_pcm(dec->dev, (const int32_t *)dec->d_pcm.ptr, (uint8_t *)dec->d_packed.ptr, (uint32_t)stride,
+                          (uint32_t)total, C, bytes)) return LINNE_APIRESULT_NG;
+    lnb_shim_d2h(dec->dev, pcm, dec->d_packed.ptr, (size_t)total * C * bytes);
+    if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+    return ret;
 }
 
 /* Packed interleaved PCM out (the bytes of a WAV data chunk), converted from the planes on the device.

@@ -30,7 +30,7 @@ struct LINNEEncoder {
     LnbDevice *dev;
     size_t scratch_budget;                 /* bytes of analysis scratch per chunk */
     LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_acorr, d_cand, d_unit_loss,
-           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train, d_packed, d_sinwin;
+           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train, d_packed, d_sinwin, d_image;
     LnbBuf h_blocks, h_welch, h_total;
     uint32_t sinwin_n;                     /* block length d_sinwin was tabulated for (0 = none) */
     const int32_t *cur_pcm;                /* device PCM planes of the call in flight */
@@ -107,7 +107,7 @@ void LINNEEncoder_Destroy(struct LINNEEncoder *enc)
         LnbBuf *dbufs[] = { &enc->d_pcm, &enc->d_blocks, &enc->d_params, &enc->d_est, &enc->d_work, &enc->d_sig_a,
                             &enc->d_sig_b, &enc->d_acorr, &enc->d_cand, &enc->d_unit_loss, &enc->d_chosen_w,
                             &enc->d_chosen_u, &enc->d_final_sum, &enc->d_welch, &enc->d_plans, &enc->d_plan_mean,
-                            &enc->d_out, &enc->d_total, &enc->d_train, &enc->d_packed, &enc->d_sinwin };
+                            &enc->d_out, &enc->d_total, &enc->d_train, &enc->d_packed, &enc->d_sinwin, &enc->d_image };
         size_t i;
         for (i = 0; i < sizeof(dbufs) / sizeof(dbufs[0]); i++) lnb_buf_release_device(enc->dev, dbufs[i]);
         lnb_buf_release_host(&enc->h_blocks);
@@ -542,6 +542,49 @@ LINNEApiResult LINNEB200_EncodeFilesResident(struct LINNEEncoder *enc, const int
     enc->ranges = NULL; enc->num_ranges = 0; enc->file_out = NULL;
     free(ranges);
     if (ret != LINNE_APIRESULT_OK) return ret;
+    *output_size = written;
+    return LINNE_APIRESULT_OK;
+}
+
+/* The same for host buffers (what a corpus tool holds after reading its files): the files' frames back to back as
+ * packed interleaved PCM (WAV data-chunk layout) in `pcm`, files[i].num_samples frames each; ONE transfer up, one
+ * conversion, one batch for the kernels, one transfer down.  The streams land one after the other in the host
+ * buffer `data`; files[i].first_sample (frame offset in `pcm`), out_offset and out_size are filled in. */
+LINNEApiResult LINNEB200_EncodeFilesPacked(struct LINNEEncoder *enc, const uint8_t *pcm, struct LINNEB200FileDesc *files,
+        uint32_t num_files, uint8_t *data, uint32_t data_size, uint32_t *output_size)
+{
+    LINNEApiResult ret;
+    uint64_t total = 0, bound = 0;
+    uint32_t i, C, bytes, written = 0, NB;
+    size_t stride, packed_bytes;
+    if (enc == NULL || pcm == NULL || files == NULL || num_files == 0 || data == NULL || output_size == NULL)
+        return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
+    C = enc->header.num_channels; NB = enc->header.num_samples_per_block;
+    bytes = enc->header.bits_per_sample / 8u;
+    if (bytes == 0 || bytes > 4u || (enc->header.bits_per_sample % 8u) != 0u) return LINNE_APIRESULT_INVALID_FORMAT;
+    for (i = 0; i < num_files; i++) {
+        if (files[i].num_samples == 0) return LINNE_APIRESULT_INVALID_ARGUMENT;
+        files[i].first_sample = (uint32_t)total;
+        total += files[i].num_samples;
+        /* no stream is longer than its raw form plus framing (blocks that would be are stored raw) -- with slack */
+        bound += LINNE_HEADER_SIZE + 2u * ((uint64_t)files[i].num_samples * C * bytes + 16u * (files[i].num_samples / NB + 2u)) + 4096u;
+    }
+    if (total > 0xFFFFFFF0ull) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (bound > data_size) bound = data_size;
+    stride = LNB_ROUNDUP((size_t)total + 4u, 4u);
+    packed_bytes = (size_t)total * C * bytes;
+    if (lnb_buf_reserve_device(enc->dev, &enc->d_pcm, stride * C * sizeof(int32_t))
+        || lnb_buf_reserve_device(enc->dev, &enc->d_packed, packed_bytes + 16u)
+        || lnb_buf_reserve_device(enc->dev, &enc->d_image, (size_t)bound + 64u)) return LINNE_APIRESULT_NG;
+    lnb_shim_h2d(enc->dev, enc->d_packed.ptr, pcm, packed_bytes);
+    if (lnb_shim_unpack_pcm(enc->dev, (const uint8_t *)enc->d_packed.ptr, (int32_t *)enc->d_pcm.ptr, (uint32_t)stride,
+                            (uint32_t)total, C, bytes)) return LINNE_APIRESULT_NG;
+    ret = LINNEB200_EncodeFilesResident(enc, (const int32_t *)enc->d_pcm.ptr, (uint32_t)stride, files, num_files,
+                                        (uint8_t *)enc->d_image.ptr, (uint32_t)bound, &written);
+    if (ret != LINNE_APIRESULT_OK) return ret;
+    lnb_shim_d2h(enc->dev, data, enc->d_image.ptr, written);
+    if (lnb_shim_sync(enc->dev)) return LINNE_APIRESULT_NG;
     *output_size = written;
     return LINNE_APIRESULT_OK;
 }

@@ -115,6 +115,49 @@ def run_batch(codec, Mem, channels, bits, preset, oracle):
         L.LINNEDecoder_Destroy(dec)
 
 
+def run_packed_batch(codec, channels, bits, preset, oracle):
+    """host buffers: the files' WAV data chunks back to back in, the streams back to back out, and back again"""
+    L = codec.lib
+    u8p = C.POINTER(C.c_uint8)
+    files, _, _ = make_corpus(channels, bits, seed=500 + preset)
+    packed = b"".join(harness.pack_pcm(f, bits) for f in files)
+    src = np.frombuffer(packed, np.uint8).copy()
+    cap = sum(30 + f.size * 4 + 4096 for f in files)
+    out = np.zeros(cap + 64, np.uint8)
+    desc = (FileDesc * len(files))(*[FileDesc(0, f.shape[1], 0, 0, 0) for f in files])
+    enc = L.LINNEEncoder_Create(C.byref(LINNEEncoderConfig(channels, BLOCK, 3, 128)), None, 0)
+    dec = L.LINNEDecoder_Create(C.byref(LINNEDecoderConfig(channels, 3, 128, 1)), None, 0)
+    try:
+        ms = 1 if channels >= 2 else 0
+        assert L.LINNEEncoder_SetEncodeParameter(enc, C.byref(LINNEEncodeParameter(channels, bits, 44100, BLOCK, preset, ms, 0, 0))) == OK
+        total = C.c_uint32(0)
+        assert L.LINNEB200_EncodeFilesPacked(enc, src.ctypes.data_as(u8p), desc, len(files), out.ctypes.data_as(u8p), cap, C.byref(total)) == OK
+        frames = 0
+        for f, d in zip(files, desc):
+            assert d.first_sample == frames
+            assert out[d.out_offset:d.out_offset + d.out_size].tobytes() == codec.encode(f, bits=bits, preset=preset, block=BLOCK)
+            frames += f.shape[1]
+        assert total.value == desc[len(files) - 1].out_offset + desc[len(files) - 1].out_size
+        back = np.zeros(len(packed), np.uint8)
+        assert L.LINNEB200_DecodeFilesPacked(dec, out.ctypes.data_as(u8p), total.value, desc, len(files), back.ctypes.data_as(u8p)) == OK
+        assert back.tobytes() == packed
+        assert L.LINNEB200_EncodeFilesPacked(enc, src.ctypes.data_as(u8p), desc, len(files), out.ctypes.data_as(u8p), 1000, C.byref(total)) == INSUFFICIENT_BUFFER
+    finally:
+        L.LINNEEncoder_Destroy(enc)
+        L.LINNEDecoder_Destroy(dec)
+
+
+@pytest.mark.parametrize("channels,bits,preset", [(2, 16, 1), (1, 24, 6), (2, 8, 2)])
+def test_corpus_batches_host_buffers_hostsim(hostsim, oracle, channels, bits, preset):
+    run_packed_batch(hostsim, channels, bits, preset, oracle)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("channels,bits,preset", [(2, 16, 1), (1, 24, 6), (8, 24, 4)])
+def test_corpus_batches_host_buffers_gpu(gpu, oracle, channels, bits, preset):
+    run_packed_batch(gpu, channels, bits, preset, oracle)
+
+
 @pytest.mark.parametrize("channels,bits,preset", [(2, 16, 0), (1, 24, 5), (2, 16, 7)])
 def test_corpus_batches_hostsim(hostsim, oracle, channels, bits, preset):
     run_batch(hostsim, HostMem, channels, bits, preset, oracle)
