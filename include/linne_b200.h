@@ -1,8 +1,9 @@
 /* linne_b200.h -- extension entry points of liblinne_b200.so next to the reference API.
  *
- * These do not exist in the reference; they expose what a GPU implementation adds: which device a
- * handle runs on, launch accounting for benchmarks, and (later rounds) device-resident batch entry
- * points.  Plain C ABI: pointers and sizes only.
+ * These do not exist in the reference; they expose what a GPU implementation adds: device-resident and
+ * packed-PCM variants of the whole-file calls, corpus batches (several files per call), block read-ahead
+ * for streaming callers, page-locked host memory, device buffers and peer mappings for multi-GPU sharding,
+ * launch accounting and per-kernel timing for benchmarks.  Plain C ABI: pointers and sizes only.
  */
 #ifndef LINNE_B200_H_INCLUDED
 #define LINNE_B200_H_INCLUDED
