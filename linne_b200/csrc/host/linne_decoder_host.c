@@ -287,9 +287,12 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
         const char *split = getenv("LINNE_B200_SPLIT_DECODE");
         batch.fused_max_n = (split && *split == '1') ? 0u : lnb_shim_fused_max_n();
         batch.num_plain_blocks = 0;
-        for (i = 0; i < scan.num_blocks; i++)
+        batch.max_nsmp = 0;
+        for (i = 0; i < scan.num_blocks; i++) {
             if (blocks[i].type != LNB_BLOCK_COMPRESSED || blocks[i].nsmp == 0u || blocks[i].nsmp > batch.fused_max_n)
                 batch.num_plain_blocks++;
+            if (blocks[i].nsmp > batch.max_nsmp) batch.max_nsmp = blocks[i].nsmp;
+        }
     }
 
     {   /* Large batches: eight lanes per block / one per (block, channel) instead of one CTA per block (lnb_tput_v1.cuh) */
@@ -390,9 +393,11 @@ static void fill_block_cache(struct LINNEDecoder *dec, const uint8_t *data, uint
     BlockScan scan;
     uint32_t first_bad = 0, i, n, span;
     dec->ra_count = dec->ra_next = 0;
-    (void)decode_range(dec, data, data_size, 0, NULL, 0xFFFFFFFFu, LNB_READAHEAD_MAX_SAMPLES, dec->readahead, 1,
-                       NULL, NULL, NULL, NULL, 0, &scan, &first_bad);
+    memset(&scan, 0, sizeof(scan));
+    if (decode_range(dec, data, data_size, 0, NULL, 0xFFFFFFFFu, LNB_READAHEAD_MAX_SAMPLES, dec->readahead, 1,
+                     NULL, NULL, NULL, NULL, 0, &scan, &first_bad) == LINNE_APIRESULT_NG) return;
     blocks = (const LnbBlockDesc *)dec->h_blocks.ptr;
+    if (blocks == NULL) return;
     n = (first_bad < scan.num_decodable) ? first_bad : scan.num_decodable;
     /* a block whose payload does not end where its size field says is left to the ordinary path */
     for (i = 0; i < n; i++) {
@@ -581,9 +586,12 @@ static LINNEApiResult decode_files(struct LINNEDecoder *dec, const uint8_t *host
             const char *split = getenv("LINNE_B200_SPLIT_DECODE");
             batch.fused_max_n = (split && *split == '1') ? 0u : lnb_shim_fused_max_n();
             batch.num_plain_blocks = 0;
-            for (k = 0; k < nb; k++)
+            batch.max_nsmp = 0;
+            for (k = 0; k < nb; k++) {
                 if (blocks[k].type != LNB_BLOCK_COMPRESSED || blocks[k].nsmp == 0u || blocks[k].nsmp > batch.fused_max_n)
                     batch.num_plain_blocks++;
+                if (blocks[k].nsmp > batch.max_nsmp) batch.max_nsmp = blocks[k].nsmp;
+            }
         }
         batch.tput = (dec->tput_min_blocks && nb >= dec->tput_min_blocks && batch.fused_max_n
                       && ((uintptr_t)d_pcm & 15u) == 0u && (pcm_stride & 3u) == 0u

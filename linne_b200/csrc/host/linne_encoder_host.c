@@ -126,8 +126,8 @@ LINNEApiResult LINNEEncoder_SetEncodeParameter(struct LINNEEncoder *enc, const s
     const LnbPreset *ps;
     int l;
     if (enc == NULL || prm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
-    if (prm->num_channels == 0 || prm->bits_per_sample == 0 || prm->sampling_rate == 0
-        || prm->num_samples_per_block == 0 || prm->preset >= LINNE_NUM_PARAMETER_PRESETS
+    if (prm->num_channels == 0 || prm->bits_per_sample == 0 || prm->bits_per_sample > LNB_MAX_BITS_PER_SAMPLE
+        || prm->sampling_rate == 0 || prm->num_samples_per_block == 0 || prm->preset >= LINNE_NUM_PARAMETER_PRESETS
         || (unsigned)prm->ch_process_method >= (unsigned)LINNE_CH_PROCESS_METHOD_INVALID)
         return LINNE_APIRESULT_INVALID_FORMAT;
     ps = &g_lnb_presets[prm->preset];

@@ -38,6 +38,10 @@ LINNEApiResult lnb_header_check_for_encode(const struct LINNEHeader *h)
 {
     if (h->num_channels == 0 || h->num_samples == 0 || h->sampling_rate == 0 || h->bits_per_sample == 0
         || h->num_samples_per_block == 0) return LINNE_APIRESULT_INVALID_FORMAT;
+    /* The pre-emphasis state travels in bits_per_sample + 1 bits and the reference's bit reader/writer take at
+     * most 32 bits per field (bit_stream.h:317 asserts it, a Release build shifts out of range), so 32-bit PCM
+     * never worked there; refuse it instead of writing or reading a field nobody can parse. */
+    if (h->bits_per_sample > LNB_MAX_BITS_PER_SAMPLE) return LINNE_APIRESULT_INVALID_FORMAT;
     if (h->preset >= LINNE_NUM_PARAMETER_PRESETS) return LINNE_APIRESULT_INVALID_FORMAT;
     if ((unsigned)h->ch_process_method >= (unsigned)LINNE_CH_PROCESS_METHOD_INVALID) return LINNE_APIRESULT_INVALID_FORMAT;
     if (h->ch_process_method == LINNE_CH_PROCESS_METHOD_MS && h->num_channels == 1) return LINNE_APIRESULT_INVALID_FORMAT;

@@ -22,6 +22,7 @@
 #define LNB_PREEM_SHIFT        5
 #define LNB_NUM_PREEM          2
 #define LNB_MAX_PORDER         10
+#define LNB_MAX_BITS_PER_SAMPLE 31    /* the (bits + 1)-bit pre-emphasis state must fit a 32-bit field (bit_stream.h:317) */
 #define LNB_MAX_PARTITIONS     1024
 #define LNB_RAW_THRESHOLD      0.95f  /* float on purpose: linne_internal.h:24 */
 

@@ -75,12 +75,14 @@ struct LnbItemDeemph {
     }
 };
 
-/* D4: M/S -> L/R; item = (block, sample) */
+/* D4: M/S -> L/R; item = (block, sample); a block may be longer than the header's block size */
+LNB_HD uint32_t lnb_ms_span(const LnbDecodeBatch &b) { return b.max_nsmp > b.cfg.block_size ? b.max_nsmp : b.cfg.block_size; }
 struct LnbItemMsInverse {
     LnbDecodeBatch b;
     LNB_HDM void operator()(uint32_t i) const
     {
-        const uint32_t blk_i = i / b.cfg.block_size, s = i % b.cfg.block_size;
+        const uint32_t span = lnb_ms_span(b);
+        const uint32_t blk_i = i / span, s = i % span;
         const LnbBlockDesc &blk = b.blocks[blk_i];
         if (blk.type != LNB_BLOCK_COMPRESSED || blk.status || s >= blk.nsmp) return;
         if (b.fused_max_n && blk.nsmp <= b.fused_max_n) return;       /* done inside the fused streaming kernel */
@@ -106,7 +108,7 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
         if (!b.fused_max_n || b.num_plain_blocks) {       /* raw / silent / long blocks (or the fused kernel switched off) */
             ex.entropy_cooperative(b);                    /* one warp per block: 32 speculative code-word starts per round */
             ex.synth_cooperative(b);                      /* one warp per (block, channel): systolic synthesis + de-emphasis */
-            if (b.cfg.block_size > ex.synth_max_n()) {    /* longer block-channels: flat kernels (they skip the short ones) */
+            if (b.max_nsmp > ex.synth_max_n()) {    /* longer block-channels: flat kernels (they skip the short ones) */
                 for (int l = (int)b.cfg.num_layers - 1; l >= 0; l--)
                     ex.run("synth", B * C * LNB_MAX_UNITS, LnbItemSynth{b, (uint32_t)l, ex.synth_max_n()});
                 ex.run("deemph", B * C, LnbItemDeemph{b, ex.synth_max_n()});
@@ -120,7 +122,7 @@ void lnb_decode_pipeline(Exec &ex, const LnbDecodeBatch &b)
         ex.run("deemph", B * C, LnbItemDeemph{b, 0u});
     }
     if (b.cfg.ms && C >= 2u && (!b.fused_max_n || b.num_plain_blocks))
-        ex.run("ms_inverse", B * b.cfg.block_size, LnbItemMsInverse{b});
+        ex.run("ms_inverse", B * lnb_ms_span(b), LnbItemMsInverse{b});
 }
 
 /* =============================================================================================

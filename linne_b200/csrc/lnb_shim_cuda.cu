@@ -19,7 +19,7 @@
 #include "lnb_entropy_v3.cuh"
 #include "lnb_refine_v2.cuh"
 #include "lnb_scan_v2.cuh"
-#include "lnb_stream_v1.cuh"
+#include "lnb_stream_v2.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -135,28 +135,24 @@ struct CudaExec {
         lnb_entropy_v3_kernel<<<(b.num_blocks + LNB_E3_WARPS - 1) / LNB_E3_WARPS, LNB_E3_THREADS, 0, dev->stream>>>(b);
         end_stage(slot);
     }
-    void stream_cooperative(const LnbDecodeBatch &b)
+    /* dynamic shared memory of the per-block decoders: one line of the longest block of the batch */
+    static uint32_t line_samples(const LnbDecodeBatch &b, uint32_t cap)
     {
-        uint32_t n_max = b.cfg.block_size < LNB_DS_MAX_N ? b.cfg.block_size : LNB_DS_MAX_N;
-        n_max = (n_max + 3u) & ~3u;
+        uint32_t n_max = b.max_nsmp < cap ? b.max_nsmp : cap;
+        if (n_max == 0u) n_max = 4u;
+        return (n_max + 3u) & ~3u;
+    }
+    void stream_cooperative(const LnbDecodeBatch &b, cudaStream_t on = nullptr)
+    {
+        const uint32_t n_max = line_samples(b, LNB_DS_MAX_N);
         const size_t smem = (size_t)n_max * sizeof(int32_t);
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(lnb_stream_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
-        const int slot = begin_stage("stream_v1");
-        lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, dev->stream>>>(b, n_max);
-        end_stage(slot);
+        const int slot = begin_stage("stream_v2", on);
+        lnb_stream_v2_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, on ? on : dev->stream>>>(b, n_max);
+        end_stage(slot, on);
     }
     template <int Q0, int Q1, int Q2> void tput_synth(const LnbDecodeBatch &b)
     {
         const size_t smem = LnbTpLayer<Q0>::smem_bytes + LnbTpLayer<Q1>::smem_bytes + LnbTpLayer<Q2>::smem_bytes + 16u;
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(lnb_tp_synth_kernel<Q0, Q1, Q2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
         const uint32_t seqs = b.num_blocks * b.cfg.num_channels;
         const int slot = begin_stage("tp_synth");
         lnb_tp_synth_kernel<Q0, Q1, Q2><<<(seqs + 31u) / 32u, 32, smem, dev->stream>>>(b);
@@ -178,18 +174,14 @@ struct CudaExec {
         cudaEventRecord(dev->ev_fork, dev->stream);
         cudaStreamWaitEvent(dev->aux_stream, dev->ev_fork, 0);
         {
-            int slot = begin_stage("crc_v2", dev->aux_stream);
+            const int slot = begin_stage("crc_v2", dev->aux_stream);
             lnb_crc_v2_kernel<<<b.num_blocks, LNB_CRC_THREADS, 0, dev->aux_stream>>>(b);
             end_stage(slot, dev->aux_stream);
-            uint32_t n_max = b.cfg.block_size < LNB_DS_MAX_N ? b.cfg.block_size : LNB_DS_MAX_N;
-            n_max = (n_max + 3u) & ~3u;
-            slot = begin_stage("stream_v1", dev->aux_stream);
-            lnb_stream_v1_kernel<<<b.num_blocks, LNB_DS_THREADS, (size_t)n_max * sizeof(int32_t), dev->aux_stream>>>(b, n_max);
-            end_stage(slot, dev->aux_stream);
+            stream_cooperative(b, dev->aux_stream);
         }
         cudaEventRecord(dev->ev_join, dev->aux_stream);
         const int slot = begin_stage("tp_entropy");
-        lnb_tp_entropy_kernel<<<(b.num_blocks + LNB_TG_PER_WARP - 1u) / LNB_TG_PER_WARP, 32, 0, dev->stream>>>(b);
+        lnb_tp_entropy_kernel<<<(b.num_blocks + 31u) / 32u, 32, 0, dev->stream>>>(b);
         end_stage(slot);
         cudaStreamWaitEvent(dev->stream, dev->ev_join, 0);
         if (shape == 1) tput_synth<32, 2, 0>(b);
@@ -206,14 +198,8 @@ struct CudaExec {
     void synth_cooperative(const LnbDecodeBatch &b)
     {
         const uint32_t items = b.num_blocks * b.cfg.num_channels;
-        uint32_t n_max = b.cfg.block_size < LNB_SY_MAX_N ? b.cfg.block_size : LNB_SY_MAX_N;
-        n_max = (n_max + 3u) & ~3u;
+        const uint32_t n_max = line_samples(b, LNB_SY_MAX_N);
         const size_t smem = (size_t)LNB_SY_WARPS * n_max * sizeof(int32_t);
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(lnb_synth_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
         const int slot = begin_stage("synth_v2");
         lnb_synth_v2_kernel<<<(items + LNB_SY_WARPS - 1) / LNB_SY_WARPS, LNB_SY_THREADS, smem, dev->stream>>>(b, n_max);
         end_stage(slot);
@@ -253,11 +239,6 @@ struct CudaExec {
         if (b.af_iterations && na_max < tri) na_max = tri;
         na_max = (na_max + 7u) & ~7u;
         const size_t smem = (size_t)2 * (na_max + LNB_RF_HIST) * sizeof(double) + sizeof(LnbRefineSmem);
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(lnb_refine_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
         const int slot = begin_stage("refine_v2");
         lnb_refine_v2_kernel<<<b.num_blocks * b.cfg.num_channels, LNB_RF_THREADS, smem, dev->stream>>>(
             b, na_max, b.af_iterations, b.enable_learning, b.train_scratch, chunks_per_slot);
@@ -274,11 +255,6 @@ struct CudaExec {
         uint32_t n_max = b.cfg.block_size < LNB_FR_MAX_N ? b.cfg.block_size : LNB_FR_MAX_N;
         n_max = (n_max + 3u) & ~3u;
         const size_t smem = (size_t)2 * n_max * sizeof(int32_t) + sizeof(LnbPlanSmem);
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(lnb_predict_plan_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
         const int slot = begin_stage("predict_plan_v2");
         lnb_predict_plan_v2_kernel<<<b.num_blocks * b.cfg.num_channels, LNB_FR_THREADS, smem, dev->stream>>>(b, n_max);
         end_stage(slot);
@@ -290,11 +266,6 @@ struct CudaExec {
         bytes += bytes / 8;
         if (bytes > 220u * 1024u) bytes = 220u * 1024u;
         const uint32_t img_words = (uint32_t)((bytes + 3) / 4);
-        static size_t configured = 0;
-        if ((size_t)img_words * 4 > configured) {
-            cudaFuncSetAttribute(lnb_pack_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(img_words * 4));
-            configured = (size_t)img_words * 4;
-        }
         const int slot = begin_stage("pack_v2");
         lnb_pack_v2_kernel<<<b.num_blocks, LNB_PK_THREADS, (size_t)img_words * 4, dev->stream>>>(b, out_capacity, img_words);
         end_stage(slot);
@@ -305,11 +276,6 @@ struct CudaExec {
         uint32_t na_max = b.cfg.block_size < LNB_A3_MAX_NA ? b.cfg.block_size : LNB_A3_MAX_NA;
         na_max = (na_max + 7u) & ~7u;
         const size_t smem = lnb_a3_smem_doubles(na_max) * sizeof(double);
-        static size_t configured = 0;
-        if (smem > configured) {
-            cudaFuncSetAttribute(lnb_analyze_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = smem;
-        }
         const int slot = begin_stage("analyze_v3");
         lnb_analyze_v3_kernel<<<S, LNB_A3_THREADS, smem, dev->stream>>>(b, na_max);
         end_stage(slot);
@@ -334,6 +300,46 @@ struct CudaExec {
     }
 };
 
+/* Dynamic shared memory above 48 KB is an opt-in per kernel AND per device.  Every kernel that may need it gets the
+ * device's maximum once, when the first context of that device is opened (under a lock: handles are opened from
+ * many worker threads), and the attribute is never lowered afterwards -- a launcher only passes the size it needs. */
+#include <mutex>
+static std::mutex g_kernel_cfg_lock;
+static unsigned char g_kernel_cfg_done[64];
+
+template <class K> static cudaError_t lnb_optin_smem(K kernel, int optin_bytes)
+{
+    cudaFuncAttributes at;
+    cudaError_t e = cudaFuncGetAttributes(&at, kernel);
+    if (e != cudaSuccess) return e;
+    const int dyn = optin_bytes - (int)at.sharedSizeBytes;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn > 0 ? dyn : 0);
+}
+static int lnb_configure_kernels(int ordinal)
+{
+    std::lock_guard<std::mutex> guard(g_kernel_cfg_lock);
+    if (ordinal >= 0 && ordinal < 64 && g_kernel_cfg_done[ordinal]) return 0;
+    int optin = 0;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ordinal) != cudaSuccess) return 1;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_stream_v2_kernel, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_tp_synth_kernel<32, 2, 0>, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_tp_synth_kernel<8, 64, 4>, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_tp_synth_kernel<16, 128, 4>, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_synth_v2_kernel, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_refine_v2_kernel, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_predict_plan_v2_kernel, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_pack_v2_kernel, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_analyze_v3_kernel, optin);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "linne_b200: cannot configure kernels on device %d: %s\n", ordinal, cudaGetErrorString(e));
+        cudaGetLastError();
+        return 1;
+    }
+    if (ordinal >= 0 && ordinal < 64) g_kernel_cfg_done[ordinal] = 1;
+    return 0;
+}
+
 extern "C" {
 
 const char *lnb_shim_backend(void) { return "cuda-sm_100a"; }
@@ -357,6 +363,7 @@ int lnb_shim_open(LnbDevice **out, int device_ordinal)
     LnbDevice *dev = (LnbDevice *)calloc(1, sizeof(LnbDevice));
     if (!dev) return 3;
     cudaGetDevice(&dev->ordinal);
+    if (lnb_configure_kernels(dev->ordinal)) { free(dev); return 7; }
     if (cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking) != cudaSuccess) { free(dev); return 4; }
     dev->owns_stream = 1;
     dev->cost_rank = -1;

@@ -86,7 +86,10 @@ typedef struct LnbDecodeBatch {
     int32_t *pcm;                   /* [C][pcm_stride] */
     uint32_t fused_max_n;           /* > 0: compressed blocks of at most this many samples take the fused streaming kernel */
     uint32_t num_plain_blocks;      /* blocks left to the split kernels (raw, silent, longer than fused_max_n) */
-    uint32_t tput;                  /* 1: full compressed blocks take the throughput kernels (lnb_tput_v1.cuh); needs fused_max_n */
+    uint32_t tput;                  /* 1: full compressed blocks take the throughput kernels (lnb_tput_v2.cuh); needs fused_max_n */
+    uint32_t max_nsmp;              /* longest block of the batch (samples per channel): sizes the shared-memory lines of the
+                                     * per-block kernels -- a block may be longer than the header's block size (the reference
+                                     * checks it against the caller's buffer only, linne_decoder.c:632-635) */
 } LnbDecodeBatch;
 
 /* ---- one encode batch (all pointers are device pointers) ---- */

@@ -347,3 +347,34 @@ def test_encode_block_loop_equals_encode_whole(codec):
     # the CLI encodes with EncodeHeader + EncodeBlock per block (tools/linne_codec/linne_codec.c:123-161)
     pcm = harness.synth_pcm(n=2500, channels=2, bits=16, seed=10)
     assert codec.encode(pcm, preset=2, block=1024, whole=False) == codec.encode(pcm, preset=2, block=1024, whole=True)
+
+
+def test_block_longer_than_header_block_size_decodes(codec, oracle):
+    """The reference checks a block's sample count against the caller's buffer only (linne_decoder.c:632-635),
+    so a stream whose header names a SMALLER block size than its blocks carry decodes all the same.  The
+    kernels' shared-memory lines must be sized from the blocks, not from the header."""
+    pcm = harness.synth_pcm(n=2048 * 3 + 300, channels=2, bits=16, seed=5)
+    for preset in (0, 5):
+        stream = bytearray(oracle.encode(pcm, preset=preset, block=2048))
+        stream[24:28] = (1024).to_bytes(4, "big")                  # header.num_samples_per_block
+        rc, out = codec.decode(bytes(stream), return_code=True)
+        assert rc == OK
+        assert np.array_equal(out, pcm), preset
+
+
+def test_32_bit_pcm_is_refused(codec):
+    """bits_per_sample + 1 bits of pre-emphasis state do not fit the format's 32-bit fields (bit_stream.h:317):
+    the reference accepts the parameter and then shifts out of range; we refuse it up front."""
+    skip_on_reference(codec, "accepts 32 bits per sample and corrupts the pre-emphasis field")
+    L = codec.lib
+    buf = np.zeros(64, np.uint8)
+    h = valid_header(); h.bits_per_sample = 32
+    assert L.LINNEEncoder_EncodeHeader(C.byref(h), u8(buf), 30) == INVALID_FORMAT
+    h.bits_per_sample = 31
+    assert L.LINNEEncoder_EncodeHeader(C.byref(h), u8(buf), 30) == OK
+    enc = codec.make_encoder(2, 4096)
+    try:
+        prm = LINNEEncodeParameter(2, 32, 44100, 4096, 0, 1, 0, 0)
+        assert L.LINNEEncoder_SetEncodeParameter(enc, C.byref(prm)) == INVALID_FORMAT
+    finally:
+        L.LINNEEncoder_Destroy(enc)

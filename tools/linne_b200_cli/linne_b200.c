@@ -80,7 +80,8 @@ static uint8_t *read_file(const char *path, struct Staging *st, size_t *size)
     return buf;
 }
 
-/* RIFF/WAVE, PCM (format tag 1, or WAVE_FORMAT_EXTENSIBLE carrying PCM), 8/16/24/32 bits */
+/* RIFF/WAVE, PCM (format tag 1, or WAVE_FORMAT_EXTENSIBLE carrying PCM), 8/16/24 bits (the format's
+ * (bits + 1)-bit pre-emphasis field rules out 32, as in the reference: bit_stream.h:317) */
 static int wav_read(const char *path, struct Staging *st, struct Wav *w)
 {
     size_t size = 0, off = 12, data_off = 0, data_len = 0;
@@ -106,7 +107,7 @@ static int wav_read(const char *path, struct Staging *st, struct Wav *w)
     }
     bytes = w->bits / 8u;
     if (!have_fmt || !data_off || w->channels == 0 || w->channels > LINNE_MAX_NUM_CHANNELS
-        || (w->bits != 8 && w->bits != 16 && w->bits != 24 && w->bits != 32)) return 3;
+        || (w->bits != 8 && w->bits != 16 && w->bits != 24)) return 3;
     w->frames = (uint32_t)(data_len / ((size_t)bytes * w->channels));
     w->data = f + data_off;
     return 0;
@@ -177,15 +178,22 @@ static int decode_one(struct Worker *wk, const char *in, const char *out)
     LINNEApiResult ret;
     uint32_t frames = 0;
     if (!buf) { SAY(stderr, "linne_b200: cannot read %s\n", in); return 1; }
+    if (size > 0xFFFFFFFFull) { SAY(stderr, "linne_b200: %s: larger than 4 GiB, not a stream this API can take\n", in); return 1; }
     if ((ret = LINNEDecoder_DecodeHeader(buf, (uint32_t)size, &h)) != LINNE_APIRESULT_OK) {
         SAY(stderr, "linne_b200: %s: not a LINNE stream (%d)\n", in, (int)ret); return 1;
     }
     memset(&w, 0, sizeof(w));
     w.channels = h.num_channels; w.rate = h.sampling_rate; w.bits = h.bits_per_sample; w.frames = h.num_samples;
-    if (w.channels == 0 || w.channels > LINNE_MAX_NUM_CHANNELS || (w.bits != 8 && w.bits != 16 && w.bits != 24 && w.bits != 32)) return 1;
+    if (w.channels == 0 || w.channels > LINNE_MAX_NUM_CHANNELS || (w.bits != 8 && w.bits != 16 && w.bits != 24)) return 1;
     if (!(wav = staging_reserve(&wk->out, 44u + (size_t)w.frames * w.channels * (w.bits / 8u) + 16u))) return 1;
     ret = LINNEB200_DecodeWholePacked(wk->dec, buf, (uint32_t)size, wav + 44, w.frames, &frames);
     if (ret != LINNE_APIRESULT_OK) { SAY(stderr, "linne_b200: %s: decode failed (%d)\n", in, (int)ret); return 1; }
+    /* a stream that ends on a block boundary before num_samples decodes OK with fewer frames (as in the reference,
+     * whose tool writes zeros there): the staging buffer is reused between files, so clear what was not written */
+    if (frames < w.frames) {
+        const size_t fb = (size_t)w.channels * (w.bits / 8u);
+        memset(wav + 44 + (size_t)frames * fb, (w.bits == 8) ? 0x80 : 0, (size_t)(w.frames - frames) * fb);
+    }
     if (wav_write(out, wav, &w) != 0) { SAY(stderr, "linne_b200: cannot write %s\n", out); return 1; }
     SAY(stdout, "%s -> %s: %u samples x %u ch\n", in, out, w.frames, w.channels);
     wk->samples += (uint64_t)w.frames * w.channels;
