@@ -50,6 +50,12 @@ __device__ __forceinline__ void lnb_bulk_load(void *smem_dst, const void *gmem_s
                  :: "r"(lnb_smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(lnb_smem_addr(bar)) : "memory");
 }
 
+/* order this thread's earlier generic-proxy accesses to shared memory before asynchronous-proxy writes it issues next */
+__device__ __forceinline__ void lnb_proxy_fence_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 /* ---- shared-memory accesses by 32-bit window address (no generic-address arithmetic on a hot path) ---- */
 __device__ __forceinline__ void lnb_sts32(uint32_t addr, uint32_t v)
 {

@@ -147,6 +147,9 @@ struct CudaExec {
         const uint32_t n_max = line_samples(b, LNB_DS_MAX_N);
         const size_t smem = (size_t)n_max * sizeof(int32_t);
         const int slot = begin_stage("stream_v2", on);
+#ifdef LNB_DS_TIMING
+        if (getenv("LINNE_B200_DBG_WALKONLY")) { LnbDecodeBatch b2 = b; b2.cfg.check_crc |= 0x100u; lnb_stream_v2_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, on ? on : dev->stream>>>(b2, n_max); end_stage(slot, on); return; }
+#endif
         lnb_stream_v2_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, on ? on : dev->stream>>>(b, n_max);
         end_stage(slot, on);
     }
@@ -181,7 +184,7 @@ struct CudaExec {
         }
         cudaEventRecord(dev->ev_join, dev->aux_stream);
         const int slot = begin_stage("tp_entropy");
-        lnb_tp_entropy_kernel<<<(b.num_blocks + 31u) / 32u, 32, 0, dev->stream>>>(b);
+        lnb_tp_entropy_kernel<<<(b.num_blocks + LNB_TG_PER_WARP - 1u) / LNB_TG_PER_WARP, 32, 0, dev->stream>>>(b);
         end_stage(slot);
         cudaStreamWaitEvent(dev->stream, dev->ev_join, 0);
         if (shape == 1) tput_synth<32, 2, 0>(b);

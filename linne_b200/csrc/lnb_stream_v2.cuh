@@ -16,8 +16,8 @@
  *                     the length  k2 + 1 + max(lz, 1)  and shifts -- four dependent instructions -- and stores the
  *                     32-bit window itself for the next stage.  (Round 1 let 32 lanes guess 32 code-word starts per
  *                     round; a round ended at the first long code word, ~3 retired per ~80 dependent instructions:
- *                     ~95 cycles per sample against ~25-30 here.)  The lane keeps its payload window in shared
- *                     memory filled by itself, four 2 KB chunks ahead, with bulk-asynchronous copies (lnb_bulk.cuh).
+ *                     ~95 cycles per sample.)  The payload reaches shared memory through bulk-asynchronous copies,
+ *                     four 2 KB chunks ahead of the walk, issued by a loader warp (lnb_bulk.cuh).
  *     stage 1         EXTRACT: 32 lanes turn 32 stored windows into residuals (everything about a code word except
  *                     its start is a function of its first 32 bits and the partition's k2).
  *     stage 2..L+1    synthesis layer L-1 .. 0, in place on the line (units walked one after the other; systolic
@@ -38,16 +38,20 @@
 
 #define LNB_DS_MAX_N       10240u
 #define LNB_DS_STAGES      (3u + LNB_MAX_LAYERS)        /* walk, extract, layers, de-emphasis */
-#define LNB_DS_HW_WARPS    7u                           /* warp 4 stays empty: it would share a scheduler with the walk */
+#define LNB_DS_HW_WARPS    7u                           /* warp 4 (the walk's scheduler) only keeps the payload ring filled */
 #define LNB_DS_THREADS     (32u * LNB_DS_HW_WARPS)
 #define LNB_DS_BATCH       32u                          /* steps between progress updates */
 #define LNB_DS_CHUNK_WORDS 512u                         /* payload window: chunks of 2 KB ... */
 #define LNB_DS_CHUNKS      4u                           /* ... four of them in flight */
 #define LNB_DS_RING_WORDS  (LNB_DS_CHUNK_WORDS * LNB_DS_CHUNKS)
+#define LNB_DS_MIRROR      16u                          /* words of the ring's head repeated behind its end */
 
 struct __align__(128) LnbDsShared {
-    uint32_t ring[LNB_DS_RING_WORDS];                  /* payload bytes as they are in the stream, word w of the block at w % RING */
+    uint32_t ring[LNB_DS_RING_WORDS + LNB_DS_MIRROR];  /* big-endian corrected payload words, word w of the block at w % RING */
     uint64_t full_bar[LNB_DS_CHUNKS];                  /* one transaction barrier per ring slot */
+    volatile uint32_t loaded_words;                    /* payload words [0, loaded_words) are in the ring (loader -> readers) */
+    volatile uint32_t walk_word;                       /* the walk has left everything below this word (walk -> loader) */
+    volatile uint32_t walk_done;
     volatile uint32_t prog[LNB_DS_STAGES];             /* samples (over all channels of the block) each stage has finished */
     volatile uint32_t abort;
     uint32_t porder[LNB_MAX_CHANNELS];                 /* partition order of each channel (walk -> extract) */
@@ -69,54 +73,142 @@ __device__ __forceinline__ void lnb_ds_publish_lane(LnbDsShared &sm, uint32_t st
     sm.prog[stage] = value;
 }
 /* wait until stage `stage` has finished at least `need` samples; false when the block was aborted */
+/* Every polling loop of this kernel gives up after LNB_DS_PATIENCE rounds (seconds of waiting: something is broken,
+ * not slow), says where, and aborts the block -- a kernel that never ends would take the whole GPU with it. */
+#define LNB_DS_PATIENCE (1u << 20)
+__device__ __noinline__ void lnb_ds_give_up(LnbDsShared &sm, const char *where, uint32_t a, uint32_t b)
+{
+    printf("linne_b200: stream_v2 block %u gave up waiting in %s (%u, %u) loaded=%u walk_word=%u prog=%u %u %u %u %u %u\n",
+           blockIdx.x, where, a, b, sm.loaded_words, sm.walk_word, sm.prog[0], sm.prog[1], sm.prog[2], sm.prog[3], sm.prog[4], sm.prog[5]);
+    sm.abort = 1u; sm.walk_done = 1u; sm.loaded_words = 0xFFFFFFFFu;
+    __threadfence_block();
+}
+#ifdef LNB_DS_TIMING
+__device__ unsigned long long lnb_ds_waited[8];                 /* cycles each hardware warp of block 0 spent in stage waits */
+__device__ unsigned int lnb_ds_count[8];                        /* block 0: fast groups of 8, of 4, generic groups, careful groups, partitions */
+#define LNB_DS_COUNT(i) do { if (blockIdx.x == 0) lnb_ds_count[i]++; } while (0)
+#define LNB_DS_T0() const long long t_wait0_ = clock64()
+#define LNB_DS_T1() do { if (blockIdx.x == 0 && (threadIdx.x & 31u) == 0u) lnb_ds_waited[threadIdx.x >> 5] += (unsigned long long)(clock64() - t_wait0_); } while (0)
+#else
+#define LNB_DS_COUNT(i) do { } while (0)
+#define LNB_DS_T0() do { } while (0)
+#define LNB_DS_T1() do { } while (0)
+#endif
 __device__ __forceinline__ bool lnb_ds_wait(LnbDsShared &sm, uint32_t stage, uint32_t need)
 {
-    for (;;) {
+    if (sm.prog[stage] >= need) { __threadfence_block(); return sm.abort == 0u; }
+    LNB_DS_T0();
+    for (uint32_t spins = 0;; spins++) {
         const uint32_t have = sm.prog[stage];
         if (have >= need) break;
         if (sm.abort) return false;
+        if (spins > LNB_DS_PATIENCE) { lnb_ds_give_up(sm, "stage wait", stage, need); return false; }
         /* the pace maker (the walk) needs ~15 ns per sample: sleep roughly until the missing samples can exist,
          * so waiting stages leave the issue slots to the warps that have work */
         const uint32_t ns = (need - have) * 8u;
         __nanosleep(ns < 32u ? 32u : (ns > 2000u ? 2000u : ns));
     }
+    LNB_DS_T1();
     __threadfence_block();
     return sm.abort == 0u;
 }
 
-/* ---- stage 0: the payload window and the walk ------------------------------------------------------------- */
-/* Geometry of a block's window: plain scalars, so that everything the walking lane touches per code word stays
- * in registers and shared-memory address space. */
+/* ---- the payload window: a ring of big-endian corrected words kept filled by the loader warp ------------------
+ * Geometry of a block's window: ring word w holds payload word w (counted from g0, the 16-byte aligned address at or
+ * below the block's first byte) modulo the ring size; LNB_DS_MIRROR words behind the ring repeat its head, so a
+ * reader may run that far past the end without wrapping. */
 struct LnbDsWin {
-    const uint8_t *g0;          /* 16-byte aligned global address of ring word 0 (at most 15 bytes before the block) */
-    uint32_t end_word;          /* words at or past this index read as zero (end of the block) */
-    uint32_t load_bytes;        /* bytes worth loading, a multiple of 16 */
+    const uint8_t *g0;
+    uint32_t rel_payload, rel_end;   /* first payload byte / end of the block, relative to g0 */
+    uint32_t end_word;               /* words at or past this index are not part of the block */
+    uint32_t load_bytes;             /* bytes worth loading, a multiple of 16 */
     uint32_t nchunks;
 };
-__device__ __forceinline__ void lnb_ds_issue(LnbDsShared &sm, const LnbDsWin &w, uint32_t c)
+__device__ __forceinline__ LnbDsWin lnb_ds_window(const LnbDecodeBatch &b, const LnbBlockDesc &blk)
 {
-    const uint32_t off = c * (LNB_DS_CHUNK_WORDS * 4u);
-    const uint32_t left = w.load_bytes - off;
-    const uint32_t bytes = left < LNB_DS_CHUNK_WORDS * 4u ? left : LNB_DS_CHUNK_WORDS * 4u;
-    uint64_t *bar = &sm.full_bar[c % LNB_DS_CHUNKS];
-    lnb_mbar_arrive_expect_tx(bar, bytes);
-    lnb_bulk_load(&sm.ring[(c % LNB_DS_CHUNKS) * LNB_DS_CHUNK_WORDS], w.g0 + off, bytes, bar);
+    LnbDsWin w;
+    const uintptr_t addr = (uintptr_t)(b.stream + blk.byte_off);
+    w.g0 = (const uint8_t *)(addr & ~(uintptr_t)15);
+    const uint32_t rel0 = (uint32_t)(addr & 15u);
+    w.rel_payload = rel0 + LNB_BLOCK_HEADER_SIZE;
+    uint32_t end_byte = blk.byte_off + blk.byte_size;
+    if (end_byte > b.stream_size || end_byte < blk.byte_off) end_byte = b.stream_size;
+    w.rel_end = rel0 + (end_byte - blk.byte_off);
+    w.end_word = (w.rel_end + 3u) >> 2;
+    /* the image is followed by >= 16 readable bytes (lnb_types.h): whole 16-byte lines up to there */
+    const uintptr_t readable = ((uintptr_t)(b.stream + b.stream_size) + 16u) & ~(uintptr_t)15;
+    const uint64_t room = (uint64_t)(readable - (uintptr_t)w.g0);
+    uint64_t want = ((uint64_t)w.rel_end + 15u) & ~(uint64_t)15;
+    if (want > room) want = room;
+    w.load_bytes = (uint32_t)want;
+    w.nchunks = (w.load_bytes + LNB_DS_CHUNK_WORDS * 4u - 1u) / (LNB_DS_CHUNK_WORDS * 4u);
+    return w;
 }
-/* The walk reaches chunk c: keep four chunks in flight (chunk c - 1 has been read completely, its slot is free)
- * and make sure chunk c has landed.  Returns the new count of issued chunks.  Out of line: once per 2 KB. */
-__device__ __noinline__ uint32_t lnb_ds_enter_chunk(LnbDsShared &sm, const uint8_t *g0, uint32_t load_bytes, uint32_t nchunks,
-                                                    uint32_t issued, uint32_t c)
+
+/* The loader (one warp): bulk-asynchronous copies of 2 KB chunks into the ring, four in flight; a chunk that has
+ * landed is byte-swapped in place (the bit readers want big-endian words) and announced through `loaded_words`; a
+ * slot is refilled once the walk has left the chunk it held (`walk_word`). */
+__device__ void lnb_ds_loader(const LnbDsWin &w, LnbDsShared &sm, uint32_t lane)
 {
-    LnbDsWin w; w.g0 = g0; w.end_word = 0; w.load_bytes = load_bytes; w.nchunks = nchunks;
-    const uint32_t want = (c + LNB_DS_CHUNKS < nchunks) ? c + LNB_DS_CHUNKS : nchunks;
-    while (issued < want) { lnb_ds_issue(sm, w, issued); issued++; }
-    if (c < nchunks) lnb_mbar_wait(&sm.full_bar[c % LNB_DS_CHUNKS], (c / LNB_DS_CHUNKS) & 1u);
-    return issued;
+    uint32_t issued = 0, swapped = 0, walk_chunk = 0, idle = 0;
+    for (;;) {
+        const uint32_t may = (walk_chunk + LNB_DS_CHUNKS < w.nchunks) ? walk_chunk + LNB_DS_CHUNKS : w.nchunks;
+        if (lane == 0) {
+            for (uint32_t c = issued; c < may; c++) {
+                const uint32_t off = c * (LNB_DS_CHUNK_WORDS * 4u);
+                const uint32_t left = w.load_bytes - off;
+                const uint32_t bytes = left < LNB_DS_CHUNK_WORDS * 4u ? left : LNB_DS_CHUNK_WORDS * 4u;
+                uint64_t *bar = &sm.full_bar[c % LNB_DS_CHUNKS];
+                lnb_proxy_fence_async();                        /* the slot was read and written through the generic proxy */
+                lnb_mbar_arrive_expect_tx(bar, bytes);
+                lnb_bulk_load(&sm.ring[(c % LNB_DS_CHUNKS) * LNB_DS_CHUNK_WORDS], w.g0 + off, bytes, bar);
+            }
+        }
+        if (issued < may) issued = may;
+        if (swapped < issued) {
+            const uint32_t c = swapped, slot = c % LNB_DS_CHUNKS;
+            lnb_mbar_wait(&sm.full_bar[slot], (c / LNB_DS_CHUNKS) & 1u);
+            uint32_t *dst = &sm.ring[slot * LNB_DS_CHUNK_WORDS];
+#pragma unroll 4
+            for (uint32_t i = lane; i < LNB_DS_CHUNK_WORDS; i += 32u) dst[i] = lnb_bswap32(dst[i]);
+            __syncwarp();
+            if (slot == 0u && lane < LNB_DS_MIRROR) sm.ring[LNB_DS_RING_WORDS + lane] = sm.ring[lane];
+            __syncwarp();
+            swapped++;
+            if (lane == 0) { __threadfence_block(); sm.loaded_words = (swapped == w.nchunks) ? 0xFFFFFFFFu : swapped * LNB_DS_CHUNK_WORDS; }
+            continue;
+        }
+        if (swapped == w.nchunks) break;
+        /* every issued chunk has landed: wait for the walk to free a slot */
+        if (sm.walk_done) break;
+        const uint32_t wc = sm.walk_word / LNB_DS_CHUNK_WORDS;
+        if (wc == walk_chunk) {
+            __nanosleep(200);
+            if (++idle > LNB_DS_PATIENCE) { if (lane == 0) lnb_ds_give_up(sm, "loader", issued, swapped); break; }
+        } else { walk_chunk = wc; idle = 0; }
+    }
+    /* nothing may still be in flight towards this CTA's shared memory when it exits */
+    while (swapped < issued) { lnb_mbar_wait(&sm.full_bar[swapped % LNB_DS_CHUNKS], (swapped / LNB_DS_CHUNKS) & 1u); swapped++; }
+    if (lane == 0 && w.nchunks == 0u) sm.loaded_words = 0xFFFFFFFFu;
 }
-/* word i of the block's window, big-endian corrected (valid for chunks that have landed) */
+
+/* wait until payload words [0, need) have landed; returns the count known to have landed */
+__device__ __noinline__ uint32_t lnb_ds_await_words(LnbDsShared &sm, uint32_t need)
+{
+    uint32_t have, spins = 0;
+    LNB_DS_T0();
+    while ((have = sm.loaded_words) < need) {
+        __nanosleep(100);
+        if (++spins > LNB_DS_PATIENCE) { lnb_ds_give_up(sm, "payload wait", need, have); break; }
+    }
+    LNB_DS_T1();
+    __threadfence_block();
+    return sm.loaded_words;
+}
+/* payload word i (valid once landed) */
 __device__ __forceinline__ uint32_t lnb_ds_word(const LnbDsShared &sm, uint32_t end_word, uint32_t i)
 {
-    return (i < end_word) ? lnb_bswap32(sm.ring[i % LNB_DS_RING_WORDS]) : 0u;
+    return (i < end_word) ? sm.ring[i % LNB_DS_RING_WORDS] : 0u;
 }
 __device__ __forceinline__ uint32_t lnb_ds_peek(const LnbDsShared &sm, uint32_t end_word, uint32_t pos)
 {
@@ -130,36 +222,6 @@ __device__ __forceinline__ uint32_t lnb_ds_get(const LnbDsShared &sm, uint32_t e
     return v;
 }
 
-/* The walking lane's reader: hi:lo = the next `cnt` (32..64) payload bits, left-aligned; `nw` = word `wi`, the next
- * one to be merged (fetched one merge ahead, so the shared-memory latency is off the chain).  A macro over plain
- * locals: nothing here may have its address taken. */
-#define LNB_DS_TAKE(len_expr)                                                                         \
-    do {                                                                                              \
-        const uint32_t len_ = (len_expr);                                                             \
-        hi = __funnelshift_lc(lo, hi, len_);                                                          \
-        lo = __funnelshift_lc(0u, lo, len_);                                                          \
-        cnt -= len_;                                                                                  \
-        if (cnt < 32u) {                                                                              \
-            hi |= nw >> cnt;                                                                          \
-            lo = __funnelshift_r(0u, nw, cnt);             /* nw << (32 - cnt), 0 when cnt == 0 */    \
-            cnt += 32u;                                                                               \
-            wi++;                                                                                     \
-            if ((wi % LNB_DS_CHUNK_WORDS) == 0u)                                                      \
-                issued = lnb_ds_enter_chunk(sm, win.g0, win.load_bytes, win.nchunks, issued, wi / LNB_DS_CHUNK_WORDS); \
-            nw = (wi < win.end_word) ? lnb_bswap32(lnb_lds32(ring_addr + ((wi * 4u) & (LNB_DS_RING_WORDS * 4u - 1u)))) : 0u; \
-        }                                                                                             \
-    } while (0)
-/* One code word of at most 32 bits: store its window, step over it.  f = index of the leading one (31 - lz);
- * length = k2 + 1 + max(lz, 1) = (k2 + 32) - min(f, 30).  A longer code word (f < k2, or an all-zero window:
- * f = -1) leaves through `long_label`. */
-#define LNB_DS_STEP(slot, long_label)                                                                 \
-    do {                                                                                              \
-        const uint32_t f_ = lnb_bfind(hi);                                                            \
-        if (__builtin_expect((int32_t)f_ < (int32_t)k2, 0)) { at = (slot); goto long_label; }         \
-        lnb_sts32(dst_addr + 4u * (slot), hi);                                                        \
-        LNB_DS_TAKE(k2p32 - (f_ < 30u ? f_ : 30u));                                                   \
-    } while (0)
-
 /* one recursive-Rice residual from a code word's first 32 bits (whole code word inside them: lz <= 31 - k2) */
 __device__ __forceinline__ int32_t lnb_ds_value(uint32_t hi, uint32_t k2)
 {
@@ -170,35 +232,54 @@ __device__ __forceinline__ int32_t lnb_ds_value(uint32_t hi, uint32_t k2)
     return lnb_zz_dec((mult << k2) + low);
 }
 
+/* ---- stage 0: the walk -----------------------------------------------------------------------------------------
+ * What the hardware dictates (tools/ubench/lat_bench.cu, walk_bench.cu on a B200): a dependent integer instruction
+ * issues 4 cycles after its producer, a warp instruction occupies its pipe (ALU or FMA) for 2 cycles, and a branch
+ * on a freshly computed predicate costs ~20 cycles whether it is taken or not.  So the walk is written as GROUPS of
+ * G code words of straight-line code without a single branch or select:
+ *     f = index of the leading one of the window;  length = (k2 + 32) - f + (window >> 31)  [= k2 + 1 + max(lz, 1)]
+ *     the 128-bit window (four registers) shifts left by the length -- four funnel shifts, all fed by that length
+ * with "a code word was longer than 32 bits" and "the group ran out of window" accumulated arithmetically and looked
+ * at ONCE per group, together with the loader's progress and the publishing of the walk's own.  After a group the
+ * window is re-read from shared memory at the new bit position (the only place its latency shows).  A group that
+ * turns out bad is simply walked again from its start position by the careful one-code-word-at-a-time reader.
+ * The walk stores each code word's 32-bit window; stage 1 turns windows into residuals. */
+template <int G>
+__device__ __forceinline__ void lnb_ds_group(uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3, uint32_t dst_addr,
+                                             uint32_t k2, uint32_t &T, uint32_t &bad)
+{
+    const uint32_t K = k2 + 32u;
+#pragma unroll
+    for (int s = 0; s < G; s++) {
+        const uint32_t f = lnb_bfind(w0);
+        const uint32_t t = w0 >> 31;
+        lnb_sts32(dst_addr + 4u * (uint32_t)s, w0);
+        const uint32_t L = K - f + t;
+        asm("mad.hi.u32 %0, %1, 2, %0;" : "+r"(bad) : "r"(f - k2));   /* + 1 whenever f < k2 (f = -1 for an all-zero window); FMA pipe */
+        w0 = __funnelshift_lc(w1, w0, L); w1 = __funnelshift_lc(w2, w1, L);
+        w2 = __funnelshift_lc(w3, w2, L); w3 = __funnelshift_lc(0u, w3, L);
+        T += L;
+    }
+}
+/* the window at bit position pos (its words have landed) */
+__device__ __forceinline__ void lnb_ds_reload(uint32_t ring_addr, uint32_t pos, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3)
+{
+    const uint32_t a = ring_addr + ((pos >> 5) % LNB_DS_RING_WORDS) * 4u, sh = pos & 31u;
+    const uint32_t v0 = lnb_lds32(a), v1 = lnb_lds32(a + 4u), v2 = lnb_lds32(a + 8u), v3 = lnb_lds32(a + 12u), v4 = lnb_lds32(a + 16u);
+    w0 = __funnelshift_l(v1, v0, sh); w1 = __funnelshift_l(v2, v1, sh);
+    w2 = __funnelshift_l(v3, v2, sh); w3 = __funnelshift_l(v4, v3, sh);
+}
+
 /* Stage 0 of one COMPRESSED block.  All lanes of the warp parse the side information (the same fields, uniform
  * control flow); lane 0 alone walks the residual code words.  `line` is the CTA's dynamic shared memory. */
-__device__ __forceinline__ void lnb_ds_walk(const LnbDecodeBatch &b, LnbBlockDesc &gblk, const LnbBlockDesc &blk, LnbDsShared &sm,
-                                            int32_t *line, uint32_t last_stage, uint32_t lane)
+__device__ __forceinline__ void lnb_ds_walk(const LnbDecodeBatch &b, LnbBlockDesc &gblk, const LnbBlockDesc &blk, const LnbDsWin &win,
+                                            LnbDsShared &sm, int32_t *line, uint32_t last_stage, uint32_t lane)
 {
     const LnbStreamCfg &cfg = b.cfg;
     const uint32_t C = cfg.num_channels, n = blk.nsmp;
-    LnbDsWin win;
-    const uintptr_t addr = (uintptr_t)(b.stream + blk.byte_off);
-    win.g0 = (const uint8_t *)(addr & ~(uintptr_t)15);
-    const uint32_t rel0 = (uint32_t)(addr & 15u);
-    const uint32_t rel_payload = rel0 + LNB_BLOCK_HEADER_SIZE;
-    uint32_t end_byte = blk.byte_off + blk.byte_size;
-    if (end_byte > b.stream_size || end_byte < blk.byte_off) end_byte = b.stream_size;
-    const uint32_t rel_end = rel0 + (end_byte - blk.byte_off);
-    win.end_word = (rel_end + 3u) >> 2;
-    {   /* the image is followed by >= 16 readable bytes (lnb_types.h): whole 16-byte lines up to there */
-        const uintptr_t readable = ((uintptr_t)(b.stream + b.stream_size) + 16u) & ~(uintptr_t)15;
-        const uint64_t room = (uint64_t)(readable - (uintptr_t)win.g0);
-        uint64_t want = ((uint64_t)rel_end + 15u) & ~(uint64_t)15;
-        if (want > room) want = room;
-        win.load_bytes = (uint32_t)want;
-    }
-    win.nchunks = (win.load_bytes + LNB_DS_CHUNK_WORDS * 4u - 1u) / (LNB_DS_CHUNK_WORDS * 4u);
-    uint32_t issued = win.nchunks < LNB_DS_CHUNKS ? win.nchunks : LNB_DS_CHUNKS;
-    if (lane == 0) for (uint32_t c = 0; c < issued; c++) lnb_ds_issue(sm, win, c);
     /* the side information lies inside the first two chunks (<= 2.2 KB for 8 channels of 24 bits at -m 7) */
-    for (uint32_t c = 0; c < issued; c++) lnb_mbar_wait(&sm.full_bar[c], 0u);
-    uint32_t pos = rel_payload * 8u;
+    uint32_t loaded = lnb_ds_await_words(sm, (win.nchunks < 2u ? win.nchunks : 2u) * LNB_DS_CHUNK_WORDS);
+    uint32_t pos = win.rel_payload * 8u;
     uint32_t overrun = 0;
 
     /* ---- side information (linne_decoder.c:457-486): every lane reads the same fields ---- */
@@ -235,92 +316,161 @@ __device__ __forceinline__ void lnb_ds_walk(const LnbDecodeBatch &b, LnbBlockDes
 
     /* ---- residuals, channel after channel (linne_coder.c:306-327): lane 0 walks ---- */
     if (lane == 0) {
-        uint32_t hi, lo, cnt, nw, wi;
-        const uint32_t ring_addr = lnb_smem_addr(sm.ring), line_addr = lnb_smem_addr(line);
-        {
-            const uint32_t s = pos & 31u;
-            wi = pos >> 5;
-            const uint32_t w0 = lnb_ds_word(sm, win.end_word, wi), w1 = lnb_ds_word(sm, win.end_word, wi + 1u);
-            hi = __funnelshift_l(w1, w0, s);
-            lo = w1 << s;
-            cnt = 64u - s;
-            wi += 2u;
-            if (wi / LNB_DS_CHUNK_WORDS) issued = lnb_ds_enter_chunk(sm, win.g0, win.load_bytes, win.nchunks, issued, wi / LNB_DS_CHUNK_WORDS);
-            nw = lnb_ds_word(sm, win.end_word, wi);
-        }
+        /* shared-window addresses, computed once: made opaque so that the compiler keeps them in registers instead of
+         * re-deriving them (a special-register read of ~40 cycles) in front of every access inside the loops */
+        uint32_t ring_addr, line_addr;
+        asm volatile("mov.u32 %0, %1;" : "=r"(ring_addr) : "r"(lnb_smem_addr(sm.ring)));
+        asm volatile("mov.u32 %0, %1;" : "=r"(line_addr) : "r"(lnb_smem_addr(line)));
+        const uint32_t pos_limit = (win.end_word + 4u) * 32u;   /* nothing sane reads past this */
+        uint32_t walk_chunk = 0;
+        /* make the words a reader at `pos` may touch available (its window and one group of code words), tell the loader */
+#define LNB_DS_TELL_LOADER()                                                                                   \
+        do {                                                                                                  \
+            if (((pos >> 5) / LNB_DS_CHUNK_WORDS) != walk_chunk) { walk_chunk = (pos >> 5) / LNB_DS_CHUNK_WORDS; sm.walk_word = pos >> 5; } \
+        } while (0)
+#define LNB_DS_SERVICE()                                                                                      \
+        do {                                                                                                  \
+            const uint32_t need_ = (pos >> 5) + 12u;                                                          \
+            LNB_DS_TELL_LOADER();                               /* first: a loader that waits for us must not be waited for */ \
+            if (need_ > loaded) loaded = lnb_ds_await_words(sm, need_ < win.nchunks * LNB_DS_CHUNK_WORDS ? need_ : win.nchunks * LNB_DS_CHUNK_WORDS); \
+        } while (0)
         for (uint32_t c = 0; c < C && !overrun; c++) {
             /* the line (and the k2 table) is free once the last stage has drained the previous channel */
             if (!lnb_ds_wait(sm, last_stage, c * n)) { overrun = 1; break; }
             const uint32_t gbase = c * n;
-            const uint32_t porder = hi >> 22;
-            LNB_DS_TAKE(10u);
-            if (porder > LNB_MAX_PORDER) { overrun = 1; break; }
+            LNB_DS_SERVICE();
+            const uint32_t first = lnb_ds_peek(sm, win.end_word, pos);
+            const uint32_t porder = first >> 22;
+            uint32_t k2 = (first >> 17) & 31u;                       /* first partition: k2 itself (linne_coder.c:313) */
+            pos += 15u;
+            if (porder > LNB_MAX_PORDER || k2 > 30u) { overrun = 1; break; }
             sm.porder[c] = porder;
             const uint32_t len = n >> porder, parts = 1u << porder;
-            uint32_t k2 = 0, done = 0, published = 0;
-            for (uint32_t part = 0; part < parts; part++) {
-                if (part == 0) {
-                    k2 = hi >> 27;
-                    LNB_DS_TAKE(5u);
-                } else {                                         /* gamma code of zigzag(k2 - previous k2) */
-                    const uint32_t lz = lnb_clz32(hi);
-                    if (lz > 15u) { overrun = 1; break; }
-                    const uint32_t v = ((hi << lz) >> (31u - lz)) - 1u;
-                    LNB_DS_TAKE(2u * lz + 1u);
+            uint32_t done = 0, published = 0;
+            uint32_t w0, w1, w2, w3;
+            lnb_ds_reload(ring_addr, pos, w0, w1, w2, w3);
+            for (uint32_t part = 0; part < parts && !overrun; part++) {
+                uint32_t T = 0, bad = 0;
+                const uint32_t k2_prev = k2;
+                bool with_header = part != 0u;
+                if (with_header) {                                   /* gamma code of zigzag(k2 - previous k2), branch-free */
+                    const uint32_t lz = lnb_clz32(w0);
+                    const uint32_t z = lz & 15u;
+                    const uint32_t v = ((w0 << z) >> (31u - z)) - 1u;
+                    const uint32_t L = 2u * z + 1u;
                     k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(v));
+                    bad = (lz > 15u ? 1u : 0u) | (k2 > 30u ? 1u : 0u);
+                    k2 &= 31u;
+                    w0 = __funnelshift_lc(w1, w0, L); w1 = __funnelshift_lc(w2, w1, L);
+                    w2 = __funnelshift_lc(w3, w2, L); w3 = __funnelshift_lc(0u, w3, L);
+                    T = L;
                 }
-                if (k2 > 30u) { overrun = 1; break; }
                 sm.k2tab[part] = (uint8_t)k2;
-                const uint32_t k2p32 = k2 + 32u;
+                LNB_DS_COUNT(4); if (k2 <= 7u) LNB_DS_COUNT(5); else if (k2 == 8u) LNB_DS_COUNT(6); else LNB_DS_COUNT(7);
+                /* code words per group: as many as safely fit the 96 bits a group may use (typical length k2 + 2, a few longer) */
+                uint32_t gmax = (k2 <= 8u) ? 8u : ((k2 <= 19u) ? 4u : 2u);
                 uint32_t rem = len;
+                bool force_careful = false;
+                /* the common case as a tight loop: whole groups of gmax code words, ONE data-dependent branch per group */
+#define LNB_DS_FAST_LOOP(G)                                                                                   \
+                while (rem >= G) {                                                                            \
+                    lnb_ds_group<G>(w0, w1, w2, w3, line_addr + 4u * done, k2, T, bad);                       \
+                    LNB_DS_COUNT(G == 8u ? 0 : 1);                                                            \
+                    const uint32_t npos_ = pos + T, ndone_ = done + G;                                        \
+                    if (__builtin_expect((bad | (T > 96u ? 1u : 0u) | ((npos_ >> 5) + 12u > loaded ? 1u : 0u) \
+                                          | (ndone_ - published >= 64u ? 1u : 0u)) != 0u, 0)) {               \
+                        if (bad | (T > 96u ? 1u : 0u)) { force_careful = true; break; }   /* nothing committed: the careful reader redoes the group */ \
+                        pos = npos_; done = ndone_;                                                           \
+                        LNB_DS_SERVICE();                                                                     \
+                        if (done - published >= 32u) { lnb_ds_publish_lane(sm, 0u, gbase + done); published = done; } \
+                    } else { pos = npos_; done = ndone_; }                                                    \
+                    rem -= G; T = 0; with_header = false;                                                     \
+                    lnb_ds_reload(ring_addr, pos, w0, w1, w2, w3);                                            \
+                }
+                if (gmax == 8u) { LNB_DS_FAST_LOOP(8u) }
+                else if (gmax == 4u) { LNB_DS_FAST_LOOP(4u) }
+#undef LNB_DS_FAST_LOOP
                 while (rem) {
-                    /* groups of eight keep the loop counter and the store address off the chain; a long code word
-                     * leaves the group, is finished below and the walk resumes behind it */
-                    uint32_t at = 0;
-                    uint32_t dst_addr = line_addr + 4u * done;
-                    if (rem >= 8u) {
-                        LNB_DS_STEP(0u, long_cw); LNB_DS_STEP(1u, long_cw); LNB_DS_STEP(2u, long_cw); LNB_DS_STEP(3u, long_cw);
-                        LNB_DS_STEP(4u, long_cw); LNB_DS_STEP(5u, long_cw); LNB_DS_STEP(6u, long_cw); LNB_DS_STEP(7u, long_cw);
-                        rem -= 8u; done += 8u;
-                    } else {
-                        LNB_DS_STEP(0u, long_cw);
-                        rem -= 1u; done += 1u;
-                    }
-                    if (done - published >= 64u) { lnb_ds_publish_lane(sm, 0u, gbase + done); published = done; }
-                    continue;
-                long_cw:
-                    {   /* code word longer than 32 bits (rare): finished here, marked as final for the next stage */
-                        uint32_t q = 0;
-                        while (hi == 0u) {
-                            q += 32u;
-                            LNB_DS_TAKE(32u);
-                            if (wi > win.end_word + 2u) { overrun = 1; break; }
+                    const uint32_t dst_addr = line_addr + 4u * done;
+                    const uint32_t room = rem < gmax ? rem : gmax;
+                    uint32_t g;
+                    LNB_DS_COUNT(2);
+                    if (force_careful) { g = gmax; bad = 1u; force_careful = false; }
+                    else if (room >= 8u) { lnb_ds_group<8>(w0, w1, w2, w3, dst_addr, k2, T, bad); g = 8u; }
+                    else if (room >= 4u) { lnb_ds_group<4>(w0, w1, w2, w3, dst_addr, k2, T, bad); g = 4u; }
+                    else if (room >= 2u) { lnb_ds_group<2>(w0, w1, w2, w3, dst_addr, k2, T, bad); g = 2u; }
+                    else { lnb_ds_group<1>(w0, w1, w2, w3, dst_addr, k2, T, bad); g = 1u; }
+                    /* the one look per group: long code word or header trouble, window exhausted, loader behind, time to publish */
+                    if (__builtin_expect((bad | (T > 96u ? 1u : 0u)) != 0u, 0)) {
+                        /* the careful reader: this group again from its first bit, one field per pass, every check in place */
+                        LNB_DS_COUNT(3);
+                        LNB_DS_SERVICE();
+                        if (with_header) {
+                            const uint32_t h = lnb_ds_peek(sm, win.end_word, pos);
+                            const uint32_t lz = lnb_clz32(h);
+                            if (lz > 15u) { overrun = 1; break; }
+                            const uint32_t v = ((h << lz) >> (31u - lz)) - 1u;
+                            pos += 2u * lz + 1u;
+                            k2 = (uint32_t)((int32_t)k2_prev + lnb_zz_dec(v));
+                            if (k2 > 30u) { overrun = 1; break; }
+                            sm.k2tab[part] = (uint8_t)k2;
+                            gmax = (k2 <= 8u) ? 8u : ((k2 <= 19u) ? 4u : 2u);
+                        }
+                        for (uint32_t s = 0; s < g; s++) {
+                            LNB_DS_SERVICE();
+                            const uint32_t h = lnb_ds_peek(sm, win.end_word, pos);
+                            const uint32_t lz = lnb_clz32(h);
+                            const uint32_t i = done + s;
+                            if (lz + k2 <= 31u) {
+                                line[i] = (int32_t)h;
+                                pos += k2 + 1u + (lz > 1u ? lz : 1u);
+                                continue;
+                            }
+                            /* code word longer than 32 bits: finished here, marked as final for the next stage */
+                            uint32_t q = 0, hh = h;
+                            while (hh == 0u) {
+                                q += 32u; pos += 32u;
+                                if (pos > pos_limit) { overrun = 1; break; }
+                                LNB_DS_SERVICE();
+                                hh = lnb_ds_peek(sm, win.end_word, pos);
+                            }
+                            if (overrun) break;
+                            const uint32_t z = lnb_clz32(hh);
+                            q += z; pos += z + 1u;
+                            LNB_DS_SERVICE();
+                            const uint32_t low = k2 ? (lnb_ds_peek(sm, win.end_word, pos) >> (32u - k2)) : 0u;
+                            pos += k2;
+                            line[i] = lnb_zz_dec(low + (2u << k2) + ((q - 1u) << k2));         /* q >= 2 here */
+                            sm.done_mask[i >> 5] |= 1u << (i & 31u);
                         }
                         if (overrun) break;
-                        const uint32_t z = lnb_clz32(hi);
-                        q += z;
-                        LNB_DS_TAKE(z + 1u);
-                        const uint32_t low = k2 ? (hi >> (32u - k2)) : 0u;
-                        LNB_DS_TAKE(k2);
-                        const uint32_t u = (q == 0u) ? 0u : low + (2u << k2) + ((q - 1u) << k2);   /* q >= 2 here */
-                        const uint32_t i = done + at;
-                        line[i] = lnb_zz_dec(u);
-                        sm.done_mask[i >> 5] |= 1u << (i & 31u);
-                        rem -= at + 1u; done += at + 1u;
+                        bad = 0;
+                    } else {
+                        pos += T;
                     }
+                    T = 0; with_header = false; rem -= g; done += g;
+                    if (((pos >> 5) + 12u > loaded) | (done - published >= 64u)) {
+                        LNB_DS_SERVICE();
+                        if (done - published >= 32u) { lnb_ds_publish_lane(sm, 0u, gbase + done); published = done; }
+                    }
+                    lnb_ds_reload(ring_addr, pos, w0, w1, w2, w3);
                 }
-                if (done - published >= 32u || part + 1u == parts) { lnb_ds_publish_lane(sm, 0u, gbase + done); published = done; }
                 if (overrun) break;
+                LNB_DS_TELL_LOADER();
+                if (done - published >= 32u || part + 1u == parts) { lnb_ds_publish_lane(sm, 0u, gbase + done); published = done; }
             }
             if (overrun) break;
             /* samples a partition order that does not divide the block leaves uncovered read as zero */
             for (uint32_t i = done; i < n; i++) { line[i] = 0; sm.done_mask[i >> 5] |= 1u << (i & 31u); }
             lnb_ds_publish_lane(sm, 0u, gbase + n);
         }
+#undef LNB_DS_SERVICE
+#undef LNB_DS_TELL_LOADER
         if (overrun) { sm.abort = 1u; __threadfence_block(); }
-        const uint32_t used = (wi * 32u - cnt - rel_payload * 8u + 7u) >> 3;
+        const uint32_t used = (pos - win.rel_payload * 8u + 7u) >> 3;
         gblk.na = used;                                          /* payload bytes consumed (reference Flush + Tell) */
-        if (overrun || rel_payload + used > rel_end) gblk.status = blk.status | LNB_ST_OVERRUN;
+        if (overrun || win.rel_payload + used > win.rel_end) gblk.status = blk.status | LNB_ST_OVERRUN;
+        sm.walk_done = 1u;
     }
     __syncwarp();
 }
@@ -552,15 +702,28 @@ __global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v2_kernel(LnbDecode
     for (uint32_t i = threadIdx.x; i < LNB_DS_MAX_N / 32u; i += LNB_DS_THREADS) sm.done_mask[i] = 0u;
     if (threadIdx.x < LNB_DS_STAGES) sm.prog[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
-        sm.abort = 0u;
+        sm.abort = 0u; sm.loaded_words = 0u; sm.walk_word = 0u; sm.walk_done = 0u;
         for (uint32_t c = 0; c < LNB_DS_CHUNKS; c++) lnb_mbar_init(&sm.full_bar[c], 1u);
         lnb_mbar_init_fence();
     }
     __syncthreads();
 
+#ifdef LNB_DS_TIMING
+    const long long t_kernel0 = clock64();
+    if (blockIdx.x == 0 && lane == 0) { lnb_ds_waited[hw_warp] = 0; if (hw_warp == 0) for (int i = 0; i < 8; i++) lnb_ds_count[i] = 0; }
+    struct LnbDsTimingReport { long long t0; uint32_t w; __device__ ~LnbDsTimingReport() {
+        if (blockIdx.x == 0 && (threadIdx.x & 31u) == 0u) printf("stream_v2 timing: warp %u ran %lld cycles, waited %llu; counts %u %u %u %u parts %u (k2<=7 %u, 8 %u, more %u)\n", w, clock64() - t0, lnb_ds_waited[w], lnb_ds_count[0], lnb_ds_count[1], lnb_ds_count[2], lnb_ds_count[3], lnb_ds_count[4], lnb_ds_count[5], lnb_ds_count[6], lnb_ds_count[7]); } } report_{t_kernel0, hw_warp};
+#endif
+#ifdef LNB_DS_TIMING
+    if (b.cfg.check_crc & 0x100u) {                            /* debug: the walk alone (results are wrong) */
+        if (hw_warp != 0u && hw_warp != 4u) return;
+        if (threadIdx.x == 0) for (uint32_t i = 1; i < LNB_DS_STAGES; i++) sm.prog[i] = 0x7FFFFFFFu;
+    }
+#endif
+    if (hw_warp == 4u) { lnb_ds_loader(lnb_ds_window(b, blk), sm, lane); return; }
     if (stage == 0xFFu) return;
     if (stage == 0u) {
-        lnb_ds_walk(b, gblk, blk, sm, lnb_ds_line, last, lane);
+        lnb_ds_walk(b, gblk, blk, lnb_ds_window(b, blk), sm, lnb_ds_line, last, lane);
         if (sm.abort) {                                        /* broken payload: the block reads as silence */
             for (uint32_t c = 0; c < C; c++) {
                 int32_t *gout = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;

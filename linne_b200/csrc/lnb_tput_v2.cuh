@@ -14,9 +14,10 @@
  * own sequence, a warp retires 32 samples per pass of the loop, and the cost drops to the ~1 (entropy) and
  * ~P/4 (synthesis) warp instructions per sample the arithmetic needs.
  *
- *   lnb_tp_entropy_kernel   lane = block.  Side information and the recursive-Rice residuals of all channels through a
- *                           64-bit register window per lane (every lane streams its own payload through L1, next
- *                           line prefetched); four residuals per lane leave as one 16-byte store.
+ *   lnb_tp_entropy_kernel   eight lanes per block, four blocks per warp: speculative code-word starts, one 32-byte
+ *                           sector of residuals per round (see below; a lane-per-block walk was measured in round 2
+ *                           and lost: every data-dependent branch of a lone warp costs ~20 cycles, and 32 lanes at 32
+ *                           different places of their blocks pay every lane's branches -- 7.1 ms against 3.7 ms).
  *   lnb_tp_synth_kernel     lane = (block, channel).  Groups of 8 samples run through the whole cascade in
  *                           registers: for layers of 16..128 taps the history lives in a lane-interleaved
  *                           shared-memory ring (conflict-free; the ring position is warp-uniform because all
@@ -51,68 +52,65 @@ LNB_HD bool lnb_tp_takes(const LnbDecodeBatch &b, const LnbBlockDesc &blk)
 #if defined(__CUDACC__)
 
 /* ------------------------------------------------------------------------------------------------------
- * entropy: one LANE per block, 32 blocks per warp, one code word (or one partition / channel header) per lane
- * and pass of a single flat loop.
+ * entropy: LNB_TG lanes per block, 32 / LNB_TG blocks per warp.
  *
- * The walk over a block's code words is serial by format; with thousands of blocks in a batch it can stay serial
- * as long as a lane's chain is short and the 32 lanes of a warp never wait for each other.  Round 1 spent eight
- * lanes per block on speculative code-word starts (~80 warp instructions per round of ~3 code words, 3.65 ms for
- * a 1-hour stream).  Here every lane keeps a 64-bit window of ITS payload in registers:
- *     lz = clz(hi);  length = k2 + 1 + max(lz, 1);  window <<= length        (the whole dependent chain)
- * and the value comes out of the same 32 bits.  Partition headers (gamma-coded delta of k2) and channel headers
- * (partition order + first k2) are just other kinds of pass, executed under one vote only when some lane is at
- * one, so lanes with different partition orders do not serialise each other.  The next payload word is fetched
- * one merge ahead through L1 (a lane streams 128-byte lines of its own payload; the line after the current one is
- * prefetched), four residuals are collected per lane and leave as one 16-byte store.
+ * One lane per block leaves the machine empty (a 1-hour stream has 15 504 blocks = 485 warps) and a lane's
+ * symbol chain of ~90 dependent instructions runs at one instruction per ~7 cycles when nothing else shares
+ * its scheduler; a whole warp per block (lnb_entropy_v3.cuh) retires ~3 code words per round on 32 lanes.  Eight
+ * lanes per block sit between: with k1 = k2 + 1 the code words of residuals below 3 * 2^k2 -- the large
+ * majority -- are all k2 + 2 bits long, so lane j of a group reads the field at  pos + j * (k2 + 2);  the first
+ * lane that sees a longer code word ('00' prefix) ends the round, every lane before it holds a valid residual
+ * (~4 per round), and the group's eight stores form one 32-byte sector.  Groups of a warp run the same flat
+ * loop (one round per pass, headers and window refills as short predicated detours), so the warp does not
+ * serialise them, and 3 876 warps keep every scheduler busy.
+ * The payload of a group is staged in a shared-memory window of LNB_TG_WIN words filled by the group itself.
  * ------------------------------------------------------------------------------------------------------ */
-struct LnbTeChain {
-    const uint32_t *words;      /* 16-byte aligned, at most 15 bytes before the block's first byte */
+#define LNB_TG            8u
+#define LNB_TG_PER_WARP   (32u / LNB_TG)
+#define LNB_TG_WIN        128u
+#define LNB_TG_ROUND_BITS (LNB_TG * 33u + 64u + 32u) /* furthest bit a partition header plus a round can look at, relative to their start */
+
+struct LnbTgWin {
+    uint32_t *buf;              /* [LNB_TG_WIN + 2] */
+    const uint32_t *words;      /* global, word 0 = aligned word holding the block's first byte */
+    uint32_t wb;                /* index of the word held in buf[0] */
     uint32_t end_word;          /* words at or past this index read as zero */
-    uint32_t hi, lo, cnt, nw, wi;
+    uint32_t limit;             /* a round may start at bit positions up to this one without a refill */
 };
-__device__ __forceinline__ uint32_t lnb_te_fetch(const LnbTeChain &r, uint32_t wi)
+__device__ __forceinline__ void lnb_tg_fill(LnbTgWin &w, uint32_t word_idx, uint32_t lg, uint32_t gmask)
 {
-    const uint32_t *p = r.words + wi;
-    /* entering a 128-byte line: ask for the next one now, it is needed ~100 code words from here */
-    if ((((uintptr_t)p) & 127u) == 0u && wi + 32u < r.end_word)
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 32));
-    return (wi < r.end_word) ? lnb_bswap32(__ldg(p)) : 0u;
-}
-__device__ __forceinline__ void lnb_te_take(LnbTeChain &r, uint32_t len)                      /* 0 <= len <= 32 */
-{
-    r.hi = __funnelshift_lc(r.lo, r.hi, len);
-    r.lo = __funnelshift_lc(0u, r.lo, len);
-    r.cnt -= len;
-    if (r.cnt < 32u) {
-        r.hi |= r.nw >> r.cnt;
-        r.lo = __funnelshift_r(0u, r.nw, r.cnt);               /* nw << (32 - cnt), 0 when cnt == 0 */
-        r.cnt += 32u;
-        r.wi++;
-        r.nw = lnb_te_fetch(r, r.wi);
+    __syncwarp(gmask);
+    w.wb = word_idx;
+    w.limit = (word_idx + LNB_TG_WIN) * 32u - LNB_TG_ROUND_BITS;
+#pragma unroll 4
+    for (uint32_t i = lg; i < LNB_TG_WIN + 2u; i += LNB_TG) {
+        const uint32_t idx = word_idx + i;
+        w.buf[i] = (idx < w.end_word) ? lnb_bswap32(w.words[idx]) : 0u;
     }
+    __syncwarp(gmask);
 }
-__device__ __forceinline__ void lnb_te_open(LnbTeChain &r, uint32_t pos)
+__device__ __forceinline__ void lnb_tg_ensure(LnbTgWin &w, uint32_t pos, uint32_t span, uint32_t lg, uint32_t gmask)
 {
-    const uint32_t wi = pos >> 5, s = pos & 31u;
-    const uint32_t w0 = (wi < r.end_word) ? lnb_bswap32(__ldg(r.words + wi)) : 0u;
-    const uint32_t w1 = (wi + 1u < r.end_word) ? lnb_bswap32(__ldg(r.words + wi + 1u)) : 0u;
-    r.hi = __funnelshift_l(w1, w0, s);
-    r.lo = w1 << s;
-    r.cnt = 64u - s;
-    r.wi = wi + 2u;
-    r.nw = (r.wi < r.end_word) ? lnb_bswap32(__ldg(r.words + r.wi)) : 0u;
+    if (((pos + span) >> 5) + 2u > w.wb + LNB_TG_WIN + 2u || (pos >> 5) < w.wb) lnb_tg_fill(w, pos >> 5, lg, gmask);
 }
-__device__ __forceinline__ uint32_t lnb_te_get(LnbTeChain &r, uint32_t n)                     /* 1 <= n <= 32 */
+__device__ __forceinline__ uint32_t lnb_tg_peek(const LnbTgWin &w, uint32_t pos)
 {
-    const uint32_t v = r.hi >> (32u - n);
-    lnb_te_take(r, n);
+    const uint32_t i = (pos >> 5) - w.wb;
+    return __funnelshift_l(w.buf[i + 1u], w.buf[i], pos & 31u);
+}
+__device__ __forceinline__ uint32_t lnb_tg_get(const LnbTgWin &w, uint32_t &pos, uint32_t n)   /* 1 <= n <= 32 */
+{
+    const uint32_t v = lnb_tg_peek(w, pos) >> (32u - n);
+    pos += n;
     return v;
 }
 
 __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
 {
-    const uint32_t lane = threadIdx.x;
-    const uint32_t blk_i = blockIdx.x * 32u + lane;
+    __shared__ uint32_t s_win[LNB_TG_PER_WARP][LNB_TG_WIN + 2u];
+    const uint32_t lane = threadIdx.x, g = lane / LNB_TG, lg = lane % LNB_TG;
+    const uint32_t gmask = ((1u << LNB_TG) - 1u) << (g * LNB_TG);
+    const uint32_t blk_i = blockIdx.x * LNB_TG_PER_WARP + g;
     const LnbStreamCfg &cfg = b.cfg;
     const uint32_t C = cfg.num_channels, n = cfg.block_size;
     LnbBlockDesc blk;
@@ -120,116 +118,130 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
     if (active) { blk = b.blocks[blk_i]; active = lnb_tp_shape_ok(b, blk); }
     if (__ballot_sync(0xffffffffu, active) == 0u) return;
 
-    LnbTeChain r;
-    r.words = (const uint32_t *)b.stream; r.end_word = 0; r.hi = r.lo = r.nw = 0; r.cnt = 64u; r.wi = 0;
-    uint32_t rel_payload = 0, rel_end = 0, overrun = 0;
+    LnbTgWin win;
+    win.buf = s_win[g];
+    win.words = (const uint32_t *)b.stream; win.wb = 0; win.end_word = 0; win.limit = 0;
+    uint32_t pos = 0, rel_payload = 0, rel_end = 0, overrun = 0;
 
-    /* ---- side information (linne_decoder.c:457-486) ---- */
+    /* ---- side information (linne_decoder.c:457-486): every lane of the group reads the same fields ---- */
     if (active) {
-        const uintptr_t addr = (uintptr_t)(b.stream + blk.byte_off);
-        const uint32_t rel0 = (uint32_t)(addr & 15u);
-        r.words = (const uint32_t *)(addr & ~(uintptr_t)15);
+        const uint32_t payload_off = blk.byte_off + LNB_BLOCK_HEADER_SIZE;
         uint32_t end_byte = blk.byte_off + blk.byte_size;
-        if (end_byte > b.stream_size || end_byte < blk.byte_off) end_byte = b.stream_size;
-        rel_payload = rel0 + LNB_BLOCK_HEADER_SIZE; rel_end = rel0 + (end_byte - blk.byte_off);
-        r.end_word = (rel_end + 3u) >> 2;
-        lnb_te_open(r, rel_payload * 8u);
+        if (end_byte > b.stream_size) end_byte = b.stream_size;
+        const uint32_t word0 = blk.byte_off >> 2;               /* bit positions relative to this word never overflow */
+        win.words = (const uint32_t *)b.stream + word0;
+        rel_payload = payload_off - word0 * 4u; rel_end = end_byte - word0 * 4u;
+        win.end_word = (rel_end + 3u) >> 2;
+        pos = rel_payload * 8u;
+        lnb_tg_fill(win, pos >> 5, lg, gmask);
         LnbChanParams *params = b.params + (size_t)blk_i * C;
         for (uint32_t c = 0; c < C; c++)
             for (int f = 0; f < LNB_NUM_PREEM; f++) {
-                params[c].preem_prev[f] = lnb_zz_dec(lnb_te_get(r, cfg.bits_per_sample + 1u));
-                params[c].preem_coef[f] = (uint8_t)lnb_te_get(r, LNB_PREEM_SHIFT - 1);
+                lnb_tg_ensure(win, pos, 64u, lg, gmask);
+                const int32_t prev = lnb_zz_dec(lnb_tg_get(win, pos, cfg.bits_per_sample + 1u));
+                const uint32_t coef = lnb_tg_get(win, pos, LNB_PREEM_SHIFT - 1);
+                if (lg == 0u) { params[c].preem_prev[f] = prev; params[c].preem_coef[f] = (uint8_t)coef; }
             }
         for (uint32_t c = 0; c < C; c++)
             for (uint32_t l = 0; l < cfg.num_layers; l++) {
                 const uint32_t P = cfg.layer_params[l];
-                params[c].log2_units[l] = (uint8_t)lnb_te_get(r, 3);
-                params[c].rshift[l] = (uint8_t)lnb_te_get(r, 4);
-                uint32_t *q = (uint32_t *)(params[c].coef + l * LNB_MAX_PARAMS);     /* 4 taps per store */
-                uint32_t four = 0;
-                for (uint32_t i = 0; i < P; i++) {
-                    const uint32_t e = b.tab.huff_lut[r.hi >> (32 - LNB_HUFF_LUT_BITS)];
-                    lnb_te_take(r, e & 15u);
-                    four |= ((uint32_t)lnb_zz_dec(e >> 4) & 0xFFu) << (8u * (i & 3u));
-                    if ((i & 3u) == 3u || i + 1u == P) { q[i >> 2] = four; four = 0; }
+                lnb_tg_ensure(win, pos, 7u + P * 14u + 32u, lg, gmask);
+                const uint32_t lu = lnb_tg_get(win, pos, 3), rs = lnb_tg_get(win, pos, 4);
+                if (lg == 0u) { params[c].log2_units[l] = (uint8_t)lu; params[c].rshift[l] = (uint8_t)rs; }
+                int8_t *q = params[c].coef + l * LNB_MAX_PARAMS;
+                for (uint32_t i0 = 0; i0 < P; i0 += LNB_TG) {    /* lane j keeps coefficients j, j + 8, ... */
+                    int32_t keep = 0;
+                    const uint32_t lim = (P - i0 < LNB_TG) ? P - i0 : LNB_TG;
+                    for (uint32_t i = 0; i < lim; i++) {
+                        const uint32_t e = b.tab.huff_lut[lnb_tg_peek(win, pos) >> (32 - LNB_HUFF_LUT_BITS)];
+                        pos += e & 15u;
+                        if (i == lg) keep = lnb_zz_dec(e >> 4);
+                    }
+                    if (lg < lim) q[i0 + lg] = (int8_t)keep;
                 }
             }
     }
 
-    /* ---- residuals: one flat loop, one code word or header per lane and pass ---- */
-    uint32_t chan = 0, left = 0, parts_left = 0, len = 0, k2 = 0, idx = 0;
-    uint32_t sh = 31u, k2p1 = 1u, k2mask = 0u, fin = 0u;
-    int32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    /* ---- residuals.  Outer pass: channel starts and the end of the block (twice per channel).  Inner loop: one
+     *      round per group and pass, with the window refill and the partition header (a gamma-coded delta of k2) of
+     *      the groups that need one as short predicated detours in front of it. ---- */
+    uint32_t chan = 0, left = 0, parts_left = 0, len = 0, k2 = 0;
+    uint32_t my_rel = 0, my_end = 0, k2mask = 0, sh = 31u;       /* per-partition constants of this lane */
     bool running = active;
-    int32_t *wp = b.pcm;
+    int32_t *wp = b.pcm;                                         /* where this lane's residual of the next round goes */
     while (__any_sync(0xffffffffu, running)) {
-        const uint32_t h = r.hi;
-        const uint32_t lz = lnb_clz32(h);
-        const bool is_rice = left != 0u;
-        /* the Rice view of the window (every lane computes it; lanes at a header ignore it) */
-        const uint32_t ml = (lz > 1u) ? lz : 1u;
-        uint32_t take = k2p1 + ml;
-        if (__any_sync(0xffffffffu, running && !is_rice)) {
-            if (running && !is_rice) {
-                if (parts_left) {                                /* partition header: gamma code of zigzag(k2 - previous k2) */
-                    const uint32_t z = lz & 15u;
-                    const uint32_t v = ((h << z) >> (31u - z)) - 1u;
-                    take = 2u * lz + 1u;
-                    k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(v));
-                    left = len; parts_left--;
-                    if (lz > 15u || k2 > 30u) { overrun = 1u; k2 = 30u; left = 0u; parts_left = 0u; take = 0u; }
-                } else if (chan < C && !overrun) {               /* channel header: partition order, first k2 (linne_coder.c:310-313) */
-                    uint32_t porder = h >> 22;
-                    k2 = (h >> 17) & 31u;
-                    take = 15u;
-                    if (porder > LNB_MAX_PORDER) { overrun = 1u; porder = 0u; }
-                    if (k2 > 30u) { overrun = 1u; k2 = 30u; }
-                    len = n >> porder; parts_left = (1u << porder) - 1u; left = len;
-                    if (overrun) { left = 0u; parts_left = 0u; take = 0u; }
-                    wp = b.pcm + (size_t)chan * cfg.pcm_stride + blk.smp_off;
-                    idx = 0u;
-                    chan++;
-                } else {                                         /* done: the lane idles along (its window reads zeros past the block) */
-                    running = false; take = 0u;
-                    fin = r.wi * 32u - r.cnt;
-                }
-                sh = 31u - k2; k2p1 = k2 + 1u; k2mask = (1u << k2) - 1u;
-            }
-        }
-        if (is_rice) {
-            int32_t v;
-            if (__builtin_expect(lz > sh, 0)) {
-                /* code word longer than 32 bits (rare): walked here */
-                uint32_t q = 0;
-                while (r.hi == 0u && !overrun) {
-                    q += 32u;
-                    lnb_te_take(r, 32u);
-                    if (r.wi > r.end_word + 2u) overrun = 1u;
-                }
-                if (!overrun) {
-                    const uint32_t z = lnb_clz32(r.hi);
-                    q += z;
-                    lnb_te_take(r, z + 1u);
-                }
-                const uint32_t low = k2 ? (r.hi >> (32u - k2)) : 0u;
-                lnb_te_take(r, k2);
-                v = lnb_zz_dec((q == 0u) ? 0u : low + (2u << k2) + ((q - 1u) << k2));
-                take = 0u;
-                if (overrun) { left = 1u; parts_left = 0u; }
+        if (running && left == 0u && parts_left == 0u) {                         /* next channel, or the end of the block */
+            if (chan == C || overrun) {
+                running = false;
             } else {
-                const uint32_t low = (h >> ((sh - ml) & 31u)) & k2mask;
-                const uint32_t mult = lz ? lz + 1u : ((h >> 30) & 1u);
-                v = lnb_zz_dec((mult << k2) + low);
+                lnb_tg_ensure(win, pos, 64u, lg, gmask);
+                uint32_t porder = lnb_tg_get(win, pos, 10);
+                if (porder > LNB_MAX_PORDER) { overrun = 1u; porder = 0u; }
+                len = n >> porder; parts_left = (1u << porder) - 1u;
+                k2 = lnb_tg_get(win, pos, 5);                                    /* first partition: k2 itself (linne_coder.c:313) */
+                if (k2 > 30u) { overrun = 1u; k2 = 30u; }
+                left = overrun ? 0u : len;
+                if (overrun) parts_left = 0u;
+                my_rel = lg * (k2 + 2u); my_end = my_rel + k2 + 1u; k2mask = (1u << k2) - 1u; sh = 31u - k2;
+                wp = b.pcm + (size_t)chan * cfg.pcm_stride + blk.smp_off + lg;
+                chan++;
             }
-            a0 = a1; a1 = a2; a2 = a3; a3 = v;
-            idx++;
-            if ((idx & 3u) == 0u) *(int4 *)(wp + idx - 4u) = make_int4(a0, a1, a2, a3);
-            left--;
         }
-        lnb_te_take(r, take);
+        if (!__any_sync(0xffffffffu, running)) break;
+        /* `running` does not change inside the round loop and a running group runs out of code words eventually */
+        while (__all_sync(0xffffffffu, !running || left != 0u || parts_left != 0u)) {
+            if (running && pos > win.limit) lnb_tg_fill(win, pos >> 5, lg, gmask);
+            if (running && left == 0u) {                                         /* partition header: gamma code of zigzag(k2 - previous k2) */
+                const uint32_t h = lnb_tg_peek(win, pos);
+                const uint32_t lz = lnb_clz32(h);
+                const uint32_t v = ((h << (lz & 15u)) >> (31u - (lz & 15u))) - 1u;
+                pos += 2u * lz + 1u;
+                k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(v));
+                left = len; parts_left--;
+                if (lz > 15u || k2 > 30u) { overrun = 1u; k2 = 30u; left = 0u; parts_left = 0u; }
+                my_rel = lg * (k2 + 2u); my_end = my_rel + k2 + 1u; k2mask = (1u << k2) - 1u; sh = 31u - k2;
+            }
+            /* the round: lane j guesses that code word j starts at pos + j * (k2 + 2) */
+            const bool go = running && left != 0u;
+            const uint32_t last = (left < LNB_TG ? left : LNB_TG) - 1u;
+            const uint32_t hi = go ? lnb_tg_peek(win, pos + my_rel) : 0xFFFFFFFFu;
+            const uint32_t lz = lnb_clz32(hi);
+            const uint32_t ml = (lz > 1u) ? lz : 1u;
+            const bool resolves = go && (hi < 0x40000000u || lg == last) && lg <= last;
+            const uint32_t is_short = (lz <= sh) ? 0x8000u : 0u;                 /* whole code word inside the 32-bit peek */
+            uint32_t r = resolves ? ((lg << 16) | is_short | (my_end + ml)) : 0xFFFFFFFFu;
+            r = __reduce_min_sync(gmask, r);                                     /* one redux per group (tiled-partition style mask) */
+            if (go) {
+                const uint32_t first = r >> 16;
+                uint32_t n_ok = first + ((r >> 15) & 1u);
+                {
+                    const uint32_t low = (hi >> (sh - ml)) & k2mask;
+                    const uint32_t mult = lz ? lz + 1u : ((hi >> 30) & 1u);
+                    if (lg < n_ok) *wp = lnb_zz_dec((mult << k2) + low);
+                }
+                if (__builtin_expect((r & 0x8000u) != 0u, 1)) {
+                    pos += r & 0x7FFFu;
+                } else {                                                         /* code word longer than 32 bits: its lane finishes it serially */
+                    uint32_t endl = 0, bad = 0;
+                    if (lg == first) {
+                        LnbFastReader fr;
+                        lnb_fr_open(fr, win.words, pos + my_rel, win.end_word);
+                        const uint32_t q = lnb_fr_zero_run(fr);
+                        const uint32_t u = (q == 0u) ? lnb_fr_get(fr, k2 + 1u) : lnb_fr_get(fr, k2) + (2u << k2) + ((q - 1u) << k2);
+                        *wp = lnb_zz_dec(u);
+                        endl = (uint32_t)lnb_fr_position(fr);
+                        bad = fr.overrun;
+                    }
+                    pos = __shfl_sync(gmask, endl, (int)(g * LNB_TG + first));
+                    n_ok = first + 1u;
+                    if (__shfl_sync(gmask, bad, (int)(g * LNB_TG + first))) { overrun = 1u; left = n_ok; parts_left = 0u; }
+                }
+                left -= n_ok; wp += n_ok;
+            }
+        }
     }
-    if (active) {
-        const uint32_t used = (fin - rel_payload * 8u + 7u) >> 3;
+    if (active && lg == 0u) {
+        const uint32_t used = (pos - rel_payload * 8u + 7u) >> 3;
         b.blocks[blk_i].na = used;                                               /* payload bytes consumed (reference Flush + Tell) */
         if (overrun || rel_payload + used > rel_end) atomicOr(&b.blocks[blk_i].status, (uint32_t)LNB_ST_OVERRUN);
     }

@@ -35,7 +35,7 @@ def main():
         for _ in range(args.reps):
             dec.decode_whole(buf.ctypes.data, len(stream), harness._chan_ptrs(out), C, n)
         st = dec.stage_stats()
-        assert np.array_equal(out, pcm), "decode differs"
+        assert os.environ.get("LINNE_B200_DBG_WALKONLY") or np.array_equal(out, pcm), "decode differs"
         print(f"ok preset={preset} samples={pcm.size} bytes={len(stream)} " +
               " ".join(f"{k}={v[1] / v[0]:.3f}ms" for k, v in st.items()), flush=True)
         dec.close()
