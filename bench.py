@@ -930,7 +930,7 @@ def run_b200(args, rank, world, local_rank):
     total_comp = sum(comp_bytes.values())
     hbm_bytes_per_sample = 4.0 + total_comp / (len(PRESETS) * n_samples)      # int32 PCM + compressed bytes
     analysis_kernels = {"analyze_v3", "to_double", "acorr", "solve", "loss", "select", "forward", "refine_v2"}
-    dec_kernels = {"crc_v2", "stream_v1", "tp_entropy", "tp_synth", "entropy_v3", "synth_v2", "crc", "entropy", "synth", "deemph", "ms_inverse"}
+    dec_kernels = {"crc_v2", "stream_v2", "tp_entropy", "tp_synth", "entropy_v3", "synth_v2", "crc", "entropy", "synth", "deemph", "ms_inverse"}
     dom = max(stage_serial.items(), key=lambda kv: kv[1][1]) if stage_serial else ("none", [1, 1.0])
     dom_name, (dom_cnt, dom_ms) = dom[0], dom[1]
     try:        # DRAM bytes per launch of that kernel from the committed ncu capture (profiles/)
@@ -969,6 +969,27 @@ def run_b200(args, rank, world, local_rank):
                        "achieved": round(by / (dec_ms / 1e3) / 1e9, 3) if dec_ms else None,
                        "peak": hbm_peak, "unit": "GB/s", "frac": round(by / (dec_ms / 1e3) / 1e9 / hbm_peak, 5) if dec_ms else None,
                        "peak_source": peak_src, "bytes_per_sample": round(hbm_bytes_per_sample, 3)}
+
+    # ---- per mode and per direction (BASELINE.json's metric is quoted per -m mode): every preset alone on the GPU,
+    #      wall clock of the synchronous calls (median), device-resident and through host buffers ----
+    per_mode = {}
+    pm_reps = max(3, min(args.steps, 7))
+
+    def _median_ms(fn):
+        ts = []
+        for _ in range(pm_reps):
+            l2_flush.fill_(1); torch.cuda.synchronize()
+            t0 = time.perf_counter(); fn(); ts.append((time.perf_counter() - t0) * 1e3)
+        return sorted(ts)[len(ts) // 2]
+    for m in PRESETS:
+        sz = sizes[m]
+        enc_res = _median_ms(lambda: encs[m].encode_whole_resident(d_pcm.data_ptr(), stride, n, d_out[m].data_ptr(), cap))
+        dec_res = _median_ms(lambda: decs[m].decode_whole_resident(None, d_out[m].data_ptr(), sz, d_backs[m].data_ptr(), stride, nch, n))
+        enc_h = _median_ms(lambda: encs[m].encode_whole(chan_in, n, h_outs[m].data_ptr(), cap))
+        dec_h = _median_ms(lambda: decs[m].decode_whole(h_outs[m].data_ptr(), sz, chan_outs[m], nch, n))
+        per_mode[str(m)] = {"enc_MSps": round(n_samples / enc_res / 1e3, 1), "dec_MSps": round(n_samples / dec_res / 1e3, 1),
+                            "enc_e2e_MSps": round(n_samples / enc_h / 1e3, 1), "dec_e2e_MSps": round(n_samples / dec_h / 1e3, 1),
+                            "enc_ms": round(enc_res, 3), "dec_ms": round(dec_res, 3), "bytes": int(sz)}
 
     # ---- at-scale legs: free the sweep's buffers first ----
     host_wait_sweep = os.environ.get("LINNE_B200_SYNC", "spin")
@@ -1045,6 +1066,23 @@ def run_b200(args, rank, world, local_rank):
     except Exception as e:  # pragma: no cover
         cpu_baseline = {"value": None, "unit": "MSamples/s", "cores": 1, "kind": "unavailable", "sample": str(e)}
 
+    # ---- the reference's compressed size of the whole clip at every mode (one host thread per mode), beside ours ----
+    try:
+        impl_sz = harness.Ref if harness.have_ref() else harness.Oracle
+        full_ref = {}
+
+        def _ref_size(m):
+            full_ref[m] = len(impl_sz().encode(pcm, preset=m))
+        ths = [threading.Thread(target=_ref_size, args=(m,)) for m in PRESETS[::-1]]
+        for t in ths: t.start()
+        for t in ths: t.join()
+        for m in PRESETS:
+            pm = per_mode[str(m)]
+            pm["ref_bytes"] = int(full_ref[m])
+            pm["delta_pct"] = round(100.0 * (pm["bytes"] - full_ref[m]) / full_ref[m], 5)
+    except Exception as e:  # pragma: no cover
+        per_mode["ref_bytes_error"] = repr(e)
+
     line = {
         "metric": "encode+decode MSamples/s over the -m 0..7 sweep", "value": round(value, 3), "unit": "MSamples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res, 3),
@@ -1062,6 +1100,7 @@ def run_b200(args, rank, world, local_rank):
         "clocks": sampler.summary(),
         "stages_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in sorted(stage.items(), key=lambda kv: -kv[1][1])},
         "stages_ms_per_step_serial": {k: round(v[1] / serial_steps, 3) for k, v in sorted(stage_serial.items(), key=lambda kv: -kv[1][1])},
+        "per_mode": per_mode,
         "compressed_bytes": {str(m): int(comp_bytes[m]) for m in PRESETS},
         "lossless": {"resident": ok_resident, "e2e": ok_e2e},
         "fp64_peak_tflops": round(fp64_peak, 3),

@@ -32,6 +32,17 @@ uint64_t LINNEB200_DecoderLaunchCount(const struct LINNEDecoder *decoder);
 void LINNEB200_EncoderUseStream(struct LINNEEncoder *encoder, void *cuda_stream);
 void LINNEB200_DecoderUseStream(struct LINNEDecoder *decoder, void *cuda_stream);
 
+/* ---- several GPUs behind one handle -------------------------------------------------------------
+ * LINNEEncoder_EncodeWhole / LINNEDecoder_DecodeWhole of a handle with N > 1 devices cut the stream's blocks into N
+ * contiguous ranges, one per device (ranges share devices round-robin when N exceeds the visible devices), each driven
+ * by its own host thread inside the call: upload of the range, kernels, and -- after an exclusive scan of the shard
+ * byte counts on the host -- the copy of every shard to its place in the caller's buffer.  Results are byte-identical
+ * with one device.  Replaces nothing in the reference (it has no threads); the environment variable
+ * LINNE_B200_GPUS=N (or "all") sets the default for every handle, so an unmodified caller of the reference API
+ * (tools/linne_codec/linne_codec.c built against this library) uses all GPUs of a box.  0 or 1: one device. */
+void LINNEB200_EncoderSetDevices(struct LINNEEncoder *encoder, uint32_t num_devices);
+void LINNEB200_DecoderSetDevices(struct LINNEDecoder *decoder, uint32_t num_devices);
+
 /* ---- device-resident entry points: bulk data stays in HBM -------------------------------------
  * EncodeWholeResident: `d_pcm` = device int32 planes [C][pcm_stride]; the stream is written to the
  * device buffer `d_data`.  DecodeWholeResident: `d_data` = device copy of the stream padded with

@@ -240,6 +240,8 @@ def bind_ext_api(lib):
     lib.LINNEB200_DecodeFilesPacked.restype = C.c_int
     lib.LINNEB200_DecoderSetReadahead.argtypes = [C.c_void_p, C.c_uint32]
     lib.LINNEB200_DecoderSetThroughputBlocks.argtypes = [C.c_void_p, C.c_uint32]
+    lib.LINNEB200_EncoderSetDevices.argtypes = [C.c_void_p, C.c_uint32]
+    lib.LINNEB200_DecoderSetDevices.argtypes = [C.c_void_p, C.c_uint32]
     lib.LINNEB200_HostAlloc.argtypes = [C.c_size_t]
     lib.LINNEB200_HostAlloc.restype = C.c_void_p
     lib.LINNEB200_HostFree.argtypes = [C.c_void_p]
@@ -319,6 +321,10 @@ class _Session:
 
     def launch_count(self):
         return int(getattr(self.lib, f"LINNEB200_{self._side}LaunchCount")(self.h))
+
+    def set_devices(self, n):
+        """shard the whole-stream calls of this handle over n block ranges / devices (include/linne_b200.h)"""
+        getattr(self.lib, f"LINNEB200_{self._side}SetDevices")(self.h, int(n))
 
     def close(self):
         if self.h:

@@ -6,11 +6,13 @@
  * of the call.  Error results and their precedence follow the reference (cited per check).
  */
 #include "linne_decoder.h"
+#include "linne_b200.h"
 #include "lnb_host_util.h"
 
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 #define DEC_FLAG_OWN_WORK   (1u << 0)
 #define DEC_FLAG_HEADER_SET (1u << 1)
@@ -35,6 +37,13 @@ struct LINNEDecoder {
     size_t ra_image_cap;
     struct LnbCachedBlock { uint32_t byte_off, byte_size, smp_off, nsmp; } *ra_blocks;
     uint32_t ra_blocks_cap;
+    /* several GPUs behind one handle: DecodeWhole splits the block table into contiguous ranges, one child
+     * handle (own device, own host thread) per range */
+    uint32_t num_devices;
+    struct LINNEDecoder *child[LNB_MAX_DEVICES];
+    struct LINNEDecoderConfig config;
+    LnbBlockDesc *shard_table;             /* host block table of the sharding hop */
+    uint32_t shard_table_cap;
 };
 #define LNB_MAX_READAHEAD 1024u
 #define LNB_READAHEAD_MAX_SAMPLES (1u << 21)  /* per channel and batch: bounds the pinned PCM cache (8 ch: 64 MiB) */
@@ -82,6 +91,7 @@ struct LINNEDecoder *LINNEDecoder_Create(const struct LINNEDecoderConfig *config
     dec->max_num_channels = config->max_num_channels;
     dec->max_num_layers = config->max_num_layers;
     dec->max_num_parameters_per_layer = config->max_num_parameters_per_layer;
+    dec->config = *config;
     if (own) dec->flags |= DEC_FLAG_OWN_WORK;
     if (config->check_crc == 1) dec->flags |= DEC_FLAG_CHECK_CRC;
     {   /* LINNE_B200_READAHEAD=K: DecodeBlock decodes K blocks per batch (same results, see decode_block_cached) */
@@ -98,13 +108,20 @@ struct LINNEDecoder *LINNEDecoder_Create(const struct LINNEDecoderConfig *config
         if (own) free(work);
         return NULL;
     }
+    {   /* LINNE_B200_GPUS=N (or "all"): DecodeWhole of this handle shards its blocks over N devices */
+        const char *e = getenv("LINNE_B200_GPUS");
+        if (e && *e) LINNEB200_DecoderSetDevices(dec, (e[0] == 'a') ? (uint32_t)lnb_shim_device_count() : (uint32_t)strtoul(e, NULL, 10));
+    }
     return dec;
 }
 
 /* reference linne_decoder.c:299-306 */
 void LINNEDecoder_Destroy(struct LINNEDecoder *dec)
 {
+    uint32_t k;
     if (dec == NULL) return;
+    for (k = 0; k < LNB_MAX_DEVICES; k++) if (dec->child[k]) { LINNEDecoder_Destroy(dec->child[k]); dec->child[k] = NULL; }
+    free(dec->shard_table); dec->shard_table = NULL; dec->shard_table_cap = 0;
     if (dec->dev) {
         lnb_buf_release_device(dec->dev, &dec->d_stream);
         lnb_buf_release_device(dec->dev, &dec->d_blocks);
@@ -462,6 +479,106 @@ LINNEApiResult LINNEDecoder_DecodeBlock(struct LINNEDecoder *dec, const uint8_t 
     return ret;
 }
 
+
+/* ---- several GPUs behind one handle -----------------------------------------------------------------------------
+ * The hop over the size fields gives the block table; contiguous block ranges go to one child handle each (own device,
+ * own host thread): a range is a stream of its own for the child -- it uploads the range's bytes, decodes, and copies
+ * its samples to their place in the caller's planes.  Outputs are disjoint, nothing is exchanged.  The call returns
+ * the first error in stream order; samples behind a failing block may have been written by later ranges (the reference
+ * leaves them untouched). */
+void LINNEB200_DecoderSetDevices(struct LINNEDecoder *dec, uint32_t num_devices)
+{
+    if (dec == NULL) return;
+    if (num_devices > LNB_MAX_DEVICES) num_devices = LNB_MAX_DEVICES;
+    dec->num_devices = num_devices;
+}
+
+struct LnbDecShard {
+    struct LINNEDecoder *child;
+    const uint8_t *data; uint32_t data_size;
+    int32_t *planes[LINNE_MAX_NUM_CHANNELS];
+    uint32_t room, sample_limit, block_limit;
+    uint32_t decoded;
+    LINNEApiResult result;
+    int ordinal;
+};
+
+static void *dec_shard_main(void *arg)
+{
+    struct LnbDecShard *sh = (struct LnbDecShard *)arg;
+    lnb_shim_set_device(sh->ordinal);
+    sh->decoded = 0;
+    sh->result = decode_range(sh->child, sh->data, sh->data_size, 0, sh->planes, sh->room, sh->sample_limit, sh->block_limit, 0,
+                              NULL, &sh->decoded, NULL, NULL, 0, NULL, NULL);
+    return NULL;
+}
+
+/* DecodeWhole over dec->num_devices block ranges; returns 0 when the stream is too short to be worth it (*ret untouched) */
+static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
+                                int32_t **buffer, uint32_t buffer_num_samples, LINNEApiResult *ret)
+{
+    const struct LINNEHeader *h = &dec->header;
+    const int ndev = lnb_shim_device_count();
+    struct LnbDecShard sh[LNB_MAX_DEVICES];
+    pthread_t th[LNB_MAX_DEVICES];
+    BlockScan scan;
+    uint32_t guess, G, k, c, started = 0;
+    int home;
+    if (ndev <= 0) return 0;
+    guess = (uint32_t)((uint64_t)(data_size - LINNE_HEADER_SIZE) / 64u + 16u);
+    if (h->num_samples_per_block) {
+        const uint32_t by_samples = h->num_samples / h->num_samples_per_block + 16u;
+        if (by_samples < guess) guess = by_samples * 2u;
+    }
+    for (;;) {
+        if (guess > dec->shard_table_cap) {
+            LnbBlockDesc *p = (LnbBlockDesc *)realloc(dec->shard_table, (size_t)guess * sizeof(LnbBlockDesc));
+            if (!p) return 0;
+            dec->shard_table = p; dec->shard_table_cap = guess;
+        }
+        if (scan_blocks(h, data, data_size, LINNE_HEADER_SIZE, buffer_num_samples, h->num_samples, 0,
+                        dec->shard_table, dec->shard_table_cap, &scan) == 0) break;
+        guess *= 2u;
+    }
+    G = dec->num_devices;
+    if (scan.num_decodable < 2u * G) return 0;                   /* a handful of blocks: one device */
+    home = lnb_shim_current_device();
+    for (k = 0; k < G; k++) {
+        if (!dec->child[k]) {
+            lnb_shim_set_device((int)(k % (uint32_t)ndev));
+            dec->child[k] = LINNEDecoder_Create(&dec->config, NULL, 0);
+            if (dec->child[k]) dec->child[k]->num_devices = 0;
+        }
+        if (!dec->child[k] || LINNEDecoder_SetHeader(dec->child[k], h) != LINNE_APIRESULT_OK) { if (home >= 0) lnb_shim_set_device(home); return 0; }
+        dec->child[k]->tput_min_blocks = dec->tput_min_blocks;
+    }
+    if (home >= 0) lnb_shim_set_device(home);
+    for (k = 0; k < G; k++) {
+        /* contiguous ranges of the decodable blocks; the last range runs to the end of the data and meets whatever ends
+         * the stream (framing error, terminal block) exactly as the single-device path does */
+        const uint32_t b0 = (uint32_t)((uint64_t)scan.num_decodable * k / G), b1 = (uint32_t)((uint64_t)scan.num_decodable * (k + 1u) / G);
+        const LnbBlockDesc *first = &dec->shard_table[b0];
+        const int last = (k + 1u == G);
+        const uint32_t end_byte = last ? data_size : dec->shard_table[b1].byte_off;
+        memset(&sh[k], 0, sizeof(sh[k]));
+        sh[k].child = dec->child[k];
+        sh[k].data = data + first->byte_off;
+        sh[k].data_size = end_byte - first->byte_off;
+        for (c = 0; c < h->num_channels; c++) sh[k].planes[c] = buffer[c] + first->smp_off;
+        sh[k].room = buffer_num_samples - first->smp_off;
+        sh[k].sample_limit = last ? h->num_samples - first->smp_off : dec->shard_table[b1].smp_off - first->smp_off;
+        sh[k].block_limit = last ? 0u : b1 - b0;
+        sh[k].ordinal = (int)(k % (uint32_t)ndev);
+        if (pthread_create(&th[k], NULL, dec_shard_main, &sh[k]) != 0) break;
+        started++;
+    }
+    for (k = 0; k < started; k++) pthread_join(th[k], NULL);
+    if (started < G) { *ret = LINNE_APIRESULT_NG; return 1; }
+    *ret = LINNE_APIRESULT_OK;
+    for (k = 0; k < G; k++) if (sh[k].result != LINNE_APIRESULT_OK) { *ret = sh[k].result; break; }   /* first error in stream order */
+    return 1;
+}
+
 /* reference linne_decoder.c:671-730 */
 LINNEApiResult LINNEDecoder_DecodeWhole(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
         int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples)
@@ -475,6 +592,7 @@ LINNEApiResult LINNEDecoder_DecodeWhole(struct LINNEDecoder *dec, const uint8_t 
     if (buffer_num_channels < header.num_channels || buffer_num_samples < header.num_samples)
         return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     for (c = 0; c < header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+    if (dec->num_devices > 1u && decode_whole_sharded(dec, data, data_size, buffer, buffer_num_samples, &ret)) return ret;
     return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, buffer, buffer_num_samples,
                         header.num_samples, 0, 0, NULL, NULL, NULL, NULL, 0, NULL, NULL);
 }

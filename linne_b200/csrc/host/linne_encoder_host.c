@@ -5,7 +5,7 @@
  * analysis scratch fits, and copying the packed chunk back.  All signal processing, analysis,
  * coding and bit packing of every block x channel runs on the GPU.
  */
-#define _POSIX_C_SOURCE 199309L
+#define _POSIX_C_SOURCE 200112L
 #include "linne_encoder.h"
 #include "linne_b200.h"
 #include "lnb_host_util.h"
@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <pthread.h>
 
 /* LINNE_B200_TRACE=1: host-side time stamps of the encode call's phases on stderr (debugging aid) */
 static int trace_on(void) { static int on = -1; if (on < 0) { const char *e = getenv("LINNE_B200_TRACE"); on = (e && *e == '1') ? 1 : 0; } return on; }
@@ -30,7 +31,7 @@ struct LINNEEncoder {
     LnbDevice *dev;
     size_t scratch_budget;                 /* bytes of analysis scratch per chunk */
     LnbBuf d_pcm, d_blocks, d_params, d_est, d_work, d_sig_a, d_sig_b, d_acorr, d_cand, d_unit_loss,
-           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train, d_packed, d_sinwin, d_image;
+           d_chosen_w, d_chosen_u, d_final_sum, d_welch, d_plans, d_plan_mean, d_out, d_total, d_train, d_refine, d_packed, d_sinwin, d_image;
     LnbBuf h_blocks, h_welch, h_total;
     uint32_t sinwin_n;                     /* block length d_sinwin was tabulated for (0 = none) */
     const int32_t *cur_pcm;                /* device PCM planes of the call in flight */
@@ -40,6 +41,12 @@ struct LINNEEncoder {
     uint32_t num_ranges;
     struct LINNEB200FileDesc *file_out;    /* per-file results of that call */
     LnbBuf h_headers;                      /* pinned 32-byte slots for the files' stream headers */
+    /* several GPUs behind ONE handle (north star): EncodeWhole splits its blocks into contiguous ranges, one
+     * child handle (own device, own host thread) per range */
+    uint32_t num_devices;                  /* 0/1: this handle's device only */
+    struct LINNEEncoder *child[LNB_MAX_DEVICES];
+    LnbBuf d_shard;                        /* a child's shard of the stream, on its device */
+    struct LINNEEncoderConfig config;      /* to create the children with */
 };
 
 /* reference linne_encoder.c:53-138 */
@@ -89,6 +96,7 @@ struct LINNEEncoder *LINNEEncoder_Create(const struct LINNEEncoderConfig *config
     enc->max_num_samples_per_block = config->max_num_samples_per_block;
     enc->max_num_layers = config->max_num_layers;
     enc->max_num_parameters_per_layer = config->max_num_parameters_per_layer;
+    enc->config = *config;
     enc->scratch_budget = (size_t)8 << 30;
     if ((budget = getenv("LINNE_B200_SCRATCH_MB")) != NULL && atol(budget) > 0) enc->scratch_budget = (size_t)atol(budget) << 20;
     if (lnb_shim_open(&enc->dev, -1) != 0) {
@@ -96,18 +104,24 @@ struct LINNEEncoder *LINNEEncoder_Create(const struct LINNEEncoderConfig *config
         if (own) free(work);
         return NULL;
     }
+    {   /* LINNE_B200_GPUS=N (or "all"): the whole-stream calls of this handle shard their blocks over N devices */
+        const char *e = getenv("LINNE_B200_GPUS");
+        if (e && *e) LINNEB200_EncoderSetDevices(enc, (e[0] == 'a') ? (uint32_t)lnb_shim_device_count() : (uint32_t)strtoul(e, NULL, 10));
+    }
     return enc;
 }
 
 /* reference linne_encoder.c:399-407 */
 void LINNEEncoder_Destroy(struct LINNEEncoder *enc)
 {
+    uint32_t k;
     if (enc == NULL) return;
+    for (k = 0; k < LNB_MAX_DEVICES; k++) if (enc->child[k]) { LINNEEncoder_Destroy(enc->child[k]); enc->child[k] = NULL; }
     if (enc->dev) {
         LnbBuf *dbufs[] = { &enc->d_pcm, &enc->d_blocks, &enc->d_params, &enc->d_est, &enc->d_work, &enc->d_sig_a,
                             &enc->d_sig_b, &enc->d_acorr, &enc->d_cand, &enc->d_unit_loss, &enc->d_chosen_w,
                             &enc->d_chosen_u, &enc->d_final_sum, &enc->d_welch, &enc->d_plans, &enc->d_plan_mean,
-                            &enc->d_out, &enc->d_total, &enc->d_train, &enc->d_packed, &enc->d_sinwin, &enc->d_image };
+                            &enc->d_out, &enc->d_total, &enc->d_train, &enc->d_refine, &enc->d_packed, &enc->d_sinwin, &enc->d_image, &enc->d_shard };
         size_t i;
         for (i = 0; i < sizeof(dbufs) / sizeof(dbufs[0]); i++) lnb_buf_release_device(enc->dev, dbufs[i]);
         lnb_buf_release_host(&enc->h_blocks);
@@ -189,7 +203,8 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     uint32_t lambdas, slots_per_block, chunk_blocks, first, out_off = 0, i, lvl;
     uint32_t fcur = 0;                     /* files mode: file of the first block of the chunk being built */
     uint32_t fdone = 0, fbytes = 0;        /* files mode: file being written out, block bytes it has received so far */
-    size_t per_block;
+    size_t per_block, refine_doubles = 0;
+    int refine_global = 0;
 
     memset(&batch, 0, sizeof(batch));
     lnb_fill_stream_cfg(&batch.cfg, h);
@@ -212,6 +227,20 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
                                  + 2u * LNB_MAX_PARTITIONS * sizeof(double) + 64u)
                   + (enc->enable_learning ? (size_t)C * (2u * LNB_MAX_LAYERS + 1u) * ws * sizeof(double) : 0u);
         const int need_sig_a = need_flat || (enc->num_afmethod_iterations && !forced);    /* IRLS scratch: one plane per slot */
+        /* IRLS / SGD on blocks too long for the refinement kernel's shared memory: its two signal buffers in HBM (lnb_shim.h) */
+        refine_global = !forced && (enc->enable_learning || enc->num_afmethod_iterations)
+                        && lnb_shim_refine_max_na() && NB > lnb_shim_refine_max_na();
+        if (refine_global) {
+            size_t na_max = NB;
+            int l;
+            for (l = 0; l < g_lnb_presets[h->preset].num_layers; l++) {
+                const size_t P = (size_t)g_lnb_presets[h->preset].layer_params[l], tri = P * (P + 1u) / 2u;
+                if (enc->num_afmethod_iterations && na_max < tri) na_max = tri;
+            }
+            na_max = (na_max + 7u) & ~(size_t)7u;
+            refine_doubles = 2u * (na_max + lnb_shim_refine_hist());
+            per_block += (size_t)C * refine_doubles * sizeof(double);
+        }
         if (need_sig_a && !need_flat) per_block += (size_t)slots_per_block * ws * sizeof(double);
         if (need_flat)
             per_block += (size_t)slots_per_block * (ws * sizeof(double) * 2u
@@ -243,7 +272,8 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
                 || lnb_buf_reserve_device(enc->dev, &enc->d_plan_mean, BC * 2u * LNB_MAX_PARTITIONS * sizeof(double))
                 || lnb_buf_reserve_device(enc->dev, &enc->d_total, 64)
                 || (enc->enable_learning && !forced
-                    && lnb_buf_reserve_device(enc->dev, &enc->d_train, BC * (2u * LNB_MAX_LAYERS + 1u) * ws * sizeof(double))))
+                    && lnb_buf_reserve_device(enc->dev, &enc->d_train, BC * (2u * LNB_MAX_LAYERS + 1u) * ws * sizeof(double)))
+                || (refine_global && lnb_buf_reserve_device(enc->dev, &enc->d_refine, BC * refine_doubles * sizeof(double))))
                 return LINNE_APIRESULT_NG;
         }
     }
@@ -274,6 +304,7 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     batch.af_iterations = forced ? 0u : enc->num_afmethod_iterations;
     batch.enable_learning = forced ? 0u : (enc->enable_learning ? 1u : 0u);
     batch.train_scratch = (double *)enc->d_train.ptr;
+    batch.refine_xy = refine_global ? (double *)enc->d_refine.ptr : NULL;
     batch.out_base = 0;
 
     for (first = 0; first < total_blocks; first += chunk_blocks) {
@@ -397,24 +428,12 @@ static LINNEApiResult encode_blocks(struct LINNEEncoder *enc, uint32_t num_sampl
     return LINNE_APIRESULT_OK;
 }
 
-static int unsupported_analysis(const struct LINNEEncoder *enc)
-{
-    if ((enc->enable_learning || enc->num_afmethod_iterations)
-        && enc->header.num_samples_per_block > lnb_shim_refine_max_na()) {
-        fprintf(stderr, "linne_b200: enable_learning / num_afmethod_iterations need blocks of at most %u samples\n",
-                (unsigned)lnb_shim_refine_max_na());
-        return 1;
-    }
-    return 0;
-}
-
 static LINNEApiResult upload_and_encode(struct LINNEEncoder *enc, const int32_t *const *input, uint32_t num_samples,
                                         uint8_t *data, uint32_t data_size, const LnbChanParams *forced, uint32_t *written)
 {
     const uint32_t C = enc->header.num_channels;
     const size_t stride = LNB_ROUNDUP((size_t)num_samples + 4u, 4u);
     uint32_t c;
-    if (!forced && unsupported_analysis(enc)) return LINNE_APIRESULT_NG;
     if (lnb_buf_reserve_device(enc->dev, &enc->d_pcm, stride * C * sizeof(int32_t))) return LINNE_APIRESULT_NG;
     for (c = 0; c < C; c++) {
         if (input[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
@@ -436,6 +455,128 @@ LINNEApiResult LINNEEncoder_EncodeBlock(struct LINNEEncoder *enc, const int32_t 
     return upload_and_encode(enc, input, num_samples, data, data_size, NULL, output_size);
 }
 
+
+/* ---- several GPUs behind one handle -----------------------------------------------------------------------------
+ * Blocks are independent, so EncodeWhole cuts [0, B) into contiguous block ranges, one per device.  Every
+ * range has a child handle bound to its device and a host thread: it uploads its samples, encodes them into a shard on
+ * its device and reports the shard's size; an exclusive scan of the sizes on the host gives every shard its place, and
+ * each child copies its shard straight into the caller's buffer there.  No collective, no inter-process machinery;
+ * the stream is byte-identical with the single-device one.  (With more ranges than devices the ranges share devices
+ * round-robin: that is how a one-GPU box exercises this path.) */
+void LINNEB200_EncoderSetDevices(struct LINNEEncoder *enc, uint32_t num_devices)
+{
+    if (enc == NULL) return;
+    if (num_devices > LNB_MAX_DEVICES) num_devices = LNB_MAX_DEVICES;
+    enc->num_devices = num_devices;
+}
+
+struct LnbEncShard {
+    struct LINNEEncoder *parent, *child;
+    const int32_t *const *input;
+    uint32_t first_sample, num_samples;
+    uint32_t size, offset;                 /* shard bytes (blocks only) / where they go in the caller's buffer */
+    uint8_t *data;
+    LINNEApiResult result;
+    LnbRendezvous *meet;
+    int ordinal;
+};
+
+static void *enc_shard_main(void *arg)
+{
+    struct LnbEncShard *sh = (struct LnbEncShard *)arg;
+    struct LINNEEncoder *enc = sh->child;
+    const uint32_t C = enc->header.num_channels;
+    const size_t stride = LNB_ROUNDUP((size_t)sh->num_samples + 4u, 4u);
+    /* worst case of a shard: every block stored raw (linne_encoder.c:556-585) */
+    const size_t NB = enc->header.num_samples_per_block, blocks = (sh->num_samples + NB - 1u) / NB;
+    const size_t cap = blocks * (LNB_BLOCK_HEADER_SIZE + NB * C * ((enc->header.bits_per_sample + 7u) / 8u)) + 64u;
+    uint32_t c, written = 0;
+    sh->result = LINNE_APIRESULT_OK;
+    sh->size = 0;
+    lnb_shim_set_device(sh->ordinal);
+    if (cap > 0xFFFFFF00u || lnb_buf_reserve_device(enc->dev, &enc->d_pcm, stride * C * sizeof(int32_t))
+        || lnb_buf_reserve_device(enc->dev, &enc->d_shard, cap)) sh->result = LINNE_APIRESULT_NG;
+    if (sh->result == LINNE_APIRESULT_OK) {
+        for (c = 0; c < C; c++)
+            lnb_shim_h2d(enc->dev, (int32_t *)enc->d_pcm.ptr + c * stride, sh->input[c] + sh->first_sample, (size_t)sh->num_samples * sizeof(int32_t));
+        enc->cur_pcm = (const int32_t *)enc->d_pcm.ptr;
+        enc->cur_pcm_stride = (uint32_t)stride;
+        sh->result = encode_blocks(enc, sh->num_samples, (uint8_t *)enc->d_shard.ptr, (uint32_t)cap, 1, NULL, &written);
+        sh->size = written;
+    }
+    lnb_rendezvous_report_and_wait(sh->meet);   /* every shard's size is known: the caller scans them and says where each goes */
+    if (sh->result == LINNE_APIRESULT_OK && sh->data) {
+        lnb_shim_d2h(enc->dev, sh->data + sh->offset, enc->d_shard.ptr, sh->size);
+        if (lnb_shim_sync(enc->dev)) sh->result = LINNE_APIRESULT_NG;
+    }
+    return NULL;
+}
+
+/* EncodeWhole over enc->num_devices block ranges; `data` starts behind the stream header */
+static LINNEApiResult encode_whole_sharded(struct LINNEEncoder *enc, const int32_t *const *input, uint32_t num_samples,
+                                           uint8_t *data, uint32_t data_size, uint32_t *written)
+{
+    const uint32_t NB = enc->header.num_samples_per_block;
+    const uint32_t total_blocks = (uint32_t)(((uint64_t)num_samples + NB - 1u) / NB);
+    const uint32_t G = enc->num_devices < total_blocks ? enc->num_devices : total_blocks;
+    const int ndev = lnb_shim_device_count();
+    struct LnbEncShard sh[LNB_MAX_DEVICES];
+    pthread_t th[LNB_MAX_DEVICES];
+    LnbRendezvous meet;
+    struct LINNEEncodeParameter prm;
+    LINNEApiResult ret = LINNE_APIRESULT_OK;
+    uint32_t k, started = 0, off = 0;
+    int home = -1;
+    if (ndev <= 0) return LINNE_APIRESULT_NG;
+    home = lnb_shim_current_device();
+    prm.num_channels = enc->header.num_channels; prm.bits_per_sample = enc->header.bits_per_sample;
+    prm.sampling_rate = enc->header.sampling_rate; prm.num_samples_per_block = (uint16_t)NB;
+    prm.preset = enc->header.preset; prm.ch_process_method = enc->header.ch_process_method;
+    prm.enable_learning = enc->enable_learning; prm.num_afmethod_iterations = enc->num_afmethod_iterations;
+    for (k = 0; k < G; k++) {
+        if (!enc->child[k]) {
+            lnb_shim_set_device((int)(k % (uint32_t)ndev));
+            enc->child[k] = LINNEEncoder_Create(&enc->config, NULL, 0);
+            if (enc->child[k]) enc->child[k]->num_devices = 0;          /* children never shard again */
+        }
+        if (!enc->child[k] || LINNEEncoder_SetEncodeParameter(enc->child[k], &prm) != LINNE_APIRESULT_OK) { ret = LINNE_APIRESULT_NG; break; }
+        enc->child[k]->scratch_budget = enc->scratch_budget;
+    }
+    if (home >= 0) lnb_shim_set_device(home);
+    if (ret != LINNE_APIRESULT_OK) return ret;
+    lnb_rendezvous_init(&meet);
+    for (k = 0; k < G; k++) {
+        /* contiguous block ranges, as even as the block count allows */
+        const uint32_t b0 = (uint32_t)((uint64_t)total_blocks * k / G), b1 = (uint32_t)((uint64_t)total_blocks * (k + 1u) / G);
+        const uint64_t s0 = (uint64_t)b0 * NB, s1 = (uint64_t)b1 * NB;
+        memset(&sh[k], 0, sizeof(sh[k]));
+        sh[k].parent = enc; sh[k].child = enc->child[k]; sh[k].input = input;
+        sh[k].first_sample = (uint32_t)s0;
+        sh[k].num_samples = (uint32_t)((s1 > num_samples ? num_samples : s1) - s0);
+        sh[k].child->header.num_samples = sh[k].num_samples;
+        sh[k].data = data; sh[k].meet = &meet;
+        sh[k].ordinal = (int)(k % (uint32_t)ndev);
+        if (pthread_create(&th[k], NULL, enc_shard_main, &sh[k]) != 0) { sh[k].result = LINNE_APIRESULT_NG; break; }
+        started++;
+    }
+    lnb_rendezvous_collect(&meet, started);
+    for (k = 0; k < started; k++) {                                /* exclusive scan of the shard byte counts */
+        if (sh[k].result != LINNE_APIRESULT_OK && ret == LINNE_APIRESULT_OK) ret = sh[k].result;
+        sh[k].offset = off;
+        off += sh[k].size;
+    }
+    if (ret == LINNE_APIRESULT_OK && (started < G || off > data_size)) ret = (started < G) ? LINNE_APIRESULT_NG : LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+    if (ret != LINNE_APIRESULT_OK) for (k = 0; k < started; k++) sh[k].data = NULL;
+    lnb_rendezvous_release(&meet);
+    for (k = 0; k < started; k++) {
+        pthread_join(th[k], NULL);
+        if (sh[k].result != LINNE_APIRESULT_OK && ret == LINNE_APIRESULT_OK) ret = sh[k].result;
+    }
+    lnb_rendezvous_destroy(&meet);
+    *written = off;
+    return ret;
+}
+
 /* reference linne_encoder.c:865-932 */
 LINNEApiResult LINNEEncoder_EncodeWhole(struct LINNEEncoder *enc, const int32_t *const *input, uint32_t num_samples,
         uint8_t *data, uint32_t data_size, uint32_t *output_size)
@@ -446,7 +587,13 @@ LINNEApiResult LINNEEncoder_EncodeWhole(struct LINNEEncoder *enc, const int32_t 
     if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
     enc->header.num_samples = num_samples;
     if ((ret = LINNEEncoder_EncodeHeader(&enc->header, data, data_size)) != LINNE_APIRESULT_OK) return ret;
-    ret = upload_and_encode(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, NULL, &written);
+    if (enc->num_devices > 1u && num_samples > 2u * enc->header.num_samples_per_block) {
+        uint32_t c;
+        for (c = 0; c < enc->header.num_channels; c++) if (input[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
+        ret = encode_whole_sharded(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, &written);
+    } else {
+        ret = upload_and_encode(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, NULL, &written);
+    }
     if (ret != LINNE_APIRESULT_OK) return ret;
     *output_size = LINNE_HEADER_SIZE + written;
     return LINNE_APIRESULT_OK;
@@ -496,7 +643,6 @@ LINNEApiResult LINNEB200_EncodeWholeResident(struct LINNEEncoder *enc, const int
     if (enc == NULL || d_pcm == NULL || d_data == NULL || output_size == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
     if (pcm_stride < num_samples) return LINNE_APIRESULT_INVALID_ARGUMENT;
-    if (unsupported_analysis(enc)) return LINNE_APIRESULT_NG;
     enc->header.num_samples = num_samples;
     if (data_size < LINNE_HEADER_SIZE) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     if ((ret = LINNEEncoder_EncodeHeader(&enc->header, hdr, sizeof(hdr))) != LINNE_APIRESULT_OK) return ret;
@@ -523,7 +669,6 @@ LINNEApiResult LINNEB200_EncodeFilesResident(struct LINNEEncoder *enc, const int
     if (enc == NULL || d_pcm == NULL || files == NULL || num_files == 0 || d_data == NULL || output_size == NULL)
         return LINNE_APIRESULT_INVALID_ARGUMENT;
     if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
-    if (unsupported_analysis(enc)) return LINNE_APIRESULT_NG;
     NB = enc->header.num_samples_per_block;
     if (!(ranges = (struct LnbFileRange *)malloc((size_t)num_files * sizeof(*ranges)))) return LINNE_APIRESULT_NG;
     for (i = 0; i < num_files; i++) {
@@ -599,7 +744,6 @@ LINNEApiResult LINNEB200_EncodeWholePacked(struct LINNEEncoder *enc, const uint8
     size_t stride, packed_bytes;
     if (enc == NULL || pcm == NULL || data == NULL || output_size == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
-    if (unsupported_analysis(enc)) return LINNE_APIRESULT_NG;
     C = enc->header.num_channels;
     bytes = enc->header.bits_per_sample / 8u;
     if (bytes == 0 || bytes > 4u || (enc->header.bits_per_sample % 8u) != 0u) return LINNE_APIRESULT_INVALID_FORMAT;

@@ -101,3 +101,30 @@ void lnb_fill_stream_cfg(LnbStreamCfg *cfg, const struct LINNEHeader *h)
     for (i = 0; i < ps->num_lambdas; i++) cfg->lambdas[i] = ps->lambdas[i];
     cfg->ms = (h->ch_process_method == LINNE_CH_PROCESS_METHOD_MS) ? 1u : 0u;
 }
+
+void lnb_rendezvous_init(LnbRendezvous *r)
+{
+    pthread_mutex_init(&r->lock, NULL); pthread_cond_init(&r->cv, NULL); r->reported = 0; r->released = 0;
+}
+void lnb_rendezvous_destroy(LnbRendezvous *r) { pthread_cond_destroy(&r->cv); pthread_mutex_destroy(&r->lock); }
+void lnb_rendezvous_report_and_wait(LnbRendezvous *r)
+{
+    pthread_mutex_lock(&r->lock);
+    r->reported++;
+    pthread_cond_broadcast(&r->cv);
+    while (!r->released) pthread_cond_wait(&r->cv, &r->lock);
+    pthread_mutex_unlock(&r->lock);
+}
+void lnb_rendezvous_collect(LnbRendezvous *r, uint32_t workers)
+{
+    pthread_mutex_lock(&r->lock);
+    while (r->reported < workers) pthread_cond_wait(&r->cv, &r->lock);
+    pthread_mutex_unlock(&r->lock);
+}
+void lnb_rendezvous_release(LnbRendezvous *r)
+{
+    pthread_mutex_lock(&r->lock);
+    r->released = 1;
+    pthread_cond_broadcast(&r->cv);
+    pthread_mutex_unlock(&r->lock);
+}

@@ -8,6 +8,7 @@
 #include "lnb_shim.h"
 
 #define LNB_ALIGNMENT 16
+#define LNB_MAX_DEVICES 16                 /* block ranges (devices) one handle shards a whole-stream call over */
 #define LNB_ROUNDUP(v, n) ((((v) + ((n) - 1)) / (n)) * (n))
 
 /* grow-only device / host buffers owned by a handle */
@@ -27,5 +28,15 @@ void lnb_header_read(const uint8_t *src, struct LINNEHeader *h);
 static inline uint32_t lnb_rd_be(const uint8_t *p, int n) { uint32_t v = 0; int i; for (i = 0; i < n; i++) v = (v << 8) | p[i]; return v; }
 
 void lnb_fill_stream_cfg(LnbStreamCfg *cfg, const struct LINNEHeader *h);
+
+/* rendezvous of the shard workers of one call with the thread that made it: every worker reports ("sized"), the caller
+ * looks at all reports and releases them ("placed") */
+#include <pthread.h>
+typedef struct LnbRendezvous { pthread_mutex_t lock; pthread_cond_t cv; uint32_t reported; int released; } LnbRendezvous;
+void lnb_rendezvous_init(LnbRendezvous *r);
+void lnb_rendezvous_destroy(LnbRendezvous *r);
+void lnb_rendezvous_report_and_wait(LnbRendezvous *r);      /* worker */
+void lnb_rendezvous_collect(LnbRendezvous *r, uint32_t workers);   /* caller: returns when all have reported (lock held off) */
+void lnb_rendezvous_release(LnbRendezvous *r);              /* caller */
 
 #endif

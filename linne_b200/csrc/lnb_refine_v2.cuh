@@ -12,7 +12,8 @@
  * and overwrites the chosen slot's unit counts / coefficients, which the finish stage then quantises.
  *
  * Written for generality rather than peak speed (these paths are off by default and used by no
- * BASELINE config): any analysis length up to LNB_RF_MAX_NA, signals row-major in shared memory,
+ * BASELINE config): any analysis length (signals row-major in shared memory up to LNB_RF_MAX_NA samples, in a
+ * global scratch beyond),
  * thread-strided loops, deterministic reductions.  Operation order inside a unit's Levinson recursion
  * and inside each residual is the reference's; sums across samples are tree-reduced.
  */
@@ -142,7 +143,8 @@ __device__ void lnb_rf_irls_unit(LnbRefineSmem &sm, const double *xs, uint32_t m
 
 __global__ void __launch_bounds__(LNB_RF_THREADS, 1) lnb_refine_v2_kernel(LnbEncodeBatch b, uint32_t na_max,
                                                                           uint32_t af_iters, uint32_t learning,
-                                                                          double *train_scratch, uint32_t chunks_per_slot)
+                                                                          double *train_scratch, uint32_t chunks_per_slot,
+                                                                          double *xy_global)
 {
     extern __shared__ __align__(16) double lnb_rf_smem[];
     const uint32_t tid = threadIdx.x, bc = blockIdx.x;
@@ -150,9 +152,12 @@ __global__ void __launch_bounds__(LNB_RF_THREADS, 1) lnb_refine_v2_kernel(LnbEnc
     const LnbBlockDesc blk = b.blocks[blk_i];
     if (blk.type != LNB_BLOCK_COMPRESSED) return;
     const uint32_t na = blk.na;
-    double *X = lnb_rf_smem + LNB_RF_HIST;                       /* [na] layer input, zero history in front */
+    /* the two signal buffers live in shared memory for blocks of up to LNB_RF_MAX_NA samples and in a global scratch
+     * (L2-resident: 2 x 8 B per sample and block-channel) for longer ones -- the code below only sees pointers */
+    double *xy = xy_global ? xy_global + (size_t)bc * 2u * (na_max + LNB_RF_HIST) : lnb_rf_smem;
+    double *X = xy + LNB_RF_HIST;                                /* [na] layer input, zero history in front */
     double *Y = X + na_max + LNB_RF_HIST;                        /* [na] layer output / IRLS scratch, zero history in front */
-    LnbRefineSmem &sm = *(LnbRefineSmem *)(Y + na_max);
+    LnbRefineSmem &sm = *(LnbRefineSmem *)(xy_global ? lnb_rf_smem : Y + na_max);
 
     /* which regulariser won (linne_network.c:618-626): same rule as the finish stage */
     uint32_t best_lam = 0;

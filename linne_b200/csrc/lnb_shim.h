@@ -30,6 +30,10 @@ void lnb_shim_use_stream(LnbDevice *dev, void *cuda_stream);
  * an externally supplied stream. */
 void lnb_shim_set_cost_rank(LnbDevice *dev, int cost_rank);
 const char *lnb_shim_backend(void);      /* "cuda-sm_100a" for the product */
+/* devices visible to the process / bind the calling host thread to one / the one it is bound to (-1: none) */
+int lnb_shim_device_count(void);
+int lnb_shim_set_device(int ordinal);
+int lnb_shim_current_device(void);
 /* Largest analysis length the cooperative (shared-memory) encoder kernels take; 0 = none. */
 uint32_t lnb_shim_fast_max_na(void);
 /* Longest block (samples per channel) the cooperative prepare / predict+plan kernels take; 0 = none. */
@@ -39,8 +43,11 @@ uint32_t lnb_shim_fused_max_n(void);
 /* 1 when the throughput decoder (one lane per block / per block-channel, for large batches) takes streams of this
  * configuration; 0 = never (the host then leaves LnbDecodeBatch.tput clear). */
 int lnb_shim_tput_supported(const LnbStreamCfg *cfg);
-/* Longest analysis length the IRLS / SGD refinement kernel takes; 0 = those paths are unavailable. */
+/* Longest analysis length the IRLS / SGD refinement kernel keeps in shared memory (0 = those paths are unavailable);
+ * longer blocks need LnbEncodeBatch.refine_xy: 2 * (roundup8(max(block, P(P+1)/2)) + lnb_shim_refine_hist()) doubles per
+ * (block, channel). */
 uint32_t lnb_shim_refine_max_na(void);
+uint32_t lnb_shim_refine_hist(void);
 
 void *lnb_shim_alloc(LnbDevice *dev, size_t bytes);
 void  lnb_shim_free(LnbDevice *dev, void *ptr);

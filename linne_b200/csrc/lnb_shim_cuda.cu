@@ -235,16 +235,18 @@ struct CudaExec {
     }
     void refine_cooperative(const LnbEncodeBatch &b, uint32_t chunks_per_slot)
     {
-        uint32_t na_max = b.cfg.block_size < LNB_RF_MAX_NA ? b.cfg.block_size : LNB_RF_MAX_NA;
+        uint32_t na_max = b.cfg.block_size;
         uint32_t max_p = 0;
         for (uint32_t l = 0; l < b.cfg.num_layers; l++) if (b.cfg.layer_params[l] > max_p) max_p = b.cfg.layer_params[l];
         const uint32_t tri = max_p * (max_p + 1u) / 2u;          /* the signal buffers double as the packed Gram matrix */
         if (b.af_iterations && na_max < tri) na_max = tri;
         na_max = (na_max + 7u) & ~7u;
-        const size_t smem = (size_t)2 * (na_max + LNB_RF_HIST) * sizeof(double) + sizeof(LnbRefineSmem);
+        /* signals in shared memory while they fit; blocks beyond LNB_RF_MAX_NA samples take the global scratch the host sized for them */
+        const bool global_xy = b.refine_xy != nullptr;
+        const size_t smem = (global_xy ? 0u : (size_t)2 * (na_max + LNB_RF_HIST) * sizeof(double)) + sizeof(LnbRefineSmem);
         const int slot = begin_stage("refine_v2");
         lnb_refine_v2_kernel<<<b.num_blocks * b.cfg.num_channels, LNB_RF_THREADS, smem, dev->stream>>>(
-            b, na_max, b.af_iterations, b.enable_learning, b.train_scratch, chunks_per_slot);
+            b, na_max, b.af_iterations, b.enable_learning, b.train_scratch, chunks_per_slot, global_xy ? b.refine_xy : nullptr);
         end_stage(slot);
     }
     void prepare_cooperative(const LnbEncodeBatch &b)
@@ -346,9 +348,13 @@ static int lnb_configure_kernels(int ordinal)
 extern "C" {
 
 const char *lnb_shim_backend(void) { return "cuda-sm_100a"; }
+int lnb_shim_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+int lnb_shim_set_device(int ordinal) { if (cudaSetDevice(ordinal) != cudaSuccess) { cudaGetLastError(); return 1; } return 0; }
+int lnb_shim_current_device(void) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; } return d; }
 uint32_t lnb_shim_fast_max_na(void) { return LNB_A3_MAX_NA; }
 uint32_t lnb_shim_coop_max_n(void) { return LNB_FR_MAX_N; }
 uint32_t lnb_shim_refine_max_na(void) { return LNB_RF_MAX_NA; }
+uint32_t lnb_shim_refine_hist(void) { return LNB_RF_HIST; }
 uint32_t lnb_shim_fused_max_n(void) { return LNB_DS_MAX_N; }
 int lnb_shim_tput_supported(const LnbStreamCfg *cfg)
 {

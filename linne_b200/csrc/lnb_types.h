@@ -124,6 +124,7 @@ typedef struct LnbEncodeBatch {
     uint32_t af_iterations;         /* IRLS iterations of the final pass (0 = off) */
     uint32_t enable_learning;       /* 1: momentum-SGD refinement of the final coefficients */
     double *train_scratch;          /* [B*C][2*layers+1][work_stride], only when enable_learning */
+    double *refine_xy;              /* NULL, or the refinement kernel's signal buffers for blocks too long for shared memory */
     uint32_t forced_params;         /* 1: `params` already hold units/shift/coefficients -- skip the analysis stages */
 } LnbEncodeBatch;
 
