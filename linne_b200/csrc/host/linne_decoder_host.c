@@ -522,8 +522,8 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
     struct LnbDecShard sh[LNB_MAX_DEVICES];
     pthread_t th[LNB_MAX_DEVICES];
     BlockScan scan;
-    uint32_t guess, G, k, c, started = 0;
-    int home;
+    uint32_t guess, G, k, c, started = 0, ndev_used = 1;
+    int home, own;
     if (ndev <= 0) return 0;
     guess = (uint32_t)((uint64_t)(data_size - LINNE_HEADER_SIZE) / 64u + 16u);
     if (h->num_samples_per_block) {
@@ -540,12 +540,15 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
                         dec->shard_table, dec->shard_table_cap, &scan) == 0) break;
         guess *= 2u;
     }
-    G = dec->num_devices;
-    if (scan.num_decodable < 2u * G) return 0;                   /* a handful of blocks: one device */
+    /* ranges per requested device (pipelining), devices shared round-robin when fewer are visible than asked for */
+    G = lnb_plan_ranges(scan.num_decodable, dec->num_devices > 1u ? dec->num_devices : 1u);
+    ndev_used = dec->num_devices > 1u ? (dec->num_devices < (uint32_t)ndev ? dec->num_devices : (uint32_t)ndev) : 1u;
+    if (G < 2u) return 0;                                        /* a handful of blocks: the handle's own device */
     home = lnb_shim_current_device();
+    own = lnb_shim_device_ordinal(dec->dev);
     for (k = 0; k < G; k++) {
         if (!dec->child[k]) {
-            lnb_shim_set_device((int)(k % (uint32_t)ndev));
+            lnb_shim_set_device(dec->num_devices > 1u ? (int)(k % ndev_used) : own);
             dec->child[k] = LINNEDecoder_Create(&dec->config, NULL, 0);
             if (dec->child[k]) dec->child[k]->num_devices = 0;
         }
@@ -568,7 +571,7 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
         sh[k].room = buffer_num_samples - first->smp_off;
         sh[k].sample_limit = last ? h->num_samples - first->smp_off : dec->shard_table[b1].smp_off - first->smp_off;
         sh[k].block_limit = last ? 0u : b1 - b0;
-        sh[k].ordinal = (int)(k % (uint32_t)ndev);
+        sh[k].ordinal = dec->num_devices > 1u ? (int)(k % ndev_used) : own;
         if (pthread_create(&th[k], NULL, dec_shard_main, &sh[k]) != 0) break;
         started++;
     }
@@ -592,7 +595,8 @@ LINNEApiResult LINNEDecoder_DecodeWhole(struct LINNEDecoder *dec, const uint8_t 
     if (buffer_num_channels < header.num_channels || buffer_num_samples < header.num_samples)
         return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     for (c = 0; c < header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
-    if (dec->num_devices > 1u && decode_whole_sharded(dec, data, data_size, buffer, buffer_num_samples, &ret)) return ret;
+    /* several devices, or a stream long enough to pipeline its transfers against its kernels on one */
+    if ((dec->num_devices > 1u || data_size >= (32u << 20)) && decode_whole_sharded(dec, data, data_size, buffer, buffer_num_samples, &ret)) return ret;
     return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, buffer, buffer_num_samples,
                         header.num_samples, 0, 0, NULL, NULL, NULL, NULL, 0, NULL, NULL);
 }

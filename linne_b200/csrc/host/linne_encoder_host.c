@@ -518,8 +518,10 @@ static LINNEApiResult encode_whole_sharded(struct LINNEEncoder *enc, const int32
 {
     const uint32_t NB = enc->header.num_samples_per_block;
     const uint32_t total_blocks = (uint32_t)(((uint64_t)num_samples + NB - 1u) / NB);
-    const uint32_t G = enc->num_devices < total_blocks ? enc->num_devices : total_blocks;
+    const uint32_t G = lnb_plan_ranges(total_blocks, enc->num_devices > 1u ? enc->num_devices : 1u);
     const int ndev = lnb_shim_device_count();
+    const uint32_t ndev_used = enc->num_devices > 1u ? (enc->num_devices < (uint32_t)(ndev > 0 ? ndev : 1) ? enc->num_devices : (uint32_t)(ndev > 0 ? ndev : 1)) : 1u;
+    const int own = lnb_shim_device_ordinal(enc->dev);
     struct LnbEncShard sh[LNB_MAX_DEVICES];
     pthread_t th[LNB_MAX_DEVICES];
     LnbRendezvous meet;
@@ -535,7 +537,7 @@ static LINNEApiResult encode_whole_sharded(struct LINNEEncoder *enc, const int32
     prm.enable_learning = enc->enable_learning; prm.num_afmethod_iterations = enc->num_afmethod_iterations;
     for (k = 0; k < G; k++) {
         if (!enc->child[k]) {
-            lnb_shim_set_device((int)(k % (uint32_t)ndev));
+            lnb_shim_set_device(enc->num_devices > 1u ? (int)(k % ndev_used) : own);
             enc->child[k] = LINNEEncoder_Create(&enc->config, NULL, 0);
             if (enc->child[k]) enc->child[k]->num_devices = 0;          /* children never shard again */
         }
@@ -555,7 +557,7 @@ static LINNEApiResult encode_whole_sharded(struct LINNEEncoder *enc, const int32
         sh[k].num_samples = (uint32_t)((s1 > num_samples ? num_samples : s1) - s0);
         sh[k].child->header.num_samples = sh[k].num_samples;
         sh[k].data = data; sh[k].meet = &meet;
-        sh[k].ordinal = (int)(k % (uint32_t)ndev);
+        sh[k].ordinal = enc->num_devices > 1u ? (int)(k % ndev_used) : own;
         if (pthread_create(&th[k], NULL, enc_shard_main, &sh[k]) != 0) { sh[k].result = LINNE_APIRESULT_NG; break; }
         started++;
     }
@@ -587,7 +589,9 @@ LINNEApiResult LINNEEncoder_EncodeWhole(struct LINNEEncoder *enc, const int32_t 
     if (enc->set_parameter != 1) return LINNE_APIRESULT_PARAMETER_NOT_SET;
     enc->header.num_samples = num_samples;
     if ((ret = LINNEEncoder_EncodeHeader(&enc->header, data, data_size)) != LINNE_APIRESULT_OK) return ret;
-    if (enc->num_devices > 1u && num_samples > 2u * enc->header.num_samples_per_block) {
+    /* several devices, or a stream long enough to pipeline its transfers against its kernels on one */
+    if (lnb_plan_ranges((uint32_t)(((uint64_t)num_samples + enc->header.num_samples_per_block - 1u) / enc->header.num_samples_per_block),
+                        enc->num_devices > 1u ? enc->num_devices : 1u) > 1u) {
         uint32_t c;
         for (c = 0; c < enc->header.num_channels; c++) if (input[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
         ret = encode_whole_sharded(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, &written);

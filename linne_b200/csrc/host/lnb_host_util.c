@@ -1,5 +1,6 @@
 /* lnb_host_util.c -- header (de)serialisation and buffer helpers for the host side. */
 #include "lnb_host_util.h"
+#include <stdlib.h>
 #include <string.h>
 
 int lnb_buf_reserve_device(LnbDevice *dev, LnbBuf *buf, size_t bytes)
@@ -127,4 +128,22 @@ void lnb_rendezvous_release(LnbRendezvous *r)
     r->released = 1;
     pthread_cond_broadcast(&r->cv);
     pthread_mutex_unlock(&r->lock);
+}
+
+uint32_t lnb_plan_ranges(uint32_t blocks, uint32_t devices)
+{
+    const char *e = getenv("LINNE_B200_PIPELINE");
+    uint32_t depth, ranges;
+    if (devices < 1u) devices = 1u;
+    if (e && *e) {
+        depth = (uint32_t)strtoul(e, NULL, 10);
+        if (depth < 1u) depth = 1u;
+    } else {
+        const uint32_t per_device = blocks / devices;
+        depth = per_device >= 8192u ? 4u : (per_device >= 4096u ? 2u : 1u);
+    }
+    ranges = devices * depth;
+    if (ranges > LNB_MAX_DEVICES) ranges = LNB_MAX_DEVICES;
+    if (ranges * 2u > blocks) ranges = blocks / 2u;              /* at least two blocks per range */
+    return ranges < 1u ? 1u : ranges;
 }

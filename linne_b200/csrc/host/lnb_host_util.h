@@ -29,6 +29,13 @@ static inline uint32_t lnb_rd_be(const uint8_t *p, int n) { uint32_t v = 0; int 
 
 void lnb_fill_stream_cfg(LnbStreamCfg *cfg, const struct LINNEHeader *h);
 
+/* Block ranges a whole-stream call of `blocks` blocks is cut into on `devices` devices (>= 1).  More than one range per
+ * device turns the call into a pipeline: the ranges run on their own streams from their own host threads, so one
+ * range's upload, another's kernels and a third's download overlap (the copy engines work beside the SMs) -- worth it
+ * from a few thousand blocks per device on.  LINNE_B200_PIPELINE=N forces N ranges per device (0 or 1: none).
+ * Returns 1 when the call should simply run on the handle's own device. */
+uint32_t lnb_plan_ranges(uint32_t blocks, uint32_t devices);
+
 /* rendezvous of the shard workers of one call with the thread that made it: every worker reports ("sized"), the caller
  * looks at all reports and releases them ("placed") */
 #include <pthread.h>

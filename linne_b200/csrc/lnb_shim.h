@@ -34,6 +34,7 @@ const char *lnb_shim_backend(void);      /* "cuda-sm_100a" for the product */
 int lnb_shim_device_count(void);
 int lnb_shim_set_device(int ordinal);
 int lnb_shim_current_device(void);
+int lnb_shim_device_ordinal(const LnbDevice *dev);    /* the device a context was opened on */
 /* Largest analysis length the cooperative (shared-memory) encoder kernels take; 0 = none. */
 uint32_t lnb_shim_fast_max_na(void);
 /* Longest block (samples per channel) the cooperative prepare / predict+plan kernels take; 0 = none. */

@@ -350,6 +350,7 @@ extern "C" {
 const char *lnb_shim_backend(void) { return "cuda-sm_100a"; }
 int lnb_shim_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
 int lnb_shim_set_device(int ordinal) { if (cudaSetDevice(ordinal) != cudaSuccess) { cudaGetLastError(); return 1; } return 0; }
+int lnb_shim_device_ordinal(const LnbDevice *dev) { return dev->ordinal; }
 int lnb_shim_current_device(void) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; } return d; }
 uint32_t lnb_shim_fast_max_na(void) { return LNB_A3_MAX_NA; }
 uint32_t lnb_shim_coop_max_n(void) { return LNB_FR_MAX_N; }

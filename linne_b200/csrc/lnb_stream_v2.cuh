@@ -38,7 +38,7 @@
 
 #define LNB_DS_MAX_N       10240u
 #define LNB_DS_STAGES      (3u + LNB_MAX_LAYERS)        /* walk, extract, layers, de-emphasis */
-#define LNB_DS_HW_WARPS    7u                           /* warp 4 (the walk's scheduler) only keeps the payload ring filled */
+#define LNB_DS_HW_WARPS    8u                           /* seven roles and a warp that leaves: the walk has a scheduler to itself */
 #define LNB_DS_THREADS     (32u * LNB_DS_HW_WARPS)
 #define LNB_DS_BATCH       32u                          /* steps between progress updates */
 #define LNB_DS_CHUNK_WORDS 512u                         /* payload window: chunks of 2 KB ... */
@@ -183,7 +183,7 @@ __device__ void lnb_ds_loader(const LnbDsWin &w, LnbDsShared &sm, uint32_t lane)
         if (sm.walk_done) break;
         const uint32_t wc = sm.walk_word / LNB_DS_CHUNK_WORDS;
         if (wc == walk_chunk) {
-            __nanosleep(200);
+            __nanosleep(1500);                                  /* a chunk lasts the walk >= 50 us: no need to look often */
             if (++idle > LNB_DS_PATIENCE) { if (lane == 0) lnb_ds_give_up(sm, "loader", issued, swapped); break; }
         } else { walk_chunk = wc; idle = 0; }
     }
@@ -667,6 +667,8 @@ __device__ bool lnb_ds_finish(LnbDsShared &sm, const LnbDecodeBatch &b, const Ln
     return true;
 }
 
+__device__ unsigned int lnb_ds_sm_ticket[256];                  /* per SM: CTAs of this kernel that started there (role rotation) */
+
 /* One CTA per block.  Dynamic shared memory: the channel line, n_max int32. */
 __global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v2_kernel(LnbDecodeBatch b, uint32_t n_max)
 {
@@ -681,20 +683,19 @@ __global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v2_kernel(LnbDecode
     /* blocks this kernel does not take are left to the split kernels (same rule on both sides: b.fused_max_n) */
     if (blk.type != LNB_BLOCK_COMPRESSED || blk.status || n > n_max || n > b.fused_max_n || n == 0u || lnb_tp_takes(b, blk)) return;
 
-    /* Warps map to the SM's four schedulers by index mod 4.  The walk (stage 0) is the pipeline's pace maker: it
-     * gets scheduler 0 to itself (hardware warp 4 exits); extract and de-emphasis (light) share scheduler 1, the
-     * first two synthesis layers -- one of them is the long one in every preset -- take schedulers 2 and 3, the
-     * short third layer sits beside the first. */
-    const uint32_t last = L + 2u;                              /* stage index of the de-emphasis warp */
-    uint32_t stage;
-    if (hw_warp == 0u) stage = 0u;
-    else if (hw_warp == 1u) stage = 1u;
-    else if (hw_warp == 2u) stage = 2u;
-    else if (hw_warp == 3u) stage = (L >= 2u) ? 3u : 0xFFu;
-    else if (hw_warp == 5u) stage = last;
-    else if (hw_warp == 6u) stage = (L >= 3u) ? 4u : 0xFFu;
-    else stage = 0xFFu;
-
+    /* Warps map to the SM's four schedulers by index mod 4, and a role keeps its scheduler busy to a very different
+     * degree: the walk (stage 0) is the pace maker and issue-bound on its own (it shares its scheduler with the warp
+     * that leaves), the long synthesis layer comes next; loader, extract and de-emphasis are light.  Virtual warp v:
+     *     v0 walk | v4 (leaves)      v1 extract | v5 loader      v2 first layer | v6 third (short) layer      v3 second
+     *     layer -- the long one in every three-layer preset | v7 de-emphasis
+     * Several CTAs share an SM (four fit); if all of them put their walk on scheduler 0 it would serve four pace makers
+     * while the others idle.  So every CTA draws a ticket from its SM and rotates its roles by it. */
+    __shared__ uint32_t s_rot;
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rot = atomicAdd(&lnb_ds_sm_ticket[smid & 255u], 1u) & 3u;
+    }
     for (uint32_t i = threadIdx.x; i < (1u << LNB_E3_HUFF1_BITS); i += LNB_DS_THREADS) {
         const uint16_t e = b.tab.huff_lut[i << (LNB_HUFF_LUT_BITS - LNB_E3_HUFF1_BITS)];
         sm.huff1[i] = ((e & 15u) <= LNB_E3_HUFF1_BITS) ? e : (uint16_t)0;
@@ -708,6 +709,17 @@ __global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v2_kernel(LnbDecode
     }
     __syncthreads();
 
+    const uint32_t vwarp = (hw_warp + 8u - s_rot) & 7u;
+    const uint32_t last = L + 2u;                              /* stage index of the de-emphasis warp */
+    uint32_t stage;
+    if (vwarp == 0u) stage = 0u;
+    else if (vwarp == 1u) stage = 1u;
+    else if (vwarp == 2u) stage = 2u;
+    else if (vwarp == 3u) stage = (L >= 2u) ? 3u : 0xFFu;
+    else if (vwarp == 6u) stage = (L >= 3u) ? 4u : 0xFFu;
+    else if (vwarp == 7u) stage = last;
+    else stage = 0xFFu;                                        /* v4 leaves, v5 is the loader (below) */
+
 #ifdef LNB_DS_TIMING
     const long long t_kernel0 = clock64();
     if (blockIdx.x == 0 && lane == 0) { lnb_ds_waited[hw_warp] = 0; if (hw_warp == 0) for (int i = 0; i < 8; i++) lnb_ds_count[i] = 0; }
@@ -716,11 +728,11 @@ __global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v2_kernel(LnbDecode
 #endif
 #ifdef LNB_DS_TIMING
     if (b.cfg.check_crc & 0x100u) {                            /* debug: the walk alone (results are wrong) */
-        if (hw_warp != 0u && hw_warp != 4u) return;
+        if (vwarp != 0u && vwarp != 5u) return;
         if (threadIdx.x == 0) for (uint32_t i = 1; i < LNB_DS_STAGES; i++) sm.prog[i] = 0x7FFFFFFFu;
     }
 #endif
-    if (hw_warp == 4u) { lnb_ds_loader(lnb_ds_window(b, blk), sm, lane); return; }
+    if (vwarp == 5u) { lnb_ds_loader(lnb_ds_window(b, blk), sm, lane); return; }
     if (stage == 0xFFu) return;
     if (stage == 0u) {
         lnb_ds_walk(b, gblk, blk, lnb_ds_window(b, blk), sm, lnb_ds_line, last, lane);

@@ -40,6 +40,7 @@ const char *lnb_shim_backend(void) { return "hostsim"; }
 int lnb_shim_device_count(void) { return 1; }
 int lnb_shim_set_device(int) { return 0; }
 int lnb_shim_current_device(void) { return 0; }
+int lnb_shim_device_ordinal(const LnbDevice *) { return 0; }
 uint32_t lnb_shim_fast_max_na(void) { return 0; }
 uint32_t lnb_shim_coop_max_n(void) { return 0; }
 uint32_t lnb_shim_refine_max_na(void) { return 0; }
