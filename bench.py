@@ -768,6 +768,57 @@ def run_sharded(args, dev, rank, world):
 # =================================================================================================
 # our arm
 # =================================================================================================
+def run_refine(args, dev, pcm, fp64_peak):
+    """The non-default analysis paths: IRLS (-a 3) and momentum SGD (-l) on the C2 clip at -m 0,
+    device-resident; the refinement kernel's time against the FP64 pipe, the reference on a bounded sample beside it.
+    FLOP counts: IRLS per iteration and unit n * p^2 / 2 (upper triangle of the weighted Gram matrix, lpc.c:452-509) +
+    n * p (residual); SGD per iteration 3 * n * sum(P) (linne_network.c:805-873), 2 flops per multiply-add."""
+    import torch
+    import harness
+    from linne_b200 import EncoderSession
+    nch, n = pcm.shape
+    stride = (n + 4 + 3) // 4 * 4
+    cap = 30 + 2 * nch * n * 4 + 65536
+    d_pcm = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
+    d_pcm[:, :n].copy_(torch.from_numpy(pcm.copy()))
+    d_out = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
+    out = {"workload": "C2 clip, -m 0, device-resident encode with the optional analysis paths", "unit": "MSamples/s"}
+    layers = [2, 32]
+    for name, opts in (("irls_a3", {"af": 3}), ("sgd_l", {"learning": 1})):
+        enc = EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=0, **opts)
+        enc.encode_whole_resident(d_pcm.data_ptr(), stride, n, d_out.data_ptr(), cap)           # warm-up
+        enc.set_profiling(True); enc.reset_stage_stats()
+        reps = 3
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            size = enc.encode_whole_resident(d_pcm.data_ptr(), stride, n, d_out.data_ptr(), cap)
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        st = enc.stage_stats()
+        enc.close()
+        k_ms = st.get("refine_v2", (1, 0.0))[1] / reps
+        leg = {"value": round(nch * n / ms / 1e3, 2), "ms": round(ms, 3), "bytes": int(size), "refine_v2_ms": round(k_ms, 3),
+               "stages_ms": {k: round(v[1] / reps, 3) for k, v in sorted(st.items(), key=lambda kv: -kv[1][1])}}
+        if name == "irls_a3":
+            # upper bound: every unit count 1, all 3 iterations run
+            flops = 2.0 * nch * n * sum(3 * (P * P / 2.0 + 2 * P) for P in layers)
+            leg["fp64_frac_upper"] = round(flops / (k_ms / 1e3) / 1e12 / fp64_peak, 5) if k_ms and fp64_peak else None
+        try:
+            impl = harness.Ref() if harness.have_ref() else harness.Oracle()
+            sub = pcm[:, :4 * BLOCK]
+            t0 = time.perf_counter()
+            ref = impl.encode(sub, preset=0, **opts)
+            dt = time.perf_counter() - t0
+            from linne_b200 import Product
+            mine = Product().encode(sub, preset=0, **opts)
+            leg["reference"] = {"value": round(sub.size / dt / 1e6, 4), "cores": 1, "sample": f"first {sub.shape[1]} frames, {dt:.1f} s",
+                                "bytes": len(ref), "b200_bytes": len(mine), "delta_pct": round(100.0 * (len(mine) - len(ref)) / len(ref), 4)}
+        except Exception as e:  # pragma: no cover
+            leg["reference"] = {"error": repr(e)}
+        out[name] = leg
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -1042,6 +1093,12 @@ def run_b200(args, rank, world, local_rank):
             streaming = run_streaming(args, pcm)
         except Exception as e:      # pragma: no cover
             streaming = {"error": repr(e)}
+    refine = None
+    if world == 1 and not args.no_refine:
+        try:
+            refine = run_refine(args, dev, pcm, fp64_peak)
+        except Exception as e:      # pragma: no cover
+            refine = {"error": repr(e)}
     c3 = None
     if world == 1 and args.c3_seconds > 0:
         try:
@@ -1115,6 +1172,8 @@ def run_b200(args, rank, world, local_rank):
         line["c5_corpus"] = c5
     if streaming is not None:
         line["streaming"] = streaming
+    if refine is not None:
+        line["refine"] = refine
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -1144,6 +1203,7 @@ def main():
                     help="C5 leg: LINNEB200_DecoderSetThroughputBlocks of its decoders (several handles in flight)")
     ap.add_argument("--c5-e2e-files", type=int, default=24, help="files per rank of the host-buffer pipeline leg; 0 = skip")
     ap.add_argument("--no-streaming", action="store_true", help="skip the EncodeBlock / DecodeBlock latency leg")
+    ap.add_argument("--no-refine", action="store_true", help="skip the IRLS / SGD leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -26,7 +26,8 @@ struct LINNEDecoder {
     LnbDevice *dev;
     LnbBuf d_stream, d_blocks, d_params, d_pcm, d_packed;
     LnbBuf h_blocks;                       /* pinned LnbBlockDesc[] */
-    LnbBuf h_stream;                       /* pinned copy of a device-resident stream (block hop) */
+    LnbBuf h_stream;                       /* pinned copy of a device-resident stream (block hop on the host: fallback only) */
+    LnbBuf d_hop_files, d_hop_res, d_hop_table, h_hop;     /* device-side block hop: records, results, table; pinned staging */
     LnbBuf h_pcm;                          /* pinned int32 [C][stage_stride]: PCM staging of DecodeBlock / read-ahead cache */
     /* DecodeBlock read-ahead: blocks decoded ahead of the caller in one batch and served from here */
     uint32_t readahead;                    /* blocks decoded per batch by DecodeBlock (<= 1: batch of one) */
@@ -128,6 +129,10 @@ void LINNEDecoder_Destroy(struct LINNEDecoder *dec)
         lnb_buf_release_device(dec->dev, &dec->d_params);
         lnb_buf_release_device(dec->dev, &dec->d_pcm);
         lnb_buf_release_device(dec->dev, &dec->d_packed);
+        lnb_buf_release_device(dec->dev, &dec->d_hop_files);
+        lnb_buf_release_device(dec->dev, &dec->d_hop_res);
+        lnb_buf_release_device(dec->dev, &dec->d_hop_table);
+        lnb_buf_release_host(&dec->h_hop);
         lnb_buf_release_host(&dec->h_blocks);
         lnb_buf_release_host(&dec->h_stream);
         lnb_buf_release_host(&dec->h_pcm);
@@ -614,6 +619,9 @@ void lnb_decoder_set_readahead(struct LINNEDecoder *dec, uint32_t blocks)
 /* ---- extension entry point (include/linne_b200.h) ---- */
 #include "linne_b200.h"
 
+static LINNEApiResult decode_files(struct LINNEDecoder *dec, const uint8_t *host_image, const uint8_t *d_data, uint32_t data_size,
+        struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride, uint32_t max_channels);
+
 LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uint8_t *data, const uint8_t *d_data,
         uint32_t data_size, int32_t *d_pcm, uint32_t pcm_stride, uint32_t buffer_num_channels, uint32_t buffer_num_samples)
 {
@@ -621,11 +629,12 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uin
     LINNEApiResult ret;
     if (dec == NULL || d_data == NULL || d_pcm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     if (data == NULL) {
-        /* no host copy supplied: fetch the image once for the block hop (it is ~4x smaller than the PCM) */
-        if (lnb_buf_reserve_host(&dec->h_stream, (size_t)data_size + 16u)) return LINNE_APIRESULT_NG;
-        lnb_shim_d2h(dec->dev, dec->h_stream.ptr, d_data, data_size);
-        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
-        data = (const uint8_t *)dec->h_stream.ptr;
+        /* no host copy supplied: the hop over the size fields runs on the device (one stream of a corpus batch) */
+        struct LINNEB200FileDesc one;
+        if (pcm_stride < buffer_num_samples) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+        one.first_sample = 0; one.num_samples = buffer_num_samples; one.out_offset = 0; one.out_size = data_size; one.status = 0;
+        (void)header;
+        return decode_files(dec, NULL, d_data, data_size, &one, 1, d_pcm, pcm_stride, buffer_num_channels);
     }
     if ((ret = LINNEDecoder_DecodeHeader(data, data_size, &header)) != LINNE_APIRESULT_OK) return ret;
     if ((ret = LINNEDecoder_SetHeader(dec, &header)) != LINNE_APIRESULT_OK) return ret;
@@ -639,34 +648,99 @@ LINNEApiResult LINNEB200_DecodeWholeResident(struct LINNEDecoder *dec, const uin
  * `d_data` (files[i].out_offset / out_size), all with the same stream parameters; the blocks of all of them go
  * through the kernels as ONE batch and every file's PCM lands at files[i].first_sample of the planes. */
 static LINNEApiResult decode_files(struct LINNEDecoder *dec, const uint8_t *host_image, const uint8_t *d_data, uint32_t data_size,
-        struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride)
+        struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride, uint32_t max_channels)
 {
     struct LINNEHeader h0, h1;
     LnbDecodeBatch batch;
     LnbBlockDesc *blocks;
     const uint8_t *img;
     LINNEApiResult ret, overall = LINNE_APIRESULT_OK;
-    uint32_t i, k, nb = 0, cap, C;
+    uint32_t i, k, nb = 0, cap, C = 0;
     uint32_t *first_block;
+    int hopped = 0;
     if (dec == NULL || d_data == NULL || files == NULL || num_files == 0 || d_pcm == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     for (i = 0; i < num_files; i++) {
         if ((uint64_t)files[i].out_offset + files[i].out_size > data_size
             || (uint64_t)files[i].first_sample + files[i].num_samples > pcm_stride) return LINNE_APIRESULT_INVALID_ARGUMENT;
         files[i].status = (int32_t)LINNE_APIRESULT_OK;
     }
-    if (host_image) {
-        img = host_image;
-    } else {
-        /* the image comes to the host once for the block hop (it is ~4x smaller than the PCM it decodes to) */
-        if (lnb_buf_reserve_host(&dec->h_stream, (size_t)data_size + 16u)) return LINNE_APIRESULT_NG;
-        lnb_shim_d2h(dec->dev, dec->h_stream.ptr, d_data, data_size);
-        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
-        img = (const uint8_t *)dec->h_stream.ptr;
-    }
-    if ((ret = LINNEDecoder_DecodeHeader(img + files[0].out_offset, files[0].out_size, &h0)) != LINNE_APIRESULT_OK) return ret;
-    if ((ret = LINNEDecoder_SetHeader(dec, &h0)) != LINNE_APIRESULT_OK) return ret;
-    C = h0.num_channels;
+    img = host_image;
     if (!(first_block = (uint32_t *)malloc(((size_t)num_files + 1u) * sizeof(uint32_t)))) return LINNE_APIRESULT_NG;
+    if (!host_image) {
+        /* The image is in HBM only: the hop over the size fields runs there (lnb_hop.cuh).  What comes back is a result
+         * record per stream (with its 30 header bytes) and the block table -- not the image. */
+        LnbHopFile *hf;
+        LnbHopResult *hr;
+        LnbBlockDesc *ht;
+        uint32_t total_cap = 0;
+        size_t staging;
+        int fallback = 0;
+        /* table slices: a conforming stream has one block per num_samples_per_block frames; the frames the caller gave
+         * room for bound that from above for any block size >= 256 (smaller: the hop reports the overflow) */
+        for (i = 0; i < num_files; i++) total_cap += files[i].num_samples / 256u + 64u;
+        staging = (size_t)num_files * (sizeof(LnbHopFile) + sizeof(LnbHopResult)) + (size_t)total_cap * sizeof(LnbBlockDesc);
+        if (lnb_buf_reserve_host(&dec->h_hop, staging)
+            || lnb_buf_reserve_device(dec->dev, &dec->d_hop_files, (size_t)num_files * sizeof(LnbHopFile))
+            || lnb_buf_reserve_device(dec->dev, &dec->d_hop_res, (size_t)num_files * sizeof(LnbHopResult))
+            || lnb_buf_reserve_device(dec->dev, &dec->d_hop_table, (size_t)total_cap * sizeof(LnbBlockDesc))
+            || lnb_buf_reserve_host(&dec->h_blocks, (size_t)total_cap * sizeof(LnbBlockDesc))) { free(first_block); return LINNE_APIRESULT_NG; }
+        hf = (LnbHopFile *)dec->h_hop.ptr;
+        hr = (LnbHopResult *)(hf + num_files);
+        ht = (LnbBlockDesc *)(hr + num_files);
+        total_cap = 0;
+        for (i = 0; i < num_files; i++) {
+            hf[i].offset = files[i].out_offset; hf[i].size = files[i].out_size; hf[i].room_samples = files[i].num_samples;
+            hf[i].table_first = total_cap; hf[i].table_cap = files[i].num_samples / 256u + 64u;
+            total_cap += hf[i].table_cap;
+        }
+        lnb_shim_h2d(dec->dev, dec->d_hop_files.ptr, hf, (size_t)num_files * sizeof(LnbHopFile));
+        if (lnb_shim_hop(dec->dev, d_data, (const LnbHopFile *)dec->d_hop_files.ptr, num_files,
+                         (LnbBlockDesc *)dec->d_hop_table.ptr, (LnbHopResult *)dec->d_hop_res.ptr)) { free(first_block); return LINNE_APIRESULT_NG; }
+        lnb_shim_d2h(dec->dev, hr, dec->d_hop_res.ptr, (size_t)num_files * sizeof(LnbHopResult));
+        if (lnb_shim_sync(dec->dev)) { free(first_block); return LINNE_APIRESULT_NG; }
+        for (i = 0; i < num_files; i++) if (hr[i].overflow) fallback = 1;
+        if (!fallback) {
+            /* only the slices that were filled travel */
+            for (i = 0; i < num_files; i++)
+                if (hr[i].num_blocks) lnb_shim_d2h(dec->dev, ht + hf[i].table_first, (LnbBlockDesc *)dec->d_hop_table.ptr + hf[i].table_first,
+                                                   (size_t)hr[i].num_blocks * sizeof(LnbBlockDesc));
+            if (lnb_shim_sync(dec->dev)) { free(first_block); return LINNE_APIRESULT_NG; }
+            if ((ret = LINNEDecoder_DecodeHeader(hr[0].header, files[0].out_size < 32u ? files[0].out_size : 32u, &h0)) != LINNE_APIRESULT_OK
+                || (ret = LINNEDecoder_SetHeader(dec, &h0)) != LINNE_APIRESULT_OK) { free(first_block); return ret; }
+            C = h0.num_channels;
+            if (max_channels && max_channels < C) { free(first_block); return LINNE_APIRESULT_INSUFFICIENT_BUFFER; }
+            blocks = (LnbBlockDesc *)dec->h_blocks.ptr;
+            for (i = 0; i < num_files; i++) {
+                first_block[i] = nb;
+                ret = LINNEDecoder_DecodeHeader(hr[i].header, files[i].out_size < 32u ? files[i].out_size : 32u, &h1);
+                if (ret == LINNE_APIRESULT_OK
+                    && (h1.num_channels != h0.num_channels || h1.bits_per_sample != h0.bits_per_sample || h1.preset != h0.preset
+                        || h1.num_samples_per_block != h0.num_samples_per_block || h1.ch_process_method != h0.ch_process_method
+                        || h1.format_version != h0.format_version || h1.codec_version != h0.codec_version))
+                    ret = LINNE_APIRESULT_INVALID_FORMAT;                     /* one set of stream parameters per batch */
+                if (ret == LINNE_APIRESULT_OK && files[i].num_samples < h1.num_samples) ret = LINNE_APIRESULT_INSUFFICIENT_BUFFER;
+                if (ret != LINNE_APIRESULT_OK) { files[i].status = (int32_t)ret; continue; }
+                memcpy(blocks + nb, ht + hf[i].table_first, (size_t)hr[i].num_blocks * sizeof(LnbBlockDesc));
+                for (k = 0; k < hr[i].num_blocks; k++) blocks[nb + k].smp_off += files[i].first_sample;
+                for (k = hr[i].num_decodable; k < hr[i].num_blocks; k++) blocks[nb + k].type = 0xFFu;    /* CRC pass only */
+                if (hr[i].num_blocks > hr[i].num_decodable) files[i].status = (int32_t)hr[i].post_crc_error;
+                else files[i].status = (int32_t)hr[i].framing_error;
+                nb += hr[i].num_blocks;
+            }
+            hopped = 1;
+        } else {
+            /* a stream of tiny blocks: the image comes to the host once and the hop runs there */
+            if (lnb_buf_reserve_host(&dec->h_stream, (size_t)data_size + 16u)) { free(first_block); return LINNE_APIRESULT_NG; }
+            lnb_shim_d2h(dec->dev, dec->h_stream.ptr, d_data, data_size);
+            if (lnb_shim_sync(dec->dev)) { free(first_block); return LINNE_APIRESULT_NG; }
+            img = (const uint8_t *)dec->h_stream.ptr;
+        }
+    }
+    if (!hopped) {
+    if ((ret = LINNEDecoder_DecodeHeader(img + files[0].out_offset, files[0].out_size, &h0)) != LINNE_APIRESULT_OK) { free(first_block); return ret; }
+    if ((ret = LINNEDecoder_SetHeader(dec, &h0)) != LINNE_APIRESULT_OK) { free(first_block); return ret; }
+    C = h0.num_channels;
+    if (max_channels && max_channels < C) { free(first_block); return LINNE_APIRESULT_INSUFFICIENT_BUFFER; }
 
     cap = 64u;
     for (i = 0; i < num_files; i++) cap += files[i].out_size / 64u + 16u;
@@ -694,6 +768,7 @@ static LINNEApiResult decode_files(struct LINNEDecoder *dec, const uint8_t *host
         if (scan.num_blocks > scan.num_decodable) files[i].status = (int32_t)scan.post_crc_error;
         else files[i].status = (int32_t)scan.framing_error;
         nb += scan.num_blocks;
+    }
     }
     first_block[num_files] = nb;
 
@@ -743,7 +818,7 @@ static LINNEApiResult decode_files(struct LINNEDecoder *dec, const uint8_t *host
 LINNEApiResult LINNEB200_DecodeFilesResident(struct LINNEDecoder *dec, const uint8_t *d_data, uint32_t data_size,
         struct LINNEB200FileDesc *files, uint32_t num_files, int32_t *d_pcm, uint32_t pcm_stride)
 {
-    return decode_files(dec, NULL, d_data, data_size, files, num_files, d_pcm, pcm_stride);
+    return decode_files(dec, NULL, d_data, data_size, files, num_files, d_pcm, pcm_stride, 0u);
 }
 
 /* The same for host buffers: the streams in the host image `data` (files[i].out_offset / out_size), the PCM of the
@@ -771,7 +846,7 @@ LINNEApiResult LINNEB200_DecodeFilesPacked(struct LINNEDecoder *dec, const uint8
         || lnb_buf_reserve_device(dec->dev, &dec->d_packed, (size_t)total * C * bytes + 16u)) return LINNE_APIRESULT_NG;
     lnb_shim_memset(dec->dev, (uint8_t *)dec->d_stream.ptr + (padded - 16u), 0, 16u);
     lnb_shim_h2d(dec->dev, dec->d_stream.ptr, data, data_size);
-    ret = decode_files(dec, data, (const uint8_t *)dec->d_stream.ptr, data_size, files, num_files, (int32_t *)dec->d_pcm.ptr, (uint32_t)stride);
+    ret = decode_files(dec, data, (const uint8_t *)dec->d_stream.ptr, data_size, files, num_files, (int32_t *)dec->d_pcm.ptr, (uint32_t)stride, 0u);
     /* every file that decoded is handed back; a failed file's frames are undefined */
     if (lnb_shim_pack_pcm(dec->dev, (const int32_t *)dec->d_pcm.ptr, (uint8_t *)dec->d_packed.ptr, (uint32_t)stride,
                           (uint32_t)total, C, bytes)) return LINNE_APIRESULT_NG;

@@ -65,6 +65,11 @@ int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *batch);
 int lnb_shim_encode_analyze(LnbDevice *dev, const LnbEncodeBatch *batch);
 int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *batch, uint32_t out_capacity);
 
+/* hop over the block size fields of `num_files` streams of a device image (enqueue only): d_files / d_table / d_results
+ * are device buffers; d_table receives byte offsets relative to the image and sample offsets relative to each stream */
+int lnb_shim_hop(LnbDevice *dev, const uint8_t *d_image, const LnbHopFile *d_files, uint32_t num_files,
+                 LnbBlockDesc *d_table, LnbHopResult *d_results);
+
 /* packed interleaved PCM (WAV data-chunk layout, `bytes` per sample) <-> int32 planes, on the device (enqueue only) */
 int lnb_shim_unpack_pcm(LnbDevice *dev, const uint8_t *d_packed, int32_t *d_pcm, uint32_t pcm_stride,
                         uint32_t frames, uint32_t channels, uint32_t bytes);

@@ -20,6 +20,7 @@
 #include "lnb_refine_v2.cuh"
 #include "lnb_scan_v2.cuh"
 #include "lnb_stream_v2.cuh"
+#include "lnb_hop.cuh"
 
 #define LNB_MAX_STAGES 32
 #define LNB_MAX_PENDING 8192
@@ -528,6 +529,18 @@ int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *batch, uint32_t o
     bind_device(dev);
     CudaExec ex{dev};
     lnb_encode_pack_pipeline(ex, *batch, out_capacity);
+    return dev->last_error == cudaSuccess ? 0 : 1;
+}
+
+int lnb_shim_hop(LnbDevice *dev, const uint8_t *d_image, const LnbHopFile *d_files, uint32_t num_files,
+                 LnbBlockDesc *d_table, LnbHopResult *d_results)
+{
+    bind_device(dev);
+    if (num_files == 0) return 0;
+    CudaExec ex{dev};
+    const int slot = ex.begin_stage("hop");
+    lnb_hop_kernel<<<num_files, 32, 0, dev->stream>>>(d_image, d_files, num_files, d_table, d_results);
+    ex.end_stage(slot);
     return dev->last_error == cudaSuccess ? 0 : 1;
 }
 

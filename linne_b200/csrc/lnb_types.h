@@ -92,6 +92,18 @@ typedef struct LnbDecodeBatch {
                                      * checks it against the caller's buffer only, linne_decoder.c:632-635) */
 } LnbDecodeBatch;
 
+/* ---- the device-side hop over block size fields (lnb_hop.cuh): one record per stream of the image ---- */
+typedef struct LnbHopFile {
+    uint32_t offset, size;          /* the stream inside the image */
+    uint32_t room_samples;          /* frames the destination planes hold for it */
+    uint32_t table_first, table_cap;/* its slice of the block table */
+} LnbHopFile;
+typedef struct LnbHopResult {
+    uint8_t  header[32];            /* the stream's 30 header bytes (for the host's header checks) */
+    uint32_t num_blocks, num_decodable, framing_error, post_crc_error, total_samples, end_offset;
+    uint32_t overflow;              /* 1: more blocks than table_cap -- the caller falls back to hopping on the host */
+} LnbHopResult;
+
 /* ---- one encode batch (all pointers are device pointers) ---- */
 typedef struct LnbEncodeBatch {
     LnbStreamCfg cfg;

@@ -9,6 +9,7 @@
 #include <string.h>
 #include "lnb_shim.h"
 #include "lnb_pipeline.cuh"
+#include "lnb_hop.cuh"
 
 struct LnbDevice { LnbDevTables tables; uint64_t launches; };
 
@@ -72,6 +73,8 @@ int lnb_shim_sync(LnbDevice *) { return 0; }
 int lnb_shim_decode(LnbDevice *dev, const LnbDecodeBatch *b) { LoopExec ex{dev}; lnb_decode_pipeline(ex, *b); return 0; }
 int lnb_shim_encode_analyze(LnbDevice *dev, const LnbEncodeBatch *b) { LoopExec ex{dev}; lnb_encode_analyze_pipeline(ex, *b); return 0; }
 int lnb_shim_encode_pack(LnbDevice *dev, const LnbEncodeBatch *b, uint32_t cap) { LoopExec ex{dev}; lnb_encode_pack_pipeline(ex, *b, cap); return 0; }
+int lnb_shim_hop(LnbDevice *dev, const uint8_t *img, const LnbHopFile *files, uint32_t n, LnbBlockDesc *table, LnbHopResult *res)
+{ for (uint32_t i = 0; i < n; i++) lnb_hop_file(img, files[i], table + files[i].table_first, res[i]); dev->launches++; return 0; }
 int lnb_shim_unpack_pcm(LnbDevice *dev, const uint8_t *pk, int32_t *pcm, uint32_t stride, uint32_t frames, uint32_t ch, uint32_t bytes)
 { LoopExec ex{dev}; lnb_unpack_pcm_pipeline(ex, pk, pcm, stride, frames, ch, bytes); return 0; }
 int lnb_shim_pack_pcm(LnbDevice *dev, const int32_t *pcm, uint8_t *pk, uint32_t stride, uint32_t frames, uint32_t ch, uint32_t bytes)
