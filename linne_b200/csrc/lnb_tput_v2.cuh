@@ -15,9 +15,12 @@
  * ~P/4 (synthesis) warp instructions per sample the arithmetic needs.
  *
  *   lnb_tp_entropy_kernel   eight lanes per block, four blocks per warp: speculative code-word starts, one 32-byte
- *                           sector of residuals per round (see below; a lane-per-block walk was measured in round 2
- *                           and lost: every data-dependent branch of a lone warp costs ~20 cycles, and 32 lanes at 32
- *                           different places of their blocks pay every lane's branches -- 7.1 ms against 3.7 ms).
+ *                           sector of residuals per round (see below).  Lane-per-block walks were measured twice in
+ *                           round 2 and lost on a 1-hour stream: a flat loop with one code word per pass (every
+ *                           data-dependent branch of a lone warp costs ~20 cycles, 32 lanes pay each other's: 7.1 ms)
+ *                           and branch-free steps of eight code-word slots per lane (8.8 ms: with 485 warps for 592
+ *                           schedulers nothing hides the ~550 dependent instructions and three memory round trips of
+ *                           a step) against 4.2 ms here, where 6.5 warps per scheduler hide each other's latency.
  *   lnb_tp_synth_kernel     lane = (block, channel).  Groups of 8 samples run through the whole cascade in
  *                           registers: for layers of 16..128 taps the history lives in a lane-interleaved
  *                           shared-memory ring (conflict-free; the ring position is warp-uniform because all
