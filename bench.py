@@ -713,28 +713,33 @@ def run_sharded(args, dev, rank, world):
     d_back = torch.zeros((nch, stride), dtype=torch.int32, device=dev)
     enc = EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=7)
     dec = DecoderSession(channels=nch)
-    res, dest = {}, None
-    for it in range(2):                                          # first pass warms allocations and the IPC path
+    res, dest, peer = {}, None, None
+    # control plane, once, outside the timed region: rank 0's destination buffer (sized for the worst case of every
+    # shard), its IPC handle to every rank, the peer mapping opened and kept
+    caps_t = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(caps_t, torch.tensor([cap], dtype=torch.int64, device=dev))
+    handle_t = torch.zeros(64, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        dest = DeviceBuffer(30 + sum(int(t.item()) for t in caps_t) + 64)
+        handle_t.copy_(torch.frombuffer(bytearray(dest.ipc_handle()), dtype=torch.uint8))
+    dist.broadcast(handle_t, src=0)
+    if rank != 0:
+        peer = PeerMapping(bytes(handle_t.cpu().numpy().tobytes()))
+    sizes_all = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.zeros(1, dtype=torch.int64, device=dev)
+    for it in range(3):                                          # first passes warm allocations and the NVLink path
         torch.cuda.synchronize(); dist.barrier()
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record()
         size = enc.encode_whole_resident(d_pcm.data_ptr(), stride, count, d_shard.data_ptr(), cap) - 30
-        sizes_t = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(sizes_t, torch.tensor([size], dtype=torch.int64, device=dev))
-        sizes = [int(t.item()) for t in sizes_t]
+        mine.fill_(size)
+        dist.all_gather_into_tensor(sizes_all, mine)             # 8 bytes per rank: the shard byte counts
+        sizes = sizes_all.tolist()
         offsets, total = shard.exclusive_scan(sizes)
-        handle_t = torch.zeros(64, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            if dest is None or dest.nbytes < 30 + total + 64:
-                dest = DeviceBuffer(30 + total + 64)
-            handle_t.copy_(torch.frombuffer(bytearray(dest.ipc_handle()), dtype=torch.uint8))
-        dist.broadcast(handle_t, src=0)
         if rank == 0:
             dest.lib.LINNEB200_DeviceCopy(dest.ptr + 30 + offsets[0], d_shard.data_ptr() + 30, size)
         else:
-            peer = PeerMapping(bytes(handle_t.cpu().numpy().tobytes()))
             peer.put(30 + offsets[rank], d_shard.data_ptr() + 30, size)
-            peer.close()
         torch.cuda.synchronize(); dist.barrier()
         e1.record()
         e2.record()
@@ -748,7 +753,7 @@ def run_sharded(args, dev, rank, world):
         if rank == 0:                                            # the gathered stream is ONE valid .lnn file
             hdr = shard.patch_num_samples(bytes(d_shard[:30].cpu().numpy().tobytes()), n)
             dest.upload(hdr, 0)
-            if it == 1:
+            if it == 2:
                 whole = dest.download(30 + total)
                 whole_ok = bool(np.array_equal(Product().decode(whole), pcm))
         res = {"workload": f"{args.shard_seconds:.0f} s stereo stream ({nch * n} samples), -m 7, contiguous block ranges over {world} GPUs, "
@@ -757,9 +762,13 @@ def run_sharded(args, dev, rank, world):
                "encode_MSamples_s": round(nch * n / (float(t[0]) / 1e3) / 1e6, 1),
                "decode_MSamples_s": round(nch * n / (float(t[1]) / 1e3) / 1e6, 1),
                "stream_bytes": 30 + total, "lossless": bool(int(ok.item())), "gathered_stream_decodes": whole_ok,
-               "exchange": "all-gather of shard byte counts (8 B per rank) + exclusive scan + one CUDA-IPC device-to-device put per rank "
-                           "into rank 0's buffer (NVLink); no data-path collective; decode: every rank its own block range, no exchange"}
+               "exchange": "timed: all-gather of shard byte counts (8 B per rank) + exclusive scan + one device-to-device put per rank into "
+                           "rank 0's buffer through a CUDA-IPC peer mapping opened once (NVLink); no data-path collective; "
+                           "decode: every rank its own block range, no exchange"}
     enc.close(); dec.close()
+    if peer is not None:
+        peer.close()
+    dist.barrier()
     if dest is not None:
         dest.free()
     return res
@@ -768,6 +777,55 @@ def run_sharded(args, dev, rank, world):
 # =================================================================================================
 # our arm
 # =================================================================================================
+def run_inlib_multi(args, dev):
+    """Several GPUs behind ONE handle of ONE process (include/linne_b200.h: LINNEB200_*SetDevices): the reference
+    API's EncodeWhole / DecodeWhole on host buffers, a 600 s stereo stream at -m 7, on one device without and with
+    pipelined block ranges and on every visible device.  Wall clock of the synchronous calls (median of 3)."""
+    import torch
+    import harness
+    from linne_b200 import EncoderSession, DecoderSession
+    pcm = long_pcm(args.shard_seconds)
+    nch, n = pcm.shape
+    cap = 30 + nch * n * 2 + 11 * (n // BLOCK + 2) + 65536
+    h_pcm = torch.from_numpy(pcm.copy()).pin_memory()
+    h_out = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    h_back = torch.zeros((nch, n), dtype=torch.int32).pin_memory()
+    chan_in = (C.POINTER(C.c_int32) * nch)(*[C.cast(h_pcm[c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
+    chan_out = (C.POINTER(C.c_int32) * nch)(*[C.cast(h_back[c].data_ptr(), C.POINTER(C.c_int32)) for c in range(nch)])
+    visible = torch.cuda.device_count()
+    out = {"workload": f"{args.shard_seconds:.0f} s stereo stream ({nch * n} samples), -m 7, host buffers through LINNEEncoder_EncodeWhole / "
+                       f"LINNEDecoder_DecodeWhole, one process", "visible_gpus": visible, "unit": "ms per call (median of 3)"}
+    reference_stream = None
+    configs = [("one_device_no_pipeline", 1, "1"), ("one_device_pipelined", 1, None)]
+    for g in (2, 4, 8):
+        if g <= visible:
+            configs.append((f"{g}_devices", g, None))
+    for name, devices, pipeline in configs:
+        if pipeline is None:
+            os.environ.pop("LINNE_B200_PIPELINE", None)
+        else:
+            os.environ["LINNE_B200_PIPELINE"] = pipeline
+        enc = EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=7)
+        dec = DecoderSession(channels=nch)
+        enc.set_devices(devices); dec.set_devices(devices)
+        te, td = [], []
+        for it in range(4):
+            t0 = time.perf_counter(); size = enc.encode_whole(chan_in, n, h_out.data_ptr(), cap); t1 = time.perf_counter()
+            h_back.zero_()
+            t2 = time.perf_counter(); dec.decode_whole(h_out.data_ptr(), size, chan_out, nch, n); t3 = time.perf_counter()
+            if it:
+                te.append((t1 - t0) * 1e3); td.append((t3 - t2) * 1e3)
+        stream = bytes(h_out[:size].numpy().tobytes())
+        if reference_stream is None:
+            reference_stream = stream
+        out[name] = {"encode_ms": round(sorted(te)[1], 2), "decode_ms": round(sorted(td)[1], 2),
+                     "encode_MSamples_s": round(nch * n / sorted(te)[1] / 1e3, 1), "decode_MSamples_s": round(nch * n / sorted(td)[1] / 1e3, 1),
+                     "same_bytes_as_one_device": stream == reference_stream, "lossless": bool(np.array_equal(h_back.numpy(), pcm))}
+        enc.close(); dec.close()
+    os.environ.pop("LINNE_B200_PIPELINE", None)
+    return out
+
+
 def run_refine(args, dev, pcm, fp64_peak):
     """The non-default analysis paths: IRLS (-a 3) and momentum SGD (-l) on the C2 clip at -m 0,
     device-resident; the refinement kernel's time against the FP64 pipe, the reference on a bounded sample beside it.
@@ -1093,6 +1151,12 @@ def run_b200(args, rank, world, local_rank):
             streaming = run_streaming(args, pcm)
         except Exception as e:      # pragma: no cover
             streaming = {"error": repr(e)}
+    inlib = None
+    if world == 1 and args.shard_seconds > 0 and not args.no_inlib:
+        try:
+            inlib = run_inlib_multi(args, dev)
+        except Exception as e:      # pragma: no cover
+            inlib = {"error": repr(e)}
     refine = None
     if world == 1 and not args.no_refine:
         try:
@@ -1174,6 +1238,8 @@ def run_b200(args, rank, world, local_rank):
         line["streaming"] = streaming
     if refine is not None:
         line["refine"] = refine
+    if inlib is not None:
+        line["inlib_multi_gpu"] = inlib
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -1204,6 +1270,7 @@ def main():
     ap.add_argument("--c5-e2e-files", type=int, default=24, help="files per rank of the host-buffer pipeline leg; 0 = skip")
     ap.add_argument("--no-streaming", action="store_true", help="skip the EncodeBlock / DecodeBlock latency leg")
     ap.add_argument("--no-refine", action="store_true", help="skip the IRLS / SGD leg")
+    ap.add_argument("--no-inlib", action="store_true", help="skip the in-library multi-GPU / pipelining leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -501,26 +501,32 @@ void LINNEB200_DecoderSetDevices(struct LINNEDecoder *dec, uint32_t num_devices)
 struct LnbDecShard {
     struct LINNEDecoder *child;
     const uint8_t *data; uint32_t data_size;
-    int32_t *planes[LINNE_MAX_NUM_CHANNELS];
+    int32_t *planes[LINNE_MAX_NUM_CHANNELS];   /* int32 planes, or ... */
+    uint8_t *packed;                       /* ... interleaved packed PCM for this range */
     uint32_t room, sample_limit, block_limit;
+    uint32_t first_sample;                 /* of the range, in the whole stream */
     uint32_t decoded;
     LINNEApiResult result;
     int ordinal;
 };
+
+static LINNEApiResult decode_packed_range(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size, uint32_t start_offset,
+        uint8_t *pcm, uint32_t room_frames, uint32_t sample_limit, uint32_t block_limit, uint32_t *decoded_out);
 
 static void *dec_shard_main(void *arg)
 {
     struct LnbDecShard *sh = (struct LnbDecShard *)arg;
     lnb_shim_set_device(sh->ordinal);
     sh->decoded = 0;
-    sh->result = decode_range(sh->child, sh->data, sh->data_size, 0, sh->planes, sh->room, sh->sample_limit, sh->block_limit, 0,
-                              NULL, &sh->decoded, NULL, NULL, 0, NULL, NULL);
+    if (sh->packed) sh->result = decode_packed_range(sh->child, sh->data, sh->data_size, 0, sh->packed, sh->room, sh->sample_limit, sh->block_limit, &sh->decoded);
+    else sh->result = decode_range(sh->child, sh->data, sh->data_size, 0, sh->planes, sh->room, sh->sample_limit, sh->block_limit, 0,
+                                   NULL, &sh->decoded, NULL, NULL, 0, NULL, NULL);
     return NULL;
 }
 
 /* DecodeWhole over dec->num_devices block ranges; returns 0 when the stream is too short to be worth it (*ret untouched) */
 static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
-                                int32_t **buffer, uint32_t buffer_num_samples, LINNEApiResult *ret)
+                                int32_t **buffer, uint8_t *packed, uint32_t buffer_num_samples, LINNEApiResult *ret, uint32_t *decoded_total)
 {
     const struct LINNEHeader *h = &dec->header;
     const int ndev = lnb_shim_device_count();
@@ -572,7 +578,9 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
         sh[k].child = dec->child[k];
         sh[k].data = data + first->byte_off;
         sh[k].data_size = end_byte - first->byte_off;
-        for (c = 0; c < h->num_channels; c++) sh[k].planes[c] = buffer[c] + first->smp_off;
+        for (c = 0; c < h->num_channels && buffer; c++) sh[k].planes[c] = buffer[c] + first->smp_off;
+        if (packed) sh[k].packed = packed + (size_t)first->smp_off * h->num_channels * (h->bits_per_sample / 8u);
+        sh[k].first_sample = first->smp_off;
         sh[k].room = buffer_num_samples - first->smp_off;
         sh[k].sample_limit = last ? h->num_samples - first->smp_off : dec->shard_table[b1].smp_off - first->smp_off;
         sh[k].block_limit = last ? 0u : b1 - b0;
@@ -583,7 +591,11 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
     for (k = 0; k < started; k++) pthread_join(th[k], NULL);
     if (started < G) { *ret = LINNE_APIRESULT_NG; return 1; }
     *ret = LINNE_APIRESULT_OK;
-    for (k = 0; k < G; k++) if (sh[k].result != LINNE_APIRESULT_OK) { *ret = sh[k].result; break; }   /* first error in stream order */
+    if (decoded_total) *decoded_total = 0;
+    for (k = 0; k < G; k++) {                                    /* first error in stream order; frames up to there count */
+        if (decoded_total) *decoded_total = sh[k].first_sample + sh[k].decoded;
+        if (sh[k].result != LINNE_APIRESULT_OK) { *ret = sh[k].result; break; }
+    }
     return 1;
 }
 
@@ -601,7 +613,7 @@ LINNEApiResult LINNEDecoder_DecodeWhole(struct LINNEDecoder *dec, const uint8_t 
         return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     for (c = 0; c < header.num_channels; c++) if (buffer[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     /* several devices, or a stream long enough to pipeline its transfers against its kernels on one */
-    if ((dec->num_devices > 1u || data_size >= (32u << 20)) && decode_whole_sharded(dec, data, data_size, buffer, buffer_num_samples, &ret)) return ret;
+    if ((dec->num_devices > 1u || data_size >= (32u << 20)) && decode_whole_sharded(dec, data, data_size, buffer, NULL, buffer_num_samples, &ret, NULL)) return ret;
     return decode_range(dec, data, data_size, LINNE_HEADER_SIZE, buffer, buffer_num_samples,
                         header.num_samples, 0, 0, NULL, NULL, NULL, NULL, 0, NULL, NULL);
 }
@@ -855,15 +867,38 @@ LINNEApiResult LINNEB200_DecodeFilesPacked(struct LINNEDecoder *dec, const uint8
     return ret;
 }
 
-/* Packed interleaved PCM out (the bytes of a WAV data chunk), converted from the planes on the device.
- * `pcm` holds `pcm_capacity_frames` frames; `num_frames` receives the frames written.  SURVEY 8f.2. */
+/* Packed interleaved PCM out (the bytes of a WAV data chunk), converted from the planes on the device: the blocks found
+ * from `start_offset` on (header already set), at most block_limit blocks (0: all) / sample_limit frames. */
+static LINNEApiResult decode_packed_range(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size, uint32_t start_offset,
+        uint8_t *pcm, uint32_t room_frames, uint32_t sample_limit, uint32_t block_limit, uint32_t *decoded_out)
+{
+    const struct LINNEHeader *h = &dec->header;
+    const uint32_t bytes = h->bits_per_sample / 8u;
+    const uint32_t frames = sample_limit < room_frames ? sample_limit : room_frames;
+    LINNEApiResult ret;
+    uint32_t decoded = 0;
+    size_t stride = LNB_ROUNDUP((size_t)frames + (size_t)h->num_samples_per_block + 65536u + 4u, 4u);   /* room for a parked terminal block */
+    if (lnb_buf_reserve_device(dec->dev, &dec->d_pcm, stride * h->num_channels * sizeof(int32_t))
+        || lnb_buf_reserve_device(dec->dev, &dec->d_packed, (size_t)frames * h->num_channels * bytes + 16u))
+        return LINNE_APIRESULT_NG;
+    ret = decode_range(dec, data, data_size, start_offset, NULL, room_frames, sample_limit, block_limit, 0,
+                       NULL, &decoded, NULL, (int32_t *)dec->d_pcm.ptr, (uint32_t)stride, NULL, NULL);
+    if (decoded) {          /* every sample the reference would have produced before stopping */
+        if (lnb_shim_pack_pcm(dec->dev, (const int32_t *)dec->d_pcm.ptr, (uint8_t *)dec->d_packed.ptr, (uint32_t)stride,
+                              decoded, h->num_channels, bytes)) return LINNE_APIRESULT_NG;
+        lnb_shim_d2h(dec->dev, pcm, dec->d_packed.ptr, (size_t)decoded * h->num_channels * bytes);
+        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+    }
+    *decoded_out = decoded;
+    return ret;
+}
+
 LINNEApiResult LINNEB200_DecodeWholePacked(struct LINNEDecoder *dec, const uint8_t *data, uint32_t data_size,
         uint8_t *pcm, uint32_t pcm_capacity_frames, uint32_t *num_frames)
 {
     struct LINNEHeader header;
     LINNEApiResult ret;
     uint32_t decoded = 0, bytes;
-    size_t stride;
     if (dec == NULL || data == NULL || pcm == NULL || num_frames == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
     *num_frames = 0;
     if ((ret = LINNEDecoder_DecodeHeader(data, data_size, &header)) != LINNE_APIRESULT_OK) return ret;
@@ -871,18 +906,13 @@ LINNEApiResult LINNEB200_DecodeWholePacked(struct LINNEDecoder *dec, const uint8
     if (pcm_capacity_frames < header.num_samples) return LINNE_APIRESULT_INSUFFICIENT_BUFFER;
     bytes = header.bits_per_sample / 8u;
     if (bytes == 0 || bytes > 4u || (header.bits_per_sample % 8u) != 0u) return LINNE_APIRESULT_INVALID_FORMAT;
-    stride = LNB_ROUNDUP((size_t)header.num_samples + (size_t)header.num_samples_per_block + 4u, 4u);   /* room for a parked terminal block */
-    if (lnb_buf_reserve_device(dec->dev, &dec->d_pcm, stride * header.num_channels * sizeof(int32_t))
-        || lnb_buf_reserve_device(dec->dev, &dec->d_packed, (size_t)header.num_samples * header.num_channels * bytes + 16u))
-        return LINNE_APIRESULT_NG;
-    ret = decode_range(dec, data, data_size, LINNE_HEADER_SIZE, NULL, header.num_samples, header.num_samples, 0, 0,
-                       NULL, &decoded, NULL, (int32_t *)dec->d_pcm.ptr, (uint32_t)stride, NULL, NULL);
-    if (decoded) {          /* every sample the reference would have produced before stopping */
-        if (lnb_shim_pack_pcm(dec->dev, (const int32_t *)dec->d_pcm.ptr, (uint8_t *)dec->d_packed.ptr, (uint32_t)stride,
-                              decoded, header.num_channels, bytes)) return LINNE_APIRESULT_NG;
-        lnb_shim_d2h(dec->dev, pcm, dec->d_packed.ptr, (size_t)decoded * header.num_channels * bytes);
-        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+    /* several devices, or a stream long enough to pipeline its transfers against its kernels on one */
+    if ((dec->num_devices > 1u || data_size >= (32u << 20))
+        && decode_whole_sharded(dec, data, data_size, NULL, pcm, header.num_samples, &ret, &decoded)) {
+        *num_frames = decoded;
+        return ret;
     }
+    ret = decode_packed_range(dec, data, data_size, LINNE_HEADER_SIZE, pcm, header.num_samples, header.num_samples, 0, &decoded);
     *num_frames = decoded;
     return ret;
 }

@@ -472,7 +472,8 @@ void LINNEB200_EncoderSetDevices(struct LINNEEncoder *enc, uint32_t num_devices)
 
 struct LnbEncShard {
     struct LINNEEncoder *parent, *child;
-    const int32_t *const *input;
+    const int32_t *const *input;           /* int32 planes, or ... */
+    const uint8_t *packed;                 /* ... interleaved packed PCM (WAV data-chunk layout) */
     uint32_t first_sample, num_samples;
     uint32_t size, offset;                 /* shard bytes (blocks only) / where they go in the caller's buffer */
     uint8_t *data;
@@ -496,8 +497,18 @@ static void *enc_shard_main(void *arg)
     lnb_shim_set_device(sh->ordinal);
     if (cap > 0xFFFFFF00u || lnb_buf_reserve_device(enc->dev, &enc->d_pcm, stride * C * sizeof(int32_t))
         || lnb_buf_reserve_device(enc->dev, &enc->d_shard, cap)) sh->result = LINNE_APIRESULT_NG;
+    if (sh->result == LINNE_APIRESULT_OK && sh->packed) {
+        const uint32_t bytes = enc->header.bits_per_sample / 8u;
+        const size_t frame = (size_t)C * bytes;
+        if (lnb_buf_reserve_device(enc->dev, &enc->d_packed, (size_t)sh->num_samples * frame + 16u)) sh->result = LINNE_APIRESULT_NG;
+        else {
+            lnb_shim_h2d(enc->dev, enc->d_packed.ptr, sh->packed + (size_t)sh->first_sample * frame, (size_t)sh->num_samples * frame);
+            if (lnb_shim_unpack_pcm(enc->dev, (const uint8_t *)enc->d_packed.ptr, (int32_t *)enc->d_pcm.ptr, (uint32_t)stride,
+                                    sh->num_samples, C, bytes)) sh->result = LINNE_APIRESULT_NG;
+        }
+    }
     if (sh->result == LINNE_APIRESULT_OK) {
-        for (c = 0; c < C; c++)
+        for (c = 0; c < C && !sh->packed; c++)
             lnb_shim_h2d(enc->dev, (int32_t *)enc->d_pcm.ptr + c * stride, sh->input[c] + sh->first_sample, (size_t)sh->num_samples * sizeof(int32_t));
         enc->cur_pcm = (const int32_t *)enc->d_pcm.ptr;
         enc->cur_pcm_stride = (uint32_t)stride;
@@ -513,7 +524,7 @@ static void *enc_shard_main(void *arg)
 }
 
 /* EncodeWhole over enc->num_devices block ranges; `data` starts behind the stream header */
-static LINNEApiResult encode_whole_sharded(struct LINNEEncoder *enc, const int32_t *const *input, uint32_t num_samples,
+static LINNEApiResult encode_whole_sharded(struct LINNEEncoder *enc, const int32_t *const *input, const uint8_t *packed, uint32_t num_samples,
                                            uint8_t *data, uint32_t data_size, uint32_t *written)
 {
     const uint32_t NB = enc->header.num_samples_per_block;
@@ -552,7 +563,7 @@ static LINNEApiResult encode_whole_sharded(struct LINNEEncoder *enc, const int32
         const uint32_t b0 = (uint32_t)((uint64_t)total_blocks * k / G), b1 = (uint32_t)((uint64_t)total_blocks * (k + 1u) / G);
         const uint64_t s0 = (uint64_t)b0 * NB, s1 = (uint64_t)b1 * NB;
         memset(&sh[k], 0, sizeof(sh[k]));
-        sh[k].parent = enc; sh[k].child = enc->child[k]; sh[k].input = input;
+        sh[k].parent = enc; sh[k].child = enc->child[k]; sh[k].input = input; sh[k].packed = packed;
         sh[k].first_sample = (uint32_t)s0;
         sh[k].num_samples = (uint32_t)((s1 > num_samples ? num_samples : s1) - s0);
         sh[k].child->header.num_samples = sh[k].num_samples;
@@ -594,7 +605,7 @@ LINNEApiResult LINNEEncoder_EncodeWhole(struct LINNEEncoder *enc, const int32_t 
                         enc->num_devices > 1u ? enc->num_devices : 1u) > 1u) {
         uint32_t c;
         for (c = 0; c < enc->header.num_channels; c++) if (input[c] == NULL) return LINNE_APIRESULT_INVALID_ARGUMENT;
-        ret = encode_whole_sharded(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, &written);
+        ret = encode_whole_sharded(enc, input, NULL, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, &written);
     } else {
         ret = upload_and_encode(enc, input, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, NULL, &written);
     }
@@ -753,6 +764,13 @@ LINNEApiResult LINNEB200_EncodeWholePacked(struct LINNEEncoder *enc, const uint8
     if (bytes == 0 || bytes > 4u || (enc->header.bits_per_sample % 8u) != 0u) return LINNE_APIRESULT_INVALID_FORMAT;
     enc->header.num_samples = num_samples;
     if ((ret = LINNEEncoder_EncodeHeader(&enc->header, data, data_size)) != LINNE_APIRESULT_OK) return ret;
+    if (lnb_plan_ranges((uint32_t)(((uint64_t)num_samples + enc->header.num_samples_per_block - 1u) / enc->header.num_samples_per_block),
+                        enc->num_devices > 1u ? enc->num_devices : 1u) > 1u) {
+        ret = encode_whole_sharded(enc, NULL, pcm, num_samples, data + LINNE_HEADER_SIZE, data_size - LINNE_HEADER_SIZE, &written);
+        if (ret != LINNE_APIRESULT_OK) return ret;
+        *output_size = LINNE_HEADER_SIZE + written;
+        return LINNE_APIRESULT_OK;
+    }
     stride = LNB_ROUNDUP((size_t)num_samples + 4u, 4u);
     packed_bytes = (size_t)num_samples * C * bytes;
     if (lnb_buf_reserve_device(enc->dev, &enc->d_pcm, stride * C * sizeof(int32_t))

@@ -68,3 +68,16 @@ def test_sharded_decode_reports_the_first_error_in_stream_order(gpu, oracle):
     assert rc1 == rc4 == harness.DATA_CORRUPTION
     n_ok = 5 * 2048
     assert np.array_equal(out4[:, :n_ok], pcm[:, :n_ok]) and np.array_equal(out1[:, :n_ok], pcm[:, :n_ok])
+
+
+def test_sharded_packed_pcm_entry_points(gpu, oracle):
+    """LINNEB200_EncodeWholePacked / DecodeWholePacked (what the command-line tool calls) take the same block ranges"""
+    pcm = harness.synth_pcm(n=4096 * 13 + 900, channels=2, bits=16, seed=41)
+    packed = harness.pack_pcm(pcm, 16)
+    single = gpu.encode_packed(packed, 2, bits=16, block=4096, preset=2)
+    with _Gpus(3):
+        sharded = gpu.encode_packed(packed, 2, bits=16, block=4096, preset=2)
+        back = gpu.decode_packed(single)
+    assert sharded == single
+    assert bytes(back) == bytes(packed)
+    assert np.array_equal(oracle.decode(sharded), pcm)
