@@ -564,7 +564,9 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
             if (dec->child[k]) dec->child[k]->num_devices = 0;
         }
         if (!dec->child[k] || LINNEDecoder_SetHeader(dec->child[k], h) != LINNE_APIRESULT_OK) { if (home >= 0) lnb_shim_set_device(home); return 0; }
-        dec->child[k]->tput_min_blocks = dec->tput_min_blocks;
+        /* ranges of one call keep each other's kernels company: the throughput kernels pay from ~1000 blocks on then
+         * (include/linne_b200.h: LINNEB200_DecoderSetThroughputBlocks) */
+        dec->child[k]->tput_min_blocks = (dec->tput_min_blocks > 1024u) ? 1024u : dec->tput_min_blocks;
     }
     if (home >= 0) lnb_shim_set_device(home);
     for (k = 0; k < G; k++) {

@@ -140,7 +140,7 @@ uint32_t lnb_plan_ranges(uint32_t blocks, uint32_t devices)
         if (depth < 1u) depth = 1u;
     } else {
         const uint32_t per_device = blocks / devices;
-        depth = per_device >= 12288u ? 8u : (per_device >= 6144u ? 4u : (per_device >= 3072u ? 2u : 1u));
+        depth = per_device >= 6144u ? 4u : (per_device >= 3072u ? 2u : 1u);      /* measured on a 1-hour stream: 8 ranges gain nothing over 4 */
     }
     ranges = devices * depth;
     if (ranges > LNB_MAX_DEVICES) ranges = LNB_MAX_DEVICES;
