@@ -1053,6 +1053,7 @@ def run_b200(args, rank, world, local_rank):
         achieved = flops / (dom_ms / 1e3) / 1e12
         roofline = {"bound": "fp64", "kernel": dom_name, "achieved": round(achieved, 4), "peak": round(fp64_peak, 3),
                     "unit": "TFLOP/s", "frac": round(achieved / fp64_peak, 5) if fp64_peak else None, "traffic": traffic,
+                    "traffic_source": "static: profiles/ncu_traffic.json (ncu --set full captures named there), not re-measured by this run",
                     "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),
                     "note": "encoder analysis is FP64-pipe bound (SURVEY 8d): algorithmic FLOPs = 2 x MAC/sample table "
                             "(un-deduplicated) over this kernel's summed launch time; peak = DFMA microbenchmark on this GPU"}
@@ -1061,6 +1062,7 @@ def run_b200(args, rank, world, local_rank):
         achieved = by / (dom_ms / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": round(achieved, 3), "peak": hbm_peak,
                     "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "peak_source": peak_src,
+                    "traffic_source": "static: profiles/ncu_traffic.json (ncu --set full captures named there), not re-measured by this run",
                     "traffic_note": "ncu dram bytes per launch at -m 7 (profiles/ncu_traffic.json); algorithmic bytes per launch = "
                                     + str(int(hbm_bytes_per_sample * n_samples)),
                     "launches": dom_cnt, "avg_launch_ms": round(dom_ms / max(dom_cnt, 1), 4),

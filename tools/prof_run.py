@@ -21,11 +21,13 @@ def main():
     ap.add_argument("--bits", type=int, default=16)
     ap.add_argument("--rate", type=int, default=44100)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--af", type=int, default=0, help="IRLS iterations (-a)")
+    ap.add_argument("--learning", type=int, default=0, help="momentum SGD (-l)")
     args = ap.parse_args()
     codec = Product()
     pcm = harness.synth_pcm(seconds=args.seconds, sr=args.rate, channels=args.channels, bits=args.bits, seed=1)
     for _ in range(args.reps):
-        stream = codec.encode(pcm, bits=args.bits, rate=args.rate, preset=args.preset)
+        stream = codec.encode(pcm, bits=args.bits, rate=args.rate, preset=args.preset, af=args.af, learning=args.learning)
         back = codec.decode(stream)
     assert np.array_equal(back, pcm), "round trip differs"
     print(f"ok preset={args.preset} samples={pcm.size} bytes={len(stream)}")
