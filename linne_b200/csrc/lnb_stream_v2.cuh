@@ -105,8 +105,10 @@ __device__ __forceinline__ bool lnb_ds_wait(LnbDsShared &sm, uint32_t stage, uin
         if (spins > LNB_DS_PATIENCE) { lnb_ds_give_up(sm, "stage wait", stage, need); return false; }
         /* the pace maker (the walk) needs ~15 ns per sample: sleep roughly until the missing samples can exist,
          * so waiting stages leave the issue slots to the warps that have work */
-        const uint32_t ns = (need - have) * 8u;
-        __nanosleep(ns < 32u ? 32u : (ns > 2000u ? 2000u : ns));
+        /* ~8 ns per missing sample when a block has an SM to itself; with several CTAs per SM the walk is ~4x slower and
+         * every needless wake-up takes issue slots from somebody's pace maker */
+        const uint32_t ns = (need - have) * (gridDim.x > 296u ? 40u : 8u);
+        __nanosleep(ns < 32u ? 32u : (ns > 4000u ? 4000u : ns));
     }
     LNB_DS_T1();
     __threadfence_block();
@@ -670,7 +672,7 @@ __device__ bool lnb_ds_finish(LnbDsShared &sm, const LnbDecodeBatch &b, const Ln
 __device__ unsigned int lnb_ds_sm_ticket[256];                  /* per SM: CTAs of this kernel that started there (role rotation) */
 
 /* One CTA per block.  Dynamic shared memory: the channel line, n_max int32. */
-__global__ void __launch_bounds__(LNB_DS_THREADS) lnb_stream_v2_kernel(LnbDecodeBatch b, uint32_t n_max)
+__global__ void __launch_bounds__(LNB_DS_THREADS, 4) lnb_stream_v2_kernel(LnbDecodeBatch b, uint32_t n_max)
 {
     extern __shared__ __align__(16) int32_t lnb_ds_line[];
     __shared__ LnbDsShared sm;

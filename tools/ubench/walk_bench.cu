@@ -255,6 +255,32 @@ __global__ void walk(const uint32_t *g, uint32_t k2, uint32_t ncw, Result *res, 
         }
         wi = (pos >> 5) + 2; cnt = 64 - (pos & 31); hi = w0;
     }
+    else if (VAR == 27) {      // v25 with the leading-one index from the FP32 adder instead of FLO
+        constexpr int G = 8;
+        uint32_t pos = 0, w0 = sm[0], w1 = sm[1], w2 = sm[2], w3 = sm[3];
+        const uint32_t K95 = K + 95u;
+        for (uint32_t i = 0; i < ncw; i += G) {
+            uint32_t bad = 0, T = 0;
+#pragma unroll
+            for (int s = 0; s < G; s++) {
+                // 1.m - 1.0 with m = the window's top 23 bits: the result's exponent field is f + 95 (f = index of the leading one)
+                const float x = __uint_as_float(__funnelshift_r(w0, 0x7Fu, 9)) - 1.0f;
+                const uint32_t E = __float_as_uint(x) >> 23;
+                const uint32_t t = w0 >> 31;
+                sts32(out + 4u * (i + s), w0);
+                const uint32_t L = K95 - E + t;
+                bad = __umulhi(E - 95u - k2, 2u) + bad;
+                w0 = __funnelshift_lc(w1, w0, L); w1 = __funnelshift_lc(w2, w1, L); w2 = __funnelshift_lc(w3, w2, L); w3 = __funnelshift_lc(0u, w3, L);
+                T += L;
+            }
+            pos += T;
+            if (bad | (T > 96u)) { check++; }
+            const uint32_t a = ring + ((pos >> 5) & (WORDS - 1u)) * 4u, sh = pos & 31u;
+            const uint32_t v0 = lds32(a), v1 = lds32(a + 4u), v2 = lds32(a + 8u), v3 = lds32(a + 12u), v4 = lds32(a + 16u);
+            w0 = __funnelshift_l(v1, v0, sh); w1 = __funnelshift_l(v2, v1, sh); w2 = __funnelshift_l(v3, v2, sh); w3 = __funnelshift_l(v4, v3, sh);
+        }
+        wi = (pos >> 5) + 2; cnt = 64 - (pos & 31); hi = w0;
+    }
     long long t1 = clock64();
     res->cycles = t1 - t0;
     res->endpos = wi * 32u - cnt;
@@ -320,6 +346,7 @@ int main()
             run<17>("v17 (hi,mid)+X ahead, LOP3 selects", d, k2, NCW, bits, dres, dsink);
             run<25>("v25 128-bit window, groups of 8", d, k2, NCW, bits, dres, dsink);
             run<26>("v26 128-bit window, groups of 4", d, k2, NCW, bits, dres, dsink);
+            run<27>("v27 groups of 8, exponent of 1.m-1", d, k2, NCW, bits, dres, dsink);
             run<18>("v17 no STS", d, k2, NCW, bits, dres, dsink);
             run<19>("v17 no LDS", d, k2, NCW, bits, dres, dsink);
             run<21>("v17 no flag", d, k2, NCW, bits, dres, dsink);
