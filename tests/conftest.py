@@ -10,6 +10,29 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # @pytest.mark.timeout comes from pytest-timeout (tests/requirements.txt); without the plugin the marker would be
+    # silently ignored and a hang would hang the suite, so a SIGALRM stand-in takes over
+    if not config.pluginmanager.hasplugin("timeout"):
+        config.addinivalue_line("markers", "timeout(seconds): fail the test after this long (stand-in for pytest-timeout)")
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_call(item):
+    marker = item.get_closest_marker("timeout")
+    if marker is None or item.config.pluginmanager.hasplugin("timeout"):
+        yield
+        return
+    import signal
+
+    def _expired(signum, frame):
+        raise TimeoutError(f"test exceeded {marker.args[0]} s (conftest stand-in for pytest-timeout)")
+    old = signal.signal(signal.SIGALRM, _expired)
+    signal.alarm(int(marker.args[0]))
+    try:
+        yield
+    finally:
+        signal.alarm(0)
+        signal.signal(signal.SIGALRM, old)
 
 
 def _ensure_built():
