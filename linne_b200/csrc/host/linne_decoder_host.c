@@ -5,6 +5,7 @@
  * table); everything that touches samples or payload bits runs on the GPU, batched over every block
  * of the call.  Error results and their precedence follow the reference (cited per check).
  */
+#define _POSIX_C_SOURCE 200112L
 #include "linne_decoder.h"
 #include "linne_b200.h"
 #include "lnb_host_util.h"
@@ -13,6 +14,12 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <time.h>
+
+/* LINNE_B200_TRACE=1: host-side time stamps of a range's phases on stderr (debugging aid) */
+static int dec_trace_on(void) { static int on = -1; if (on < 0) { const char *e = getenv("LINNE_B200_TRACE"); on = (e && *e == '1') ? 1 : 0; } return on; }
+static double dec_now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+#define DEC_TRACE(dec, what) do { if (dec_trace_on()) fprintf(stderr, "[trace] range %2u %-16s %.3f\n", (unsigned)(dec)->turn_index, what, dec_now_ms()); } while (0)
 
 #define DEC_FLAG_OWN_WORK   (1u << 0)
 #define DEC_FLAG_HEADER_SET (1u << 1)
@@ -42,6 +49,9 @@ struct LINNEDecoder {
      * handle (own device, own host thread) per range */
     uint32_t num_devices;
     struct LINNEDecoder *child[LNB_MAX_DEVICES];
+    LnbTurnstile *turn;                    /* a child: the turnstile of the call it works for (else NULL) and its range index */
+    uint32_t turn_index;
+    int rank_override;                     /* >= 0: the stream priority rank of a child (its place in the pipeline) instead of the preset's */
     struct LINNEDecoderConfig config;
     LnbBlockDesc *shard_table;             /* host block table of the sharding hop */
     uint32_t shard_table_cap;
@@ -88,6 +98,7 @@ struct LINNEDecoder *LINNEDecoder_Create(const struct LINNEDecoderConfig *config
     }
     dec = (struct LINNEDecoder *)LNB_ROUNDUP((uintptr_t)work, LNB_ALIGNMENT);
     memset(dec, 0, sizeof(*dec));
+    dec->rank_override = -1;
     dec->work = work;
     dec->max_num_channels = config->max_num_channels;
     dec->max_num_layers = config->max_num_layers;
@@ -161,7 +172,7 @@ LINNEApiResult LINNEDecoder_SetHeader(struct LINNEDecoder *dec, const struct LIN
     dec->header = *header;
     dec->flags |= DEC_FLAG_HEADER_SET;
     dec->ra_count = dec->ra_next = 0;                          /* cached blocks belong to the previous header */
-    lnb_shim_set_cost_rank(dec->dev, (int)header->preset);     /* longer predictors first (scheduling hint) */
+    lnb_shim_set_cost_rank(dec->dev, dec->rank_override >= 0 ? dec->rank_override : (int)header->preset);     /* longer predictors first (scheduling hint) */
     return LINNE_APIRESULT_OK;
 }
 
@@ -333,12 +344,22 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
     batch.params = (LnbChanParams *)dec->d_params.ptr;
     batch.pcm = d_pcm_ext ? d_pcm_ext : (int32_t *)dec->d_pcm.ptr;
 
+    DEC_TRACE(dec, "hopped");
     if (!d_stream_ext) {
+        if (dec->turn) lnb_turnstile_wait(dec->turn, 0, dec->turn_index);
+        DEC_TRACE(dec, "upload turn");
         lnb_shim_memset(dec->dev, (uint8_t *)dec->d_stream.ptr + (padded - 16u), 0, 16u);
         lnb_shim_h2d(dec->dev, dec->d_stream.ptr, data, used);
     }
     lnb_shim_h2d(dec->dev, dec->d_blocks.ptr, blocks, (size_t)scan.num_blocks * sizeof(LnbBlockDesc));
+    if (dec->turn && !d_stream_ext) {                            /* the next range of this device may upload while this one computes */
+        const int bad = lnb_shim_sync(dec->dev);
+        lnb_turnstile_pass(dec->turn, 0, dec->turn_index);
+        DEC_TRACE(dec, "uploaded");
+        if (bad) return LINNE_APIRESULT_NG;
+    }
     if (lnb_shim_decode(dec->dev, &batch)) return LINNE_APIRESULT_NG;
+    DEC_TRACE(dec, "launched");
     lnb_shim_d2h(dec->dev, blocks, dec->d_blocks.ptr, (size_t)scan.num_blocks * sizeof(LnbBlockDesc));
     if (staged && scan.total_samples) {
         /* pinned planes: the samples travel with the block table, the verdict below decides what is handed on */
@@ -349,6 +370,7 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
                          (size_t)scan.total_samples * sizeof(int32_t));
     }
     if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+    DEC_TRACE(dec, "kernels done");
 
     /* first block (stream order) whose CRC failed outranks everything after it */
     first_bad = scan.num_blocks;
@@ -370,10 +392,16 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
 
     /* hand back every sample the reference would have produced before stopping */
     if (!d_pcm_ext && !staged) {
+        int bad;
+        if (dec->turn) lnb_turnstile_wait(dec->turn, 1, dec->turn_index);
+        DEC_TRACE(dec, "download turn");
         for (c = 0; c < C; c++)
             lnb_shim_d2h(dec->dev, buffer[c], (int32_t *)dec->d_pcm.ptr + (size_t)c * batch.cfg.pcm_stride,
                          (size_t)ok_samples * sizeof(int32_t));
-        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+        bad = lnb_shim_sync(dec->dev);
+        if (dec->turn) lnb_turnstile_pass(dec->turn, 1, dec->turn_index);
+        DEC_TRACE(dec, "downloaded");
+        if (bad) return LINNE_APIRESULT_NG;
     }
 
     if (consumed_bytes) *consumed_bytes = scan.end_offset - start_offset;
@@ -521,6 +549,11 @@ static void *dec_shard_main(void *arg)
     if (sh->packed) sh->result = decode_packed_range(sh->child, sh->data, sh->data_size, 0, sh->packed, sh->room, sh->sample_limit, sh->block_limit, &sh->decoded);
     else sh->result = decode_range(sh->child, sh->data, sh->data_size, 0, sh->planes, sh->room, sh->sample_limit, sh->block_limit, 0,
                                    NULL, &sh->decoded, NULL, NULL, 0, NULL, NULL);
+    if (sh->child->turn) {                                       /* whatever happened: nobody waits for this range any more */
+        lnb_turnstile_pass(sh->child->turn, 0, sh->child->turn_index);
+        lnb_turnstile_pass(sh->child->turn, 1, sh->child->turn_index);
+        sh->child->turn = NULL;
+    }
     return NULL;
 }
 
@@ -532,6 +565,7 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
     const int ndev = lnb_shim_device_count();
     struct LnbDecShard sh[LNB_MAX_DEVICES];
     pthread_t th[LNB_MAX_DEVICES];
+    LnbTurnstile turn;
     BlockScan scan;
     uint32_t guess, G, k, c, started = 0, ndev_used = 1;
     int home, own;
@@ -563,12 +597,19 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
             dec->child[k] = LINNEDecoder_Create(&dec->config, NULL, 0);
             if (dec->child[k]) dec->child[k]->num_devices = 0;
         }
+        if (dec->child[k]) {
+            /* the kernels of an earlier range of a device go first wherever SMs free up: its download can start while the
+             * later ranges still compute (without this all ranges' kernels end together and the link idles until then) */
+            const uint32_t depth = (G + ndev_used - 1u) / ndev_used, place = k / ndev_used;
+            dec->child[k]->rank_override = depth > 1u ? (int)(7u - (place * 7u) / (depth - 1u)) : -1;
+        }
         if (!dec->child[k] || LINNEDecoder_SetHeader(dec->child[k], h) != LINNE_APIRESULT_OK) { if (home >= 0) lnb_shim_set_device(home); return 0; }
         /* ranges of one call keep each other's kernels company: the throughput kernels pay from ~1000 blocks on then
          * (include/linne_b200.h: LINNEB200_DecoderSetThroughputBlocks) */
         dec->child[k]->tput_min_blocks = (dec->tput_min_blocks > 1024u) ? 1024u : dec->tput_min_blocks;
     }
     if (home >= 0) lnb_shim_set_device(home);
+    lnb_turnstile_init(&turn, dec->num_devices > 1u ? ndev_used : 1u);
     for (k = 0; k < G; k++) {
         /* contiguous ranges of the decodable blocks; the last range runs to the end of the data and meets whatever ends
          * the stream (framing error, terminal block) exactly as the single-device path does */
@@ -587,10 +628,16 @@ static int decode_whole_sharded(struct LINNEDecoder *dec, const uint8_t *data, u
         sh[k].sample_limit = last ? h->num_samples - first->smp_off : dec->shard_table[b1].smp_off - first->smp_off;
         sh[k].block_limit = last ? 0u : b1 - b0;
         sh[k].ordinal = dec->num_devices > 1u ? (int)(k % ndev_used) : own;
-        if (pthread_create(&th[k], NULL, dec_shard_main, &sh[k]) != 0) break;
+        dec->child[k]->turn = &turn; dec->child[k]->turn_index = k;
+        if (pthread_create(&th[k], NULL, dec_shard_main, &sh[k]) != 0) {
+            dec->child[k]->turn = NULL;
+            lnb_turnstile_pass(&turn, 0, k); lnb_turnstile_pass(&turn, 1, k);
+            break;
+        }
         started++;
     }
     for (k = 0; k < started; k++) pthread_join(th[k], NULL);
+    lnb_turnstile_destroy(&turn);
     if (started < G) { *ret = LINNE_APIRESULT_NG; return 1; }
     *ret = LINNE_APIRESULT_OK;
     if (decoded_total) *decoded_total = 0;
@@ -888,8 +935,16 @@ static LINNEApiResult decode_packed_range(struct LINNEDecoder *dec, const uint8_
     if (decoded) {          /* every sample the reference would have produced before stopping */
         if (lnb_shim_pack_pcm(dec->dev, (const int32_t *)dec->d_pcm.ptr, (uint8_t *)dec->d_packed.ptr, (uint32_t)stride,
                               decoded, h->num_channels, bytes)) return LINNE_APIRESULT_NG;
+        if (dec->turn) {                                         /* kernels done before this range takes its turn on the link */
+            if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+            lnb_turnstile_wait(dec->turn, 1, dec->turn_index);
+        }
         lnb_shim_d2h(dec->dev, pcm, dec->d_packed.ptr, (size_t)decoded * h->num_channels * bytes);
-        if (lnb_shim_sync(dec->dev)) return LINNE_APIRESULT_NG;
+        {
+            const int bad = lnb_shim_sync(dec->dev);
+            if (dec->turn) lnb_turnstile_pass(dec->turn, 1, dec->turn_index);
+            if (bad) return LINNE_APIRESULT_NG;
+        }
     }
     *decoded_out = decoded;
     return ret;

@@ -130,6 +130,29 @@ void lnb_rendezvous_release(LnbRendezvous *r)
     pthread_mutex_unlock(&r->lock);
 }
 
+void lnb_turnstile_init(LnbTurnstile *t, uint32_t stride)
+{
+    pthread_mutex_init(&t->lock, NULL); pthread_cond_init(&t->cv, NULL);
+    t->stride = stride ? stride : 1u;
+    memset(t->passed, 0, sizeof(t->passed));
+}
+void lnb_turnstile_destroy(LnbTurnstile *t) { pthread_cond_destroy(&t->cv); pthread_mutex_destroy(&t->lock); }
+void lnb_turnstile_wait(LnbTurnstile *t, int phase, uint32_t k)
+{
+    if (k < t->stride || k >= LNB_MAX_DEVICES) return;
+    pthread_mutex_lock(&t->lock);
+    while (!t->passed[phase][k - t->stride]) pthread_cond_wait(&t->cv, &t->lock);
+    pthread_mutex_unlock(&t->lock);
+}
+void lnb_turnstile_pass(LnbTurnstile *t, int phase, uint32_t k)
+{
+    if (k >= LNB_MAX_DEVICES) return;
+    pthread_mutex_lock(&t->lock);
+    t->passed[phase][k] = 1;
+    pthread_cond_broadcast(&t->cv);
+    pthread_mutex_unlock(&t->lock);
+}
+
 uint32_t lnb_plan_ranges(uint32_t blocks, uint32_t devices)
 {
     const char *e = getenv("LINNE_B200_PIPELINE");

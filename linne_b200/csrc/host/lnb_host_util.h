@@ -46,4 +46,15 @@ void lnb_rendezvous_report_and_wait(LnbRendezvous *r);      /* worker */
 void lnb_rendezvous_collect(LnbRendezvous *r, uint32_t workers);   /* caller: returns when all have reported (lock held off) */
 void lnb_rendezvous_release(LnbRendezvous *r);              /* caller */
 
+/* Turnstile of the ranges of one call that share a device: their bulk transfers take turns in range order (phase 0:
+ * host -> device, phase 1: device -> host).  Ranges started side by side otherwise move in lockstep -- all uploads
+ * share the link, then all kernels share the SMs, then all downloads share the link -- and nothing overlaps; with the
+ * turnstile range k + 1 uploads while range k computes and range k - 1 downloads.  `stride` = ranges between two
+ * that share a device (the number of devices in use). */
+typedef struct LnbTurnstile { pthread_mutex_t lock; pthread_cond_t cv; uint32_t stride; uint8_t passed[2][LNB_MAX_DEVICES]; } LnbTurnstile;
+void lnb_turnstile_init(LnbTurnstile *t, uint32_t stride);
+void lnb_turnstile_destroy(LnbTurnstile *t);
+void lnb_turnstile_wait(LnbTurnstile *t, int phase, uint32_t k);    /* until range k - stride has passed `phase` */
+void lnb_turnstile_pass(LnbTurnstile *t, int phase, uint32_t k);    /* idempotent */
+
 #endif

@@ -170,7 +170,9 @@ struct CudaExec {
     {
         const int shape = lnb_tput_shape(&b.cfg);           /* non-zero: the host asked lnb_shim_tput_supported(cfg) */
         if (!dev->aux_created) {
-            cudaStreamCreateWithFlags(&dev->aux_stream, cudaStreamNonBlocking);
+            int prio = 0;                                       /* the side stream runs at the priority of the handle's own */
+            if (cudaStreamGetPriority(dev->stream, &prio) != cudaSuccess) { cudaGetLastError(); prio = 0; }
+            cudaStreamCreateWithPriority(&dev->aux_stream, cudaStreamNonBlocking, prio);
             cudaEventCreateWithFlags(&dev->ev_fork, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&dev->ev_join, cudaEventDisableTiming);
             dev->aux_created = 1;
@@ -185,7 +187,14 @@ struct CudaExec {
         }
         cudaEventRecord(dev->ev_join, dev->aux_stream);
         const int slot = begin_stage("tp_entropy");
-        lnb_tp_entropy_kernel<<<(b.num_blocks + LNB_TG_PER_WARP - 1u) / LNB_TG_PER_WARP, 32, 0, dev->stream>>>(b);
+        /* eight lanes per block with fix-up rounds (default); LINNE_B200_TP_ENTROPY=8: rounds that end at the first long code
+         * word (round 1), =w: a warp per block, =l: a lane per block (A/B runs, profiles/r2_tp_entropy_forms.md) */
+        static const char form = [] { const char *e = getenv("LINNE_B200_TP_ENTROPY"); return e && e[0] ? e[0] : 'i'; }();
+        const uint32_t grid8 = (b.num_blocks + LNB_TG_PER_WARP - 1u) / LNB_TG_PER_WARP;
+        if (form == '8') lnb_tp_entropy_kernel<false><<<grid8, 32, 0, dev->stream>>>(b);
+        else if (form == 'w') lnb_tp_entropy_w_kernel<<<(b.num_blocks + LNB_TW_WARPS - 1u) / LNB_TW_WARPS, 32u * LNB_TW_WARPS, 0, dev->stream>>>(b);
+        else if (form == 'l') lnb_tp_entropy_l_kernel<<<(b.num_blocks + 31u) / 32u, 32, 0, dev->stream>>>(b);
+        else lnb_tp_entropy_kernel<true><<<grid8, 32, 0, dev->stream>>>(b);
         end_stage(slot);
         cudaStreamWaitEvent(dev->stream, dev->ev_join, 0);
         if (shape == 1) tput_synth<32, 2, 0>(b);
@@ -367,6 +376,10 @@ int lnb_shim_tput_supported(const LnbStreamCfg *cfg)
 int lnb_shim_open(LnbDevice **out, int device_ordinal)
 {
     int count = 0;
+    /* Handles, their side streams and the ranges of a pipelined call each own a stream; with the default of eight
+     * hardware queues unrelated streams share one and wait for each other's copies and kernels.  Only effective while
+     * the process has not created its CUDA context yet (a host that did so first sets the variable itself). */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return 1;
     if (device_ordinal >= 0) {
         if (device_ordinal >= count || cudaSetDevice(device_ordinal) != cudaSuccess) return 2;
@@ -445,6 +458,11 @@ void lnb_shim_set_cost_rank(LnbDevice *dev, int cost_rank)
     cudaStreamDestroy(dev->stream);
     dev->stream = s;
     dev->cost_rank = cost_rank;
+    if (dev->aux_created) {                                      /* re-created at the new priority when next needed */
+        cudaStreamSynchronize(dev->aux_stream);
+        cudaStreamDestroy(dev->aux_stream); cudaEventDestroy(dev->ev_fork); cudaEventDestroy(dev->ev_join);
+        dev->aux_created = 0;
+    }
 }
 
 void *lnb_shim_alloc(LnbDevice *dev, size_t bytes)

@@ -38,7 +38,7 @@
 #pragma once
 #include "lnb_common.cuh"
 #include "lnb_decode_core.cuh"
-
+#include "lnb_rice_warp.cuh"
 
 /* same rule on every side: the host only sets `tput`, the kernels decide per block */
 LNB_HD bool lnb_tp_shape_ok(const LnbDecodeBatch &b, const LnbBlockDesc &blk)
@@ -108,6 +108,10 @@ __device__ __forceinline__ uint32_t lnb_tg_get(const LnbTgWin &w, uint32_t &pos,
     return v;
 }
 
+/* ITER: a round does not end at the first long code word -- the lanes behind it shift inside their 64-bit windows by its
+ * extra bits and look again (the scheme of lnb_rice_warp.cuh at a width of eight; the four groups of a warp iterate
+ * together, so one pass of the fix-up loop serves four blocks). */
+template <bool ITER>
 __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
 {
     __shared__ uint32_t s_win[LNB_TG_PER_WARP][LNB_TG_WIN + 2u];
@@ -204,48 +208,418 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_kernel(LnbDecodeBatch b)
                 if (lz > 15u || k2 > 30u) { overrun = 1u; k2 = 30u; left = 0u; parts_left = 0u; }
                 my_rel = lg * (k2 + 2u); my_end = my_rel + k2 + 1u; k2mask = (1u << k2) - 1u; sh = 31u - k2;
             }
-            /* the round: lane j guesses that code word j starts at pos + j * (k2 + 2) */
-            const bool go = running && left != 0u;
-            const uint32_t last = (left < LNB_TG ? left : LNB_TG) - 1u;
-            const uint32_t hi = go ? lnb_tg_peek(win, pos + my_rel) : 0xFFFFFFFFu;
-            const uint32_t lz = lnb_clz32(hi);
-            const uint32_t ml = (lz > 1u) ? lz : 1u;
-            const bool resolves = go && (hi < 0x40000000u || lg == last) && lg <= last;
-            const uint32_t is_short = (lz <= sh) ? 0x8000u : 0u;                 /* whole code word inside the 32-bit peek */
-            uint32_t r = resolves ? ((lg << 16) | is_short | (my_end + ml)) : 0xFFFFFFFFu;
-            r = __reduce_min_sync(gmask, r);                                     /* one redux per group (tiled-partition style mask) */
-            if (go) {
-                const uint32_t first = r >> 16;
-                uint32_t n_ok = first + ((r >> 15) & 1u);
-                {
-                    const uint32_t low = (hi >> (sh - ml)) & k2mask;
-                    const uint32_t mult = lz ? lz + 1u : ((hi >> 30) & 1u);
-                    if (lg < n_ok) *wp = lnb_zz_dec((mult << k2) + low);
+            if constexpr (ITER) {
+                /* the round: lane j keeps 64 bits at its guess pos + j * (k2 + 2) and an offset e inside them */
+                const bool go = running && left != 0u;
+                const uint32_t R = go ? (left < LNB_TG ? left : LNB_TG) : 0u;
+                const uint32_t L = k2 + 2u;
+                uint32_t hi = 0xFFFFFFFFu, lo = 0xFFFFFFFFu;
+                if (go) {
+                    const uint32_t p = pos + my_rel, i = (p >> 5) - win.wb;
+                    const uint32_t b0 = win.buf[i], b1 = win.buf[i + 1u], b2 = win.buf[i + 2u];
+                    hi = __funnelshift_l(b1, b0, p); lo = __funnelshift_l(b2, b1, p);
                 }
-                if (__builtin_expect((r & 0x8000u) != 0u, 1)) {
-                    pos += r & 0x7FFFu;
-                } else {                                                         /* code word longer than 32 bits: its lane finishes it serially */
-                    uint32_t endl = 0, bad = 0;
-                    if (lg == first) {
-                        LnbFastReader fr;
-                        lnb_fr_open(fr, win.words, pos + my_rel, win.end_word);
-                        const uint32_t q = lnb_fr_zero_run(fr);
-                        const uint32_t u = (q == 0u) ? lnb_fr_get(fr, k2 + 1u) : lnb_fr_get(fr, k2) + (2u << k2) + ((q - 1u) << k2);
-                        *wp = lnb_zz_dec(u);
-                        endl = (uint32_t)lnb_fr_position(fr);
-                        bad = fr.overrun;
+                const uint32_t lgkey = lg << 8;
+                uint32_t e = 0u, klive = (lg < R) ? lgkey : 0xFFFFFFFFu, v;
+                int32_t t;
+                for (;;) {
+                    v = __funnelshift_lc(lo, hi, e);
+                    t = (int32_t)__clz((int)v) - 2;                              /* extra - 1; -1: a short code word */
+                    t = t < -1 ? -1 : t;
+                    uint32_t key = klive | (uint32_t)t;
+                    key = min(key, __shfl_xor_sync(0xffffffffu, key, 1));
+                    key = min(key, __shfl_xor_sync(0xffffffffu, key, 2));
+                    key = min(key, __shfl_xor_sync(0xffffffffu, key, 4));        /* the group's first live lane with a long code word */
+                    if (__all_sync(0xffffffffu, key == 0xFFFFFFFFu)) break;
+                    if (key != 0xFFFFFFFFu) { if (lgkey > key) e += (key & 255u) + 1u; else klive = 0xFFFFFFFFu; }
+                }
+                /* the first lane that cannot vouch for its code word ends the round (lnb_rw_round) */
+                const bool invalid = e > 32u || t > 29 - (int32_t)k2 || lg >= R;
+                const uint32_t m8 = (__ballot_sync(0xffffffffu, invalid) >> (g * LNB_TG)) & ((1u << LNB_TG) - 1u);
+                const uint32_t n_ok = m8 ? (uint32_t)__ffs((int)m8) - 1u : LNB_TG;
+                const uint32_t end = my_rel + e + L + (uint32_t)(t + 1);
+                const uint32_t bits = __shfl_sync(0xffffffffu, end, (int)(g * LNB_TG + (n_ok ? n_ok - 1u : 0u)));
+                if (lg < n_ok) {
+                    const uint32_t lz = lnb_clz32(v), ml = (lz > 1u) ? lz : 1u;
+                    const uint32_t low = (v >> ((sh - ml) & 31u)) & k2mask;
+                    const uint32_t mult = lz ? lz + 1u : ((v >> 30) & 1u);
+                    *wp = lnb_zz_dec((mult << k2) + low);
+                }
+                if (n_ok) { pos += bits; left -= n_ok; wp += n_ok; }
+                if (go && n_ok < R) {                                            /* the code word behind them is read serially (rare) */
+                    LnbFastReader fr;
+                    lnb_fr_open(fr, win.words, pos, win.end_word);
+                    const uint32_t u = lnb_get_rice(fr, k2 + 1u, k2);
+                    if (lg == 0u) *wp = lnb_zz_dec(u);
+                    pos = (uint32_t)lnb_fr_position(fr);
+                    wp++; left--;
+                    if (fr.overrun) { overrun = 1u; left = 0u; parts_left = 0u; }
+                }
+            } else {
+                /* the round: lane j guesses that code word j starts at pos + j * (k2 + 2) */
+                const bool go = running && left != 0u;
+                const uint32_t last = (left < LNB_TG ? left : LNB_TG) - 1u;
+                const uint32_t hi = go ? lnb_tg_peek(win, pos + my_rel) : 0xFFFFFFFFu;
+                const uint32_t lz = lnb_clz32(hi);
+                const uint32_t ml = (lz > 1u) ? lz : 1u;
+                const bool resolves = go && (hi < 0x40000000u || lg == last) && lg <= last;
+                const uint32_t is_short = (lz <= sh) ? 0x8000u : 0u;                 /* whole code word inside the 32-bit peek */
+                uint32_t r = resolves ? ((lg << 16) | is_short | (my_end + ml)) : 0xFFFFFFFFu;
+                r = __reduce_min_sync(gmask, r);                                     /* one redux per group (tiled-partition style mask) */
+                if (go) {
+                    const uint32_t first = r >> 16;
+                    uint32_t n_ok = first + ((r >> 15) & 1u);
+                    {
+                        const uint32_t low = (hi >> (sh - ml)) & k2mask;
+                        const uint32_t mult = lz ? lz + 1u : ((hi >> 30) & 1u);
+                        if (lg < n_ok) *wp = lnb_zz_dec((mult << k2) + low);
                     }
-                    pos = __shfl_sync(gmask, endl, (int)(g * LNB_TG + first));
-                    n_ok = first + 1u;
-                    if (__shfl_sync(gmask, bad, (int)(g * LNB_TG + first))) { overrun = 1u; left = n_ok; parts_left = 0u; }
+                    if (__builtin_expect((r & 0x8000u) != 0u, 1)) {
+                        pos += r & 0x7FFFu;
+                    } else {                                                         /* code word longer than 32 bits: its lane finishes it serially */
+                        uint32_t endl = 0, bad = 0;
+                        if (lg == first) {
+                            LnbFastReader fr;
+                            lnb_fr_open(fr, win.words, pos + my_rel, win.end_word);
+                            const uint32_t q = lnb_fr_zero_run(fr);
+                            const uint32_t u = (q == 0u) ? lnb_fr_get(fr, k2 + 1u) : lnb_fr_get(fr, k2) + (2u << k2) + ((q - 1u) << k2);
+                            *wp = lnb_zz_dec(u);
+                            endl = (uint32_t)lnb_fr_position(fr);
+                            bad = fr.overrun;
+                        }
+                        pos = __shfl_sync(gmask, endl, (int)(g * LNB_TG + first));
+                        n_ok = first + 1u;
+                        if (__shfl_sync(gmask, bad, (int)(g * LNB_TG + first))) { overrun = 1u; left = n_ok; parts_left = 0u; }
+                    }
+                    left -= n_ok; wp += n_ok;
                 }
-                left -= n_ok; wp += n_ok;
             }
         }
     }
     if (active && lg == 0u) {
         const uint32_t used = (pos - rel_payload * 8u + 7u) >> 3;
         b.blocks[blk_i].na = used;                                               /* payload bytes consumed (reference Flush + Tell) */
+        if (overrun || rel_payload + used > rel_end) atomicOr(&b.blocks[blk_i].status, (uint32_t)LNB_ST_OVERRUN);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * entropy, second form: ONE WARP per block, rounds of 32 code words (lnb_rice_warp.cuh).
+ *
+ * The eight-lane rounds above end at the first long code word (~3.1 of 8 lanes retire per ~80 instructions: ~26 warp
+ * instructions per code word, the kernel is issue-bound).  Here a round goes on past a long code word -- the lanes behind
+ * it shift inside their 64-bit windows by its extra bits and look again, one warp-wide minimum per long code word -- so
+ * the per-round work (window loads, residual arithmetic, one coalesced 128-byte store, bookkeeping) is paid once per 32
+ * code words.  The payload comes through a per-warp ring filled one 512-byte chunk ahead with 16-byte loads.
+ * ------------------------------------------------------------------------------------------------------ */
+#define LNB_TW_WARPS 4u
+
+__global__ void __launch_bounds__(32 * LNB_TW_WARPS) lnb_tp_entropy_w_kernel(LnbDecodeBatch b)
+{
+    __shared__ __align__(16) uint32_t s_ring[LNB_TW_WARPS][LNB_RW_WORDS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t blk_i = blockIdx.x * LNB_TW_WARPS + warp;
+    const LnbStreamCfg &cfg = b.cfg;
+    const uint32_t C = cfg.num_channels, n = cfg.block_size;
+    if (blk_i >= b.num_blocks) return;
+    const LnbBlockDesc blk = b.blocks[blk_i];
+    if (!lnb_tp_shape_ok(b, blk)) return;
+
+    /* geometry of the block's payload: bit positions count from g0, the 16-byte aligned address at or below its first byte */
+    const uintptr_t addr = (uintptr_t)(b.stream + blk.byte_off);
+    const uint8_t *g0 = (const uint8_t *)(addr & ~(uintptr_t)15);
+    const uint32_t rel0 = (uint32_t)(addr & 15u);
+    const uint32_t rel_payload = rel0 + LNB_BLOCK_HEADER_SIZE;
+    uint32_t end_byte = blk.byte_off + blk.byte_size;
+    if (end_byte > b.stream_size || end_byte < blk.byte_off) end_byte = b.stream_size;
+    const uint32_t rel_end = rel0 + (end_byte - blk.byte_off);
+    const uint32_t end_word = (rel_end + 3u) >> 2;
+    /* the image is followed by >= 16 readable bytes (lnb_types.h): whole 16-byte lines up to there */
+    const uintptr_t readable = ((uintptr_t)(b.stream + b.stream_size) + 16u) & ~(uintptr_t)15;
+    uint64_t want = ((uint64_t)rel_end + 15u) & ~(uint64_t)15;
+    if (want > (uint64_t)(readable - (uintptr_t)g0)) want = (uint64_t)(readable - (uintptr_t)g0);
+    LnbRwRing ring;
+    lnb_rw_open(ring, s_ring[warp], g0, (uint32_t)(want >> 4), end_word, lane);
+    const uint32_t pos_limit = (end_word + 4u) * 32u;            /* nothing sane reads past this */
+    uint32_t lane_key;
+    asm volatile("shl.b32 %0, %1, 8;" : "=r"(lane_key) : "r"(lane));
+
+    uint32_t pos = rel_payload * 8u, overrun = 0u;
+    /* ---- side information (linne_decoder.c:457-486): every lane reads the same fields ---- */
+    {
+        LnbChanParams *params = b.params + (size_t)blk_i * C;
+        for (uint32_t c = 0; c < C; c++)
+            for (int f = 0; f < LNB_NUM_PREEM; f++) {
+                lnb_rw_ensure(ring, (pos >> 5) + 4u, lane);
+                const int32_t prev = lnb_zz_dec(lnb_rw_get(ring, pos, cfg.bits_per_sample + 1u));
+                const uint32_t coef = lnb_rw_get(ring, pos, LNB_PREEM_SHIFT - 1);
+                if (lane == 0u) { params[c].preem_prev[f] = prev; params[c].preem_coef[f] = (uint8_t)coef; }
+            }
+        for (uint32_t c = 0; c < C; c++)
+            for (uint32_t l = 0; l < cfg.num_layers; l++) {
+                const uint32_t P = cfg.layer_params[l];
+                lnb_rw_ensure(ring, ((pos + 7u + P * 16u) >> 5) + 2u, lane);     /* a coefficient code is at most 15 bits long */
+                const uint32_t lu = lnb_rw_get(ring, pos, 3), rs = lnb_rw_get(ring, pos, 4);
+                if (lane == 0u) { params[c].log2_units[l] = (uint8_t)lu; params[c].rshift[l] = (uint8_t)rs; }
+                int8_t *q = params[c].coef + l * LNB_MAX_PARAMS;
+                for (uint32_t i0 = 0; i0 < P; i0 += 32u) {       /* lane j keeps coefficients j, j + 32, ... */
+                    int32_t keep = 0;
+                    const uint32_t lim = (P - i0 < 32u) ? P - i0 : 32u;
+                    for (uint32_t i = 0; i < lim; i++) {
+                        const uint32_t e = b.tab.huff_lut[lnb_rw_peek(ring, pos) >> (32 - LNB_HUFF_LUT_BITS)];
+                        pos += e & 15u;
+                        if (i == lane) keep = lnb_zz_dec(e >> 4);
+                    }
+                    if (lane < lim) q[i0 + lane] = (int8_t)keep;
+                }
+            }
+    }
+
+    /* ---- residuals, channel after channel (linne_coder.c:306-327) ---- */
+    for (uint32_t c = 0; c < C && !overrun; c++) {
+        lnb_rw_ensure(ring, (pos >> 5) + 4u, lane);
+        const uint32_t porder = lnb_rw_get(ring, pos, 10);
+        uint32_t k2 = lnb_rw_get(ring, pos, 5);                   /* first partition: k2 itself (linne_coder.c:313) */
+        if (porder > LNB_MAX_PORDER || k2 > 30u) { overrun = 1u; break; }
+        const uint32_t len = n >> porder, parts = 1u << porder;
+        int32_t *wp = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;
+        for (uint32_t part = 0; part < parts; part++) {
+            if (part) {                                          /* gamma code of zigzag(k2 - previous k2) */
+                lnb_rw_ensure(ring, (pos >> 5) + 4u, lane);
+                const uint32_t h = lnb_rw_peek(ring, pos);
+                const uint32_t lz = lnb_clz32(h);
+                if (lz > 15u) { overrun = 1u; break; }
+                const uint32_t gv = ((h << lz) >> (31u - lz)) - 1u;
+                pos += 2u * lz + 1u;
+                k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(gv));
+                if (k2 > 30u) { overrun = 1u; break; }
+            }
+            uint32_t left = len;
+            while (left) {
+                if (pos > pos_limit) { overrun = 1u; break; }
+                const uint32_t R = left < 32u ? left : 32u;
+                lnb_rw_ensure(ring, ((pos + 32u * (k2 + 2u) + 128u) >> 5) + 1u, lane);
+                uint32_t v, bits;
+                const uint32_t n_ok = lnb_rw_round(ring.saddr, LNB_RW_RING, pos, R, k2, lane_key, v, bits);
+                if (lane < n_ok) wp[lane] = lnb_rw_value(v, k2);
+                pos += bits; wp += n_ok; left -= n_ok;
+                if (n_ok < R) {                                  /* rare: the next code word is read serially from global memory */
+                    LnbFastReader fr;
+                    lnb_fr_open(fr, (const uint32_t *)g0, pos, end_word);
+                    const uint32_t u = lnb_get_rice(fr, k2 + 1u, k2);
+                    if (lane == 0u) *wp = lnb_zz_dec(u);
+                    pos = (uint32_t)lnb_fr_position(fr);
+                    wp++; left--;
+                    if (fr.overrun) { overrun = 1u; break; }
+                }
+            }
+            if (overrun) break;
+        }
+    }
+    if (lane == 0u) {
+        const uint32_t used = (pos - rel_payload * 8u + 7u) >> 3;
+        b.blocks[blk_i].na = used;                               /* payload bytes consumed (reference Flush + Tell) */
+        if (overrun || rel_payload + used > rel_end) atomicOr(&b.blocks[blk_i].status, (uint32_t)LNB_ST_OVERRUN);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * entropy, third form: ONE LANE per block, everything a lane touches staged through shared memory.
+ *
+ * A lane that walks its own block needs ~1 warp instruction per code word (32 code words per pass of a ~30-instruction
+ * loop) -- an order of magnitude less than any form that spends several lanes on one block's serial chain.  The two
+ * lane-per-block kernels measured earlier in round 2 lost (7.1 / 8.8 ms on the 1-hour stream) because every pass paid
+ * global-memory round trips: 32 lanes reading 32 different streams and writing 32 different output lines.  Here
+ *   - the payload of the 32 blocks comes in through cp.async (LDGSTS): per lane a ring of 128 words, interleaved
+ *     [word][lane] so that 32 lanes at 32 different positions never meet in a bank; a block's next 64 words are
+ *     requested by the whole warp (two coalesced 128-byte copies) a thousand code words before its lane gets there,
+ *     and nobody waits for them: the copies of one check have landed by the next;
+ *   - residuals go to a [32 samples][32 lanes] tile and leave it transposed, 128 contiguous bytes per block;
+ *   - all lanes decode exactly one code word per pass, so channel ends and tile flushes are warp-uniform; only the
+ *     partition headers (a gamma-coded delta of k2) and code words longer than 32 bits are divergent detours.
+ * What is left on a pass is the lane's own chain (window from shared memory, leading zeros, length): ~100 cycles,
+ * latency-bound with one warp per scheduler -- 20 480 passes per stereo block.
+ * ------------------------------------------------------------------------------------------------------ */
+#define LNB_TL_RING   128u                                     /* words per lane */
+#define LNB_TL_HALF   64u                                      /* words per request */
+#define LNB_TL_CHECK  16u                                      /* passes between refill checks */
+
+struct LnbTlLane {
+    const uint32_t *gw;         /* the 32-bit word holding the block's first byte */
+    uint32_t end_word;          /* words at or past this index read as zero */
+    uint32_t issued;            /* words [0, issued) of this block have been requested into the ring */
+    uint32_t saddr;             /* shared address of ring word 0 of this lane */
+};
+__device__ __forceinline__ void lnb_tl_cp4(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+/* the warp requests the next LNB_TL_HALF words of every lane whose bit in `m` is set */
+__device__ __forceinline__ void lnb_tl_request(LnbTlLane &st, uint32_t ring_saddr, uint32_t m, uint32_t lane)
+{
+    while (m) {
+        const int l = __ffs((int)m) - 1;
+        m &= m - 1u;
+        const unsigned long long gp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)st.gw, l);
+        const uint32_t first = __shfl_sync(0xffffffffu, st.issued, l), endw = __shfl_sync(0xffffffffu, st.end_word, l);
+        const uint32_t *g = (const uint32_t *)(uintptr_t)gp;
+#pragma unroll
+        for (uint32_t h = 0; h < LNB_TL_HALF; h += 32u) {
+            const uint32_t w = first + h + lane;
+            const bool in = w < endw;
+            lnb_tl_cp4(ring_saddr + ((w % LNB_TL_RING) * 32u + (uint32_t)l) * 4u, in ? g + w : g, in ? 4u : 0u);
+        }
+        if ((int)lane == l) st.issued += LNB_TL_HALF;
+    }
+}
+/* keep every lane at least LNB_TL_HALF words ahead of its reader (bit position pos); with `all` the caller wants
+ * the data now (side information, after a jump), otherwise the copies of the previous check are waited for */
+__device__ __forceinline__ void lnb_tl_check(LnbTlLane &st, uint32_t ring_saddr, uint32_t pos, bool live, bool all, uint32_t lane)
+{
+    if (live && (pos >> 5) >= st.issued) st.issued = (pos >> 5) & ~(LNB_TL_HALF - 1u);      /* jumped past the ring (long code word) */
+    for (;;) {
+        const uint32_t m = __ballot_sync(0xffffffffu, live && (pos >> 5) + LNB_TL_HALF >= st.issued);
+        if (m == 0u) break;
+        lnb_tl_request(st, ring_saddr, m, lane);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (all) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+}
+__device__ __forceinline__ uint32_t lnb_tl_peek(const LnbTlLane &st, uint32_t pos)
+{
+    const uint32_t i = pos >> 5;
+    const uint32_t w0 = lnb_lds32(st.saddr + (i % LNB_TL_RING) * 128u), w1 = lnb_lds32(st.saddr + ((i + 1u) % LNB_TL_RING) * 128u);
+    return __funnelshift_l(lnb_bswap32(w1), lnb_bswap32(w0), pos);
+}
+__device__ __forceinline__ uint32_t lnb_tl_get(const LnbTlLane &st, uint32_t &pos, uint32_t n)   /* 1 <= n <= 32 */
+{
+    const uint32_t v = lnb_tl_peek(st, pos) >> (32u - n);
+    pos += n;
+    return v;
+}
+
+__global__ void __launch_bounds__(32) lnb_tp_entropy_l_kernel(LnbDecodeBatch b)
+{
+    __shared__ __align__(16) uint32_t s_ring[LNB_TL_RING * 32u];
+    __shared__ int32_t s_tile[32u * 33u];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t blk_i = blockIdx.x * 32u + lane;
+    const LnbStreamCfg &cfg = b.cfg;
+    const uint32_t C = cfg.num_channels, n = cfg.block_size;
+    LnbBlockDesc blk;
+    bool active = blk_i < b.num_blocks;
+    if (active) { blk = b.blocks[blk_i]; active = lnb_tp_shape_ok(b, blk); }
+    const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
+    if (act_mask == 0u) return;
+
+    const uint32_t ring_saddr = lnb_smem_addr(s_ring);
+    LnbTlLane st;
+    st.gw = (const uint32_t *)b.stream; st.end_word = 0u; st.issued = 0u; st.saddr = ring_saddr + lane * 4u;
+    uint32_t pos = 0u, rel_payload = 0u, rel_end = 0u, overrun = 0u, smp_off = 0u;
+    if (active) {
+        const uint32_t word0 = blk.byte_off >> 2;                /* bit positions relative to this word never overflow */
+        uint32_t end_byte = blk.byte_off + blk.byte_size;
+        if (end_byte > b.stream_size || end_byte < blk.byte_off) end_byte = b.stream_size;
+        st.gw = (const uint32_t *)b.stream + word0;
+        rel_payload = blk.byte_off + LNB_BLOCK_HEADER_SIZE - word0 * 4u; rel_end = end_byte - word0 * 4u;
+        st.end_word = (rel_end + 3u) >> 2;
+        pos = rel_payload * 8u;
+        smp_off = blk.smp_off;
+    }
+    const uint32_t pos_limit = (st.end_word + 4u) * 32u;          /* nothing sane reads past this */
+    lnb_tl_check(st, ring_saddr, pos, active, true, lane);        /* the first 128 words of every block */
+    lnb_tl_check(st, ring_saddr, pos, active, true, lane);
+
+    /* ---- side information (linne_decoder.c:457-486): each lane parses its own block ---- */
+    {
+        LnbChanParams *params = b.params + (size_t)(active ? blk_i : 0u) * C;
+        for (uint32_t c = 0; c < C; c++) {
+            for (int f = 0; f < LNB_NUM_PREEM; f++) {
+                const int32_t prev = lnb_zz_dec(lnb_tl_get(st, pos, cfg.bits_per_sample + 1u));
+                const uint32_t coef = lnb_tl_get(st, pos, LNB_PREEM_SHIFT - 1);
+                if (active) { params[c].preem_prev[f] = prev; params[c].preem_coef[f] = (uint8_t)coef; }
+            }
+        }
+        lnb_tl_check(st, ring_saddr, pos, active, true, lane);
+        for (uint32_t c = 0; c < C; c++)
+            for (uint32_t l = 0; l < cfg.num_layers; l++) {
+                const uint32_t P = cfg.layer_params[l];
+                const uint32_t lu = lnb_tl_get(st, pos, 3), rs = lnb_tl_get(st, pos, 4);
+                if (active) { params[c].log2_units[l] = (uint8_t)lu; params[c].rshift[l] = (uint8_t)rs; }
+                int8_t *q = params[c].coef + l * LNB_MAX_PARAMS;
+                for (uint32_t i0 = 0; i0 < P; i0 += 32u) {       /* at most 32 x 15 bits between two checks */
+                    const uint32_t lim = (P - i0 < 32u) ? P - i0 : 32u;
+                    for (uint32_t i = 0; i < lim; i++) {
+                        const uint32_t e = b.tab.huff_lut[lnb_tl_peek(st, pos) >> (32 - LNB_HUFF_LUT_BITS)];
+                        pos += e & 15u;
+                        if (active) q[i0 + i] = (int8_t)lnb_zz_dec(e >> 4);
+                    }
+                    lnb_tl_check(st, ring_saddr, pos, active, true, lane);
+                }
+            }
+    }
+
+    /* ---- residuals (linne_coder.c:306-327): one code word per lane and pass ---- */
+    for (uint32_t c = 0; c < C; c++) {
+        const uint32_t porder = lnb_tl_get(st, pos, 10);
+        uint32_t k2 = lnb_tl_get(st, pos, 5);                     /* first partition: k2 itself (linne_coder.c:313) */
+        if (porder > LNB_MAX_PORDER || k2 > 30u) { overrun = 1u; k2 = 0u; }
+        const uint32_t len = n >> (porder > LNB_MAX_PORDER ? 0u : porder);
+        uint32_t left = len;
+        const size_t plane = (size_t)c * cfg.pcm_stride;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
+#pragma unroll 1
+            for (uint32_t s = 0; s < 32u; s++) {
+                if ((s % LNB_TL_CHECK) == 0u) lnb_tl_check(st, ring_saddr, pos, active && !overrun, false, lane);
+                int32_t val = 0;
+                if (active && !overrun) {
+                    if (left == 0u) {                            /* partition header: gamma code of zigzag(k2 - previous k2) */
+                        const uint32_t h = lnb_tl_peek(st, pos);
+                        const uint32_t lz = lnb_clz32(h);
+                        const uint32_t z = lz & 15u;
+                        const uint32_t gv = ((h << z) >> (31u - z)) - 1u;
+                        pos += 2u * lz + 1u;
+                        k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(gv));
+                        left = len;
+                        if (lz > 15u || k2 > 30u) { overrun = 1u; k2 = 0u; }
+                    }
+                    const uint32_t v = lnb_tl_peek(st, pos);
+                    const uint32_t lz = lnb_clz32(v);
+                    if (__builtin_expect(lz + k2 <= 31u, 1)) {
+                        const uint32_t ml = (lz > 1u) ? lz : 1u;
+                        const uint32_t low = (v >> ((31u - k2 - ml) & 31u)) & ((1u << k2) - 1u);
+                        const uint32_t mult = lz ? lz + 1u : ((v >> 30) & 1u);
+                        val = lnb_zz_dec((mult << k2) + low);
+                        pos += k2 + 1u + ml;
+                    } else {                                     /* longer than 32 bits: read from global memory, then re-prime the ring */
+                        LnbFastReader fr;
+                        lnb_fr_open(fr, st.gw, pos, st.end_word);
+                        val = lnb_zz_dec(lnb_get_rice(fr, k2 + 1u, k2));
+                        pos = (uint32_t)lnb_fr_position(fr);
+                        if (fr.overrun || pos > pos_limit) overrun = 1u;
+                    }
+                    left--;
+                    if (overrun) val = 0;
+                }
+                const bool jumped = active && !overrun && (pos >> 5) + 2u >= st.issued;
+                if (__any_sync(0xffffffffu, jumped)) lnb_tl_check(st, ring_saddr, pos, active && !overrun, true, lane);
+                s_tile[s * 33u + lane] = val;
+            }
+            __syncwarp();
+            /* the tile leaves transposed: 32 samples of one block per store instruction */
+#pragma unroll 4
+            for (uint32_t r = 0; r < 32u; r++) {
+                const uint32_t off = __shfl_sync(0xffffffffu, smp_off, (int)r);
+                if ((act_mask >> r) & 1u) b.pcm[plane + off + i0 + lane] = s_tile[lane * 33u + r];
+            }
+            __syncwarp();
+        }
+    }
+    if (active) {
+        const uint32_t used = (pos - rel_payload * 8u + 7u) >> 3;
+        b.blocks[blk_i].na = used;                               /* payload bytes consumed (reference Flush + Tell) */
         if (overrun || rel_payload + used > rel_end) atomicOr(&b.blocks[blk_i].status, (uint32_t)LNB_ST_OVERRUN);
     }
 }
