@@ -148,10 +148,15 @@ struct CudaExec {
         const uint32_t n_max = line_samples(b, LNB_DS_MAX_N);
         const size_t smem = (size_t)n_max * sizeof(int32_t);
         const int slot = begin_stage("stream_v2", on);
+        /* the walk on one lane (default) or as a warp (LINNE_B200_WALK=warp; measured slower inside this kernel, kept for
+         * A/B runs): lnb_stream_v2.cuh */
+        static const bool lane_walk = [] { const char *e = getenv("LINNE_B200_WALK"); return !(e && e[0] == 'w'); }();
+        LnbDecodeBatch b2 = b;
 #ifdef LNB_DS_TIMING
-        if (getenv("LINNE_B200_DBG_WALKONLY")) { LnbDecodeBatch b2 = b; b2.cfg.check_crc |= 0x100u; lnb_stream_v2_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, on ? on : dev->stream>>>(b2, n_max); end_stage(slot, on); return; }
+        if (getenv("LINNE_B200_DBG_WALKONLY")) b2.cfg.check_crc |= 0x100u;
 #endif
-        lnb_stream_v2_kernel<<<b.num_blocks, LNB_DS_THREADS, smem, on ? on : dev->stream>>>(b, n_max);
+        if (lane_walk) lnb_stream_v2_kernel<false><<<b.num_blocks, LNB_DS_THREADS, smem, on ? on : dev->stream>>>(b2, n_max);
+        else lnb_stream_v2_kernel<true><<<b.num_blocks, LNB_DS_THREADS, smem, on ? on : dev->stream>>>(b2, n_max);
         end_stage(slot, on);
     }
     template <int Q0, int Q1, int Q2> void tput_synth(const LnbDecodeBatch &b)
@@ -337,7 +342,8 @@ static int lnb_configure_kernels(int ordinal)
     int optin = 0;
     if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ordinal) != cudaSuccess) return 1;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = lnb_optin_smem(lnb_stream_v2_kernel, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_stream_v2_kernel<true>, optin);
+    if (e == cudaSuccess) e = lnb_optin_smem(lnb_stream_v2_kernel<false>, optin);
     if (e == cudaSuccess) e = lnb_optin_smem(lnb_tp_synth_kernel<32, 2, 0>, optin);
     if (e == cudaSuccess) e = lnb_optin_smem(lnb_tp_synth_kernel<8, 64, 4>, optin);
     if (e == cudaSuccess) e = lnb_optin_smem(lnb_tp_synth_kernel<16, 128, 4>, optin);

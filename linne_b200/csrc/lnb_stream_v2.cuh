@@ -35,6 +35,7 @@
 #include "lnb_synth_v2.cuh"
 #include "lnb_tput_v2.cuh"
 #include "lnb_bulk.cuh"
+#include "lnb_rice_warp.cuh"
 
 #define LNB_DS_MAX_N       10240u
 #define LNB_DS_STAGES      (3u + LNB_MAX_LAYERS)        /* walk, extract, layers, de-emphasis */
@@ -477,6 +478,155 @@ __device__ __forceinline__ void lnb_ds_walk(const LnbDecodeBatch &b, LnbBlockDes
     __syncwarp();
 }
 
+/* The walk as a WARP (kernel template argument WARP_WALK; LINNE_B200_WALK=warp): rounds of 32 code words that continue
+ * past long code words (lnb_rice_warp.cuh) and leave RESIDUALS on the line -- the extract stage has nothing left to do,
+ * its warp leaves and the walk publishes as stage 1.  Measured inside this kernel on the 10-second clip: 0.84-0.86 ms per
+ * launch against 0.79-0.80 ms with the one-lane walk (a fix-up pass costs ~160 cycles -- leading-zero count, warp-wide
+ * minimum through the uniform datapath, a branch on its result -- and a quarter of the code words need one), so the
+ * one-lane walk stays the default; the warp form is kept as the measured alternative. */
+template <int UNUSED = 0>
+__device__ __forceinline__ void lnb_ds_walk_warp(const LnbDecodeBatch &b, LnbBlockDesc &gblk, const LnbBlockDesc &blk, const LnbDsWin &win,
+                                            LnbDsShared &sm, int32_t *line, uint32_t last_stage, uint32_t lane)
+{
+    const LnbStreamCfg &cfg = b.cfg;
+    const uint32_t C = cfg.num_channels, n = blk.nsmp;
+    /* the side information lies inside the first two chunks (<= 2.2 KB for 8 channels of 24 bits at -m 7) */
+    uint32_t loaded = lnb_ds_await_words(sm, (win.nchunks < 2u ? win.nchunks : 2u) * LNB_DS_CHUNK_WORDS);
+    uint32_t pos = win.rel_payload * 8u;
+    uint32_t overrun = 0;
+
+    /* ---- side information (linne_decoder.c:457-486): every lane reads the same fields ---- */
+    {
+        LnbChanParams *params = sm.params;
+        for (uint32_t c = 0; c < C; c++)
+            for (int f = 0; f < LNB_NUM_PREEM; f++) {
+                const int32_t prev = lnb_zz_dec(lnb_ds_get(sm, win.end_word, pos, cfg.bits_per_sample + 1u));
+                const uint32_t coef = lnb_ds_get(sm, win.end_word, pos, LNB_PREEM_SHIFT - 1);
+                if (lane == 0) { params[c].preem_prev[f] = prev; params[c].preem_coef[f] = (uint8_t)coef; }
+            }
+        for (uint32_t c = 0; c < C; c++)
+            for (uint32_t l = 0; l < cfg.num_layers; l++) {
+                const uint32_t P = cfg.layer_params[l];
+                const uint32_t lu = lnb_ds_get(sm, win.end_word, pos, 3), rs = lnb_ds_get(sm, win.end_word, pos, 4);
+                if (lane == 0) { params[c].log2_units[l] = (uint8_t)lu; params[c].rshift[l] = (uint8_t)rs; }
+                int8_t *q = params[c].coef + l * LNB_MAX_PARAMS;
+                /* lane j keeps coefficients j, j+32, ... */
+                for (uint32_t i0 = 0; i0 < P; i0 += 32u) {
+                    int32_t mine = 0;
+                    const uint32_t lim = (P - i0 < 32u) ? P - i0 : 32u;
+                    for (uint32_t i = 0; i < lim; i++) {
+                        const uint32_t top = lnb_ds_peek(sm, win.end_word, pos);
+                        uint32_t e = sm.huff1[top >> (32 - LNB_E3_HUFF1_BITS)];
+                        if (e == 0u) e = b.tab.huff_lut[top >> (32 - LNB_HUFF_LUT_BITS)];
+                        pos += e & 15u;
+                        if (i == lane) mine = lnb_zz_dec(e >> 4);
+                    }
+                    if (lane < lim) q[i0 + lane] = (int8_t)mine;
+                }
+            }
+    }
+    __syncwarp();
+
+    /* ---- residuals, channel after channel (linne_coder.c:306-327): the warp walks, 32 code words per round ---- */
+    {
+        uint32_t ring_addr, lane_key;
+        asm volatile("mov.u32 %0, %1;" : "=r"(ring_addr) : "r"(lnb_smem_addr(sm.ring)));
+        asm volatile("shl.b32 %0, %1, 8;" : "=r"(lane_key) : "r"(lane));
+        const uint32_t pos_limit = (win.end_word + 4u) * 32u;   /* nothing sane reads past this */
+        const uint32_t all_words = win.nchunks * LNB_DS_CHUNK_WORDS;
+        uint32_t walk_chunk = 0;
+        /* make the words a reader at `pos` may touch within `span` bits available, tell the loader where the walk is */
+#define LNB_DS_SERVICE(span)                                                                                  \
+        do {                                                                                                  \
+            const uint32_t need_ = ((pos + (span)) >> 5) + 2u;                                                \
+            if (((pos >> 5) / LNB_DS_CHUNK_WORDS) != walk_chunk) {  /* first: a loader that waits for us must not be waited for */ \
+                walk_chunk = (pos >> 5) / LNB_DS_CHUNK_WORDS;                                                 \
+                if (lane == 0) sm.walk_word = pos >> 5;                                                       \
+            }                                                                                                 \
+            if (need_ > loaded) loaded = lnb_ds_await_words(sm, need_ < all_words ? need_ : all_words);       \
+        } while (0)
+        for (uint32_t c = 0; c < C && !overrun; c++) {
+            /* the line is free once the last stage has drained the previous channel */
+            if (!lnb_ds_wait(sm, last_stage, c * n)) { overrun = 1; break; }
+            const uint32_t gbase = c * n;
+            LNB_DS_SERVICE(64u);
+            const uint32_t first = lnb_ds_peek(sm, win.end_word, pos);
+            const uint32_t porder = first >> 22;
+            uint32_t k2 = (first >> 17) & 31u;                       /* first partition: k2 itself (linne_coder.c:313) */
+            pos += 15u;
+            if (porder > LNB_MAX_PORDER || k2 > 30u) { overrun = 1; break; }
+            const uint32_t len = n >> porder, parts = 1u << porder;
+            uint32_t done = 0;
+            for (uint32_t part = 0; part < parts && !overrun; part++) {
+                if (part) {                                          /* gamma code of zigzag(k2 - previous k2) */
+                    LNB_DS_SERVICE(64u);
+                    const uint32_t h = lnb_ds_peek(sm, win.end_word, pos);
+                    const uint32_t lz = lnb_clz32(h);
+                    if (lz > 15u) { overrun = 1; break; }
+                    const uint32_t gv = ((h << lz) >> (31u - lz)) - 1u;
+                    pos += 2u * lz + 1u;
+                    k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(gv));
+                    if (k2 > 30u) { overrun = 1; break; }
+                }
+                LNB_DS_COUNT(4);
+                uint32_t left = len;
+                while (left) {
+                    if (pos > pos_limit) { overrun = 1; break; }
+                    const uint32_t R = left < 32u ? left : 32u;
+                    LNB_DS_SERVICE(32u * (k2 + 2u) + 96u);
+                    uint32_t v, bits;
+                    const uint32_t n_ok = lnb_rw_round(ring_addr, LNB_DS_RING_WORDS, pos, R, k2, lane_key, v, bits);
+                    if (lane < n_ok) line[done + lane] = lnb_rw_value(v, k2);
+                    pos += bits; done += n_ok; left -= n_ok;
+                    LNB_DS_COUNT(0);
+                    if (n_ok < R) {                              /* the code word behind them, read with every check in place (rare) */
+                        LNB_DS_COUNT(3);
+                        LNB_DS_SERVICE(64u);
+                        const uint32_t h = lnb_ds_peek(sm, win.end_word, pos);
+                        const uint32_t lz = lnb_clz32(h);
+                        int32_t val;
+                        if (lz + k2 <= 31u) {
+                            val = lnb_rw_value(h, k2);
+                            pos += k2 + 1u + (lz > 1u ? lz : 1u);
+                        } else {                                 /* longer than 32 bits */
+                            uint32_t q = 0, hh = h;
+                            while (hh == 0u) {
+                                q += 32u; pos += 32u;
+                                if (pos > pos_limit) { overrun = 1; break; }
+                                LNB_DS_SERVICE(64u);
+                                hh = lnb_ds_peek(sm, win.end_word, pos);
+                            }
+                            if (overrun) break;
+                            const uint32_t z = lnb_clz32(hh);
+                            q += z; pos += z + 1u;
+                            LNB_DS_SERVICE(64u);
+                            const uint32_t low = k2 ? (lnb_ds_peek(sm, win.end_word, pos) >> (32u - k2)) : 0u;
+                            pos += k2;
+                            val = lnb_zz_dec(low + (2u << k2) + ((q - 1u) << k2));             /* q >= 2 here */
+                        }
+                        if (lane == 0) line[done] = val;
+                        done++; left--;
+                    }
+                    lnb_ds_publish(sm, 1u, gbase + done, lane);
+                }
+            }
+            if (overrun) break;
+            /* samples a partition order that does not divide the block leaves uncovered read as zero */
+            for (uint32_t i = done + lane; i < n; i += 32u) line[i] = 0;
+            lnb_ds_publish(sm, 1u, gbase + n, lane);
+        }
+#undef LNB_DS_SERVICE
+        if (lane == 0) {
+            if (overrun) { sm.abort = 1u; __threadfence_block(); }
+            const uint32_t used = (pos - win.rel_payload * 8u + 7u) >> 3;
+            gblk.na = used;                                      /* payload bytes consumed (reference Flush + Tell) */
+            if (overrun || win.rel_payload + used > win.rel_end) gblk.status = blk.status | LNB_ST_OVERRUN;
+            sm.walk_done = 1u;
+        }
+    }
+    __syncwarp();
+}
+
 /* ---- stage 1: stored code-word windows -> residuals, 32 at a time ---- */
 __device__ bool lnb_ds_extract(LnbDsShared &sm, int32_t *line, uint32_t ch, uint32_t n)
 {
@@ -672,6 +822,7 @@ __device__ bool lnb_ds_finish(LnbDsShared &sm, const LnbDecodeBatch &b, const Ln
 __device__ unsigned int lnb_ds_sm_ticket[256];                  /* per SM: CTAs of this kernel that started there (role rotation) */
 
 /* One CTA per block.  Dynamic shared memory: the channel line, n_max int32. */
+template <bool WARP_WALK>
 __global__ void __launch_bounds__(LNB_DS_THREADS, 4) lnb_stream_v2_kernel(LnbDecodeBatch b, uint32_t n_max)
 {
     extern __shared__ __align__(16) int32_t lnb_ds_line[];
@@ -714,8 +865,8 @@ __global__ void __launch_bounds__(LNB_DS_THREADS, 4) lnb_stream_v2_kernel(LnbDec
     const uint32_t vwarp = (hw_warp + 8u - s_rot) & 7u;
     const uint32_t last = L + 2u;                              /* stage index of the de-emphasis warp */
     uint32_t stage;
-    if (vwarp == 0u) stage = 0u;
-    else if (vwarp == 1u) stage = 1u;
+    if (vwarp == 0u) stage = WARP_WALK ? 1u : 0u;               /* the warp walk delivers residuals: it is stage 1 and v1 leaves */
+    else if (vwarp == 1u) stage = WARP_WALK ? 0xFFu : 1u;
     else if (vwarp == 2u) stage = 2u;
     else if (vwarp == 3u) stage = (L >= 2u) ? 3u : 0xFFu;
     else if (vwarp == 6u) stage = (L >= 3u) ? 4u : 0xFFu;
@@ -731,13 +882,14 @@ __global__ void __launch_bounds__(LNB_DS_THREADS, 4) lnb_stream_v2_kernel(LnbDec
 #ifdef LNB_DS_TIMING
     if (b.cfg.check_crc & 0x100u) {                            /* debug: the walk alone (results are wrong) */
         if (vwarp != 0u && vwarp != 5u) return;
-        if (threadIdx.x == 0) for (uint32_t i = 1; i < LNB_DS_STAGES; i++) sm.prog[i] = 0x7FFFFFFFu;
+        if (threadIdx.x == 0) for (uint32_t i = WARP_WALK ? 2u : 1u; i < LNB_DS_STAGES; i++) sm.prog[i] = 0x7FFFFFFFu;
     }
 #endif
     if (vwarp == 5u) { lnb_ds_loader(lnb_ds_window(b, blk), sm, lane); return; }
     if (stage == 0xFFu) return;
-    if (stage == 0u) {
-        lnb_ds_walk(b, gblk, blk, lnb_ds_window(b, blk), sm, lnb_ds_line, last, lane);
+    if (vwarp == 0u) {
+        if (WARP_WALK) lnb_ds_walk_warp(b, gblk, blk, lnb_ds_window(b, blk), sm, lnb_ds_line, last, lane);
+        else lnb_ds_walk(b, gblk, blk, lnb_ds_window(b, blk), sm, lnb_ds_line, last, lane);
         if (sm.abort) {                                        /* broken payload: the block reads as silence */
             for (uint32_t c = 0; c < C; c++) {
                 int32_t *gout = b.pcm + (size_t)c * cfg.pcm_stride + blk.smp_off;
@@ -749,7 +901,7 @@ __global__ void __launch_bounds__(LNB_DS_THREADS, 4) lnb_stream_v2_kernel(LnbDec
     /* side information is complete once the walk has published anything at all */
     for (uint32_t ch = 0; ch < C; ch++) {
         const uint32_t gbase = ch * n;
-        if (stage == 1u) {
+        if (!WARP_WALK && stage == 1u) {
             if (!lnb_ds_extract(sm, lnb_ds_line, ch, n)) return;
             continue;
         }
