@@ -150,7 +150,8 @@ struct CudaExec {
         const int slot = begin_stage("stream_v2", on);
         /* the walk on one lane (default) or as a warp (LINNE_B200_WALK=warp; measured slower inside this kernel, kept for
          * A/B runs): lnb_stream_v2.cuh */
-        static const bool lane_walk = [] { const char *e = getenv("LINNE_B200_WALK"); return !(e && e[0] == 'w'); }();
+        const char *walk_env = getenv("LINNE_B200_WALK");         /* read per call: the tests switch forms inside one process */
+        const bool lane_walk = !(walk_env && walk_env[0] == 'w');
         LnbDecodeBatch b2 = b;
 #ifdef LNB_DS_TIMING
         if (getenv("LINNE_B200_DBG_WALKONLY")) b2.cfg.check_crc |= 0x100u;
@@ -193,12 +194,15 @@ struct CudaExec {
         cudaEventRecord(dev->ev_join, dev->aux_stream);
         const int slot = begin_stage("tp_entropy");
         /* eight lanes per block with fix-up rounds (default); LINNE_B200_TP_ENTROPY=8: rounds that end at the first long code
-         * word (round 1), =w: a warp per block, =l: a lane per block (A/B runs, profiles/r2_tp_entropy_forms.md) */
-        static const char form = [] { const char *e = getenv("LINNE_B200_TP_ENTROPY"); return e && e[0] ? e[0] : 'i'; }();
+         * word (round 1), =w: a warp per block, =l / =s: a lane per block, one code word per pass / groups of eight (measured
+         * alternatives, profiles/r2_tp_entropy_forms.md) */
+        const char *form_env = getenv("LINNE_B200_TP_ENTROPY");  /* read per call: the tests switch forms inside one process */
+        const char form = form_env && form_env[0] ? form_env[0] : 'i';
         const uint32_t grid8 = (b.num_blocks + LNB_TG_PER_WARP - 1u) / LNB_TG_PER_WARP;
         if (form == '8') lnb_tp_entropy_kernel<false><<<grid8, 32, 0, dev->stream>>>(b);
         else if (form == 'w') lnb_tp_entropy_w_kernel<<<(b.num_blocks + LNB_TW_WARPS - 1u) / LNB_TW_WARPS, 32u * LNB_TW_WARPS, 0, dev->stream>>>(b);
         else if (form == 'l') lnb_tp_entropy_l_kernel<<<(b.num_blocks + 31u) / 32u, 32, 0, dev->stream>>>(b);
+        else if (form == 's') lnb_tp_entropy_s_kernel<<<(b.num_blocks + 31u) / 32u, 32, 0, dev->stream>>>(b);
         else lnb_tp_entropy_kernel<true><<<grid8, 32, 0, dev->stream>>>(b);
         end_stage(slot);
         cudaStreamWaitEvent(dev->stream, dev->ev_join, 0);

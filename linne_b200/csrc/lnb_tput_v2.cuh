@@ -474,6 +474,10 @@ __device__ __forceinline__ void lnb_tl_request(LnbTlLane &st, uint32_t ring_sadd
 }
 /* keep every lane at least LNB_TL_HALF words ahead of its reader (bit position pos); with `all` the caller wants
  * the data now (side information, after a jump), otherwise the copies of the previous check are waited for */
+/* LAG: copy groups (one per check) that may still be in flight when a lazy check returns.  A lane reaches the words it
+ * asks for no earlier than LNB_TL_HALF - (words read between two checks) words later, i.e. several checks on: waiting for
+ * the previous check's copies (LAG 1) stalls every check for a DRAM round trip. */
+template <int LAG>
 __device__ __forceinline__ void lnb_tl_check(LnbTlLane &st, uint32_t ring_saddr, uint32_t pos, bool live, bool all, uint32_t lane)
 {
     if (live && (pos >> 5) >= st.issued) st.issued = (pos >> 5) & ~(LNB_TL_HALF - 1u);      /* jumped past the ring (long code word) */
@@ -484,7 +488,7 @@ __device__ __forceinline__ void lnb_tl_check(LnbTlLane &st, uint32_t ring_saddr,
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (all) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    else asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group %0;" :: "n"(LAG) : "memory");
     __syncwarp();
 }
 __device__ __forceinline__ uint32_t lnb_tl_peek(const LnbTlLane &st, uint32_t pos)
@@ -529,8 +533,8 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_l_kernel(LnbDecodeBatch b)
         smp_off = blk.smp_off;
     }
     const uint32_t pos_limit = (st.end_word + 4u) * 32u;          /* nothing sane reads past this */
-    lnb_tl_check(st, ring_saddr, pos, active, true, lane);        /* the first 128 words of every block */
-    lnb_tl_check(st, ring_saddr, pos, active, true, lane);
+    lnb_tl_check<2>(st, ring_saddr, pos, active, true, lane);        /* the first 128 words of every block */
+    lnb_tl_check<2>(st, ring_saddr, pos, active, true, lane);
 
     /* ---- side information (linne_decoder.c:457-486): each lane parses its own block ---- */
     {
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_l_kernel(LnbDecodeBatch b)
                 if (active) { params[c].preem_prev[f] = prev; params[c].preem_coef[f] = (uint8_t)coef; }
             }
         }
-        lnb_tl_check(st, ring_saddr, pos, active, true, lane);
+        lnb_tl_check<2>(st, ring_saddr, pos, active, true, lane);
         for (uint32_t c = 0; c < C; c++)
             for (uint32_t l = 0; l < cfg.num_layers; l++) {
                 const uint32_t P = cfg.layer_params[l];
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_l_kernel(LnbDecodeBatch b)
                         pos += e & 15u;
                         if (active) q[i0 + i] = (int8_t)lnb_zz_dec(e >> 4);
                     }
-                    lnb_tl_check(st, ring_saddr, pos, active, true, lane);
+                    lnb_tl_check<2>(st, ring_saddr, pos, active, true, lane);
                 }
             }
     }
@@ -572,7 +576,7 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_l_kernel(LnbDecodeBatch b)
         for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
 #pragma unroll 1
             for (uint32_t s = 0; s < 32u; s++) {
-                if ((s % LNB_TL_CHECK) == 0u) lnb_tl_check(st, ring_saddr, pos, active && !overrun, false, lane);
+                if ((s % LNB_TL_CHECK) == 0u) lnb_tl_check<2>(st, ring_saddr, pos, active && !overrun, false, lane);
                 int32_t val = 0;
                 if (active && !overrun) {
                     if (left == 0u) {                            /* partition header: gamma code of zigzag(k2 - previous k2) */
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_l_kernel(LnbDecodeBatch b)
                     if (overrun) val = 0;
                 }
                 const bool jumped = active && !overrun && (pos >> 5) + 2u >= st.issued;
-                if (__any_sync(0xffffffffu, jumped)) lnb_tl_check(st, ring_saddr, pos, active && !overrun, true, lane);
+                if (__any_sync(0xffffffffu, jumped)) lnb_tl_check<2>(st, ring_saddr, pos, active && !overrun, true, lane);
                 s_tile[s * 33u + lane] = val;
             }
             __syncwarp();
@@ -615,6 +619,183 @@ __global__ void __launch_bounds__(32) lnb_tp_entropy_l_kernel(LnbDecodeBatch b)
                 if ((act_mask >> r) & 1u) b.pcm[plane + off + i0 + lane] = s_tile[lane * 33u + r];
             }
             __syncwarp();
+        }
+    }
+    if (active) {
+        const uint32_t used = (pos - rel_payload * 8u + 7u) >> 3;
+        b.blocks[blk_i].na = used;                               /* payload bytes consumed (reference Flush + Tell) */
+        if (overrun || rel_payload + used > rel_end) atomicOr(&b.blocks[blk_i].status, (uint32_t)LNB_ST_OVERRUN);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * entropy, fourth form: ONE LANE per block walking GROUPS of eight code words without a branch.
+ *
+ * The one-code-word-per-pass kernel above needs few instructions but every pass is one long dependent chain (~100
+ * instructions at the ~5 cycles a lone warp gets per dependent instruction), and a batch has only one warp per scheduler.
+ * Here a lane keeps a 128-bit window of its payload in registers and walks up to eight code words per step the way the
+ * fused decoder's walk does (lnb_stream_v2.cuh: length = (k2 + 32) - leading-one index + top bit, four funnel shifts), with
+ * the residual of every slot computed beside the chain.  A slot counts while the window still covers it and no code word
+ * before it was longer than 32 bits; what does not count is simply walked again by the next step, so nothing needs a
+ * second reader except a code word longer than 32 bits at the head of a step (read from global memory, rare).  Lanes run
+ * out of step with each other (partition ends differ), so residuals leave through a per-lane staging ring, 32 at a time,
+ * written by the whole warp (128 contiguous bytes per store).
+ * ------------------------------------------------------------------------------------------------------ */
+#define LNB_TS_OROWS 64u                                       /* staging rows per lane (a lane holds at most 31 + 8) */
+
+__device__ __forceinline__ void lnb_tl_window128(const LnbTlLane &st, uint32_t pos, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3)
+{
+    const uint32_t i = pos >> 5;
+    const uint32_t v0 = lnb_bswap32(lnb_lds32(st.saddr + (i % LNB_TL_RING) * 128u)), v1 = lnb_bswap32(lnb_lds32(st.saddr + ((i + 1u) % LNB_TL_RING) * 128u));
+    const uint32_t v2 = lnb_bswap32(lnb_lds32(st.saddr + ((i + 2u) % LNB_TL_RING) * 128u)), v3 = lnb_bswap32(lnb_lds32(st.saddr + ((i + 3u) % LNB_TL_RING) * 128u));
+    const uint32_t v4 = lnb_bswap32(lnb_lds32(st.saddr + ((i + 4u) % LNB_TL_RING) * 128u));
+    w0 = __funnelshift_l(v1, v0, pos); w1 = __funnelshift_l(v2, v1, pos);
+    w2 = __funnelshift_l(v3, v2, pos); w3 = __funnelshift_l(v4, v3, pos);
+}
+
+__global__ void __launch_bounds__(32) lnb_tp_entropy_s_kernel(LnbDecodeBatch b)
+{
+    __shared__ __align__(16) uint32_t s_ring[LNB_TL_RING * 32u];
+    __shared__ int32_t s_out[LNB_TS_OROWS * 33u];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t blk_i = blockIdx.x * 32u + lane;
+    const LnbStreamCfg &cfg = b.cfg;
+    const uint32_t C = cfg.num_channels, n = cfg.block_size;
+    LnbBlockDesc blk;
+    bool active = blk_i < b.num_blocks;
+    if (active) { blk = b.blocks[blk_i]; active = lnb_tp_shape_ok(b, blk); }
+    if (__ballot_sync(0xffffffffu, active) == 0u) return;
+
+    const uint32_t ring_saddr = lnb_smem_addr(s_ring);
+    LnbTlLane st;
+    st.gw = (const uint32_t *)b.stream; st.end_word = 0u; st.issued = 0u; st.saddr = ring_saddr + lane * 4u;
+    uint32_t pos = 0u, rel_payload = 0u, rel_end = 0u, overrun = 0u;
+    int32_t *obase = b.pcm;                                       /* plane 0 of this lane's block */
+    if (active) {
+        const uint32_t word0 = blk.byte_off >> 2;                /* bit positions relative to this word never overflow */
+        uint32_t end_byte = blk.byte_off + blk.byte_size;
+        if (end_byte > b.stream_size || end_byte < blk.byte_off) end_byte = b.stream_size;
+        st.gw = (const uint32_t *)b.stream + word0;
+        rel_payload = blk.byte_off + LNB_BLOCK_HEADER_SIZE - word0 * 4u; rel_end = end_byte - word0 * 4u;
+        st.end_word = (rel_end + 3u) >> 2;
+        pos = rel_payload * 8u;
+        obase = b.pcm + blk.smp_off;
+    }
+    const uint32_t pos_limit = (st.end_word + 4u) * 32u;          /* nothing sane reads past this */
+    lnb_tl_check<2>(st, ring_saddr, pos, active, true, lane);        /* the first 128 words of every block */
+
+    /* ---- side information (linne_decoder.c:457-486): each lane parses its own block ---- */
+    {
+        LnbChanParams *params = b.params + (size_t)(active ? blk_i : 0u) * C;
+        for (uint32_t c = 0; c < C; c++) {
+            for (int f = 0; f < LNB_NUM_PREEM; f++) {
+                const int32_t prev = lnb_zz_dec(lnb_tl_get(st, pos, cfg.bits_per_sample + 1u));
+                const uint32_t coef = lnb_tl_get(st, pos, LNB_PREEM_SHIFT - 1);
+                if (active) { params[c].preem_prev[f] = prev; params[c].preem_coef[f] = (uint8_t)coef; }
+            }
+        }
+        lnb_tl_check<2>(st, ring_saddr, pos, active, true, lane);
+        for (uint32_t c = 0; c < C; c++)
+            for (uint32_t l = 0; l < cfg.num_layers; l++) {
+                const uint32_t P = cfg.layer_params[l];
+                const uint32_t lu = lnb_tl_get(st, pos, 3), rs = lnb_tl_get(st, pos, 4);
+                if (active) { params[c].log2_units[l] = (uint8_t)lu; params[c].rshift[l] = (uint8_t)rs; }
+                int8_t *q = params[c].coef + l * LNB_MAX_PARAMS;
+                for (uint32_t i0 = 0; i0 < P; i0 += 32u) {       /* at most 32 x 15 bits between two checks */
+                    const uint32_t lim = (P - i0 < 32u) ? P - i0 : 32u;
+                    for (uint32_t i = 0; i < lim; i++) {
+                        const uint32_t e = b.tab.huff_lut[lnb_tl_peek(st, pos) >> (32 - LNB_HUFF_LUT_BITS)];
+                        pos += e & 15u;
+                        if (active) q[i0 + i] = (int8_t)lnb_zz_dec(e >> 4);
+                    }
+                    lnb_tl_check<2>(st, ring_saddr, pos, active, true, lane);
+                }
+            }
+    }
+
+    /* ---- residuals (linne_coder.c:306-327) ---- */
+    const uint32_t out_saddr = lnb_smem_addr(s_out) + lane * 4u;  /* row r of this lane: out_saddr + r * 33 * 4 */
+    uint32_t chan = 0u, left = 0u, parts_left = 0u, len = 0u, k2 = 0u;
+    uint32_t produced = 0u;                                      /* residuals of the current channel walked so far */
+    uint32_t wr = 0u, flushed = 0u;                              /* staging ring: rows written / rows sent, over the whole block */
+    bool running = active;
+    for (uint32_t step = 0;; step++) {
+        if (!__any_sync(0xffffffffu, running)) break;
+        if ((step & 3u) == 0u) lnb_tl_check<2>(st, ring_saddr, pos, running, false, lane);
+        /* channel and partition headers of the lanes that stand in front of one */
+        if (running && left == 0u) {
+            if (parts_left == 0u) {
+                if (chan == C) {
+                    running = false;
+                } else {
+                    const uint32_t porder = lnb_tl_get(st, pos, 10);
+                    k2 = lnb_tl_get(st, pos, 5);                  /* first partition: k2 itself (linne_coder.c:313) */
+                    if (porder > LNB_MAX_PORDER || k2 > 30u) { overrun = 1u; running = false; }
+                    else { len = n >> porder; parts_left = (1u << porder) - 1u; left = len; produced = 0u; chan++; }
+                }
+            } else {                                             /* gamma code of zigzag(k2 - previous k2) */
+                const uint32_t h = lnb_tl_peek(st, pos);
+                const uint32_t lz = lnb_clz32(h);
+                const uint32_t z = lz & 15u;
+                const uint32_t gv = ((h << z) >> (31u - z)) - 1u;
+                pos += 2u * lz + 1u;
+                k2 = (uint32_t)((int32_t)k2 + lnb_zz_dec(gv));
+                parts_left--; left = len;
+                if (lz > 15u || k2 > 30u) { overrun = 1u; running = false; }
+            }
+        }
+        /* the group: up to eight code words from a 128-bit window, no branch */
+        uint32_t w0, w1, w2, w3;
+        lnb_tl_window128(st, pos, w0, w1, w2, w3);
+        const uint32_t gmax = (k2 <= 8u) ? 8u : ((k2 <= 19u) ? 4u : 2u);
+        const uint32_t G = running ? (left < gmax ? left : gmax) : 0u;
+        const uint32_t K = k2 + 32u, sh = 31u - k2, k2mask = (1u << k2) - 1u;
+        uint32_t T = 0u, taken = 0u, adv = 0u, good = 1u;
+#pragma unroll
+        for (uint32_t s = 0; s < 8u; s++) {
+            const uint32_t f = lnb_bfind(w0);                    /* 31 - leading zeros; 0xFFFFFFFF for an all-zero window */
+            const uint32_t lz = 31u - f, ml = (lz > 1u) ? lz : 1u;
+            const uint32_t low = (w0 >> ((sh - ml) & 31u)) & k2mask;
+            const uint32_t mult = lz ? lz + 1u : ((w0 >> 30) & 1u);
+            const int32_t val = lnb_zz_dec((mult << k2) + low);
+            /* the slot counts: asked for, window still covers its 32 bits, inside them, and so did every slot before */
+            good &= (s < G && T <= 96u && (int32_t)f >= (int32_t)k2) ? 1u : 0u;
+            const uint32_t L = K - f + (w0 >> 31);               /* k2 + 1 + max(lz, 1) */
+            lnb_sts32(out_saddr + ((wr + s) % LNB_TS_OROWS) * 132u, (uint32_t)val);
+            w0 = __funnelshift_lc(w1, w0, L); w1 = __funnelshift_lc(w2, w1, L);
+            w2 = __funnelshift_lc(w3, w2, L); w3 = __funnelshift_lc(0u, w3, L);
+            T += L;
+            taken += good;
+            adv = good ? T : adv;
+        }
+        if (running) {
+            if (__builtin_expect(taken == 0u, 0)) {              /* a code word longer than 32 bits heads the step: global memory */
+                LnbFastReader fr;
+                lnb_fr_open(fr, st.gw, pos, st.end_word);
+                const int32_t val = lnb_zz_dec(lnb_get_rice(fr, k2 + 1u, k2));
+                lnb_sts32(out_saddr + (wr % LNB_TS_OROWS) * 132u, (uint32_t)val);
+                pos = (uint32_t)lnb_fr_position(fr);
+                taken = 1u;
+                if (fr.overrun || pos > pos_limit) { overrun = 1u; running = false; }
+            } else {
+                pos += adv;
+            }
+            wr += taken; left -= taken; produced += taken;
+        }
+        /* a lane that left its ring behind (long code word) gets it re-primed now */
+        if (__any_sync(0xffffffffu, running && (pos >> 5) + 6u >= st.issued)) lnb_tl_check<2>(st, ring_saddr, pos, running, true, lane);
+        /* residuals leave 32 at a time, one lane's rows per store instruction */
+        for (;;) {
+            const uint32_t m = __ballot_sync(0xffffffffu, active && wr - flushed >= 32u);
+            if (m == 0u) break;
+            const int l = __ffs((int)m) - 1;
+            const unsigned long long op = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)obase, l);
+            const uint32_t fl = __shfl_sync(0xffffffffu, flushed, l);
+            /* row fl + j of lane l is sample (fl + j) of the block's concatenated channels: channel (fl / n), index (fl % n) */
+            const uint32_t ch = fl / n, idx = fl - ch * n;
+            const int32_t v = (int32_t)lnb_lds32(lnb_smem_addr(s_out) + (((fl + lane) % LNB_TS_OROWS) * 33u + (uint32_t)l) * 4u);
+            ((int32_t *)(uintptr_t)op)[(size_t)ch * cfg.pcm_stride + idx + lane] = v;
+            if ((int)lane == l) flushed += 32u;
         }
     }
     if (active) {

@@ -128,3 +128,57 @@ def test_tput_damaged_streams_same_as_per_block_path(gpu, oracle, tput):
                 if crc:                     # with the CRC check on, the delivered samples are defined by the reference
                     assert np.array_equal(out, out2), (preset, trial)
         assert np.array_equal(gpu.decode(good), pcm)
+
+
+@pytest.fixture
+def env_switch():
+    """set environment switches the library reads per call, restored afterwards"""
+    saved = {}
+
+    def setenv(name, value):
+        saved.setdefault(name, os.environ.get(name))
+        os.environ[name] = value
+    yield setenv
+    for name, old in saved.items():
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("form", ["i", "8", "w", "l", "s"])
+def test_tput_entropy_forms_bit_exact(gpu, oracle, tput, env_switch, form):
+    """every form of the throughput entropy stage (default: fix-up rounds at eight lanes per block; the measured
+    alternatives stay selectable) decodes the same streams to the oracle's PCM, including damaged ones"""
+    env_switch("LINNE_B200_TP_ENTROPY", form)
+    rng = np.random.default_rng(7)
+    for channels, bits, block, preset in [(2, 16, 10240, 7), (2, 16, 1024, 0), (8, 24, 2048, 5), (1, 8, 1024, 2)]:
+        pcm = harness.synth_pcm(n=block * 6 + block // 2, channels=channels, bits=bits, seed=3 + channels + preset)
+        if channels == 2 and block == 1024:
+            pcm[:, 700:712] = np.array([30000, -30000] * 6, np.int32)        # a click in a quiet partition: code words longer than 32 bits
+        stream = oracle.encode(pcm, bits=bits, preset=preset, block=block)
+        names, out = _stages(gpu, stream, channels)
+        assert {"tp_entropy", "tp_synth"} <= names, names
+        assert np.array_equal(out, pcm), (form, channels, bits, block, preset)
+    pcm = harness.synth_pcm(n=2048 * 6 + 500, channels=2, bits=16, seed=56)
+    good = oracle.encode(pcm, preset=3, block=2048)
+    for trial in range(8):
+        bad = bytearray(good)
+        for _ in range(int(rng.integers(1, 5))):
+            bad[int(rng.integers(41, len(bad)))] = int(rng.integers(0, 256))
+        rc, out = gpu.decode(bytes(bad), check_crc=1, return_code=True, fill=-7)
+        rc2, out2 = _without(lambda: gpu.decode(bytes(bad), check_crc=1, return_code=True, fill=-7))
+        assert rc == rc2 and np.array_equal(out, out2), (form, trial)
+
+
+@pytest.mark.parametrize("walk", ["lane", "warp"])
+def test_fused_decoder_walk_forms_bit_exact(gpu, oracle, env_switch, walk):
+    """the fused per-block decoder with its walk on one lane (default) and as a warp (rounds of 32 code words)"""
+    env_switch("LINNE_B200_WALK", walk)
+    env_switch("LINNE_B200_TPUT_MIN_BLOCKS", "0")
+    for channels, bits, block, preset in [(2, 16, 10240, 7), (2, 16, 4096, 0), (8, 24, 2048, 4), (1, 8, 1024, 2)]:
+        pcm = harness.synth_pcm(n=block * 3 + block // 3, channels=channels, bits=bits, seed=11 + channels + preset)
+        if channels == 2 and block == 4096:
+            pcm[:, 900:906] = np.array([32000, -32000] * 3, np.int32)
+        stream = oracle.encode(pcm, bits=bits, preset=preset, block=block)
+        assert np.array_equal(gpu.decode(stream), pcm), (walk, channels, bits, block, preset)
