@@ -1291,6 +1291,7 @@ def main():
                     help="order of the sweep's calls: every preset encodes then decodes on its own thread (interleaved), or all "
                          "presets encode, meet, and then all decode (phased)")
     ap.add_argument("--sweep-only", action="store_true", help="skip every leg but the headline sweep")
+    ap.add_argument("--with-inlib", action="store_true", help="with --sweep-only: keep the in-library multi-GPU / pipelining leg")
     ap.add_argument("--c3-seconds", type=float, default=3600.0,
                     help="N=1: length of the C3 decode-only stream (BASELINE.json configs[2]); 0 = skip")
     ap.add_argument("--shard-seconds", type=float, default=600.0,
@@ -1312,9 +1313,12 @@ def main():
     ap.add_argument("--no-inlib", action="store_true", help="skip the in-library multi-GPU / pipelining leg")
     args = ap.parse_args()
     if args.sweep_only:
-        args.c3_seconds = args.c4_seconds = args.shard_seconds = 0.0
+        args.c3_seconds = args.c4_seconds = 0.0
+        if not args.with_inlib:
+            args.shard_seconds = 0.0
         args.c5_files = 0
-        args.no_streaming = args.no_refine = args.no_inlib = True
+        args.no_streaming = args.no_refine = True
+        args.no_inlib = not args.with_inlib
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
