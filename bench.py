@@ -886,11 +886,13 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- linne_b200 has no CPU fallback")
     # Eight host threads per rank wait on their streams; when the ranks of a box outnumber its cores, spinning waits
-    # starve each other, so the library's waits are switched to sleeping ones (LINNE_B200_SYNC=block).
+    # starve each other, so the library's waits poll and yield the core between polls (LINNE_B200_SYNC=yield; measured on a
+    # 32-core box: 4 GPUs 4.45 ms per sweep against 5.0 ms with sleeping waits and 4.55 ms spinning, 8 GPUs 4.89 against
+    # 5.25 ms -- profiles/RESULTS.md).
     oversubscribed = world * len(PRESETS) > 0.75 * (os.cpu_count() or 1)
     sync_mode_forced = oversubscribed and "LINNE_B200_SYNC" not in os.environ
     if oversubscribed:
-        os.environ.setdefault("LINNE_B200_SYNC", "block")
+        os.environ.setdefault("LINNE_B200_SYNC", args.oversub_wait)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -1290,6 +1292,8 @@ def main():
     ap.add_argument("--schedule", default="interleaved", choices=["interleaved", "phased"],
                     help="order of the sweep's calls: every preset encodes then decodes on its own thread (interleaved), or all "
                          "presets encode, meet, and then all decode (phased)")
+    ap.add_argument("--oversub-wait", default="yield", choices=["block", "yield", "spin"],
+                    help="host wait mode (LINNE_B200_SYNC) chosen when the waiting threads of the box outnumber its cores")
     ap.add_argument("--sweep-only", action="store_true", help="skip every leg but the headline sweep")
     ap.add_argument("--with-inlib", action="store_true", help="with --sweep-only: keep the in-library multi-GPU / pipelining leg")
     ap.add_argument("--c3-seconds", type=float, default=3600.0,

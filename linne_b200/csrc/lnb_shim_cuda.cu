@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sched.h>
 #include <string.h>
 
 #include "lnb_shim.h"
@@ -47,6 +48,7 @@ struct LnbDevice {
     LnbTimelineEntry timeline[LNB_MAX_TIMELINE];
     cudaEvent_t sync_event;              /* LINNE_B200_SYNC=block: host threads sleep in the driver instead of spinning */
     int blocking_sync;
+    int yield_sync;
     /* side stream of the throughput decoder: the per-block pipeline kernel for the few blocks the lane-per-block
      * kernels leave (tail blocks) runs beside them instead of behind them */
     cudaStream_t aux_stream;
@@ -406,6 +408,9 @@ int lnb_shim_open(LnbDevice **out, int device_ordinal)
         const char *mode = getenv("LINNE_B200_SYNC");
         if (mode && mode[0] == 'b' && cudaEventCreateWithFlags(&dev->sync_event, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess)
             dev->blocking_sync = 1;
+        /* LINNE_B200_SYNC=yield: poll the stream and give the core away between polls -- no wake-up latency, and waiting
+         * threads that outnumber the cores do not starve the ones with work */
+        if (mode && mode[0] == 'y') dev->yield_sync = 1;
     }
 
     const LnbHostTables *ht = lnb_tables_get();
@@ -524,6 +529,8 @@ int lnb_shim_sync(LnbDevice *dev)
     if (dev->blocking_sync) {
         e = cudaEventRecord(dev->sync_event, dev->stream);
         if (e == cudaSuccess) e = cudaEventSynchronize(dev->sync_event);
+    } else if (dev->yield_sync) {
+        while ((e = cudaStreamQuery(dev->stream)) == cudaErrorNotReady) sched_yield();
     } else {
         e = cudaStreamSynchronize(dev->stream);
     }
