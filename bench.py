@@ -1151,8 +1151,8 @@ def run_b200(args, rank, world, local_rank):
         if user_sync_mode:
             return os.environ["LINNE_B200_SYNC"]
         if world * threads_per_rank > (os.cpu_count() or 1):
-            os.environ["LINNE_B200_SYNC"] = "block"
-            return "block"
+            os.environ["LINNE_B200_SYNC"] = args.oversub_wait
+            return args.oversub_wait
         os.environ.pop("LINNE_B200_SYNC", None)
         return "spin"
     del d_out, d_backs, h_outs, h_backs, l2_flush
