@@ -9,6 +9,8 @@ import pytest
 import harness
 from linne_b200 import shard
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_block_ranges_cover_everything():
     for n, block, world in ((441000, 10240, 8), (5000, 2048, 2), (1000, 4096, 4), (10240 * 3, 10240, 2)):
@@ -129,3 +131,58 @@ def test_gloo_world_size_2_corpus_by_file_ranges(hostsim, oracle):
     for f, st in zip(corpus, streams):
         assert st == hostsim.encode(f, preset=3, block=2048)
         assert np.array_equal(oracle.decode(st), f)
+
+
+def test_turnstile_orders_the_ranges_of_a_device():
+    """LnbTurnstile (csrc/host/lnb_host_util.c): range k may pass a phase only after range k - stride has; passing is
+    idempotent and a range that bails out early unblocks its successors.  Driven from Python threads against the
+    host-simulator build of the same host C code (no GPU involved)."""
+    import ctypes as C
+    import threading
+    import time
+    lib = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "liblinne_hostsim.so"))
+    buf = C.create_string_buffer(512)                  # room for the struct (mutex + condition variable + flags)
+    for f in (lib.lnb_turnstile_init, lib.lnb_turnstile_wait, lib.lnb_turnstile_pass, lib.lnb_turnstile_destroy):
+        f.restype = None
+    for stride, ranges in ((1, 6), (2, 8)):
+        lib.lnb_turnstile_init(buf, C.c_uint32(stride))
+        order = {0: [], 1: []}
+        lock = threading.Lock()
+
+        def work(k):
+            for phase in (0, 1):
+                lib.lnb_turnstile_wait(buf, C.c_int(phase), C.c_uint32(k))
+                with lock:
+                    order[phase].append(k)
+                time.sleep(0.002 * ((k * 7 + phase) % 3))
+                if k == 3 and phase == 0:              # range 3 gives up after its upload: both phases are passed for it
+                    lib.lnb_turnstile_pass(buf, C.c_int(0), C.c_uint32(k))
+                    lib.lnb_turnstile_pass(buf, C.c_int(1), C.c_uint32(k))
+                    return
+                lib.lnb_turnstile_pass(buf, C.c_int(phase), C.c_uint32(k))
+                lib.lnb_turnstile_pass(buf, C.c_int(phase), C.c_uint32(k))      # idempotent
+        threads = [threading.Thread(target=work, args=(k,)) for k in reversed(range(ranges))]
+        for t in threads: t.start()
+        for t in threads: t.join(timeout=20)
+        assert not any(t.is_alive() for t in threads), "turnstile deadlock"
+        lib.lnb_turnstile_destroy(buf)
+        for phase in (0, 1):
+            seen = order[phase]
+            assert sorted(seen) == [k for k in range(ranges) if not (phase == 1 and k == 3)]
+            for lane in range(stride):                 # ranges that share a device went through in range order
+                mine = [k for k in seen if k % stride == lane]
+                assert mine == sorted(mine), (stride, phase, seen)
+
+
+def test_plan_ranges_pipeline_depth(monkeypatch):
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "liblinne_hostsim.so"))
+    lib.lnb_plan_ranges.restype = C.c_uint32
+    monkeypatch.delenv("LINNE_B200_PIPELINE", raising=False)
+    assert lib.lnb_plan_ranges(C.c_uint32(44), C.c_uint32(1)) == 1           # a clip: the handle's own device, no ranges
+    assert lib.lnb_plan_ranges(C.c_uint32(3072), C.c_uint32(1)) == 2
+    assert lib.lnb_plan_ranges(C.c_uint32(15504), C.c_uint32(1)) == 4        # the 1-hour stream
+    assert lib.lnb_plan_ranges(C.c_uint32(15504), C.c_uint32(8)) == 8
+    assert lib.lnb_plan_ranges(C.c_uint32(5), C.c_uint32(8)) == 2            # at least two blocks per range
+    monkeypatch.setenv("LINNE_B200_PIPELINE", "3")
+    assert lib.lnb_plan_ranges(C.c_uint32(15504), C.c_uint32(2)) == 6
