@@ -627,7 +627,7 @@ def run_c5(args, dev, rank, world):
             host_pcm_k = torch.zeros(K2max * host_pcm.numel(), dtype=torch.uint8).pin_memory()
             for s_ in range(K2max):
                 host_pcm_k[s_ * host_pcm.numel():(s_ + 1) * host_pcm.numel()].copy_(host_pcm)
-        for J2, K2 in ((1, 1), (3, 1), (3, K2max), (4, K2max)):
+        for J2, K2 in ((1, 1), (3, 1), (3, K2max)):
             encs = [EncoderSession(nch, bits=BITS, rate=RATE, block=BLOCK, preset=0) for _ in range(J2)]
             decs = [DecoderSession(channels=nch) for _ in range(J2)]
             for s_ in decs:
