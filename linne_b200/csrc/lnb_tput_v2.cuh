@@ -15,12 +15,16 @@
  * ~P/4 (synthesis) warp instructions per sample the arithmetic needs.
  *
  *   lnb_tp_entropy_kernel   eight lanes per block, four blocks per warp: speculative code-word starts, one 32-byte
- *                           sector of residuals per round (see below).  Lane-per-block walks were measured twice in
- *                           round 2 and lost on a 1-hour stream: a flat loop with one code word per pass (every
- *                           data-dependent branch of a lone warp costs ~20 cycles, 32 lanes pay each other's: 7.1 ms)
- *                           and branch-free steps of eight code-word slots per lane (8.8 ms: with 485 warps for 592
- *                           schedulers nothing hides the ~550 dependent instructions and three memory round trips of
- *                           a step) against 4.2 ms here, where 6.5 warps per scheduler hide each other's latency.
+ *                           sector of residuals per round; with ITER (the default) a round goes on past a long code
+ *                           word -- the lanes behind it shift inside their 64-bit windows by its extra bits and look
+ *                           again -- so all eight code words retire (see below).  How many lanes a block should get
+ *                           was measured at every width in round 2 (profiles/r2_tp_entropy_forms.md; all forms stay
+ *                           selectable through LINNE_B200_TP_ENTROPY and are tested): a warp per block
+ *                           (lnb_tp_entropy_w_kernel, 11 warp instructions per code word, issue-bound, 3.9 ms on a
+ *                           1-hour stream), eight lanes with fix-up rounds (6.6, 3.65 ms: the default), eight lanes
+ *                           without (26, 4.3 ms: round 1), one lane per block with everything staged through shared
+ *                           memory (lnb_tp_entropy_l_kernel / _s_kernel, 2.8 instructions per code word but one warp
+ *                           per scheduler: a lone warp's ~5.4 cycles per dependent instruction, 6 ms).
  *   lnb_tp_synth_kernel     lane = (block, channel).  Groups of 8 samples run through the whole cascade in
  *                           registers: for layers of 16..128 taps the history lives in a lane-interleaved
  *                           shared-memory ring (conflict-free; the ring position is warp-uniform because all

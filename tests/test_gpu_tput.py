@@ -1,4 +1,4 @@
-"""GPU parity tests of the throughput decoder (linne_b200/csrc/lnb_tput_v1.cuh: one lane per block / per
+"""GPU parity tests of the throughput decoder (linne_b200/csrc/lnb_tput_v2.cuh: eight lanes per block / one lane per
 (block, channel), taken by large batches).  LINNE_B200_TPUT_MIN_BLOCKS moves the switch-over point, so the same
 small streams run through it (=1) and through the per-block pipeline (=0); both must equal the oracle's PCM bit for
 bit, and result codes and partial outputs of damaged streams must be the same on both paths."""
