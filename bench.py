@@ -931,7 +931,7 @@ def run_b200(args, rank, world, local_rank):
     # --schedule phased: the eight presets encode side by side, meet, then decode side by side.  The analysis kernel takes
     # a whole SM per CTA (224 KB of shared memory) while a decode CTA lives ~0.8 ms on a quarter of one: interleaved, the
     # early presets' decode CTAs spread over the SMs and keep the late presets' analysis CTAs waiting for an empty SM.
-    phase_gate = threading.Barrier(len(PRESETS)) if (args.schedule == "phased" and not args.serial) else None
+    phase_gate = threading.Barrier(len(PRESETS)) if (args.schedule == "phased" and not args.serial and args.sweep_threads >= len(PRESETS)) else None
 
     def one_e2e(m):
         sz = encs[m].encode_whole(chan_in, n, h_outs[m].data_ptr(), cap)
@@ -954,17 +954,25 @@ def run_b200(args, rank, world, local_rank):
     class SweepPool:
         def __init__(self):
             self.fn = None; self.errs = []; self.stop = False
-            self.go = threading.Barrier(len(PRESETS) + 1); self.done = threading.Barrier(len(PRESETS) + 1)
-            self.threads = [threading.Thread(target=self.work, args=(m,), daemon=True) for m in PRESETS[::-1]]   # longest presets first
+            # --sweep-threads T < 8: thread j runs presets 7 - j, then j, ... (a cheap one after an expensive one)
+            T = max(1, min(len(PRESETS), args.sweep_threads))
+            order = PRESETS[::-1]                                  # longest presets first
+            self.lists = [[] for _ in range(T)]
+            for i, m in enumerate(order):
+                j = i % (2 * T)
+                self.lists[j if j < T else 2 * T - 1 - j].append(m)
+            self.go = threading.Barrier(T + 1); self.done = threading.Barrier(T + 1)
+            self.threads = [threading.Thread(target=self.work, args=(ms,), daemon=True) for ms in self.lists]
             for t in self.threads: t.start()
 
-        def work(self, m):
+        def work(self, ms):
             while True:
                 self.go.wait()
                 if self.stop:
                     return
                 try:
-                    self.fn(m)
+                    for m in ms:
+                        self.fn(m)
                 except Exception as e:      # pragma: no cover
                     self.errs.append(e)
                     if phase_gate is not None:
@@ -1248,7 +1256,7 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": "C2: 10 s 44.1 kHz 16-bit stereo synthetic clip, -m 0..7 sweep, encode+decode",
                    "block": BLOCK, "ms": 1, "presets": PRESETS, "l2": "256 MiB flush write between timed iterations",
                    "per_rank": "each rank runs the whole sweep on its own clip",
-                   "concurrency": "serial" if args.serial else "8 presets on 8 persistent host threads / CUDA streams", "schedule": args.schedule,
+                   "concurrency": "serial" if args.serial else f"8 presets on {max(1, min(8, args.sweep_threads))} persistent host threads / CUDA streams", "schedule": args.schedule,
                    "host_wait": host_wait_sweep, "host_cores": os.cpu_count()},
         "e2e": {"value": round(e2e_value, 3), "unit": "MSamples/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
@@ -1294,6 +1302,7 @@ def main():
                          "presets encode, meet, and then all decode (phased)")
     ap.add_argument("--oversub-wait", default="yield", choices=["block", "yield", "spin"],
                     help="host wait mode (LINNE_B200_SYNC) chosen when the waiting threads of the box outnumber its cores")
+    ap.add_argument("--sweep-threads", type=int, default=8, help="host threads (CUDA streams in flight) the sweep's eight presets run on")
     ap.add_argument("--sweep-only", action="store_true", help="skip every leg but the headline sweep")
     ap.add_argument("--with-inlib", action="store_true", help="with --sweep-only: keep the in-library multi-GPU / pipelining leg")
     ap.add_argument("--c3-seconds", type=float, default=3600.0,
