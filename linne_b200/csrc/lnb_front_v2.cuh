@@ -32,13 +32,39 @@ __device__ __forceinline__ double lnb_fr_sum(double v, double *scratch /* [8] */
     return s;
 }
 
+/* the same for N values at once: every value sees exactly the operations (and their order) lnb_fr_sum gives it, behind
+ * three barriers instead of 3 N.  scratch: [N * 8] */
+template <int N>
+__device__ __forceinline__ void lnb_fr_sum_n(double (&v)[N], double *scratch)
+{
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k++) scratch[k * 8 + (threadIdx.x >> 5)] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < LNB_FR_THREADS / 32; w++) s += scratch[k * 8 + w];
+        v[k] = s;
+    }
+    __syncthreads();
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Prepare: reference linne_encoder.c:480-529 (type decision, via lpc.c:810-865) and :613-641.
  * Thread c owns samples [c*T, c*T+T), T = ceil(n/256) <= 40, held in registers.
  * ------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(LNB_FR_THREADS) lnb_prepare_v2_kernel(LnbEncodeBatch b)
 {
-    __shared__ double red[8];
+    __shared__ double red[9 * 8];
     __shared__ double est_sum;
     __shared__ int32_t edge_first[LNB_FR_THREADS + 1], edge_last[LNB_FR_THREADS + 1];
     __shared__ int32_t bcast[4];
@@ -87,7 +113,9 @@ __global__ void __launch_bounds__(LNB_FR_THREADS) lnb_prepare_v2_kernel(LnbEncod
                 }
             }
             double rr[9];
-            for (uint32_t k = 0; k <= p0; k++) rr[k] = lnb_fr_sum(r[k], red);
+#pragma unroll
+            for (int k = 0; k < 9; k++) rr[k] = r[k];            /* lags beyond p0 are zero and unused */
+            lnb_fr_sum_n<9>(rr, red);                            /* one reduction for all lags: 3 barriers instead of 27 */
             if (tid == 0) {
                 double a[12], coef[10], parcor[10];
                 for (uint32_t k = 0; k <= p0; k++) parcor[k] = 0.0;
@@ -166,8 +194,11 @@ __global__ void __launch_bounds__(LNB_FR_THREADS) lnb_prepare_v2_kernel(LnbEncod
                     c1 += cur * nxt;
                 }
             }
-            c0 = lnb_fr_sum(c0, red);
-            c1 = lnb_fr_sum(c1, red);
+            {
+                double cc[2] = {c0, c1};
+                lnb_fr_sum_n<2>(cc, red);
+                c0 = cc[0]; c1 = cc[1];
+            }
             int32_t coef = 0;
             {
                 const double q = c1 / c0;
