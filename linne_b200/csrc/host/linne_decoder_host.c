@@ -328,7 +328,7 @@ static LINNEApiResult decode_range(struct LINNEDecoder *dec, const uint8_t *data
         }
     }
 
-    {   /* Large batches: eight lanes per block / one per (block, channel) instead of one CTA per block (lnb_tput_v1.cuh) */
+    {   /* Large batches: eight lanes per block / one per (block, channel) instead of one CTA per block (lnb_tput_v2.cuh) */
         const uint32_t min_blocks = dec->tput_min_blocks;
         const int32_t *pcm_base = d_pcm_ext ? d_pcm_ext : (const int32_t *)dec->d_pcm.ptr;
         batch.tput = (min_blocks && scan.num_blocks >= min_blocks && batch.fused_max_n

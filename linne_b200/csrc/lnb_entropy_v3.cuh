@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t lnb_e3_get(const LnbE3Win &w, uint32_t &pos,
 }
 
 /* Where the residuals of a compressed block go.  The stand-alone kernel writes them to the PCM planes; the
- * fused decoder (lnb_stream_v1.cuh) writes them to shared memory and publishes its progress to the synthesis
+ * fused decoder (lnb_stream_v2.cuh) writes them to shared memory and publishes its progress to the synthesis
  * warps.  `params` receives the side information of the block's channels. */
 struct LnbE3PlaneSink {
     static constexpr bool kPublish = false;

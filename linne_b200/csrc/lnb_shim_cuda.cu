@@ -170,10 +170,10 @@ struct CudaExec {
         lnb_tp_synth_kernel<Q0, Q1, Q2><<<(seqs + 31u) / 32u, 32, smem, dev->stream>>>(b);
         end_stage(slot);
     }
-    /* Large batches (b.tput, lnb_tput_v1.cuh).  The entropy stage needs nothing from the CRC pass -- it decodes every
+    /* Large batches (b.tput, lnb_tput_v2.cuh).  The entropy stage needs nothing from the CRC pass -- it decodes every
      * full block and the synthesis stage drops those whose CRC failed -- so the CRC pass and the per-block pipeline
      * kernel for what the lane-per-block kernels leave (tail blocks) run beside it on a side stream:
-     *     side:  crc_v2 -> stream_v1            main:  tp_entropy -> (join) -> tp_synth                          */
+     *     side:  crc_v2 -> stream_v2            main:  tp_entropy -> (join) -> tp_synth                          */
     void tput_decode(const LnbDecodeBatch &b)
     {
         const int shape = lnb_tput_shape(&b.cfg);           /* non-zero: the host asked lnb_shim_tput_supported(cfg) */
