@@ -186,3 +186,45 @@ def test_plan_ranges_pipeline_depth(monkeypatch):
     assert lib.lnb_plan_ranges(C.c_uint32(5), C.c_uint32(8)) == 2            # at least two blocks per range
     monkeypatch.setenv("LINNE_B200_PIPELINE", "3")
     assert lib.lnb_plan_ranges(C.c_uint32(15504), C.c_uint32(2)) == 6
+
+
+class _Ranges:
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        self.old = os.environ.get("LINNE_B200_GPUS")
+        os.environ["LINNE_B200_GPUS"] = str(self.n)
+
+    def __exit__(self, *a):
+        if self.old is None:
+            del os.environ["LINNE_B200_GPUS"]
+        else:
+            os.environ["LINNE_B200_GPUS"] = self.old
+
+
+@pytest.mark.parametrize("ranges", [2, 5])
+def test_in_library_block_ranges_on_the_host_simulator(hostsim, oracle, ranges):
+    """EncodeWhole / DecodeWhole over several block ranges behind one handle (child handles, one host thread per range,
+    host-side scan of the shard sizes, transfers taking turns): the host C code of the product, run against the CPU
+    stand-in of the shim.  Same bytes and samples as the single-range call; a damaged stream reports its first error."""
+    pcm = harness.synth_pcm(n=1024 * 13 + 300, channels=2, bits=16, seed=91)
+    single = hostsim.encode(pcm, preset=1, block=1024)
+    with _Ranges(ranges):
+        sharded = hostsim.encode(pcm, preset=1, block=1024)
+        back = hostsim.decode(single)
+    assert sharded == single
+    assert np.array_equal(back, pcm)
+    assert np.array_equal(oracle.decode(sharded), pcm)
+    sizes, off = [], 30
+    while off < len(single):
+        size = int.from_bytes(single[off + 2:off + 6], "big") + 6
+        sizes.append(size); off += size
+    bad = bytearray(single)
+    bad[30 + sum(sizes[:4]) + 30] ^= 0x10                       # block 4: CRC mismatch
+    bad[30 + sum(sizes[:9]) + 30] ^= 0x10                       # block 9 too: the earlier one decides
+    rc1, out1 = hostsim.decode(bytes(bad), return_code=True, fill=-7)
+    with _Ranges(ranges):
+        rc2, out2 = hostsim.decode(bytes(bad), return_code=True, fill=-7)
+    assert rc1 == rc2 == harness.DATA_CORRUPTION
+    assert np.array_equal(out1[:, :4 * 1024], pcm[:, :4 * 1024]) and np.array_equal(out2[:, :4 * 1024], pcm[:, :4 * 1024])
