@@ -391,7 +391,10 @@ int lnb_shim_open(LnbDevice **out, int device_ordinal)
     /* Handles, their side streams and the ranges of a pipelined call each own a stream; with the default of eight
      * hardware queues unrelated streams share one and wait for each other's copies and kernels.  Only effective while
      * the process has not created its CUDA context yet (a host that did so first sets the variable itself). */
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    {
+        static int once = 0;                                     /* the environment is touched by the first open only */
+        if (!__atomic_exchange_n(&once, 1, __ATOMIC_ACQ_REL)) setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    }
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return 1;
     if (device_ordinal >= 0) {
         if (device_ordinal >= count || cudaSetDevice(device_ordinal) != cudaSuccess) return 2;
