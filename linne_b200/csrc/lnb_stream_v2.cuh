@@ -391,14 +391,15 @@ __device__ __forceinline__ void lnb_ds_walk(const LnbDecodeBatch &b, LnbBlockDes
                     lnb_ds_reload(ring_addr, pos, w0, w1, w2, w3);                                            \
                 }
                 if (gmax == 8u) { LNB_DS_FAST_LOOP(8u) }
-                else if (gmax == 4u) { LNB_DS_FAST_LOOP(4u) }
+                /* ... and a rest of four to seven code words the same way (short partitions: 20 = 8 + 8 + 4) */
+                if (gmax >= 4u && !force_careful) { LNB_DS_FAST_LOOP(4u) }
 #undef LNB_DS_FAST_LOOP
                 while (rem) {
                     const uint32_t dst_addr = line_addr + 4u * done;
                     const uint32_t room = rem < gmax ? rem : gmax;
                     uint32_t g;
                     LNB_DS_COUNT(2);
-                    if (force_careful) { g = gmax; bad = 1u; force_careful = false; }
+                    if (force_careful) { g = room; bad = 1u; force_careful = false; }   /* the group that failed: min(gmax, rem) */
                     else if (room >= 8u) { lnb_ds_group<8>(w0, w1, w2, w3, dst_addr, k2, T, bad); g = 8u; }
                     else if (room >= 4u) { lnb_ds_group<4>(w0, w1, w2, w3, dst_addr, k2, T, bad); g = 4u; }
                     else if (room >= 2u) { lnb_ds_group<2>(w0, w1, w2, w3, dst_addr, k2, T, bad); g = 2u; }
